@@ -1,0 +1,326 @@
+/*
+ * ibu_b200.h — C ABI of the B200-native bulk record path of the `ibu` format.
+ *
+ * This is the drop-in boundary: plain pointers and sizes, no C++/torch types.
+ * A Rust `ibu` fork binds these symbols with an `extern "C"` block (see
+ * INTEGRATION.md).  Each entry point names the reference interface it replaces
+ * or extends (paths relative to the reference crate root).
+ *
+ * Conventions
+ *   - every function returns an ibu_status (0 = ok); when `err` is non-NULL it
+ *     receives the payload of the corresponding IbuError variant
+ *     (src/error.rs:56-128).  Nothing aborts or throws across this boundary.
+ *   - record-level invalidity (barcode/UMI word wider than bc_len/umi_len,
+ *     non-ACGT base on pack) is DATA (counters, flags), never an error:
+ *     the reference's own generator writes such records (examples/random.rs:46).
+ *   - `d_*` pointers are device pointers on the context's GPU, `h_*` host.
+ *     `stream` is a cudaStream_t passed as void* (NULL = the context's stream).
+ *     Functions ending in `_async` only enqueue work; the others block.
+ *   - there is no CPU fallback: GPU entry points return IBU_ERR_CUDA when no
+ *     sm_100 device is usable.
+ */
+#ifndef IBU_B200_H
+#define IBU_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ------------------------------------------------------------------ format */
+
+#define IBU_MAGIC 0x21554249u /* "IBU!" little-endian; src/constructs/header.rs:5 */
+#define IBU_VERSION 2u        /* src/constructs/header.rs:6 */
+#define IBU_HEADER_SIZE 32u   /* src/constructs/header.rs:7 */
+#define IBU_RECORD_SIZE 24u   /* src/constructs/record.rs:3 */
+#define IBU_BATCH_SIZE (1024u * 1024u) /* src/io/mmap.rs:284 */
+#define IBU_FLAG_SORTED 1ull  /* src/constructs/header.rs:111-113 */
+
+/* byte-identical to `#[repr(C)] struct Header` (src/constructs/header.rs:44-61) */
+typedef struct ibu_header {
+    uint32_t magic;
+    uint32_t version;
+    uint32_t bc_len;
+    uint32_t umi_len;
+    uint64_t flags;
+    uint8_t reserved[8];
+} ibu_header_t;
+
+/* byte-identical to `#[repr(C)] struct Record` (src/constructs/record.rs:58-66) */
+typedef struct ibu_record {
+    uint64_t barcode;
+    uint64_t umi;
+    uint64_t index;
+} ibu_record_t;
+
+/* ------------------------------------------------------------------ errors */
+
+/* 1:1 with the IbuError variants (src/error.rs:56-128) + device-side codes */
+typedef enum ibu_status {
+    IBU_OK = 0,
+    IBU_ERR_IO = 1,                     /* Io(std::io::Error): sys = errno */
+    IBU_ERR_NIFFLER = 2,                /* kept for numbering; never produced */
+    IBU_ERR_INVALID_MAGIC = 3,          /* a = expected, b = actual */
+    IBU_ERR_TRUNCATED_RECORD = 4,       /* a = pos */
+    IBU_ERR_INVALID_VERSION = 5,        /* a = expected, b = actual */
+    IBU_ERR_INVALID_BARCODE_LENGTH = 6, /* a = bc_len */
+    IBU_ERR_INVALID_UMI_LENGTH = 7,     /* a = umi_len */
+    IBU_ERR_INVALID_MAP_SIZE = 8,
+    IBU_ERR_INVALID_INDEX = 9,          /* a = idx, b = max */
+    IBU_ERR_PROCESS = 10,               /* Process(Box<dyn Error>): callback failure */
+    IBU_ERR_CUDA = 11,                  /* sys = cudaError_t */
+    IBU_ERR_NCCL = 12,
+    IBU_ERR_ARG = 13,                   /* NULL / misaligned / out-of-range argument */
+    IBU_ERR_NOMEM = 14
+} ibu_status;
+
+typedef struct ibu_error {
+    int32_t code; /* ibu_status */
+    int32_t sys;  /* errno or cudaError_t */
+    uint64_t a;
+    uint64_t b;
+    char msg[232];
+} ibu_error_t;
+
+/* Display string of the variant, formatted like src/error.rs:56-128. */
+const char *ibu_strerror(int code);
+const char *ibu_version(void);
+
+/* ------------------------------------------------------------------ header */
+
+/* Header::new (src/constructs/header.rs:84-93) */
+void ibu_header_init(ibu_header_t *h, uint32_t bc_len, uint32_t umi_len);
+/* Header::set_sorted / Header::sorted (header.rs:111-113, 130-132) */
+void ibu_header_set_sorted(ibu_header_t *h);
+int ibu_header_sorted(const ibu_header_t *h);
+/* Header::validate (header.rs:167-187): magic, version, bc_len, umi_len — first failure wins */
+int ibu_header_validate(const ibu_header_t *h, ibu_error_t *err);
+
+/* ------------------------------------------------------------- mmap reader */
+
+typedef struct ibu_mmap_reader ibu_mmap_reader_t;
+
+/* MmapReader::new (src/io/mmap.rs:143-161).  A file shorter than 32 bytes
+ * (a panic in the reference) is reported as IBU_ERR_IO. */
+int ibu_mmap_open(const char *path, ibu_mmap_reader_t **out, ibu_error_t *err);
+/* Clone = Arc bump (mmap.rs:99-107); each clone is closed separately. */
+ibu_mmap_reader_t *ibu_mmap_clone(ibu_mmap_reader_t *r);
+void ibu_mmap_close(ibu_mmap_reader_t *r);
+/* MmapReader::len / header (mmap.rs:178-180, 201-203) */
+size_t ibu_mmap_len(const ibu_mmap_reader_t *r);
+ibu_header_t ibu_mmap_header(const ibu_mmap_reader_t *r);
+/* MmapReader::slice (mmap.rs:253-270): zero-copy view, valid until the last clone closes. */
+int ibu_mmap_slice(const ibu_mmap_reader_t *r, size_t start, size_t end,
+                   const ibu_record_t **out, size_t *n_out, ibu_error_t *err);
+
+/* load_to_vec (src/io/reader.rs:510-535).  *records is released with ibu_free. */
+int ibu_load_to_vec(const char *path, ibu_header_t *header, ibu_record_t **records,
+                    size_t *n, ibu_error_t *err);
+void ibu_free(void *p);
+
+/* Contiguous range of shard `rank` of `world` over `len` records, the
+ * partition rule of process_parallel (mmap.rs:297-307): len/world each, the
+ * last shard takes the remainder. */
+void ibu_shard_range(uint64_t len, uint32_t rank, uint32_t world, uint64_t *start,
+                     uint64_t *end);
+
+/* ------------------------------------------------------------------ writer */
+
+typedef struct ibu_writer ibu_writer_t;
+
+/* Writer::from_path / Writer::new (src/io/writer.rs:129-143, 525-536): header
+ * bytes are written immediately and NOT validated (as in the reference). */
+int ibu_writer_open(const char *path, const ibu_header_t *header, ibu_writer_t **out,
+                    ibu_error_t *err);
+/* Writer::new_headless (writer.rs:169-179) onto a file (append = 1 opens O_APPEND). */
+int ibu_writer_open_headless(const char *path, int append, ibu_writer_t **out,
+                             ibu_error_t *err);
+/* Writer::write_record (writer.rs:260-273) */
+int ibu_writer_write_record(ibu_writer_t *w, const ibu_record_t *rec, ibu_error_t *err);
+/* Writer::write_batch (writer.rs:315-351): batches larger than the 48 Ki-record buffer bypass it */
+int ibu_writer_write_batch(ibu_writer_t *w, const ibu_record_t *recs, size_t n,
+                           ibu_error_t *err);
+/* Writer::records_written (writer.rs:207-209) */
+uint64_t ibu_writer_records_written(const ibu_writer_t *w);
+/* Writer::finish (writer.rs:429-433) */
+int ibu_writer_finish(ibu_writer_t *w, ibu_error_t *err);
+/* Drop (writer.rs:519-523): finish().ok() then release */
+void ibu_writer_close(ibu_writer_t *w);
+
+/* ------------------------------------------------------------- GPU context */
+
+typedef struct ibu_gpu_ctx ibu_gpu_ctx_t;
+
+typedef struct ibu_gpu_config {
+    uint32_t chunk_records; /* records per staged chunk; 0 = 4 * IBU_BATCH_SIZE */
+    uint32_t n_slots;       /* chunk slots (streams) in flight; 0 = 3 */
+    uint32_t copy_threads;  /* host threads for pageable->pinned staging; 0 = auto */
+    uint32_t reserved;
+} ibu_gpu_config_t;
+
+int ibu_gpu_device_count(void);
+/* One context per GPU (one process per GPU under torchrun; several contexts
+ * per process also work).  cfg may be NULL. */
+int ibu_gpu_ctx_create(int device, const ibu_gpu_config_t *cfg, ibu_gpu_ctx_t **out,
+                       ibu_error_t *err);
+void ibu_gpu_ctx_destroy(ibu_gpu_ctx_t *ctx);
+int ibu_gpu_ctx_device(const ibu_gpu_ctx_t *ctx);
+int ibu_gpu_ctx_sm_count(const ibu_gpu_ctx_t *ctx);
+/* number of kernels this library has launched in this process (all contexts) */
+uint64_t ibu_gpu_launch_count(void);
+int ibu_gpu_synchronize(ibu_gpu_ctx_t *ctx, void *stream, ibu_error_t *err);
+
+/* device / pinned-host memory helpers for callers without a CUDA runtime of their own */
+int ibu_gpu_malloc(ibu_gpu_ctx_t *ctx, size_t bytes, void **d_out, ibu_error_t *err);
+void ibu_gpu_free(ibu_gpu_ctx_t *ctx, void *d_ptr);
+int ibu_gpu_memcpy_h2d(ibu_gpu_ctx_t *ctx, void *d_dst, const void *h_src, size_t bytes,
+                       ibu_error_t *err);
+int ibu_gpu_memcpy_d2h(ibu_gpu_ctx_t *ctx, void *h_dst, const void *d_src, size_t bytes,
+                       ibu_error_t *err);
+int ibu_gpu_memset(ibu_gpu_ctx_t *ctx, void *d_dst, int value, size_t bytes, ibu_error_t *err);
+int ibu_host_alloc(size_t bytes, void **h_out, ibu_error_t *err); /* pinned */
+void ibu_host_free(void *h_ptr);
+int ibu_host_register(void *h_ptr, size_t bytes, int read_only, ibu_error_t *err);
+void ibu_host_unregister(void *h_ptr);
+
+/* ---------------------------------------------------------- device kernels */
+
+/* Result of one pass of the built-in reductions — the device counterpart of
+ * the reference processors run through process_parallel (a12 in SURVEY §8a):
+ *   n_records                         mmap.rs:350-373 (local_count)
+ *   sum_barcode/sum_umi/sum_index     examples/parallel.rs:21-27 (wrapping u64)
+ *   xor_all                           examples/roundtrip.rs:84-87
+ *   n_bad_barcode / n_bad_umi         word >> 2*len != 0 (len < 32); new semantics
+ *   n_bad_records                     records with either word bad (unpack) or
+ *                                     any non-ACGT base (pack)
+ * mmap.rs's count+sum processor value is sum_barcode+sum_umi+sum_index. */
+typedef struct ibu_reduce_result {
+    uint64_t n_records;
+    uint64_t sum_barcode;
+    uint64_t sum_umi;
+    uint64_t sum_index;
+    uint64_t xor_all;
+    uint64_t n_bad_barcode;
+    uint64_t n_bad_umi;
+    uint64_t n_bad_records;
+} ibu_reduce_result_t;
+
+/* K1: validate + reduce over device-resident records.  d_records must be
+ * 16-byte aligned.  *d_result (device) is OVERWRITTEN with this pass's values. */
+int ibu_gpu_validate_reduce_async(ibu_gpu_ctx_t *ctx, const ibu_record_t *d_records,
+                                  uint64_t n, uint32_t bc_len, uint32_t umi_len,
+                                  ibu_reduce_result_t *d_result, void *stream,
+                                  ibu_error_t *err);
+
+/* K2: 2-bit unpack to ASCII (bitnuc from_2bit convention: base i at bits
+ * [2i,2i+1], A=0 C=1 G=2 T=3; src/constructs/record.rs:19-27) fused with
+ * validation.  d_bc_ascii is [n][bc_len], d_umi_ascii is [n][umi_len], dense,
+ * no terminators, 16-byte aligned bases.  d_flags (nullable) gets one byte per
+ * record: bit0 = bad barcode, bit1 = bad umi.  d_result (nullable) is overwritten
+ * (sums/xor are NOT computed by this kernel and are written as 0). */
+int ibu_gpu_unpack_async(ibu_gpu_ctx_t *ctx, const ibu_record_t *d_records, uint64_t n,
+                         uint32_t bc_len, uint32_t umi_len, uint8_t *d_bc_ascii,
+                         uint8_t *d_umi_ascii, uint8_t *d_flags,
+                         ibu_reduce_result_t *d_result, void *stream, ibu_error_t *err);
+
+/* K3: ASCII -> Record pack (bitnuc as_2bit convention, case-insensitive).
+ * d_index nullable: index = index_base + i.  Non-ACGT bytes: the record is
+ * flagged (d_flags bit0 = barcode, bit1 = umi; nullable) and counted in
+ * d_result->n_bad_*; its code is the branch-free formula's output
+ * (c' = (c>>1)&3; code = c' ^ (c'>>1)), which is deterministic. */
+int ibu_gpu_pack_async(ibu_gpu_ctx_t *ctx, const uint8_t *d_bc_ascii,
+                       const uint8_t *d_umi_ascii, const uint64_t *d_index,
+                       uint64_t index_base, uint64_t n, uint32_t bc_len, uint32_t umi_len,
+                       ibu_record_t *d_records, uint8_t *d_flags,
+                       ibu_reduce_result_t *d_result, void *stream, ibu_error_t *err);
+
+/* K4: per-barcode table — the device form of the HashMap<barcode,count>
+ * processor of src/parallel.rs:79-98, extended with distinct-UMI counts.
+ * Rows are emitted sorted by barcode (Record's Ord, record.rs:58). */
+typedef struct ibu_barcode_row {
+    uint64_t barcode;
+    uint64_t n_records;
+    uint64_t n_distinct_umi;
+} ibu_barcode_row_t;
+
+typedef struct ibu_barcode_table {
+    ibu_barcode_row_t *d_rows; /* device, owned by the library: ibu_gpu_table_free */
+    uint64_t n_rows;
+    uint64_t n_records;
+    uint64_t n_distinct_pairs; /* distinct (barcode, umi) */
+    uint32_t input_was_sorted; /* 1 = the streaming sorted path ran */
+    uint32_t reserved;
+} ibu_barcode_table_t;
+
+/* Blocking (the table size is data dependent).  mode: 0 = auto (verify
+ * sortedness on device, stream if sorted else sort-then-segment),
+ * 1 = require sorted (IBU_ERR_ARG-free: returns input_was_sorted = 0 and no rows
+ * if the data is not sorted), 2 = force the unsorted path. */
+int ibu_gpu_barcode_count(ibu_gpu_ctx_t *ctx, const ibu_record_t *d_records, uint64_t n,
+                          int mode, ibu_barcode_table_t *table, void *stream,
+                          ibu_error_t *err);
+void ibu_gpu_table_free(ibu_gpu_ctx_t *ctx, ibu_barcode_table_t *table);
+
+/* ------------------------------------------------ synthetic data (benches) */
+
+/* Counter-based generators (splitmix64 of seed and record number) shared by the
+ * oracle so that CPU and GPU regenerate identical inputs without files. */
+enum {
+    IBU_GEN_CLEAN = 0,     /* barcode/umi masked to bc_len/umi_len, index = i */
+    IBU_GEN_DIRTY = 1,     /* as CLEAN, `param` ppm of records carry an unmasked word */
+    IBU_GEN_PATTERN = 2,   /* (i % 1e6, 31 i % 1e6, i): examples/parallel.rs:65-69 */
+    IBU_GEN_WHITELIST = 3  /* `param` distinct barcodes, 4^min(umi_len,6)... umis; unsorted */
+};
+int ibu_gpu_generate_records_async(ibu_gpu_ctx_t *ctx, ibu_record_t *d_records,
+                                   uint64_t first, uint64_t n, uint32_t bc_len,
+                                   uint32_t umi_len, int mode, uint64_t param, uint64_t seed,
+                                   void *stream, ibu_error_t *err);
+/* ASCII rows uniform over ACGT; `dirty_ppm` of bytes become 'N', `lower_ppm` lower-case. */
+int ibu_gpu_generate_ascii_async(ibu_gpu_ctx_t *ctx, uint8_t *d_ascii, uint64_t first_row,
+                                 uint64_t n_rows, uint32_t len, uint64_t dirty_ppm,
+                                 uint64_t lower_ppm, uint64_t seed, void *stream,
+                                 ibu_error_t *err);
+
+/* ---------------------------------------------- host-buffer (end-to-end) path */
+
+/* GPU counterpart of MmapReader::process_parallel (src/io/mmap.rs:286-332) for
+ * the built-in reductions: records [start,end) of the reader are staged chunk
+ * by chunk through pinned buffers on double-buffered streams, validated and
+ * reduced on device.  `on_chunk` (nullable) is the on_batch_complete analogue
+ * (parallel.rs:141-151): called on the calling thread after each chunk's result
+ * has landed, in chunk order, with that chunk's result; a non-zero return
+ * aborts with IBU_ERR_PROCESS. */
+typedef int (*ibu_chunk_cb)(void *user, uint64_t chunk_start, uint64_t chunk_n,
+                            const ibu_reduce_result_t *chunk_result);
+int ibu_gpu_process_mmap(ibu_gpu_ctx_t *ctx, const ibu_mmap_reader_t *reader, uint64_t start,
+                         uint64_t end, ibu_reduce_result_t *h_result, ibu_chunk_cb on_chunk,
+                         void *user, ibu_error_t *err);
+/* Same over a host array (pinned: copied directly; pageable: staged). */
+int ibu_gpu_process_host(ibu_gpu_ctx_t *ctx, const ibu_record_t *h_records, uint64_t n,
+                         uint32_t bc_len, uint32_t umi_len, ibu_reduce_result_t *h_result,
+                         ibu_chunk_cb on_chunk, void *user, ibu_error_t *err);
+
+/* Device path of load_to_vec (src/io/reader.rs:510-535): header validated, size
+ * checked, records [start,end) of the file land in one device allocation
+ * (*d_records, release with ibu_gpu_free).  end = UINT64_MAX means "to the end". */
+int ibu_gpu_load_to_device(ibu_gpu_ctx_t *ctx, const char *path, uint64_t start, uint64_t end,
+                           ibu_header_t *header, ibu_record_t **d_records, uint64_t *n,
+                           ibu_error_t *err);
+
+/* End-to-end unpack: host records -> host ASCII, pipelined H2D / K2 / D2H. */
+int ibu_gpu_unpack_host(ibu_gpu_ctx_t *ctx, const ibu_record_t *h_records, uint64_t n,
+                        uint32_t bc_len, uint32_t umi_len, uint8_t *h_bc_ascii,
+                        uint8_t *h_umi_ascii, uint8_t *h_flags, ibu_reduce_result_t *h_result,
+                        ibu_error_t *err);
+/* End-to-end pack: host ASCII -> host records (the Writer::write_batch source). */
+int ibu_gpu_pack_host(ibu_gpu_ctx_t *ctx, const uint8_t *h_bc_ascii, const uint8_t *h_umi_ascii,
+                      const uint64_t *h_index, uint64_t index_base, uint64_t n, uint32_t bc_len,
+                      uint32_t umi_len, ibu_record_t *h_records, uint8_t *h_flags,
+                      ibu_reduce_result_t *h_result, ibu_error_t *err);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* IBU_B200_H */
