@@ -1,0 +1,61 @@
+// ctx.h — the GPU context behind ibu_gpu_ctx_t (internal).
+#pragma once
+#include <atomic>
+#include <cuda_runtime.h>
+#include <vector>
+
+#include "common.h"
+
+struct ibu_chunk_slot {
+    cudaStream_t stream = nullptr;
+    cudaEvent_t done = nullptr;
+    void *h_in = nullptr;    // pinned staging for pageable sources
+    void *h_out = nullptr;   // pinned staging for pageable destinations
+    void *d_in = nullptr;
+    void *d_out = nullptr;
+    size_t h_in_bytes = 0, h_out_bytes = 0, d_in_bytes = 0, d_out_bytes = 0;
+    ibu_reduce_result_t *d_result = nullptr;  // device
+    ibu_reduce_result_t *h_result = nullptr;  // pinned
+};
+
+struct ibu_gpu_ctx {
+    int device = 0;
+    int sm_count = 0;
+    cudaStream_t stream = nullptr;  // default stream of the context (non-blocking)
+    ibu_gpu_config_t cfg{};
+    std::vector<ibu_chunk_slot> slots;
+    int variant = 0;  // kernel variant override (IBU_B200_VARIANT env; tuning only)
+};
+
+namespace ibu {
+
+extern std::atomic<uint64_t> g_launches;
+
+inline int cuda_fail(ibu_error_t *err, cudaError_t e, const char *what) {
+    return set_error(err, IBU_ERR_CUDA, (int)e, 0, 0, "CUDA error in %s: %s", what,
+                     cudaGetErrorString(e));
+}
+
+#define IBU_CUDA(call)                                                   \
+    do {                                                                 \
+        cudaError_t e__ = (call);                                        \
+        if (e__ != cudaSuccess) return ibu::cuda_fail(err, e__, #call);  \
+    } while (0)
+
+struct DeviceGuard {
+    int prev = -1;
+    explicit DeviceGuard(int dev) {
+        cudaGetDevice(&prev);
+        if (prev != dev) cudaSetDevice(dev);
+        else prev = -1;
+    }
+    ~DeviceGuard() {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+};
+
+inline cudaStream_t pick_stream(ibu_gpu_ctx *ctx, void *stream) {
+    return stream ? (cudaStream_t)stream : ctx->stream;
+}
+
+}  // namespace ibu

@@ -1,0 +1,367 @@
+// host_format.cpp — file-format side of libibu_b200: Header, MmapReader, load_to_vec, Writer.
+//
+// These are the host entry points of the C ABI (include/ibu_b200.h).  They keep the on-disk
+// format and the reader/writer semantics of the reference so files stay a drop-in; the
+// record-processing work itself only exists on the GPU (kernels.cu, pipeline.cu).
+#include <atomic>
+#include <cerrno>
+#include <cstdlib>
+#include <fcntl.h>
+#include <new>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
+#include <vector>
+
+#include "common.h"
+
+using ibu::clear_error;
+using ibu::set_error;
+
+struct ibu_mmap_shared {
+    const uint8_t *base;
+    size_t bytes;
+    std::atomic<long> refs;
+};
+
+const uint8_t *ibu_mmap_base(const ibu_mmap_reader *r) { return r->shared->base; }
+
+namespace {
+
+int io_error(ibu_error_t *err, int e, const char *what, const char *path) {
+    return set_error(err, IBU_ERR_IO, e, 0, 0, "I/O error: %s %s: %s", what, path ? path : "",
+                     strerror(e));
+}
+
+// write(2) until done; the reference's write_all
+bool write_all(int fd, const void *buf, size_t len) {
+    const uint8_t *p = (const uint8_t *)buf;
+    while (len) {
+        ssize_t w = ::write(fd, p, len);
+        if (w < 0) {
+            if (errno == EINTR) continue;
+            return false;
+        }
+        p += w;
+        len -= (size_t)w;
+    }
+    return true;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char *ibu_version(void) { return "ibu_b200 0.1.0 (format v2, sm_100a)"; }
+
+const char *ibu_strerror(int code) {
+    switch (code) {  // Display strings of src/error.rs:56-128 (payload-free part)
+        case IBU_OK: return "ok";
+        case IBU_ERR_IO: return "I/O error";
+        case IBU_ERR_NIFFLER: return "Niffler error";
+        case IBU_ERR_INVALID_MAGIC: return "Invalid magic number";
+        case IBU_ERR_TRUNCATED_RECORD: return "Truncated record";
+        case IBU_ERR_INVALID_VERSION: return "Invalid version found";
+        case IBU_ERR_INVALID_BARCODE_LENGTH: return "Invalid barcode length (must be 1-32)";
+        case IBU_ERR_INVALID_UMI_LENGTH: return "Invalid UMI length (must be 1-32)";
+        case IBU_ERR_INVALID_MAP_SIZE: return "Invalid map size - not a multiple of record size";
+        case IBU_ERR_INVALID_INDEX: return "Invalid index";
+        case IBU_ERR_PROCESS: return "Processing error";
+        case IBU_ERR_CUDA: return "CUDA error";
+        case IBU_ERR_NCCL: return "NCCL error";
+        case IBU_ERR_ARG: return "Invalid argument";
+        case IBU_ERR_NOMEM: return "Out of memory";
+        default: return "unknown error";
+    }
+}
+
+// ---- Header (src/constructs/header.rs) ---------------------------------------------------
+
+void ibu_header_init(ibu_header_t *h, uint32_t bc_len, uint32_t umi_len) {
+    memset(h, 0, sizeof(*h));
+    h->magic = IBU_MAGIC;
+    h->version = IBU_VERSION;
+    h->bc_len = bc_len;
+    h->umi_len = umi_len;
+}
+
+void ibu_header_set_sorted(ibu_header_t *h) { h->flags |= IBU_FLAG_SORTED; }
+int ibu_header_sorted(const ibu_header_t *h) { return (h->flags & IBU_FLAG_SORTED) != 0; }
+
+int ibu_header_validate(const ibu_header_t *h, ibu_error_t *err) {
+    clear_error(err);
+    if (!h) return set_error(err, IBU_ERR_ARG, 0, 0, 0, "null header");
+    if (h->magic != IBU_MAGIC)
+        return set_error(err, IBU_ERR_INVALID_MAGIC, 0, IBU_MAGIC, h->magic,
+                         "Invalid magic number, expected (%#x), found (%#x)", IBU_MAGIC, h->magic);
+    if (h->version != IBU_VERSION)
+        return set_error(err, IBU_ERR_INVALID_VERSION, 0, IBU_VERSION, h->version,
+                         "Invalid version found, expected (%u), found (%u)", IBU_VERSION,
+                         h->version);
+    if (h->bc_len == 0 || h->bc_len > 32)
+        return set_error(err, IBU_ERR_INVALID_BARCODE_LENGTH, 0, h->bc_len, 0,
+                         "Invalid barcode length: %u (must be 1-32)", h->bc_len);
+    if (h->umi_len == 0 || h->umi_len > 32)
+        return set_error(err, IBU_ERR_INVALID_UMI_LENGTH, 0, h->umi_len, 0,
+                         "Invalid UMI length: %u (must be 1-32)", h->umi_len);
+    return IBU_OK;
+}
+
+// ---- MmapReader (src/io/mmap.rs) ---------------------------------------------------------
+
+int ibu_mmap_open(const char *path, ibu_mmap_reader_t **out, ibu_error_t *err) {
+    clear_error(err);
+    if (!path || !out) return set_error(err, IBU_ERR_ARG, 0, 0, 0, "null argument");
+    *out = nullptr;
+    int fd = ::open(path, O_RDONLY | O_CLOEXEC);
+    if (fd < 0) return io_error(err, errno, "open", path);
+    struct stat st;
+    if (fstat(fd, &st) != 0) {
+        int e = errno;
+        ::close(fd);
+        return io_error(err, e, "stat", path);
+    }
+    size_t bytes = (size_t)st.st_size;
+    if (bytes < IBU_HEADER_SIZE) {  // mmap of an empty file fails; a short map panics upstream
+        ::close(fd);
+        return io_error(err, EINVAL, "file shorter than the 32-byte header:", path);
+    }
+    void *p = mmap(nullptr, bytes, PROT_READ, MAP_PRIVATE, fd, 0);
+    int e = errno;
+    ::close(fd);
+    if (p == MAP_FAILED) return io_error(err, e, "mmap", path);
+
+    ibu_header_t header;
+    memcpy(&header, p, sizeof(header));
+    int rc = ibu_header_validate(&header, err);
+    if (rc == IBU_OK && (bytes - IBU_HEADER_SIZE) % IBU_RECORD_SIZE != 0)
+        rc = set_error(err, IBU_ERR_INVALID_MAP_SIZE, 0, bytes, 0,
+                       "Invalid map size - not a multiple of record size");
+    if (rc != IBU_OK) {
+        munmap(p, bytes);
+        return rc;
+    }
+    auto *shared = new (std::nothrow) ibu_mmap_shared{(const uint8_t *)p, bytes, {1}};
+    auto *r = new (std::nothrow) ibu_mmap_reader{shared, header, (bytes - IBU_HEADER_SIZE) / IBU_RECORD_SIZE};
+    if (!shared || !r) {
+        munmap(p, bytes);
+        delete shared;
+        delete r;
+        return set_error(err, IBU_ERR_NOMEM, 0, 0, 0, "out of memory");
+    }
+    *out = r;
+    return IBU_OK;
+}
+
+ibu_mmap_reader_t *ibu_mmap_clone(ibu_mmap_reader_t *r) {
+    if (!r) return nullptr;
+    auto *c = new (std::nothrow) ibu_mmap_reader(*r);
+    if (c) r->shared->refs.fetch_add(1, std::memory_order_relaxed);
+    return c;
+}
+
+void ibu_mmap_close(ibu_mmap_reader_t *r) {
+    if (!r) return;
+    if (r->shared->refs.fetch_sub(1, std::memory_order_acq_rel) == 1) {
+        munmap((void *)r->shared->base, r->shared->bytes);
+        delete r->shared;
+    }
+    delete r;
+}
+
+size_t ibu_mmap_len(const ibu_mmap_reader_t *r) { return r ? r->len : 0; }
+
+ibu_header_t ibu_mmap_header(const ibu_mmap_reader_t *r) {
+    ibu_header_t h;
+    if (r) h = r->header; else memset(&h, 0, sizeof(h));
+    return h;
+}
+
+int ibu_mmap_slice(const ibu_mmap_reader_t *r, size_t start, size_t end, const ibu_record_t **out,
+                   size_t *n_out, ibu_error_t *err) {
+    clear_error(err);
+    if (!r || !out || !n_out) return set_error(err, IBU_ERR_ARG, 0, 0, 0, "null argument");
+    // both reference checks report {idx: end, max: len} (mmap.rs:254-265)
+    if (start >= r->len || end > r->len || end <= start)
+        return set_error(err, IBU_ERR_INVALID_INDEX, 0, end, r->len,
+                         "Invalid index (%zu) - Must be less than %zu", end, r->len);
+    *out = (const ibu_record_t *)(r->shared->base + IBU_HEADER_SIZE + start * IBU_RECORD_SIZE);
+    *n_out = end - start;
+    return IBU_OK;
+}
+
+void ibu_shard_range(uint64_t len, uint32_t rank, uint32_t world, uint64_t *start, uint64_t *end) {
+    if (world == 0) world = 1;
+    uint64_t per = len / world, rem = len % world;
+    uint64_t s = (uint64_t)rank * per;
+    uint64_t e = s + per + (rank == world - 1 ? rem : 0);
+    if (start) *start = s;
+    if (end) *end = e;
+}
+
+// ---- load_to_vec (src/io/reader.rs:510-535) ----------------------------------------------
+
+int ibu_load_to_vec(const char *path, ibu_header_t *header, ibu_record_t **records, size_t *n,
+                    ibu_error_t *err) {
+    clear_error(err);
+    if (!path || !header || !records || !n) return set_error(err, IBU_ERR_ARG, 0, 0, 0, "null argument");
+    *records = nullptr;
+    *n = 0;
+    int fd = ::open(path, O_RDONLY | O_CLOEXEC);
+    if (fd < 0) return io_error(err, errno, "open", path);
+    auto read_exact = [&](void *dst, size_t len) {
+        uint8_t *p = (uint8_t *)dst;
+        while (len) {
+            ssize_t got = ::read(fd, p, len);
+            if (got < 0 && errno == EINTR) continue;
+            if (got <= 0) return false;  // error or unexpected EOF
+            p += got;
+            len -= (size_t)got;
+        }
+        return true;
+    };
+    int rc = IBU_OK;
+    ibu_record_t *buf = nullptr;
+    struct stat st;
+    if (!read_exact(header, IBU_HEADER_SIZE)) {
+        rc = io_error(err, errno ? errno : EIO, "read header of", path);
+    } else if ((rc = ibu_header_validate(header, err)) != IBU_OK) {
+    } else if (fstat(fd, &st) != 0) {
+        rc = io_error(err, errno, "stat", path);
+    } else {
+        size_t data = (size_t)st.st_size - IBU_HEADER_SIZE;
+        if (data % IBU_RECORD_SIZE != 0) {
+            rc = set_error(err, IBU_ERR_INVALID_MAP_SIZE, 0, st.st_size, 0,
+                           "Invalid map size - not a multiple of record size");
+        } else {
+            size_t count = data / IBU_RECORD_SIZE;
+            // the reference zero-fills a Vec first; the bytes are overwritten right away, so
+            // an uninitialised 64-byte aligned block is equivalent and skips a pass over memory
+            if (posix_memalign((void **)&buf, 64, data ? data : 64) != 0) {
+                rc = set_error(err, IBU_ERR_NOMEM, 0, data, 0, "cannot allocate %zu bytes", data);
+            } else if (!read_exact(buf, data)) {
+                rc = io_error(err, errno ? errno : EIO, "read records of", path);
+            } else {
+                *records = buf;
+                *n = count;
+                buf = nullptr;
+            }
+        }
+    }
+    free(buf);
+    ::close(fd);
+    return rc;
+}
+
+void ibu_free(void *p) { free(p); }
+
+}  // extern "C"
+
+// ---- Writer (src/io/writer.rs) -----------------------------------------------------------
+
+struct ibu_writer {
+    int fd;
+    std::vector<uint8_t> buffer;  // DEFAULT_BUFFER_SIZE = 48 Ki records (writer.rs:10)
+    size_t pos = 0;
+    uint64_t records_written = 0;
+    bool failed = false;
+
+    bool flush_buffer() {
+        if (pos > 0) {
+            if (!write_all(fd, buffer.data(), pos)) return false;
+            pos = 0;
+        }
+        return true;
+    }
+};
+
+namespace {
+constexpr size_t WRITER_BUFFER = 48 * 1024 * IBU_RECORD_SIZE;
+
+int writer_open(const char *path, int flags, const ibu_header_t *header, ibu_writer_t **out,
+                ibu_error_t *err) {
+    clear_error(err);
+    if (!path || !out) return set_error(err, IBU_ERR_ARG, 0, 0, 0, "null argument");
+    *out = nullptr;
+    int fd = ::open(path, flags | O_WRONLY | O_CREAT | O_CLOEXEC, 0644);
+    if (fd < 0) return io_error(err, errno, "create", path);
+    if (header && !write_all(fd, header, IBU_HEADER_SIZE)) {  // written immediately, unvalidated
+        int e = errno;
+        ::close(fd);
+        return io_error(err, e, "write header to", path);
+    }
+    auto *w = new (std::nothrow) ibu_writer;
+    if (!w) {
+        ::close(fd);
+        return set_error(err, IBU_ERR_NOMEM, 0, 0, 0, "out of memory");
+    }
+    w->fd = fd;
+    w->buffer.assign(WRITER_BUFFER, 0);
+    *out = w;
+    return IBU_OK;
+}
+}  // namespace
+
+extern "C" {
+
+int ibu_writer_open(const char *path, const ibu_header_t *header, ibu_writer_t **out,
+                    ibu_error_t *err) {
+    if (!header) return set_error(err, IBU_ERR_ARG, 0, 0, 0, "null header");
+    return writer_open(path, O_TRUNC, header, out, err);
+}
+
+int ibu_writer_open_headless(const char *path, int append, ibu_writer_t **out, ibu_error_t *err) {
+    return writer_open(path, append ? O_APPEND : O_TRUNC, nullptr, out, err);
+}
+
+int ibu_writer_write_record(ibu_writer_t *w, const ibu_record_t *rec, ibu_error_t *err) {
+    clear_error(err);
+    if (!w || !rec) return set_error(err, IBU_ERR_ARG, 0, 0, 0, "null argument");
+    if (w->pos + IBU_RECORD_SIZE > w->buffer.size() && !w->flush_buffer())
+        return io_error(err, errno, "write", nullptr);
+    memcpy(w->buffer.data() + w->pos, rec, IBU_RECORD_SIZE);
+    w->pos += IBU_RECORD_SIZE;
+    w->records_written += 1;
+    return IBU_OK;
+}
+
+int ibu_writer_write_batch(ibu_writer_t *w, const ibu_record_t *recs, size_t n, ibu_error_t *err) {
+    clear_error(err);
+    if (!w || (!recs && n)) return set_error(err, IBU_ERR_ARG, 0, 0, 0, "null argument");
+    const uint8_t *src = (const uint8_t *)recs;
+    size_t len = n * IBU_RECORD_SIZE;
+    if (len > w->buffer.size()) {  // larger than the buffer: flush pending, then write through
+        if (!w->flush_buffer() || !write_all(w->fd, src, len)) return io_error(err, errno, "write", nullptr);
+        w->records_written += n;
+        return IBU_OK;
+    }
+    while (len) {
+        size_t take = w->buffer.size() - w->pos;
+        if (take > len) take = len;
+        memcpy(w->buffer.data() + w->pos, src, take);
+        w->pos += take;
+        src += take;
+        len -= take;
+        if (w->pos >= w->buffer.size() && !w->flush_buffer()) return io_error(err, errno, "write", nullptr);
+    }
+    w->records_written += n;
+    return IBU_OK;
+}
+
+uint64_t ibu_writer_records_written(const ibu_writer_t *w) { return w ? w->records_written : 0; }
+
+int ibu_writer_finish(ibu_writer_t *w, ibu_error_t *err) {
+    clear_error(err);
+    if (!w) return set_error(err, IBU_ERR_ARG, 0, 0, 0, "null writer");
+    if (!w->flush_buffer()) return io_error(err, errno, "flush", nullptr);
+    return IBU_OK;  // inner.flush() on a raw fd is a no-op
+}
+
+void ibu_writer_close(ibu_writer_t *w) {
+    if (!w) return;
+    w->flush_buffer();  // Drop: finish().ok()
+    ::close(w->fd);
+    delete w;
+}
+
+}  // extern "C"

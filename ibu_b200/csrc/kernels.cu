@@ -1,0 +1,726 @@
+// kernels.cu — sm_100a kernels of the bulk record path and their stream-ordered launchers.
+//
+//   K1 k_validate_reduce   24 B/record read            built-in reductions of process_parallel
+//   K2 k_unpack            24 + bc_len + umi_len B     2-bit -> ASCII + validation
+//   K3 k_pack              bc_len + umi_len + 24 B     ASCII -> Record + validation
+//   generators             synthetic inputs shared with the oracle
+//
+// All three are HBM-bound streamers: every global access is a 128/256-bit fully coalesced
+// vector access of read-once / write-once data (L1 no-allocate, L2 evict-first), the 24-byte
+// AoS records are transposed to per-lane records through shared memory (K2) or consumed in
+// place with a lane-static field rotation (K1), decode/encode is branch-free SWAR with the
+// ACGT table held in a register (PRMT).  No tensor cores: nothing here is a contraction.
+#include "ctx.h"
+#include "kernels.cuh"
+
+namespace ibu {
+
+std::atomic<uint64_t> g_launches{0};
+
+// ============================================================================ K1
+// One warp consumes tiles of 128 records = 96 x 32 B.  Lane l loads 32-byte units
+// l, l+32, l+64 of the tile (three LDG.256, perfectly coalesced).  u64 number e of the
+// tile is field e % 3 of a record; for lane l, unit k, element j: e = 4(l+32k)+j, so the
+// field is (l + 2k + j) % 3 = (c + g) % 3 with c = l % 3 (lane constant) and
+// g = (2k + j) % 3 (compile-time constant).  Elements are therefore accumulated into three
+// groups g and rotated to fields once, after the loop.
+struct ReduceAcc {
+    uint64_t a0 = 0, a1 = 0, a2 = 0, x = 0;
+    uint32_t b0 = 0, b1 = 0, b2 = 0;
+};
+
+#define IBU_ACC(G, V, SLOT)                           \
+    do {                                              \
+        acc.a##G += (V);                              \
+        acc.x ^= (V);                                 \
+        uint32_t bit__ = ((V) & m##G) != 0ull;        \
+        acc.b##G += bit__;                            \
+        bm |= bit__ << (SLOT);                        \
+    } while (0)
+
+__global__ void __launch_bounds__(kBlockThreads)
+k_validate_reduce(const uint8_t *__restrict__ recs, uint64_t n, uint64_t bc_hi, uint64_t umi_hi,
+                  ibu_reduce_result_t *__restrict__ res) {
+    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    const uint64_t gwarp = (uint64_t)blockIdx.x * kWarpsPerBlock + warp;
+    const uint64_t total_warps = (uint64_t)gridDim.x * kWarpsPerBlock;
+    const uint32_t c = lane % 3u;
+    // mask of group g = mask of field (c + g) % 3; field 2 (index) is never invalid
+    const uint64_t m0 = c == 0 ? bc_hi : c == 1 ? umi_hi : 0ull;
+    const uint64_t m1 = c == 0 ? umi_hi : c == 1 ? 0ull : bc_hi;
+    const uint64_t m2 = c == 0 ? 0ull : c == 1 ? bc_hi : umi_hi;
+
+    ReduceAcc acc;
+    uint32_t both = 0;  // records whose barcode AND umi are invalid
+    const uint64_t n_tiles = n / kTileRecords;
+    for (uint64_t t = gwarp; t < n_tiles; t += total_warps) {
+        const u64x4 *base = reinterpret_cast<const u64x4 *>(recs) + t * kTileU8 + lane;
+        const u64x4 v0 = ldg_stream256(base), v1 = ldg_stream256(base + 32),
+                    v2 = ldg_stream256(base + 64);
+        uint32_t bm = 0;  // bit 4k+j: element (k, j) failed its mask
+        IBU_ACC(0, v0.x, 0); IBU_ACC(1, v0.y, 1); IBU_ACC(2, v0.z, 2);  IBU_ACC(0, v0.w, 3);
+        IBU_ACC(2, v1.x, 4); IBU_ACC(0, v1.y, 5); IBU_ACC(1, v1.z, 6);  IBU_ACC(2, v1.w, 7);
+        IBU_ACC(1, v2.x, 8); IBU_ACC(2, v2.y, 9); IBU_ACC(0, v2.z, 10); IBU_ACC(1, v2.w, 11);
+        if (__any_sync(0xffffffffu, bm != 0)) {
+            // rare path: pair each invalid barcode with the word that follows it (its umi).
+            // Two adjacent failing words are always (barcode, umi): the index never fails.
+            // The word after element (k,3) of lane l is element (k,0) of lane l+1, or
+            // element (k+1,0) of lane 0 when l == 31.
+            uint32_t firsts = (bm & 1u) | ((bm >> 3) & 2u) | ((bm >> 6) & 4u);
+            uint32_t nxt = __shfl_sync(0xffffffffu, firsts, (lane + 1) & 31u);
+            if (lane == 31) nxt >>= 1;
+#pragma unroll
+            for (int k = 0; k < 3; k++) {
+                uint32_t nib = (bm >> (4 * k)) & 0xFu;
+                uint32_t ext = nib | (((nxt >> k) & 1u) << 4);
+                both += __popc(nib & (ext >> 1));
+            }
+        }
+    }
+    // rotate groups to fields: field f lives in group (f - c) mod 3
+    uint64_t s_bc = c == 0 ? acc.a0 : c == 1 ? acc.a2 : acc.a1;
+    uint64_t s_umi = c == 0 ? acc.a1 : c == 1 ? acc.a0 : acc.a2;
+    uint64_t s_idx = c == 0 ? acc.a2 : c == 1 ? acc.a1 : acc.a0;
+    uint64_t n_bb = c == 0 ? acc.b0 : c == 1 ? acc.b2 : acc.b1;
+    uint64_t n_bu = c == 0 ? acc.b1 : c == 1 ? acc.b0 : acc.b2;
+    uint64_t x = acc.x, n_both = both;
+
+    if (gwarp == 0) {  // ragged tail (< 128 records), one record per lane per step
+        const uint64_t *r64 = reinterpret_cast<const uint64_t *>(recs);
+        for (uint64_t r = n_tiles * kTileRecords + lane; r < n; r += 32) {
+            uint64_t b = ldg_stream64(r64 + 3 * r), u = ldg_stream64(r64 + 3 * r + 1),
+                     i = ldg_stream64(r64 + 3 * r + 2);
+            s_bc += b; s_umi += u; s_idx += i; x ^= b ^ u ^ i;
+            bool bb = (b & bc_hi) != 0, bu = (u & umi_hi) != 0;
+            n_bb += bb; n_bu += bu; n_both += (bb && bu);
+        }
+    }
+
+    __shared__ uint64_t red[kWarpsPerBlock][7];
+    s_bc = warp_sum64(s_bc); s_umi = warp_sum64(s_umi); s_idx = warp_sum64(s_idx);
+    x = warp_xor64(x);
+    n_bb = warp_sum64(n_bb); n_bu = warp_sum64(n_bu); n_both = warp_sum64(n_both);
+    if (lane == 0) {
+        red[warp][0] = s_bc; red[warp][1] = s_umi; red[warp][2] = s_idx; red[warp][3] = x;
+        red[warp][4] = n_bb; red[warp][5] = n_bu; red[warp][6] = n_both;
+    }
+    __syncthreads();
+    if (threadIdx.x < 7) {
+        uint64_t v = 0;
+        for (int w = 0; w < kWarpsPerBlock; w++) {
+            if (threadIdx.x == 3) v ^= red[w][3]; else v += red[w][threadIdx.x];
+        }
+        unsigned long long *out = reinterpret_cast<unsigned long long *>(res);
+        switch (threadIdx.x) {  // field order of ibu_reduce_result_t
+            case 0: atomicAdd(out + 1, v); break;                 // sum_barcode
+            case 1: atomicAdd(out + 2, v); break;                 // sum_umi
+            case 2: atomicAdd(out + 3, v); break;                 // sum_index
+            case 3: atomicXor(out + 4, v); break;                 // xor_all
+            case 4: atomicAdd(out + 5, v); atomicAdd(out + 7, v); break;  // bad barcode; records +=
+            case 5: atomicAdd(out + 6, v); atomicAdd(out + 7, v); break;  // bad umi; records +=
+            case 6: atomicAdd(out + 7, 0ull - v); break;          // records -= both (wrapping)
+        }
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0)
+        atomicAdd(reinterpret_cast<unsigned long long *>(res), (unsigned long long)n);  // n_records
+}
+
+// ============================================================================ K2
+struct UnpackArgs {
+    const uint8_t *recs;
+    uint64_t n;
+    uint8_t *bc_out, *umi_out, *flags;
+    uint64_t bc_hi, umi_hi;
+    ibu_reduce_result_t *res;
+    uint32_t bc_len, umi_len;
+    uint32_t warp_smem_bytes;  // per-warp shared memory: input tile + staged outputs
+    uint32_t bc_stage_off, umi_stage_off;
+};
+
+template <int L>
+struct LenOf {
+    static __device__ __forceinline__ uint32_t get(uint32_t) { return L; }
+};
+template <>
+struct LenOf<0> {
+    static __device__ __forceinline__ uint32_t get(uint32_t rt) { return rt; }
+};
+
+// Emit one decoded row.  L = 32 / 16: straight from registers with a 256 / 128-bit store
+// (a warp covers 1024 / 512 contiguous bytes).  Otherwise the row is staged in shared memory
+// and the whole tile (128 x len bytes, 16-byte aligned in the output) is copied out afterwards.
+template <int L>
+__device__ __forceinline__ void emit_row(uint64_t w, uint32_t len, uint8_t *gout, uint64_t rec,
+                                         uint8_t *stage, uint32_t r) {
+    uint32_t asc[8];
+    if (L == 32) {
+        decode_word<8>(w, asc);
+        stg_stream256(gout + rec * 32, make_uint4(asc[0], asc[1], asc[2], asc[3]),
+                      make_uint4(asc[4], asc[5], asc[6], asc[7]));
+    } else if (L == 16) {
+        decode_word<4>(w, asc);
+        stg_stream(reinterpret_cast<uint4 *>(gout) + rec, make_uint4(asc[0], asc[1], asc[2], asc[3]));
+    } else if (L > 0) {  // compile-time length, multiple of 4: word stores into the stage
+        static_assert(L % 4 == 0, "compile-time staged lengths are multiples of 4");
+        decode_word<L / 4>(w, asc);
+        uint32_t *s32 = reinterpret_cast<uint32_t *>(stage) + r * (L / 4);
+#pragma unroll
+        for (int g = 0; g < L / 4; g++) s32[g] = asc[g];
+    } else {  // runtime length
+        const uint32_t ng = (len + 3) >> 2;
+        const uint32_t lo = (uint32_t)w, hi = (uint32_t)(w >> 32);
+        decode8<0>(lo, asc[0], asc[1]);
+        if (ng > 2) decode8<1>(lo, asc[2], asc[3]);
+        if (ng > 4) decode8<0>(hi, asc[4], asc[5]);
+        if (ng > 6) decode8<1>(hi, asc[6], asc[7]);
+        if ((len & 3u) == 0) {
+            uint32_t *s32 = reinterpret_cast<uint32_t *>(stage) + r * (len >> 2);
+#pragma unroll
+            for (int g = 0; g < 8; g++)
+                if (g < ng) s32[g] = asc[g];
+        } else {
+            uint8_t *s8 = stage + r * len;
+#pragma unroll
+            for (int g = 0; g < 8; g++)
+#pragma unroll
+                for (int b = 0; b < 4; b++)
+                    if (4 * g + b < len) s8[4 * g + b] = (uint8_t)(asc[g] >> (8 * b));
+        }
+    }
+}
+
+template <int L>
+__device__ __forceinline__ void copy_out_stage(uint32_t len, uint8_t *gout, uint64_t tile,
+                                               const uint8_t *stage, uint32_t lane) {
+    if (L == 32 || L == 16) return;  // rows were stored directly
+    const uint32_t n16 = 8 * len;    // 128 rows x len bytes / 16
+    uint4 *dst = reinterpret_cast<uint4 *>(gout) + tile * n16;
+    const uint4 *src = reinterpret_cast<const uint4 *>(stage);
+    for (uint32_t i = lane; i < n16; i += 32) stg_stream(dst + i, src[i]);
+}
+
+template <int BC, int UMI>
+__global__ void __launch_bounds__(kBlockThreads) k_unpack(const UnpackArgs a) {
+    extern __shared__ __align__(16) uint8_t smem[];
+    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    const uint64_t gwarp = (uint64_t)blockIdx.x * kWarpsPerBlock + warp;
+    const uint64_t total_warps = (uint64_t)gridDim.x * kWarpsPerBlock;
+    uint8_t *wsm = smem + warp * a.warp_smem_bytes;
+    uint4 *in4 = reinterpret_cast<uint4 *>(wsm);
+    const uint64_t *in64 = reinterpret_cast<const uint64_t *>(wsm);
+    uint8_t *bc_stage = wsm + a.bc_stage_off, *umi_stage = wsm + a.umi_stage_off;
+    const uint32_t bc_len = LenOf<BC>::get(a.bc_len), umi_len = LenOf<UMI>::get(a.umi_len);
+
+    uint32_t n_bb = 0, n_bu = 0, n_br = 0;
+    const uint64_t n_tiles = a.n / kTileRecords;
+    const uint4 *g4 = reinterpret_cast<const uint4 *>(a.recs);
+
+    uint4 pre[6];  // software prefetch: the next tile is in flight while this one is decoded
+    uint64_t t = gwarp;
+    if (t < n_tiles) {
+#pragma unroll
+        for (int k = 0; k < 6; k++) pre[k] = ldg_stream(g4 + t * kTileU4 + lane + 32 * k);
+    }
+    while (t < n_tiles) {
+#pragma unroll
+        for (int k = 0; k < 6; k++) in4[lane + 32 * k] = pre[k];
+        __syncwarp();
+        const uint64_t t_next = t + total_warps;
+        if (t_next < n_tiles) {
+#pragma unroll
+            for (int k = 0; k < 6; k++) pre[k] = ldg_stream(g4 + t_next * kTileU4 + lane + 32 * k);
+        }
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            const uint32_t r = lane + 32 * q;  // record of the tile handled by this lane
+            // 64-bit shared loads at a 24-byte stride: conflict-free per half-warp
+            const uint64_t bc = in64[3 * r], umi = in64[3 * r + 1];
+            const uint64_t rec = t * kTileRecords + r;
+            emit_row<BC>(bc, bc_len, a.bc_out, rec, bc_stage, r);
+            emit_row<UMI>(umi, umi_len, a.umi_out, rec, umi_stage, r);
+            const uint32_t bb = (bc & a.bc_hi) != 0ull, bu = (umi & a.umi_hi) != 0ull;
+            n_bb += bb; n_bu += bu; n_br += (bb | bu);
+            if (a.flags) a.flags[rec] = (uint8_t)(bb | (bu << 1));
+        }
+        __syncwarp();
+        copy_out_stage<BC>(bc_len, a.bc_out, t, bc_stage, lane);
+        copy_out_stage<UMI>(umi_len, a.umi_out, t, umi_stage, lane);
+        __syncwarp();
+        t = t_next;
+    }
+
+    if (gwarp == total_warps - 1) {  // ragged tail: plain per-record code
+        const uint64_t *r64 = reinterpret_cast<const uint64_t *>(a.recs);
+        for (uint64_t rec = n_tiles * kTileRecords + lane; rec < a.n; rec += 32) {
+            const uint64_t bc = ldg_stream64(r64 + 3 * rec), umi = ldg_stream64(r64 + 3 * rec + 1);
+            for (uint32_t i = 0; i < bc_len; i++)
+                a.bc_out[rec * bc_len + i] = (uint8_t)(kAcgt >> (8 * ((bc >> (2 * i)) & 3u)));
+            for (uint32_t i = 0; i < umi_len; i++)
+                a.umi_out[rec * umi_len + i] = (uint8_t)(kAcgt >> (8 * ((umi >> (2 * i)) & 3u)));
+            const uint32_t bb = (bc & a.bc_hi) != 0ull, bu = (umi & a.umi_hi) != 0ull;
+            n_bb += bb; n_bu += bu; n_br += (bb | bu);
+            if (a.flags) a.flags[rec] = (uint8_t)(bb | (bu << 1));
+        }
+    }
+
+    if (a.res) {
+        n_bb = __reduce_add_sync(0xffffffffu, n_bb);
+        n_bu = __reduce_add_sync(0xffffffffu, n_bu);
+        n_br = __reduce_add_sync(0xffffffffu, n_br);
+        unsigned long long *out = reinterpret_cast<unsigned long long *>(a.res);
+        if (lane == 0) {
+            if (n_bb) atomicAdd(out + 5, (unsigned long long)n_bb);
+            if (n_bu) atomicAdd(out + 6, (unsigned long long)n_bu);
+            if (n_br) atomicAdd(out + 7, (unsigned long long)n_br);
+            if (gwarp == 0) atomicAdd(out, (unsigned long long)a.n);
+        }
+    }
+}
+
+// ============================================================================ K3
+struct PackArgs {
+    const uint8_t *bc_in, *umi_in;
+    const uint64_t *index;
+    uint64_t index_base, n;
+    uint8_t *recs_out, *flags;
+    ibu_reduce_result_t *res;
+    uint32_t bc_len, umi_len;
+    uint32_t warp_smem_bytes, bc_stage_off, umi_stage_off;
+};
+
+// One ASCII row as two 16-byte halves.  L = 32 / 16: the lane loads its own row with one
+// 256 / 128-bit load (a warp covers 1024 / 512 contiguous bytes) and the next tile's rows are
+// prefetched into registers.  L = 0: runtime length, rows reach the lane through shared memory.
+template <int L>
+struct RowRegs;
+template <>
+struct RowRegs<32> {
+    u64x4 v[2];
+    __device__ __forceinline__ void load(const uint8_t *g, uint64_t tile, uint32_t lane) {
+#pragma unroll
+        for (int q = 0; q < 2; q++) v[q] = ldg_stream256(g + (tile * kPackTileRows + lane + 32 * q) * 32);
+    }
+    __device__ __forceinline__ void get(int q, uint4 &lo, uint4 &hi) const {
+        lo = make_uint4((uint32_t)v[q].x, (uint32_t)(v[q].x >> 32), (uint32_t)v[q].y, (uint32_t)(v[q].y >> 32));
+        hi = make_uint4((uint32_t)v[q].z, (uint32_t)(v[q].z >> 32), (uint32_t)v[q].w, (uint32_t)(v[q].w >> 32));
+    }
+};
+template <>
+struct RowRegs<16> {
+    uint4 v[2];
+    __device__ __forceinline__ void load(const uint8_t *g, uint64_t tile, uint32_t lane) {
+#pragma unroll
+        for (int q = 0; q < 2; q++)
+            v[q] = ldg_stream(reinterpret_cast<const uint4 *>(g) + tile * kPackTileRows + lane + 32 * q);
+    }
+    __device__ __forceinline__ void get(int q, uint4 &lo, uint4 &hi) const {
+        lo = v[q];
+        hi = make_uint4(0x41414141u, 0x41414141u, 0x41414141u, 0x41414141u);
+    }
+};
+template <>
+struct RowRegs<0> {
+    __device__ __forceinline__ void load(const uint8_t *, uint64_t, uint32_t) {}
+};
+
+// copy a 64-row tile (64 x len bytes, 16-byte aligned in the input) into shared memory
+__device__ __forceinline__ void stage_rows(const uint8_t *g, uint64_t tile, uint32_t len,
+                                           uint8_t *stage, uint32_t lane) {
+    const uint32_t n16 = 4 * len;
+    const uint4 *src = reinterpret_cast<const uint4 *>(g) + tile * n16;
+    uint4 *dst = reinterpret_cast<uint4 *>(stage);
+    for (uint32_t i = lane; i < n16; i += 32) dst[i] = ldg_stream(src + i);
+}
+
+// gather one staged row into two 16-byte halves, padded with 'A' (code 0, valid)
+__device__ __forceinline__ void staged_row(const uint8_t *stage, uint32_t r, uint32_t len,
+                                           uint4 &lo, uint4 &hi) {
+    uint32_t w[8];
+#pragma unroll
+    for (int g = 0; g < 8; g++) w[g] = 0x41414141u;
+    const uint8_t *row = stage + r * len;
+    if ((len & 3u) == 0) {
+        const uint32_t *r32 = reinterpret_cast<const uint32_t *>(row);
+#pragma unroll
+        for (int g = 0; g < 8; g++)
+            if (4u * g < len) w[g] = r32[g];
+    } else {
+#pragma unroll
+        for (int g = 0; g < 8; g++) {
+            if (4u * g < len) {
+                uint32_t v = 0x41414141u;
+#pragma unroll
+                for (int b = 0; b < 4; b++)
+                    if (4u * g + b < len) v = (v & ~(0xFFu << (8 * b))) | ((uint32_t)row[4 * g + b] << (8 * b));
+                w[g] = v;
+            }
+        }
+    }
+    lo = make_uint4(w[0], w[1], w[2], w[3]);
+    hi = make_uint4(w[4], w[5], w[6], w[7]);
+}
+
+template <int L>
+__device__ __forceinline__ uint64_t pack_row(uint4 lo, uint4 hi, uint32_t len, uint32_t &badflag) {
+    uint32_t bad = 0;
+    uint64_t w = pack16(lo, bad);
+    if (L == 32 || (L == 0 && len > 16)) w |= (uint64_t)pack16(hi, bad) << 32;
+    badflag = bad != 0;
+    return w;
+}
+
+template <int BC, int UMI>
+__global__ void __launch_bounds__(kBlockThreads) k_pack(const PackArgs a) {
+    extern __shared__ __align__(16) uint8_t smem[];
+    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    const uint64_t gwarp = (uint64_t)blockIdx.x * kWarpsPerBlock + warp;
+    const uint64_t total_warps = (uint64_t)gridDim.x * kWarpsPerBlock;
+    uint8_t *wsm = smem + warp * a.warp_smem_bytes;
+    uint64_t *out64 = reinterpret_cast<uint64_t *>(wsm);  // 64 records x 24 B staged output
+    const uint4 *out4 = reinterpret_cast<const uint4 *>(wsm);
+    uint8_t *bc_stage = wsm + a.bc_stage_off, *umi_stage = wsm + a.umi_stage_off;
+    const uint32_t bc_len = LenOf<BC>::get(a.bc_len), umi_len = LenOf<UMI>::get(a.umi_len);
+
+    uint32_t n_bb = 0, n_bu = 0, n_br = 0;
+    const uint64_t n_tiles = a.n / kPackTileRows;
+    RowRegs<BC> bc_rows;
+    RowRegs<UMI> umi_rows;
+    uint64_t t = gwarp;
+    if (t < n_tiles) {
+        bc_rows.load(a.bc_in, t, lane);
+        umi_rows.load(a.umi_in, t, lane);
+    }
+    while (t < n_tiles) {
+        if (BC == 0) stage_rows(a.bc_in, t, bc_len, bc_stage, lane);
+        if (UMI == 0) stage_rows(a.umi_in, t, umi_len, umi_stage, lane);
+        if (BC == 0 || UMI == 0) __syncwarp();
+        uint4 bl[2], bh[2], ul[2], uh[2];
+#pragma unroll
+        for (int q = 0; q < 2; q++) {
+            if constexpr (BC != 0) bc_rows.get(q, bl[q], bh[q]);
+            else staged_row(bc_stage, lane + 32 * q, bc_len, bl[q], bh[q]);
+            if constexpr (UMI != 0) umi_rows.get(q, ul[q], uh[q]);
+            else staged_row(umi_stage, lane + 32 * q, umi_len, ul[q], uh[q]);
+        }
+        const uint64_t t_next = t + total_warps;
+        if (t_next < n_tiles) {  // prefetch while this tile is encoded
+            bc_rows.load(a.bc_in, t_next, lane);
+            umi_rows.load(a.umi_in, t_next, lane);
+        }
+#pragma unroll
+        for (int q = 0; q < 2; q++) {
+            const uint32_t r = lane + 32 * q;
+            const uint64_t row = t * kPackTileRows + r;
+            uint32_t bb, bu;
+            const uint64_t bw = pack_row<BC>(bl[q], bh[q], bc_len, bb);
+            const uint64_t uw = pack_row<UMI>(ul[q], uh[q], umi_len, bu);
+            const uint64_t idx = a.index ? ldg_stream64(a.index + row) : a.index_base + row;
+            out64[3 * r] = bw; out64[3 * r + 1] = uw; out64[3 * r + 2] = idx;
+            n_bb += bb; n_bu += bu; n_br += (bb | bu);
+            if (a.flags) a.flags[row] = (uint8_t)(bb | (bu << 1));
+        }
+        __syncwarp();
+        uint4 *dst = reinterpret_cast<uint4 *>(a.recs_out) + t * (kPackTileRows * 24 / 16);
+#pragma unroll
+        for (int k = 0; k < 3; k++) stg_stream(dst + lane + 32 * k, out4[lane + 32 * k]);
+        __syncwarp();
+        t = t_next;
+    }
+
+    if (gwarp == total_warps - 1) {  // ragged tail (< 64 rows): plain per-row code
+        uint64_t *o64 = reinterpret_cast<uint64_t *>(a.recs_out);
+        for (uint64_t row = n_tiles * kPackTileRows + lane; row < a.n; row += 32) {
+            uint64_t w[2];
+            uint32_t bad[2];
+            for (int s = 0; s < 2; s++) {
+                const uint8_t *p = s ? a.umi_in + row * umi_len : a.bc_in + row * bc_len;
+                const uint32_t len = s ? umi_len : bc_len;
+                uint64_t acc = 0;
+                uint32_t b = 0;
+                for (uint32_t i = 0; i < len; i++) {
+                    const uint32_t ch = p[i], c1 = (ch >> 1) & 3u, up = ch & 0xDFu;
+                    acc |= (uint64_t)(c1 ^ (c1 >> 1)) << (2 * i);
+                    b |= !(up == 0x41u || up == 0x43u || up == 0x47u || up == 0x54u);
+                }
+                w[s] = acc;
+                bad[s] = b;
+            }
+            o64[3 * row] = w[0]; o64[3 * row + 1] = w[1];
+            o64[3 * row + 2] = a.index ? a.index[row] : a.index_base + row;
+            n_bb += bad[0]; n_bu += bad[1]; n_br += (bad[0] | bad[1]);
+            if (a.flags) a.flags[row] = (uint8_t)(bad[0] | (bad[1] << 1));
+        }
+    }
+
+    if (a.res) {
+        n_bb = __reduce_add_sync(0xffffffffu, n_bb);
+        n_bu = __reduce_add_sync(0xffffffffu, n_bu);
+        n_br = __reduce_add_sync(0xffffffffu, n_br);
+        unsigned long long *out = reinterpret_cast<unsigned long long *>(a.res);
+        if (lane == 0) {
+            if (n_bb) atomicAdd(out + 5, (unsigned long long)n_bb);
+            if (n_bu) atomicAdd(out + 6, (unsigned long long)n_bu);
+            if (n_br) atomicAdd(out + 7, (unsigned long long)n_br);
+            if (gwarp == 0) atomicAdd(out, (unsigned long long)a.n);
+        }
+    }
+}
+
+// ============================================================================ generators
+__device__ __forceinline__ uint64_t low_mask_dev(uint32_t len) {
+    return len >= 32 ? ~0ull : ((1ull << (2 * len)) - 1);
+}
+
+__global__ void __launch_bounds__(kBlockThreads)
+k_generate_records(uint64_t *__restrict__ out, uint64_t first, uint64_t n, uint32_t bc_len,
+                   uint32_t umi_len, int mode, uint64_t param, uint64_t seed) {
+    const uint64_t mb = low_mask_dev(bc_len), mu = low_mask_dev(umi_len);
+    for (uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; k < n;
+         k += (uint64_t)gridDim.x * blockDim.x) {
+        const uint64_t i = first + k;
+        const uint64_t key = splitmix64(seed ^ splitmix64(i));
+        const uint64_t rb = splitmix64(key ^ 1), ru = splitmix64(key ^ 2);
+        uint64_t b, u;
+        if (mode == IBU_GEN_PATTERN) {
+            b = i % 1000000ull;
+            u = (i * 31ull) % 1000000ull;
+        } else if (mode == IBU_GEN_WHITELIST) {
+            uint64_t nb = param & 0xFFFFFFFFull, us = param >> 32;
+            if (nb == 0) nb = 1000;
+            b = splitmix64((rb % nb) ^ seed ^ 0xB) & mb;
+            u = (us ? ru % us : ru) & mu;
+        } else {
+            b = rb & mb;
+            u = ru & mu;
+            if (mode == IBU_GEN_DIRTY) {
+                const uint64_t rd = splitmix64(key ^ 3);
+                if (rd % 1000000ull < param) {
+                    if (rd >> 63) b = rb; else u = ru;
+                }
+            }
+        }
+        out[3 * k] = b; out[3 * k + 1] = u; out[3 * k + 2] = i;
+    }
+}
+
+__global__ void __launch_bounds__(kBlockThreads)
+k_generate_ascii(uint8_t *__restrict__ out, uint64_t first_row, uint64_t n_rows, uint32_t len,
+                 uint64_t dirty_ppm, uint64_t lower_ppm, uint64_t seed) {
+    for (uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; k < n_rows;
+         k += (uint64_t)gridDim.x * blockDim.x) {
+        const uint64_t key = splitmix64(seed ^ splitmix64(first_row + k));
+        const uint64_t w = splitmix64(key ^ 4), rd = splitmix64(key ^ 5), rl = splitmix64(key ^ 6);
+        const uint32_t lower = (rl % 1000000ull < lower_ppm) ? 0x20u : 0u;
+        const uint32_t npos = (rd % 1000000ull < dirty_ppm) ? (uint32_t)((rd >> 40) % len) : 0xFFFFFFFFu;
+        uint8_t *row = out + k * len;
+        for (uint32_t i = 0; i < len; i++) {
+            uint32_t ch = ((kAcgt >> (8 * ((w >> (2 * i)) & 3u))) & 0xFFu) | lower;
+            row[i] = (uint8_t)(i == npos ? 'N' : ch);
+        }
+    }
+}
+
+// ============================================================================ launch helpers
+static int grid_for(ibu_gpu_ctx *ctx, const void *kernel, size_t smem, uint64_t n_tiles,
+                    ibu_error_t *err) {
+    int per_sm = 0;
+    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kBlockThreads, smem);
+    if (e != cudaSuccess) return -cuda_fail(err, e, "cudaOccupancyMaxActiveBlocksPerMultiprocessor");
+    if (per_sm < 1) per_sm = 1;
+    // a whole number of resident waves: sm_count x resident CTAs, shrunk for small inputs
+    uint64_t grid = (uint64_t)ctx->sm_count * per_sm;
+    uint64_t need = (n_tiles + kWarpsPerBlock - 1) / kWarpsPerBlock;
+    if (need < 1) need = 1;
+    if (grid > need) grid = need;
+    return (int)grid;
+}
+
+static bool aligned(const void *p, size_t a) { return ((uintptr_t)p & (a - 1)) == 0; }
+
+template <int BC, int UMI>
+static int launch_unpack(ibu_gpu_ctx *ctx, UnpackArgs &a, cudaStream_t s, ibu_error_t *err) {
+    // per-warp shared memory: input tile, then the staged outputs that are not stored directly
+    uint32_t off = kTileBytes;
+    a.bc_stage_off = off;
+    if (!(BC == 32 || BC == 16)) off += (kTileRecords * a.bc_len + 15u) & ~15u;
+    a.umi_stage_off = off;
+    if (!(UMI == 32 || UMI == 16)) off += (kTileRecords * a.umi_len + 15u) & ~15u;
+    a.warp_smem_bytes = off;
+    const size_t smem = (size_t)off * kWarpsPerBlock;
+    auto kern = k_unpack<BC, UMI>;
+    IBU_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int grid = grid_for(ctx, (const void *)kern, smem, a.n / kTileRecords, err);
+    if (grid < 0) return -grid;
+    kern<<<grid, kBlockThreads, smem, s>>>(a);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    IBU_CUDA(cudaGetLastError());
+    return IBU_OK;
+}
+
+template <int BC, int UMI>
+static int launch_pack(ibu_gpu_ctx *ctx, PackArgs &a, cudaStream_t s, ibu_error_t *err) {
+    uint32_t off = kPackTileRows * 24;
+    a.bc_stage_off = off;
+    if (BC == 0) off += (kPackTileRows * a.bc_len + 15u) & ~15u;
+    a.umi_stage_off = off;
+    if (UMI == 0) off += (kPackTileRows * a.umi_len + 15u) & ~15u;
+    a.warp_smem_bytes = off;
+    const size_t smem = (size_t)off * kWarpsPerBlock;
+    auto kern = k_pack<BC, UMI>;
+    IBU_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int grid = grid_for(ctx, (const void *)kern, smem, a.n / kPackTileRows, err);
+    if (grid < 0) return -grid;
+    kern<<<grid, kBlockThreads, smem, s>>>(a);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    IBU_CUDA(cudaGetLastError());
+    return IBU_OK;
+}
+
+static int check_lens(uint32_t bc_len, uint32_t umi_len, ibu_error_t *err) {
+    // same bounds as Header::validate (header.rs:179-184)
+    if (bc_len == 0 || bc_len > 32)
+        return set_error(err, IBU_ERR_INVALID_BARCODE_LENGTH, 0, bc_len, 0,
+                         "Invalid barcode length: %u (must be 1-32)", bc_len);
+    if (umi_len == 0 || umi_len > 32)
+        return set_error(err, IBU_ERR_INVALID_UMI_LENGTH, 0, umi_len, 0,
+                         "Invalid UMI length: %u (must be 1-32)", umi_len);
+    return IBU_OK;
+}
+
+}  // namespace ibu
+
+using namespace ibu;
+
+extern "C" {
+
+int ibu_gpu_validate_reduce_async(ibu_gpu_ctx_t *ctx, const ibu_record_t *d_records, uint64_t n,
+                                  uint32_t bc_len, uint32_t umi_len, ibu_reduce_result_t *d_result,
+                                  void *stream, ibu_error_t *err) {
+    clear_error(err);
+    if (!ctx || !d_result || (!d_records && n)) return set_error(err, IBU_ERR_ARG, 0, 0, 0, "null argument");
+    if (int rc = check_lens(bc_len, umi_len, err)) return rc;
+    if (!aligned(d_records, 32)) return set_error(err, IBU_ERR_ARG, 0, 0, 0, "d_records must be 32-byte aligned");
+    DeviceGuard guard(ctx->device);
+    cudaStream_t s = pick_stream(ctx, stream);
+    IBU_CUDA(cudaMemsetAsync(d_result, 0, sizeof(*d_result), s));
+    int grid = grid_for(ctx, (const void *)k_validate_reduce, 0, n / kTileRecords, err);
+    if (grid < 0) return -grid;
+    k_validate_reduce<<<grid, kBlockThreads, 0, s>>>((const uint8_t *)d_records, n, high_mask(bc_len),
+                                                     high_mask(umi_len), d_result);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    IBU_CUDA(cudaGetLastError());
+    return IBU_OK;
+}
+
+int ibu_gpu_unpack_async(ibu_gpu_ctx_t *ctx, const ibu_record_t *d_records, uint64_t n,
+                         uint32_t bc_len, uint32_t umi_len, uint8_t *d_bc_ascii, uint8_t *d_umi_ascii,
+                         uint8_t *d_flags, ibu_reduce_result_t *d_result, void *stream,
+                         ibu_error_t *err) {
+    clear_error(err);
+    if (!ctx || (n && (!d_records || !d_bc_ascii || !d_umi_ascii)))
+        return set_error(err, IBU_ERR_ARG, 0, 0, 0, "null argument");
+    if (int rc = check_lens(bc_len, umi_len, err)) return rc;
+    if (!aligned(d_records, 16) || !aligned(d_bc_ascii, 16) || !aligned(d_umi_ascii, 16))
+        return set_error(err, IBU_ERR_ARG, 0, 0, 0, "device pointers must be 16-byte aligned");
+    DeviceGuard guard(ctx->device);
+    cudaStream_t s = pick_stream(ctx, stream);
+    if (d_result) IBU_CUDA(cudaMemsetAsync(d_result, 0, sizeof(*d_result), s));
+    UnpackArgs a{};
+    a.recs = (const uint8_t *)d_records;
+    a.n = n;
+    a.bc_out = d_bc_ascii;
+    a.umi_out = d_umi_ascii;
+    a.flags = d_flags;
+    a.bc_hi = high_mask(bc_len);
+    a.umi_hi = high_mask(umi_len);
+    a.res = d_result;
+    a.bc_len = bc_len;
+    a.umi_len = umi_len;
+    // store mode per output: 32 / 16 = direct vector store (needs that alignment), 12 =
+    // compile-time staged, 0 = runtime-length staged
+    const int bm = (bc_len == 32 && aligned(d_bc_ascii, 32)) ? 32 : bc_len == 16 ? 16 : 0;
+    const int um = (umi_len == 32 && aligned(d_umi_ascii, 32)) ? 32
+                   : umi_len == 16 ? 16 : umi_len == 12 ? 12 : 0;
+#define IBU_UNPACK_CASE(B, U) \
+    if (bm == B && um == U) return launch_unpack<B, U>(ctx, a, s, err);
+    IBU_UNPACK_CASE(16, 12) IBU_UNPACK_CASE(16, 16) IBU_UNPACK_CASE(16, 32) IBU_UNPACK_CASE(16, 0)
+    IBU_UNPACK_CASE(32, 12) IBU_UNPACK_CASE(32, 16) IBU_UNPACK_CASE(32, 32) IBU_UNPACK_CASE(32, 0)
+    IBU_UNPACK_CASE(0, 12) IBU_UNPACK_CASE(0, 16) IBU_UNPACK_CASE(0, 32) IBU_UNPACK_CASE(0, 0)
+#undef IBU_UNPACK_CASE
+    return set_error(err, IBU_ERR_ARG, 0, 0, 0, "no unpack kernel for this shape");
+}
+
+int ibu_gpu_pack_async(ibu_gpu_ctx_t *ctx, const uint8_t *d_bc_ascii, const uint8_t *d_umi_ascii,
+                       const uint64_t *d_index, uint64_t index_base, uint64_t n, uint32_t bc_len,
+                       uint32_t umi_len, ibu_record_t *d_records, uint8_t *d_flags,
+                       ibu_reduce_result_t *d_result, void *stream, ibu_error_t *err) {
+    clear_error(err);
+    if (!ctx || (n && (!d_records || !d_bc_ascii || !d_umi_ascii)))
+        return set_error(err, IBU_ERR_ARG, 0, 0, 0, "null argument");
+    if (int rc = check_lens(bc_len, umi_len, err)) return rc;
+    if (!aligned(d_records, 16) || !aligned(d_bc_ascii, 16) || !aligned(d_umi_ascii, 16) ||
+        !aligned(d_index, 8))
+        return set_error(err, IBU_ERR_ARG, 0, 0, 0, "device pointers must be 16-byte aligned");
+    DeviceGuard guard(ctx->device);
+    cudaStream_t s = pick_stream(ctx, stream);
+    if (d_result) IBU_CUDA(cudaMemsetAsync(d_result, 0, sizeof(*d_result), s));
+    PackArgs a{};
+    a.bc_in = d_bc_ascii;
+    a.umi_in = d_umi_ascii;
+    a.index = d_index;
+    a.index_base = index_base;
+    a.n = n;
+    a.recs_out = (uint8_t *)d_records;
+    a.flags = d_flags;
+    a.res = d_result;
+    a.bc_len = bc_len;
+    a.umi_len = umi_len;
+    const int bm = (bc_len == 32 && aligned(d_bc_ascii, 32)) ? 32 : bc_len == 16 ? 16 : 0;
+    const int um = (umi_len == 32 && aligned(d_umi_ascii, 32)) ? 32 : umi_len == 16 ? 16 : 0;
+#define IBU_PACK_CASE(B, U) \
+    if (bm == B && um == U) return launch_pack<B, U>(ctx, a, s, err);
+    IBU_PACK_CASE(32, 32) IBU_PACK_CASE(32, 16) IBU_PACK_CASE(32, 0)
+    IBU_PACK_CASE(16, 32) IBU_PACK_CASE(16, 16) IBU_PACK_CASE(16, 0)
+    IBU_PACK_CASE(0, 32) IBU_PACK_CASE(0, 16) IBU_PACK_CASE(0, 0)
+#undef IBU_PACK_CASE
+    return set_error(err, IBU_ERR_ARG, 0, 0, 0, "no pack kernel for this shape");
+}
+
+int ibu_gpu_generate_records_async(ibu_gpu_ctx_t *ctx, ibu_record_t *d_records, uint64_t first,
+                                   uint64_t n, uint32_t bc_len, uint32_t umi_len, int mode,
+                                   uint64_t param, uint64_t seed, void *stream, ibu_error_t *err) {
+    clear_error(err);
+    if (!ctx || (!d_records && n)) return set_error(err, IBU_ERR_ARG, 0, 0, 0, "null argument");
+    if (int rc = check_lens(bc_len, umi_len, err)) return rc;
+    if (mode < IBU_GEN_CLEAN || mode > IBU_GEN_WHITELIST) return set_error(err, IBU_ERR_ARG, 0, 0, 0, "bad mode");
+    if (n == 0) return IBU_OK;
+    DeviceGuard guard(ctx->device);
+    cudaStream_t s = pick_stream(ctx, stream);
+    uint64_t blocks = (n + kBlockThreads - 1) / kBlockThreads;
+    uint64_t cap = (uint64_t)ctx->sm_count * 16;
+    k_generate_records<<<(int)(blocks < cap ? blocks : cap), kBlockThreads, 0, s>>>(
+        (uint64_t *)d_records, first, n, bc_len, umi_len, mode, param, seed);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    IBU_CUDA(cudaGetLastError());
+    return IBU_OK;
+}
+
+int ibu_gpu_generate_ascii_async(ibu_gpu_ctx_t *ctx, uint8_t *d_ascii, uint64_t first_row,
+                                 uint64_t n_rows, uint32_t len, uint64_t dirty_ppm, uint64_t lower_ppm,
+                                 uint64_t seed, void *stream, ibu_error_t *err) {
+    clear_error(err);
+    if (!ctx || (!d_ascii && n_rows)) return set_error(err, IBU_ERR_ARG, 0, 0, 0, "null argument");
+    if (len == 0 || len > 32) return set_error(err, IBU_ERR_ARG, 0, len, 0, "row length must be 1-32");
+    if (n_rows == 0) return IBU_OK;
+    DeviceGuard guard(ctx->device);
+    cudaStream_t s = pick_stream(ctx, stream);
+    uint64_t blocks = (n_rows + kBlockThreads - 1) / kBlockThreads;
+    uint64_t cap = (uint64_t)ctx->sm_count * 16;
+    k_generate_ascii<<<(int)(blocks < cap ? blocks : cap), kBlockThreads, 0, s>>>(
+        d_ascii, first_row, n_rows, len, dirty_ppm, lower_ppm, seed);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    IBU_CUDA(cudaGetLastError());
+    return IBU_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,568 @@
+// pipeline.cu — GPU context, memory helpers and the host-buffer (end-to-end) paths:
+// the device counterparts of MmapReader::process_parallel (src/io/mmap.rs:286-332) and
+// load_to_vec (src/io/reader.rs:510-535), plus host->host unpack/pack through the GPU.
+//
+// Staging model: the record range is cut into chunks (a multiple of BATCH_SIZE, mmap.rs:284).
+// Each chunk owns a slot = {stream, event, pinned staging, device buffers}.  For chunk c the
+// host thread (1) waits for slot c % n_slots to drain and consumes its result, (2) brings the
+// chunk's bytes into pinned memory if the source is pageable (parallel memcpy from the
+// mmap / user buffer), (3) enqueues H2D -> kernel -> D2H on the slot's stream.  With >= 2 slots
+// the copy engines, the SMs and the host memcpy of the next chunk all overlap.
+#include <algorithm>
+#include <cerrno>
+#include <cstdlib>
+#include <fcntl.h>
+#include <thread>
+#include <unistd.h>
+
+#include "ctx.h"
+
+using namespace ibu;
+
+namespace {
+
+constexpr size_t kAlign = 256;
+inline size_t align_up(size_t v, size_t a = kAlign) { return (v + a - 1) / a * a; }
+
+bool is_pinned(const void *p) {
+    cudaPointerAttributes attr;
+    cudaError_t e = cudaPointerGetAttributes(&attr, p);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    return attr.type == cudaMemoryTypeHost;
+}
+
+void parallel_memcpy(void *dst, const void *src, size_t bytes, unsigned threads) {
+    if (threads <= 1 || bytes < (8u << 20)) {
+        memcpy(dst, src, bytes);
+        return;
+    }
+    size_t per = align_up(bytes / threads, 4096);
+    std::vector<std::thread> pool;
+    for (unsigned i = 0; i < threads; i++) {
+        size_t off = (size_t)i * per;
+        if (off >= bytes) break;
+        size_t len = std::min(per, bytes - off);
+        pool.emplace_back([=] { memcpy((uint8_t *)dst + off, (const uint8_t *)src + off, len); });
+    }
+    for (auto &t : pool) t.join();
+}
+
+int ensure(void **p, size_t *have, size_t want, bool host, ibu_error_t *err) {
+    if (*have >= want) return IBU_OK;
+    if (*p) {
+        if (host) cudaFreeHost(*p); else cudaFree(*p);
+        *p = nullptr;
+        *have = 0;
+    }
+    cudaError_t e = host ? cudaHostAlloc(p, want, cudaHostAllocDefault) : cudaMalloc(p, want);
+    if (e != cudaSuccess) return cuda_fail(err, e, host ? "cudaHostAlloc" : "cudaMalloc");
+    *have = want;
+    return IBU_OK;
+}
+
+void merge(ibu_reduce_result_t &t, const ibu_reduce_result_t &c) {
+    // the on_batch_complete merge of the reference processors (mmap.rs:365-372,
+    // examples/parallel.rs:28-35): wrapping adds; xor for the checksum
+    t.n_records += c.n_records;
+    t.sum_barcode += c.sum_barcode;
+    t.sum_umi += c.sum_umi;
+    t.sum_index += c.sum_index;
+    t.xor_all ^= c.xor_all;
+    t.n_bad_barcode += c.n_bad_barcode;
+    t.n_bad_umi += c.n_bad_umi;
+    t.n_bad_records += c.n_bad_records;
+}
+
+unsigned copy_threads(const ibu_gpu_ctx *ctx) {
+    if (ctx->cfg.copy_threads) return ctx->cfg.copy_threads;
+    unsigned hc = std::thread::hardware_concurrency();
+    return std::max(1u, std::min(16u, hc / 2));
+}
+
+// What one chunk moves: inputs (host -> device) and outputs (device -> host) as byte spans
+// relative to the slot's device buffers.
+struct Span {
+    const void *h_src = nullptr;  // host source (inputs)
+    void *h_dst = nullptr;        // host destination (outputs)
+    size_t bytes = 0;
+    size_t d_off = 0;             // offset in slot.d_in / slot.d_out
+    bool pinned = false;          // host side is pinned: DMA straight from / to it
+};
+
+struct ChunkPlan {
+    Span in[3];
+    Span out[3];
+    int n_in = 0, n_out = 0;
+    size_t d_in_bytes = 0, d_out_bytes = 0;
+};
+
+// Drives chunks through the slots.  `enqueue(slot, chunk_idx)` launches the kernel(s) for a
+// chunk whose inputs are already in flight on slot.stream; `consume(chunk_idx, result)` runs
+// on the host, in chunk order, once the chunk's outputs have landed.
+template <class PlanFn, class EnqueueFn, class ConsumeFn>
+int run_chunks_impl(ibu_gpu_ctx *ctx, uint64_t n_chunks, PlanFn plan_of, EnqueueFn enqueue,
+                    ConsumeFn consume, ibu_error_t *err) {
+    const unsigned threads = copy_threads(ctx);
+    const size_t n_slots = ctx->slots.size();
+    std::vector<ChunkPlan> inflight(n_slots);
+    std::vector<int64_t> owner(n_slots, -1);
+
+    auto drain = [&](size_t s) -> int {
+        if (owner[s] < 0) return IBU_OK;
+        ibu_chunk_slot &slot = ctx->slots[s];
+        IBU_CUDA(cudaEventSynchronize(slot.done));
+        ChunkPlan &p = inflight[s];
+        for (int k = 0; k < p.n_out; k++)
+            if (!p.out[k].pinned && p.out[k].bytes)
+                parallel_memcpy(p.out[k].h_dst, (uint8_t *)slot.h_out + p.out[k].d_off, p.out[k].bytes, threads);
+        int rc = consume((uint64_t)owner[s], *slot.h_result);
+        owner[s] = -1;
+        if (rc) return set_error(err, IBU_ERR_PROCESS, rc, 0, 0, "Processing error: chunk callback returned %d", rc);
+        return IBU_OK;
+    };
+
+    for (uint64_t c = 0; c < n_chunks; c++) {
+        const size_t s = c % n_slots;
+        if (int rc = drain(s)) return rc;
+        ibu_chunk_slot &slot = ctx->slots[s];
+        ChunkPlan p = plan_of(c);
+        if (int rc = ensure(&slot.d_in, &slot.d_in_bytes, p.d_in_bytes, false, err)) return rc;
+        if (int rc = ensure(&slot.d_out, &slot.d_out_bytes, p.d_out_bytes, false, err)) return rc;
+        bool need_h_in = false, need_h_out = false;
+        for (int k = 0; k < p.n_in; k++) need_h_in |= !p.in[k].pinned;
+        for (int k = 0; k < p.n_out; k++) need_h_out |= !p.out[k].pinned;
+        if (need_h_in)
+            if (int rc = ensure(&slot.h_in, &slot.h_in_bytes, p.d_in_bytes, true, err)) return rc;
+        if (need_h_out)
+            if (int rc = ensure(&slot.h_out, &slot.h_out_bytes, p.d_out_bytes, true, err)) return rc;
+        for (int k = 0; k < p.n_in; k++) {
+            const Span &sp = p.in[k];
+            if (!sp.bytes) continue;
+            const void *src = sp.h_src;
+            if (!sp.pinned) {
+                parallel_memcpy((uint8_t *)slot.h_in + sp.d_off, sp.h_src, sp.bytes, threads);
+                src = (uint8_t *)slot.h_in + sp.d_off;
+            }
+            IBU_CUDA(cudaMemcpyAsync((uint8_t *)slot.d_in + sp.d_off, src, sp.bytes,
+                                     cudaMemcpyHostToDevice, slot.stream));
+        }
+        if (int rc = enqueue(slot, c)) return rc;
+        for (int k = 0; k < p.n_out; k++) {
+            const Span &sp = p.out[k];
+            if (!sp.bytes) continue;
+            void *dst = sp.pinned ? sp.h_dst : (void *)((uint8_t *)slot.h_out + sp.d_off);
+            IBU_CUDA(cudaMemcpyAsync(dst, (uint8_t *)slot.d_out + sp.d_off, sp.bytes,
+                                     cudaMemcpyDeviceToHost, slot.stream));
+        }
+        IBU_CUDA(cudaMemcpyAsync(slot.h_result, slot.d_result, sizeof(ibu_reduce_result_t),
+                                 cudaMemcpyDeviceToHost, slot.stream));
+        IBU_CUDA(cudaEventRecord(slot.done, slot.stream));
+        inflight[s] = p;
+        owner[s] = (int64_t)c;
+    }
+    // drain in chunk order
+    for (uint64_t c = n_chunks > n_slots ? n_chunks - n_slots : 0; c < n_chunks; c++)
+        if (int rc = drain(c % n_slots)) return rc;
+    return IBU_OK;
+}
+
+template <class PlanFn, class EnqueueFn, class ConsumeFn>
+int run_chunks(ibu_gpu_ctx *ctx, uint64_t n_chunks, PlanFn plan_of, EnqueueFn enqueue,
+               ConsumeFn consume, ibu_error_t *err) {
+    int rc = run_chunks_impl(ctx, n_chunks, plan_of, enqueue, consume, err);
+    if (rc != IBU_OK)  // nothing may still be reading or writing caller memory once we return
+        for (auto &slot : ctx->slots)
+            if (cudaStreamSynchronize(slot.stream) != cudaSuccess) cudaGetLastError();
+    return rc;
+}
+
+uint64_t chunk_records(const ibu_gpu_ctx *ctx) {
+    return ctx->cfg.chunk_records ? ctx->cfg.chunk_records : 4ull * IBU_BATCH_SIZE;
+}
+
+int process_host_records(ibu_gpu_ctx *ctx, const ibu_record_t *h_records, uint64_t n, uint32_t bc_len,
+                         uint32_t umi_len, uint64_t first_record, ibu_reduce_result_t *h_result,
+                         ibu_chunk_cb on_chunk, void *user, ibu_error_t *err) {
+    DeviceGuard guard(ctx->device);
+    memset(h_result, 0, sizeof(*h_result));
+    if (n == 0) return IBU_OK;  // an empty range never calls on_batch_complete (mmap.rs:502-519)
+    const uint64_t chunk = chunk_records(ctx);
+    const uint64_t n_chunks = (n + chunk - 1) / chunk;
+    const bool pinned = is_pinned(h_records);
+    auto span = [&](uint64_t c, uint64_t &start, uint64_t &cnt) {
+        start = c * chunk;
+        cnt = std::min(chunk, n - start);
+    };
+    return run_chunks(
+        ctx, n_chunks,
+        [&](uint64_t c) {
+            uint64_t start, cnt;
+            span(c, start, cnt);
+            ChunkPlan p;
+            p.n_in = 1;
+            p.in[0].h_src = h_records + start;
+            p.in[0].bytes = cnt * IBU_RECORD_SIZE;
+            p.in[0].pinned = pinned;
+            p.d_in_bytes = align_up(chunk * IBU_RECORD_SIZE);
+            p.d_out_bytes = kAlign;
+            return p;
+        },
+        [&](ibu_chunk_slot &slot, uint64_t c) {
+            uint64_t start, cnt;
+            span(c, start, cnt);
+            return ibu_gpu_validate_reduce_async(ctx, (const ibu_record_t *)slot.d_in, cnt, bc_len, umi_len,
+                                                 slot.d_result, slot.stream, err);
+        },
+        [&](uint64_t c, const ibu_reduce_result_t &r) {
+            uint64_t start, cnt;
+            span(c, start, cnt);
+            merge(*h_result, r);
+            return on_chunk ? on_chunk(user, first_record + start, cnt, &r) : 0;
+        },
+        err);
+}
+
+}  // namespace
+
+extern "C" {
+
+int ibu_gpu_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+int ibu_gpu_ctx_create(int device, const ibu_gpu_config_t *cfg, ibu_gpu_ctx_t **out, ibu_error_t *err) {
+    clear_error(err);
+    if (!out) return set_error(err, IBU_ERR_ARG, 0, 0, 0, "null argument");
+    *out = nullptr;
+    int count = 0;
+    IBU_CUDA(cudaGetDeviceCount(&count));
+    if (device < 0 || device >= count)
+        return set_error(err, IBU_ERR_ARG, 0, device, count, "device %d out of range (%d visible)", device, count);
+    cudaDeviceProp prop;
+    IBU_CUDA(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10)  // the only code in this library is sm_100a SASS: no fallback
+        return set_error(err, IBU_ERR_CUDA, (int)cudaErrorNoKernelImageForDevice, prop.major, prop.minor,
+                         "device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major,
+                         prop.minor);
+    DeviceGuard guard(device);
+    auto *ctx = new (std::nothrow) ibu_gpu_ctx;
+    if (!ctx) return set_error(err, IBU_ERR_NOMEM, 0, 0, 0, "out of memory");
+    ctx->device = device;
+    ctx->sm_count = prop.multiProcessorCount;
+    if (cfg) ctx->cfg = *cfg;
+    if (const char *v = getenv("IBU_B200_VARIANT")) ctx->variant = atoi(v);
+    cudaError_t e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
+    const uint32_t n_slots = ctx->cfg.n_slots ? ctx->cfg.n_slots : 3;
+    ctx->slots.resize(n_slots);
+    for (auto &s : ctx->slots) {
+        if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming);
+        if (e == cudaSuccess) e = cudaMalloc((void **)&s.d_result, sizeof(ibu_reduce_result_t));
+        if (e == cudaSuccess) e = cudaHostAlloc((void **)&s.h_result, sizeof(ibu_reduce_result_t), cudaHostAllocDefault);
+    }
+    if (e != cudaSuccess) {
+        ibu_gpu_ctx_destroy(ctx);
+        return cuda_fail(err, e, "context creation");
+    }
+    *out = ctx;
+    return IBU_OK;
+}
+
+void ibu_gpu_ctx_destroy(ibu_gpu_ctx_t *ctx) {
+    if (!ctx) return;
+    DeviceGuard guard(ctx->device);
+    for (auto &s : ctx->slots) {
+        if (s.stream) {
+            cudaStreamSynchronize(s.stream);
+            cudaStreamDestroy(s.stream);
+        }
+        if (s.done) cudaEventDestroy(s.done);
+        if (s.h_in) cudaFreeHost(s.h_in);
+        if (s.h_out) cudaFreeHost(s.h_out);
+        if (s.d_in) cudaFree(s.d_in);
+        if (s.d_out) cudaFree(s.d_out);
+        if (s.d_result) cudaFree(s.d_result);
+        if (s.h_result) cudaFreeHost(s.h_result);
+    }
+    if (ctx->stream) {
+        cudaStreamSynchronize(ctx->stream);
+        cudaStreamDestroy(ctx->stream);
+    }
+    delete ctx;
+}
+
+int ibu_gpu_ctx_device(const ibu_gpu_ctx_t *ctx) { return ctx ? ctx->device : -1; }
+int ibu_gpu_ctx_sm_count(const ibu_gpu_ctx_t *ctx) { return ctx ? ctx->sm_count : 0; }
+uint64_t ibu_gpu_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+
+int ibu_gpu_synchronize(ibu_gpu_ctx_t *ctx, void *stream, ibu_error_t *err) {
+    clear_error(err);
+    if (!ctx) return set_error(err, IBU_ERR_ARG, 0, 0, 0, "null context");
+    DeviceGuard guard(ctx->device);
+    IBU_CUDA(cudaStreamSynchronize(pick_stream(ctx, stream)));
+    return IBU_OK;
+}
+
+int ibu_gpu_malloc(ibu_gpu_ctx_t *ctx, size_t bytes, void **d_out, ibu_error_t *err) {
+    clear_error(err);
+    if (!ctx || !d_out) return set_error(err, IBU_ERR_ARG, 0, 0, 0, "null argument");
+    DeviceGuard guard(ctx->device);
+    IBU_CUDA(cudaMalloc(d_out, bytes ? bytes : 1));
+    return IBU_OK;
+}
+
+void ibu_gpu_free(ibu_gpu_ctx_t *ctx, void *d_ptr) {
+    if (!ctx || !d_ptr) return;
+    DeviceGuard guard(ctx->device);
+    cudaFree(d_ptr);
+}
+
+int ibu_gpu_memcpy_h2d(ibu_gpu_ctx_t *ctx, void *d_dst, const void *h_src, size_t bytes, ibu_error_t *err) {
+    clear_error(err);
+    if (!ctx) return set_error(err, IBU_ERR_ARG, 0, 0, 0, "null context");
+    DeviceGuard guard(ctx->device);
+    IBU_CUDA(cudaMemcpyAsync(d_dst, h_src, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    IBU_CUDA(cudaStreamSynchronize(ctx->stream));
+    return IBU_OK;
+}
+
+int ibu_gpu_memcpy_d2h(ibu_gpu_ctx_t *ctx, void *h_dst, const void *d_src, size_t bytes, ibu_error_t *err) {
+    clear_error(err);
+    if (!ctx) return set_error(err, IBU_ERR_ARG, 0, 0, 0, "null context");
+    DeviceGuard guard(ctx->device);
+    IBU_CUDA(cudaMemcpyAsync(h_dst, d_src, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    IBU_CUDA(cudaStreamSynchronize(ctx->stream));
+    return IBU_OK;
+}
+
+int ibu_gpu_memset(ibu_gpu_ctx_t *ctx, void *d_dst, int value, size_t bytes, ibu_error_t *err) {
+    clear_error(err);
+    if (!ctx) return set_error(err, IBU_ERR_ARG, 0, 0, 0, "null context");
+    DeviceGuard guard(ctx->device);
+    IBU_CUDA(cudaMemsetAsync(d_dst, value, bytes, ctx->stream));
+    IBU_CUDA(cudaStreamSynchronize(ctx->stream));
+    return IBU_OK;
+}
+
+int ibu_host_alloc(size_t bytes, void **h_out, ibu_error_t *err) {
+    clear_error(err);
+    if (!h_out) return set_error(err, IBU_ERR_ARG, 0, 0, 0, "null argument");
+    IBU_CUDA(cudaHostAlloc(h_out, bytes ? bytes : 1, cudaHostAllocPortable));
+    return IBU_OK;
+}
+
+void ibu_host_free(void *h_ptr) {
+    if (h_ptr) cudaFreeHost(h_ptr);
+}
+
+int ibu_host_register(void *h_ptr, size_t bytes, int read_only, ibu_error_t *err) {
+    clear_error(err);
+    unsigned flags = cudaHostRegisterPortable | (read_only ? cudaHostRegisterReadOnly : 0u);
+    IBU_CUDA(cudaHostRegister(h_ptr, bytes, flags));
+    return IBU_OK;
+}
+
+void ibu_host_unregister(void *h_ptr) {
+    if (h_ptr && cudaHostUnregister(h_ptr) != cudaSuccess) cudaGetLastError();
+}
+
+// ---- GPU counterpart of process_parallel -------------------------------------------------
+
+int ibu_gpu_process_host(ibu_gpu_ctx_t *ctx, const ibu_record_t *h_records, uint64_t n, uint32_t bc_len,
+                         uint32_t umi_len, ibu_reduce_result_t *h_result, ibu_chunk_cb on_chunk,
+                         void *user, ibu_error_t *err) {
+    clear_error(err);
+    if (!ctx || !h_result || (!h_records && n)) return set_error(err, IBU_ERR_ARG, 0, 0, 0, "null argument");
+    return process_host_records(ctx, h_records, n, bc_len, umi_len, 0, h_result, on_chunk, user, err);
+}
+
+int ibu_gpu_process_mmap(ibu_gpu_ctx_t *ctx, const ibu_mmap_reader_t *reader, uint64_t start, uint64_t end,
+                         ibu_reduce_result_t *h_result, ibu_chunk_cb on_chunk, void *user,
+                         ibu_error_t *err) {
+    clear_error(err);
+    if (!ctx || !reader || !h_result) return set_error(err, IBU_ERR_ARG, 0, 0, 0, "null argument");
+    if (end == UINT64_MAX) end = reader->len;
+    if (start > end || end > reader->len)
+        return set_error(err, IBU_ERR_INVALID_INDEX, 0, end, reader->len,
+                         "Invalid index (%llu) - Must be less than %zu", (unsigned long long)end, reader->len);
+    const ibu_record_t *recs =
+        (const ibu_record_t *)(ibu_mmap_base(reader) + IBU_HEADER_SIZE) + start;
+    return process_host_records(ctx, recs, end - start, reader->header.bc_len, reader->header.umi_len,
+                                start, h_result, on_chunk, user, err);
+}
+
+// ---- device path of load_to_vec -----------------------------------------------------------
+
+int ibu_gpu_load_to_device(ibu_gpu_ctx_t *ctx, const char *path, uint64_t start, uint64_t end,
+                           ibu_header_t *header, ibu_record_t **d_records, uint64_t *n, ibu_error_t *err) {
+    clear_error(err);
+    if (!ctx || !path || !header || !d_records || !n) return set_error(err, IBU_ERR_ARG, 0, 0, 0, "null argument");
+    *d_records = nullptr;
+    *n = 0;
+    ibu_mmap_reader_t *reader = nullptr;
+    // same checks, same order as load_to_vec: header read + validate, then the size rule
+    if (int rc = ibu_mmap_open(path, &reader, err)) return rc;
+    *header = reader->header;
+    if (end == UINT64_MAX) end = reader->len;
+    if (start > end || end > reader->len) {
+        int rc = set_error(err, IBU_ERR_INVALID_INDEX, 0, end, reader->len,
+                           "Invalid index (%llu) - Must be less than %zu", (unsigned long long)end, reader->len);
+        ibu_mmap_close(reader);
+        return rc;
+    }
+    DeviceGuard guard(ctx->device);
+    const uint64_t count = end - start;
+    void *dev = nullptr;
+    cudaError_t e = cudaMalloc(&dev, count ? count * IBU_RECORD_SIZE : kAlign);
+    if (e != cudaSuccess) {
+        ibu_mmap_close(reader);
+        return cuda_fail(err, e, "cudaMalloc");
+    }
+    int rc = IBU_OK;
+    if (count) {
+        const uint8_t *src = ibu_mmap_base(reader) + IBU_HEADER_SIZE + start * IBU_RECORD_SIZE;
+        const uint64_t chunk = chunk_records(ctx);
+        const uint64_t n_chunks = (count + chunk - 1) / chunk;
+        const unsigned threads = copy_threads(ctx);
+        const size_t n_slots = ctx->slots.size();
+        // pageable mmap -> pinned slot buffer (host threads) -> DMA into the final allocation
+        for (uint64_t c = 0; c < n_chunks && rc == IBU_OK; c++) {
+            ibu_chunk_slot &slot = ctx->slots[c % n_slots];
+            const uint64_t off = c * chunk * IBU_RECORD_SIZE;
+            const uint64_t bytes = std::min(chunk, count - c * chunk) * IBU_RECORD_SIZE;
+            if (c >= n_slots && (e = cudaEventSynchronize(slot.done)) != cudaSuccess) {
+                rc = cuda_fail(err, e, "cudaEventSynchronize");
+                break;
+            }
+            if ((rc = ensure(&slot.h_in, &slot.h_in_bytes, align_up(chunk * IBU_RECORD_SIZE), true, err))) break;
+            parallel_memcpy(slot.h_in, src + off, bytes, threads);
+            e = cudaMemcpyAsync((uint8_t *)dev + off, slot.h_in, bytes, cudaMemcpyHostToDevice, slot.stream);
+            if (e == cudaSuccess) e = cudaEventRecord(slot.done, slot.stream);
+            if (e != cudaSuccess) rc = cuda_fail(err, e, "cudaMemcpyAsync");
+        }
+        for (auto &slot : ctx->slots) {
+            e = cudaStreamSynchronize(slot.stream);
+            if (e != cudaSuccess && rc == IBU_OK) rc = cuda_fail(err, e, "cudaStreamSynchronize");
+        }
+    }
+    ibu_mmap_close(reader);
+    if (rc != IBU_OK) {
+        cudaFree(dev);
+        return rc;
+    }
+    *d_records = (ibu_record_t *)dev;
+    *n = count;
+    return IBU_OK;
+}
+
+// ---- host -> host unpack / pack through the GPU --------------------------------------------
+
+int ibu_gpu_unpack_host(ibu_gpu_ctx_t *ctx, const ibu_record_t *h_records, uint64_t n, uint32_t bc_len,
+                        uint32_t umi_len, uint8_t *h_bc_ascii, uint8_t *h_umi_ascii, uint8_t *h_flags,
+                        ibu_reduce_result_t *h_result, ibu_error_t *err) {
+    clear_error(err);
+    if (!ctx || (n && (!h_records || !h_bc_ascii || !h_umi_ascii)))
+        return set_error(err, IBU_ERR_ARG, 0, 0, 0, "null argument");
+    ibu_reduce_result_t total{};
+    if (h_result) *h_result = total;
+    if (n == 0) return IBU_OK;
+    DeviceGuard guard(ctx->device);
+    const uint64_t chunk = chunk_records(ctx);
+    const uint64_t n_chunks = (n + chunk - 1) / chunk;
+    const bool pin_in = is_pinned(h_records), pin_bc = is_pinned(h_bc_ascii), pin_umi = is_pinned(h_umi_ascii),
+               pin_fl = h_flags && is_pinned(h_flags);
+    const size_t off_umi = align_up(chunk * bc_len), off_fl = off_umi + align_up(chunk * umi_len);
+    const size_t out_bytes = off_fl + (h_flags ? align_up(chunk) : 0);
+    int rc = run_chunks(
+        ctx, n_chunks,
+        [&](uint64_t c) {
+            const uint64_t start = c * chunk, cnt = std::min(chunk, n - start);
+            ChunkPlan p;
+            p.n_in = 1;
+            p.in[0] = {h_records + start, nullptr, cnt * IBU_RECORD_SIZE, 0, pin_in};
+            p.out[0] = {nullptr, h_bc_ascii + start * bc_len, cnt * bc_len, 0, pin_bc};
+            p.out[1] = {nullptr, h_umi_ascii + start * umi_len, cnt * umi_len, off_umi, pin_umi};
+            p.n_out = 2;
+            if (h_flags) p.out[p.n_out++] = {nullptr, h_flags + start, cnt, off_fl, pin_fl};
+            p.d_in_bytes = align_up(chunk * IBU_RECORD_SIZE);
+            p.d_out_bytes = out_bytes;
+            return p;
+        },
+        [&](ibu_chunk_slot &slot, uint64_t c) {
+            const uint64_t start = c * chunk, cnt = std::min(chunk, n - start);
+            uint8_t *d_out = (uint8_t *)slot.d_out;
+            return ibu_gpu_unpack_async(ctx, (const ibu_record_t *)slot.d_in, cnt, bc_len, umi_len, d_out,
+                                        d_out + off_umi, h_flags ? d_out + off_fl : nullptr, slot.d_result,
+                                        slot.stream, err);
+        },
+        [&](uint64_t, const ibu_reduce_result_t &r) {
+            merge(total, r);
+            return 0;
+        },
+        err);
+    if (h_result) *h_result = total;
+    return rc;
+}
+
+int ibu_gpu_pack_host(ibu_gpu_ctx_t *ctx, const uint8_t *h_bc_ascii, const uint8_t *h_umi_ascii,
+                      const uint64_t *h_index, uint64_t index_base, uint64_t n, uint32_t bc_len,
+                      uint32_t umi_len, ibu_record_t *h_records, uint8_t *h_flags,
+                      ibu_reduce_result_t *h_result, ibu_error_t *err) {
+    clear_error(err);
+    if (!ctx || (n && (!h_records || !h_bc_ascii || !h_umi_ascii)))
+        return set_error(err, IBU_ERR_ARG, 0, 0, 0, "null argument");
+    ibu_reduce_result_t total{};
+    if (h_result) *h_result = total;
+    if (n == 0) return IBU_OK;
+    DeviceGuard guard(ctx->device);
+    const uint64_t chunk = chunk_records(ctx);
+    const uint64_t n_chunks = (n + chunk - 1) / chunk;
+    const bool pin_bc = is_pinned(h_bc_ascii), pin_umi = is_pinned(h_umi_ascii),
+               pin_idx = h_index && is_pinned(h_index), pin_out = is_pinned(h_records),
+               pin_fl = h_flags && is_pinned(h_flags);
+    const size_t in_umi = align_up(chunk * bc_len), in_idx = in_umi + align_up(chunk * umi_len);
+    const size_t in_bytes = in_idx + (h_index ? align_up(chunk * 8) : 0);
+    const size_t off_fl = align_up(chunk * IBU_RECORD_SIZE);
+    const size_t out_bytes = off_fl + (h_flags ? align_up(chunk) : 0);
+    int rc = run_chunks(
+        ctx, n_chunks,
+        [&](uint64_t c) {
+            const uint64_t start = c * chunk, cnt = std::min(chunk, n - start);
+            ChunkPlan p;
+            p.in[0] = {h_bc_ascii + start * bc_len, nullptr, cnt * bc_len, 0, pin_bc};
+            p.in[1] = {h_umi_ascii + start * umi_len, nullptr, cnt * umi_len, in_umi, pin_umi};
+            p.n_in = 2;
+            if (h_index) p.in[p.n_in++] = {h_index + start, nullptr, cnt * 8, in_idx, pin_idx};
+            p.out[0] = {nullptr, h_records + start, cnt * IBU_RECORD_SIZE, 0, pin_out};
+            p.n_out = 1;
+            if (h_flags) p.out[p.n_out++] = {nullptr, h_flags + start, cnt, off_fl, pin_fl};
+            p.d_in_bytes = in_bytes;
+            p.d_out_bytes = out_bytes;
+            return p;
+        },
+        [&](ibu_chunk_slot &slot, uint64_t c) {
+            const uint64_t start = c * chunk, cnt = std::min(chunk, n - start);
+            const uint8_t *d_in = (const uint8_t *)slot.d_in;
+            uint8_t *d_out = (uint8_t *)slot.d_out;
+            return ibu_gpu_pack_async(ctx, d_in, d_in + in_umi, h_index ? (const uint64_t *)(d_in + in_idx) : nullptr,
+                                      index_base + start, cnt, bc_len, umi_len, (ibu_record_t *)d_out,
+                                      h_flags ? d_out + off_fl : nullptr, slot.d_result, slot.stream, err);
+        },
+        [&](uint64_t, const ibu_reduce_result_t &r) {
+            merge(total, r);
+            return 0;
+        },
+        err);
+    if (h_result) *h_result = total;
+    return rc;
+}
+
+}  // extern "C"

@@ -1,0 +1,236 @@
+"""GPU parity tests: the CUDA path, called through the C ABI, against the CPU oracle on the same
+seeded inputs — bit-exact (all arithmetic is u64/u8 integer).  Run with `-m gpu` on a B200."""
+import numpy as np
+import pytest
+
+import ibu_b200 as ibu
+from oracle import oracle_c as oc
+from oracle import oracle_np as on
+
+pytestmark = pytest.mark.gpu
+
+SIZES = [0, 1, 2, 63, 64, 65, 127, 128, 129, 1000, 128 * 1000 + 77, (1 << 20) + 1, 3_000_005]
+U64 = np.uint64
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    c = ibu.GpuContext(0, chunk_records=1 << 20, n_slots=3)
+    yield c
+    c.close()
+
+
+class Dev:
+    """Device buffer from the library's own allocator (256-byte aligned)."""
+
+    def __init__(self, ctx, nbytes, host=None):
+        self.ctx, self.nbytes = ctx, nbytes
+        self.ptr = ctx.malloc(max(nbytes, 1))
+        if host is not None and nbytes:
+            ctx.h2d(self.ptr, host)
+
+    def data_ptr(self):
+        return self.ptr
+
+    def get(self, dtype, shape):
+        out = np.zeros(shape, dtype)
+        if out.nbytes:
+            self.ctx.d2h(out, self.ptr)
+        return out
+
+    def free(self):
+        self.ctx.free(self.ptr)
+
+
+def gpu_reduce(ctx, recs, bc, umi):
+    d = Dev(ctx, recs.nbytes, recs)
+    r = Dev(ctx, 64)
+    ctx.memset(r.ptr, 0xAB, 64)  # the kernel must overwrite, not accumulate
+    ctx.validate_reduce_async(d, len(recs), bc, umi, r)
+    ctx.synchronize()
+    out = ctx.read_result(r.ptr)
+    d.free(), r.free()
+    return out
+
+
+# ---- K1 -----------------------------------------------------------------------------------
+@pytest.mark.parametrize("n", SIZES)
+@pytest.mark.parametrize("bc,umi,mode,param", [(16, 12, 0, 0), (16, 12, 1, 10_000), (16, 12, 1, 1_000_000),
+                                               (32, 32, 1, 1_000_000), (1, 1, 1, 500_000), (7, 31, 1, 300_000),
+                                               (16, 12, 2, 0)])
+def test_validate_reduce(ctx, n, bc, umi, mode, param):
+    recs = oc.generate_records(5, n, bc, umi, mode, param, 1234)
+    assert gpu_reduce(ctx, recs, bc, umi) == oc.reduce_records(recs, bc, umi)
+
+
+def test_validate_reduce_both_words_bad(ctx):
+    """Adjacent invalid barcode+umi at every lane/tile position (the shuffle pairing path)."""
+    rng = np.random.default_rng(0)
+    n = 128 * 40 + 17
+    recs = ibu.records(n)
+    recs["barcode"] = rng.integers(0, 2**32, n, dtype=U64)
+    recs["umi"] = rng.integers(0, 2**24, n, dtype=U64)
+    recs["index"] = rng.integers(0, 2**64, n, dtype=U64)
+    kind = rng.integers(0, 4, n)
+    recs["barcode"][kind & 1 == 1] |= U64(1 << 40)
+    recs["umi"][kind & 2 == 2] |= U64(1 << 50)
+    got = gpu_reduce(ctx, recs, 16, 12)
+    assert got == oc.reduce_records(recs, 16, 12) == on.reduce_records(recs, 16, 12)
+    assert got["n_bad_records"] == int((kind != 0).sum())
+    recs["barcode"] |= U64(1 << 63)
+    recs["umi"] |= U64(1 << 63)
+    got = gpu_reduce(ctx, recs, 16, 12)
+    assert got["n_bad_records"] == n and got == oc.reduce_records(recs, 16, 12)
+
+
+def test_reference_kat_on_gpu(ctx):
+    """mmap.rs:454-481: 10 000 records (i, 2i, 3i): count 10 000, sum 299 970 000."""
+    i = np.arange(10_000, dtype=U64)
+    recs = ibu.records(10_000)
+    recs["barcode"], recs["umi"], recs["index"] = i, 2 * i, 3 * i
+    got = gpu_reduce(ctx, recs, 16, 12)
+    assert got["n_records"] == 10_000 and got.count_sum == 299_970_000
+
+
+# ---- K2 -----------------------------------------------------------------------------------
+def gpu_unpack(ctx, recs, bc, umi, flags=True):
+    n = len(recs)
+    d = Dev(ctx, recs.nbytes, recs)
+    db, du, df, dr = Dev(ctx, n * bc), Dev(ctx, n * umi), Dev(ctx, n), Dev(ctx, 64)
+    ctx.memset(db.ptr, 0, max(n * bc, 1)), ctx.memset(du.ptr, 0, max(n * umi, 1))
+    ctx.unpack_async(d, n, bc, umi, db, du, df if flags else None, dr)
+    ctx.synchronize()
+    out = db.get(np.uint8, (n, bc)), du.get(np.uint8, (n, umi)), df.get(np.uint8, n), ctx.read_result(dr.ptr)
+    for x in (d, db, du, df, dr):
+        x.free()
+    return out
+
+
+@pytest.mark.parametrize("n", SIZES)
+@pytest.mark.parametrize("bc,umi", [(16, 12), (16, 16), (32, 32), (12, 8), (5, 3), (32, 12), (1, 1), (20, 10), (31, 32),
+                                    (16, 32), (28, 16)])
+def test_unpack(ctx, n, bc, umi):
+    recs = oc.generate_records(0, n, bc, umi, 1, 100_000, 99)
+    gb, gu, gf, gr = gpu_unpack(ctx, recs, bc, umi)
+    ob, ou, of, orr = oc.unpack_records(recs, bc, umi, 2)
+    assert np.array_equal(gb, ob) and np.array_equal(gu, ou) and np.array_equal(gf, of)
+    for k in ("n_records", "n_bad_barcode", "n_bad_umi", "n_bad_records"):
+        assert gr[k] == orr[k], k
+
+
+def test_unpack_without_flags_and_result(ctx):
+    recs = oc.generate_records(0, 70_001, 16, 12, 0, 0, 5)
+    gb, gu, _, _ = gpu_unpack(ctx, recs, 16, 12, flags=False)
+    assert np.array_equal(gb, on.unpack_words(recs["barcode"], 16))
+    assert np.array_equal(gu, on.unpack_words(recs["umi"], 12))
+
+
+def test_unpack_codec_kats(ctx):  # record.rs:19-27 + bitnuc order
+    recs = ibu.records(3)
+    recs["barcode"] = [0xE4, 2**64 - 1, 0]
+    recs["umi"] = [0xFFFFFF, 0x1B, 2**64 - 1]
+    gb, gu, gf, _ = gpu_unpack(ctx, recs, 4, 12)
+    assert gb.tobytes() == b"ACGT" + b"TTTT" + b"AAAA"
+    assert gu.tobytes() == b"T" * 12 + b"TGCA" + b"A" * 8 + b"T" * 12
+    assert gf.tolist() == [0, 1, 2]
+
+
+# ---- K3 -----------------------------------------------------------------------------------
+def gpu_pack(ctx, bc_rows, umi_rows, index=None, index_base=0):
+    n, bc = bc_rows.shape
+    umi = umi_rows.shape[1]
+    db, du = Dev(ctx, bc_rows.nbytes, bc_rows), Dev(ctx, umi_rows.nbytes, umi_rows)
+    di = Dev(ctx, 8 * n, index) if index is not None else None
+    dr, df, res = Dev(ctx, 24 * n), Dev(ctx, n), Dev(ctx, 64)
+    ctx.pack_async(db, du, n, bc, umi, dr, d_index=di, index_base=index_base, d_flags=df, d_result=res)
+    ctx.synchronize()
+    out = dr.get(ibu.RECORD_DTYPE, n), df.get(np.uint8, n), ctx.read_result(res.ptr)
+    for x in (db, du, dr, df, res) + ((di,) if di else ()):
+        x.free()
+    return out
+
+
+@pytest.mark.parametrize("n", SIZES)
+@pytest.mark.parametrize("bc,umi", [(32, 32), (16, 16), (16, 12), (32, 16), (16, 32), (5, 3), (1, 1), (31, 7), (20, 28)])
+def test_pack(ctx, n, bc, umi):
+    b = oc.generate_ascii(3, n, bc, 30_000, 200_000, 7)
+    u = oc.generate_ascii(3, n, umi, 30_000, 200_000, 8)
+    idx = (np.arange(n, dtype=U64) * U64(0x9E3779B97F4A7C15)) if n % 2 else None
+    gr, gf, gres = gpu_pack(ctx, b, u, idx, 1 << 40)
+    orr, of, ores = oc.pack_records(b, u, idx, 1 << 40)
+    assert np.array_equal(gr, orr) and np.array_equal(gf, of)
+    for k in ("n_records", "n_bad_barcode", "n_bad_umi", "n_bad_records"):
+        assert gres[k] == ores[k], k
+
+
+def test_pack_every_byte_value(ctx):
+    """Validity and the deterministic fill for all 256 byte values in every row position."""
+    rows = np.full((256 * 32, 32), ord("A"), np.uint8)
+    for pos in range(32):
+        rows[pos * 256:(pos + 1) * 256, pos] = np.arange(256)
+    gr, gf, _ = gpu_pack(ctx, rows, rows[:, :16].copy())
+    orr, of, _ = oc.pack_records(rows, rows[:, :16].copy())
+    assert np.array_equal(gr, orr) and np.array_equal(gf, of)
+    valid = np.isin(np.arange(256), np.frombuffer(b"ACGTacgt", np.uint8))
+    assert np.array_equal((gf[:256] & 1) == 0, valid)
+
+
+# ---- generators ---------------------------------------------------------------------------
+@pytest.mark.parametrize("mode,param", [(0, 0), (1, 100_000), (2, 0), (3, (4096 << 32) | 10_000)])
+@pytest.mark.parametrize("bc,umi", [(16, 12), (32, 32), (3, 9)])
+def test_device_generators_match_oracle(ctx, mode, param, bc, umi):
+    n = 100_003
+    d = Dev(ctx, 24 * n)
+    ctx.generate_records_async(d, 77, n, bc, umi, mode, param, 42)
+    ctx.synchronize()
+    assert np.array_equal(d.get(ibu.RECORD_DTYPE, n), oc.generate_records(77, n, bc, umi, mode, param, 42))
+    d.free()
+    a = Dev(ctx, n * bc)
+    ctx.generate_ascii_async(a, 5, n, bc, 20_000, 100_000, 9)
+    ctx.synchronize()
+    assert np.array_equal(a.get(np.uint8, (n, bc)), oc.generate_ascii(5, n, bc, 20_000, 100_000, 9))
+    a.free()
+
+
+# ---- size-independent properties at BASELINE sizes ----------------------------------------------
+@pytest.mark.parametrize("bc,umi,n", [(16, 12, 100_000_000), (32, 32, 100_000_000)])
+def test_full_size_roundtrip(ctx, bc, umi, n):
+    """configs[1]/[2] sizes: generate -> K1, unpack (K2) -> pack (K3) -> K1 again.  The repacked
+    records equal the masked originals, checked by a checksum of checksums (sums + xor) and by
+    closed-form counts of the injected invalid words."""
+    recs, b, u, back, res = (Dev(ctx, s) for s in (24 * n, bc * n, umi * n, 24 * n, 64))
+    ctx.generate_records_async(recs, 0, n, bc, umi, ibu.GEN_DIRTY, 10_000, 2024)
+    ctx.validate_reduce_async(recs, n, bc, umi, res)
+    ctx.synchronize()
+    r0 = ctx.read_result(res.ptr)
+    ctx.unpack_async(recs, n, bc, umi, b, u, None, res)
+    ctx.synchronize()
+    r1 = ctx.read_result(res.ptr)
+    for k in ("n_records", "n_bad_barcode", "n_bad_umi", "n_bad_records"):
+        assert r0[k] == r1[k], k
+    assert r0["n_records"] == n
+    if bc < 32:
+        assert 0.8 * n / 100 < r0["n_bad_records"] < 1.2 * n / 100  # 10 000 ppm carry a raw word
+    else:
+        assert r0["n_bad_records"] == 0  # a 32-base word has no invalid bits
+    ctx.pack_async(b, u, n, bc, umi, back, d_result=res)
+    ctx.synchronize()
+    r2 = ctx.read_result(res.ptr)
+    assert r2["n_records"] == n and r2["n_bad_records"] == 0  # unpack only emits ACGT
+    # clean twin: same generator without the dirt == masked originals
+    ctx.generate_records_async(recs, 0, n, bc, umi, ibu.GEN_CLEAN, 0, 2024)
+    ctx.validate_reduce_async(recs, n, bc, umi, res)
+    ctx.synchronize()
+    want = ctx.read_result(res.ptr)
+    ctx.validate_reduce_async(back, n, bc, umi, res)
+    ctx.synchronize()
+    got = ctx.read_result(res.ptr)
+    assert got == want and got["n_bad_records"] == 0
+    assert got["sum_index"] == n * (n - 1) // 2
+    # spot-check a window against the oracle
+    w0, wn = 77_777_777, 4096
+    host = np.zeros(wn, ibu.RECORD_DTYPE)
+    ctx.d2h(host, back.ptr + 24 * w0)
+    assert np.array_equal(host, oc.generate_records(w0, wn, bc, umi, 0, 0, 2024))
+    for x in (recs, b, u, back, res):
+        x.free()

@@ -1,0 +1,154 @@
+"""GPU end-to-end paths through the C ABI with HOST buffers: the device counterparts of
+MmapReader::process_parallel (mmap.rs:286-332) and load_to_vec (reader.rs:510-535), and the
+host->host unpack/pack pipelines, against the oracle's process_parallel on the same files."""
+import numpy as np
+import pytest
+
+import ibu_b200 as ibu
+from oracle import oracle_c as oc
+from oracle import oracle_np as on
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    c = ibu.GpuContext(0, chunk_records=1 << 18, n_slots=3, copy_threads=4)
+    yield c
+    c.close()
+
+
+def write(path, recs, bc=16, umi=12):
+    with ibu.Writer(path, ibu.Header(bc, umi)) as w:
+        w.write_batch(recs)
+
+
+@pytest.mark.parametrize("n", [0, 1, 10_000, (1 << 18), (1 << 18) + 1, 1_000_000])
+def test_process_gpu_matches_process_parallel(ctx, tmp_ibu, n):
+    """configs[0] shape: Writer -> MmapReader -> process (count+sum, field sums, xor, validation)."""
+    recs = oc.generate_records(0, n, 16, 12, 1, 20_000, 42)
+    write(tmp_ibu, recs)
+    want, _ = oc.MmapReader(tmp_ibu).process_parallel_reduce(0)
+    reader = ibu.MmapReader(tmp_ibu)
+    chunks = []
+    got = reader.process_gpu(ctx, on_chunk=lambda s, c, r: chunks.append((s, c, r)))
+    assert got == want
+    # on_batch_complete analogue: chunk order, full coverage, never called for an empty file
+    csz = 1 << 18
+    assert [(s, c) for s, c, _ in chunks] == [(s, min(csz, n - s)) for s in range(0, n, csz)]
+    merged = ibu.ReduceResult({k: 0 for k in want})
+    for _, _, r in chunks:
+        merged = merged.merge(r)
+    if n:
+        assert merged == want
+
+
+def test_process_gpu_reference_kat(ctx, tmp_ibu):  # mmap.rs:454-481
+    i = np.arange(10_000, dtype=np.uint64)
+    recs = ibu.records(10_000)
+    recs["barcode"], recs["umi"], recs["index"] = i, 2 * i, 3 * i
+    write(tmp_ibu, recs)
+    got = ibu.MmapReader(tmp_ibu).process_gpu(ctx)
+    assert got["n_records"] == 10_000 and got.count_sum == 299_970_000
+
+
+def test_process_gpu_shards_merge_to_whole(ctx, tmp_ibu):
+    """Range sharding (mmap.rs:297-307 with n = #GPUs): shard results merge to the file's."""
+    n = 777_777
+    recs = oc.generate_records(0, n, 16, 12, 1, 50_000, 3)
+    write(tmp_ibu, recs)
+    reader = ibu.MmapReader(tmp_ibu)
+    whole = reader.process_gpu(ctx)
+    for world in (2, 3, 8):
+        merged = ibu.ReduceResult({k: 0 for k in whole})
+        for rank in range(world):
+            s, e = ibu.shard_range(n, rank, world)
+            merged = merged.merge(reader.process_gpu(ctx, s, e))
+        assert merged == whole == oc.reduce_records(recs, 16, 12)
+    with pytest.raises(ibu.InvalidIndex):
+        reader.process_gpu(ctx, 0, n + 1)
+
+
+def test_process_gpu_callback_error_aborts(ctx, tmp_ibu):  # parallel.rs:338-352 -> IbuError::Process
+    write(tmp_ibu, oc.generate_records(0, 1_000_000, 16, 12, 0, 0, 1))
+    calls = []
+
+    def boom(start, cnt, res):
+        calls.append(start)
+        return 1 if start >= (1 << 18) else 0
+
+    with pytest.raises(ibu.Process):
+        ibu.MmapReader(tmp_ibu).process_gpu(ctx, on_chunk=boom)
+    assert calls == [0, 1 << 18]
+
+
+def test_process_host_pinned_and_pageable(ctx):
+    n = 600_001
+    recs = oc.generate_records(9, n, 20, 10, 1, 10_000, 8)
+    want = oc.reduce_records(recs, 20, 10)
+    assert ctx.process_host(recs, 20, 10) == want
+    pin = ibu.PinnedBuffer(recs.nbytes)
+    p = pin.array(ibu.RECORD_DTYPE)
+    p[:] = recs
+    assert ctx.process_host(p, 20, 10) == want
+    del p
+    pin.free()
+
+
+@pytest.mark.parametrize("n", [0, 3, 300_000, 1_000_003])
+def test_load_to_device_matches_load_to_vec(ctx, tmp_ibu, n):
+    recs = oc.generate_records(0, n, 16, 12, 0, 0, 4)
+    write(tmp_ibu, recs)
+    h, d = ibu.load_to_device(ctx, tmp_ibu)
+    ho, want = oc.load_to_vec(tmp_ibu)
+    assert h.as_bytes() == bytes(ho) and len(d) == n
+    assert np.array_equal(d.to_host(), want)
+    d.free()
+    if n > 10:
+        h, d = ibu.load_to_device(ctx, tmp_ibu, 5, n - 2)  # a shard of the file
+        assert np.array_equal(d.to_host(), want[5:n - 2])
+        d.free()
+
+
+def test_load_to_device_errors(ctx, tmp_ibu, tmp_path):
+    write(tmp_ibu, oc.generate_records(0, 10, 16, 12, 0, 0, 4))
+    with open(tmp_ibu, "r+b") as f:
+        f.truncate(32 + 24 * 10 - 5)
+    with pytest.raises(ibu.InvalidMapSize):
+        ibu.load_to_device(ctx, tmp_ibu)
+    with pytest.raises(ibu.Io):
+        ibu.load_to_device(ctx, str(tmp_path / "nope.ibu"))
+
+
+@pytest.mark.parametrize("bc,umi", [(16, 12), (32, 32), (9, 5)])
+@pytest.mark.parametrize("pinned", [False, True])
+def test_unpack_host_and_pack_host(ctx, bc, umi, pinned):
+    n = 700_003
+    recs = oc.generate_records(0, n, bc, umi, 1, 30_000, 6)
+    ob, ou, of, ores = oc.unpack_records(recs, bc, umi, 0)
+    bufs = []
+    if pinned:
+        def alloc(dtype, shape):
+            b = ibu.PinnedBuffer(int(np.prod(shape)) * np.dtype(dtype).itemsize)
+            bufs.append(b)
+            return b.array(dtype, shape)
+        src = alloc(ibu.RECORD_DTYPE, (n,))
+        src[:] = recs
+        gb, gu, gf = alloc(np.uint8, (n, bc)), alloc(np.uint8, (n, umi)), alloc(np.uint8, (n,))
+    else:
+        src, gb, gu, gf = recs, np.zeros((n, bc), np.uint8), np.zeros((n, umi), np.uint8), np.zeros(n, np.uint8)
+    _, _, res = ctx.unpack_host(src, bc, umi, gb, gu, gf)
+    assert np.array_equal(gb, ob) and np.array_equal(gu, ou) and np.array_equal(gf, of)
+    for k in ("n_records", "n_bad_barcode", "n_bad_umi", "n_bad_records"):
+        assert res[k] == ores[k]
+    # pack the decoded rows back: masked originals, explicit index array
+    idx = np.ascontiguousarray(recs["index"])
+    back, pres = ctx.pack_host(gb, gu, index=idx)
+    want, _, wres = oc.pack_records(ob, ou, idx)
+    assert np.array_equal(back, want) and pres["n_bad_records"] == wres["n_bad_records"] == 0
+    back2, _ = ctx.pack_host(np.ascontiguousarray(gb), np.ascontiguousarray(gu), index_base=0)
+    assert np.array_equal(back2["index"], np.arange(n, dtype=np.uint64))
+    assert np.array_equal(back2["barcode"], recs["barcode"] & np.uint64(on.low_mask(bc)))
+    del src, gb, gu, gf
+    for b in bufs:
+        b.free()
