@@ -323,13 +323,13 @@ class GpuContext:
         _check(lib.ibu_gpu_barcode_count(self._h, _ptr(d_records), n, mode, C.byref(table), _stream(stream),
                                          C.byref(err)), err)
         rows = np.zeros(int(table.n_rows), ROW_DTYPE)
+        info = dict(n_rows=int(table.n_rows), n_records=int(table.n_records),
+                    n_distinct_pairs=int(table.n_distinct_pairs), input_was_sorted=bool(table.input_was_sorted))
         try:
             if table.n_rows:
                 self.d2h(rows, int(table.d_rows))
         finally:
             lib.ibu_gpu_table_free(self._h, C.byref(table))
-        info = dict(n_rows=int(table.n_rows), n_records=int(table.n_records),
-                    n_distinct_pairs=int(table.n_distinct_pairs), input_was_sorted=bool(table.input_was_sorted))
         return rows, info
 
     # -- host-buffer (end-to-end) paths

@@ -234,3 +234,74 @@ def test_full_size_roundtrip(ctx, bc, umi, n):
     assert np.array_equal(host, oc.generate_records(w0, wn, bc, umi, 0, 0, 2024))
     for x in (recs, b, u, back, res):
         x.free()
+
+
+# ---- K4: per-barcode table --------------------------------------------------------------------
+def gpu_table(ctx, recs, mode=0):
+    d = Dev(ctx, recs.nbytes, recs)
+    rows, info = ctx.barcode_count(d, len(recs), mode)
+    d.free()
+    return rows, info
+
+
+def sort_records(recs):
+    return recs[np.lexsort((recs["index"], recs["umi"], recs["barcode"]))]  # Record's Ord (record.rs:58)
+
+
+@pytest.mark.parametrize("n", [0, 1, 2, 255, 2047, 2048, 2049, 100_003, 3_000_005])
+@pytest.mark.parametrize("mode,param", [(3, (64 << 32) | 1000), (3, (4 << 32) | 50), (2, 0), (0, 0), (1, 300_000)])
+def test_barcode_table_sorted_stream(ctx, n, mode, param):
+    recs = sort_records(oc.generate_records(0, n, 16, 12, mode, param, 21))
+    rows, info = gpu_table(ctx, recs)
+    want = on.barcode_table(recs)
+    assert info["input_was_sorted"] and info["n_records"] == n
+    assert np.array_equal(rows, want)
+    assert info["n_distinct_pairs"] == int(want["n_distinct_umi"].sum())
+    if 0 < n <= 100_003:
+        t, pairs = oc.barcode_table(recs)
+        assert np.array_equal(rows, t) and pairs == info["n_distinct_pairs"]
+
+
+@pytest.mark.parametrize("n", [1, 2, 2049, 100_003, 3_000_005])
+@pytest.mark.parametrize("bc,umi,mode,param", [(16, 12, 3, (64 << 32) | 1000), (16, 12, 2, 0), (16, 12, 0, 0),
+                                               (16, 12, 1, 300_000), (32, 32, 3, (1000 << 32) | 77), (5, 3, 0, 0)])
+def test_barcode_table_unsorted(ctx, n, bc, umi, mode, param):
+    recs = oc.generate_records(0, n, bc, umi, mode, param, 22)
+    rows, info = gpu_table(ctx, recs)
+    want = on.barcode_table(recs)
+    assert np.array_equal(rows, want)
+    assert info["n_distinct_pairs"] == int(want["n_distinct_umi"].sum())
+    rows2, info2 = gpu_table(ctx, recs, mode=2)  # forced sort path gives the same table
+    assert np.array_equal(rows2, want) and not info2["input_was_sorted"]
+
+
+def test_barcode_table_require_sorted_mode(ctx):
+    recs = oc.generate_records(0, 50_000, 16, 12, 0, 0, 23)
+    rows, info = gpu_table(ctx, recs, mode=1)
+    assert not info["input_was_sorted"] and len(rows) == 0
+    rows, info = gpu_table(ctx, sort_records(recs), mode=1)
+    assert info["input_was_sorted"] and np.array_equal(rows, on.barcode_table(recs))
+
+
+def test_barcode_table_reference_pattern_closed_form(ctx):
+    """examples/parallel.rs:65-69 pattern at N = 10^7: 10^6 barcodes x 10 records x 1 UMI."""
+    n = 10_000_000
+    d = Dev(ctx, 24 * n)
+    ctx.generate_records_async(d, 0, n, 16, 12, ibu.GEN_PATTERN, 0, 0)
+    ctx.synchronize()
+    rows, info = ctx.barcode_count(d, n)
+    d.free()
+    assert not info["input_was_sorted"] and len(rows) == 1_000_000 and info["n_distinct_pairs"] == 1_000_000
+    assert np.array_equal(rows["barcode"], np.arange(1_000_000, dtype=U64))
+    assert np.all(rows["n_records"] == 10) and np.all(rows["n_distinct_umi"] == 1)
+
+
+def test_barcode_table_capacity_retry(ctx):
+    """More distinct barcodes than the optimistic 8 Mi-row table: the exact-size second pass."""
+    n = 9_000_000
+    recs = oc.generate_records(0, n, 16, 12, 0, 0, 24)
+    recs = recs[np.lexsort((recs["umi"], recs["barcode"]))]
+    rows, info = gpu_table(ctx, recs)
+    want = on.barcode_table(recs)
+    assert info["input_was_sorted"] and len(rows) > (8 << 20)
+    assert np.array_equal(rows, want)
