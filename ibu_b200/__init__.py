@@ -32,7 +32,7 @@ BATCH_SIZE = 1024 * 1024
 RECORD_DTYPE = np.dtype([("barcode", "<u8"), ("umi", "<u8"), ("index", "<u8")])
 ROW_DTYPE = np.dtype([("barcode", "<u8"), ("n_records", "<u8"), ("n_distinct_umi", "<u8")])
 
-GEN_CLEAN, GEN_DIRTY, GEN_PATTERN, GEN_WHITELIST = 0, 1, 2, 3
+GEN_CLEAN, GEN_DIRTY, GEN_PATTERN, GEN_WHITELIST, GEN_SORTED = 0, 1, 2, 3, 4
 
 
 # ---- errors (src/error.rs:56-128) ---------------------------------------------------------
@@ -471,6 +471,14 @@ class MmapReader:
         a.flags.writeable = False
         a._owner = self  # the slice borrows from the map (mmap.rs:253): keep the reader alive
         return a
+
+    def pin(self):
+        """Page-lock the mapping so process_gpu DMAs straight from the page cache (optional)."""
+        err = _lib.Error()
+        _check(lib.ibu_mmap_pin(self._h, C.byref(err)), err)
+
+    def unpin(self):
+        lib.ibu_mmap_unpin(self._h)
 
     def process_gpu(self, ctx: GpuContext, start: int = 0, end: int | None = None, on_chunk=None) -> ReduceResult:
         """GPU counterpart of process_parallel for the built-in reductions (mmap.rs:286-332):

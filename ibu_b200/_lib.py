@@ -103,6 +103,8 @@ SIGNATURES = {
     "ibu_gpu_table_free": (None, [_vp, _P(BarcodeTable)]),
     "ibu_gpu_generate_records_async": (_int, [_vp, _vp, _u64, _u64, _u32, _u32, _int, _u64, _u64, _vp, _err]),
     "ibu_gpu_generate_ascii_async": (_int, [_vp, _vp, _u64, _u64, _u32, _u64, _u64, _u64, _vp, _err]),
+    "ibu_mmap_pin": (_int, [_vp, _err]),
+    "ibu_mmap_unpin": (None, [_vp]),
     "ibu_gpu_process_mmap": (_int, [_vp, _vp, _u64, _u64, _P(ReduceResult), CHUNK_CB, _vp, _err]),
     "ibu_gpu_process_host": (_int, [_vp, _vp, _u64, _u32, _u32, _P(ReduceResult), CHUNK_CB, _vp, _err]),
     "ibu_gpu_load_to_device": (_int, [_vp, C.c_char_p, _u64, _u64, _P(Header), _P(_vp), _P(_u64), _err]),

@@ -5,28 +5,33 @@
 // emitted in barcode order (Record's Ord, src/constructs/record.rs:58).
 //
 // Sorted input (by barcode, then umi) — the streaming path, 24 B/record, ONE pass over HBM:
-//   k_segments   tiles of 2048 records, tile ids handed out in order by an atomic counter.
-//                Each record is compared with its predecessor: barcode change = a new table
-//                row (head), (barcode, umi) change = a new distinct pair.  Tile-local ranks
-//                come from warp ballots; the global row number of the tile's first head
-//                comes from a decoupled look-back over per-tile descriptors (status | count
-//                in one 64-bit word), so no second pass over the records is needed.  A head
-//                writes {barcode, start position, distinct pairs before it in its tile}.
+//   k_segments   every warp claims tiles of 2048 records in order from an atomic counter.
+//                A lane owns 4 consecutive records (three LDG.E.256, whole sectors, static
+//                register layout), so each record is compared with its predecessor register
+//                to register: barcode change = a new table row (head), (barcode, umi) change
+//                = a new distinct pair.  Ranks inside the tile come from ballots; the global
+//                number of heads / pairs before the tile
+//                comes from a decoupled look-back over per-tile descriptors (two 64-bit
+//                words, each status | count), so no second pass over the records is needed.
+//                A head writes {barcode, start position, distinct pairs before it}.
 //                The same pass verifies the order; a violation raises a flag and the host
 //                falls back to the unsorted path.
-//   k_scan_tiles exclusive scan of the per-tile pair counts (n/2048 values).
 //   k_finalize   row r: n_records = start[r+1] - start[r]; n_distinct = pairs[r+1] - pairs[r].
 // Unsorted input: (barcode, umi) pairs are extracted (16 B), LSD radix sorted 8 bits at a time
 // over the bits that actually vary, and fed to the same segment kernel (stride 2 instead of 3).
 #include <algorithm>
+#include <chrono>
+#include <cstdlib>
 
 #include "ctx.h"
 #include "kernels.cuh"
 
 namespace ibu {
 
-constexpr int kSegTile = 2048;                       // records per tile
-constexpr int kSegPerThread = kSegTile / kBlockThreads;  // 8
+constexpr int kSegSub = 128;                     // records per sub-tile (4 per lane)
+// sub-tiles per (warp) tile: 16 = 2048 records.  Measured on B200 at 10^8 records: 4 -> 1.20 ms,
+// 8 -> 0.66 ms, 16 -> 0.44 ms (short tiles leave the deferred look-back too little slack).
+constexpr int kSegSubsDefault = 16;
 #define kStatusAgg (1ull << 62)
 #define kStatusPrefix (2ull << 62)
 #define kValueMask ((1ull << 62) - 1)
@@ -35,197 +40,278 @@ struct SegArgs {
     const uint64_t *src;     // records (stride 3 u64) or sorted pairs (stride 2 u64)
     uint64_t n;
     uint64_t n_tiles;
-    uint64_t *desc;          // [n_tiles] look-back descriptors, zeroed
-    uint32_t *tile_pairs;    // [n_tiles] distinct pairs that start in the tile
-    uint64_t *tmp_rows;      // [capacity][3]: barcode, start position, pairs before it in its tile
+    ulonglong2 *desc;        // [n_tiles] look-back descriptors {status|heads, status|pairs}, zeroed
+    uint64_t *tmp_rows;      // [capacity][3]: barcode, start position, distinct pairs before it
     uint64_t capacity;
-    unsigned long long *counters;  // [0] next tile id, [1] total heads, [2] unsorted flag
+    unsigned long long *counters;  // [0] next tile id, [1] total heads, [2] flags, [3] total pairs
+};
+
+// The (barcode, umi) keys of the 4 consecutive elements a lane owns in a 128-element sub-tile.
+// Records (STRIDE 3): 96 contiguous bytes = three LDG.E.256; pairs (STRIDE 2): 64 bytes = two.
+// Every access is a whole 32-byte sector and the words land in registers in a static layout,
+// so consecutive elements are compared register to register (no shared-memory transpose).
+template <int STRIDE>
+struct Keys4 {
+    uint64_t bc[4], um[4];
+    __device__ __forceinline__ void load(const uint64_t *sub, uint32_t lane) {
+        if constexpr (STRIDE == 3) {
+            const uint8_t *p = reinterpret_cast<const uint8_t *>(sub) + lane * 96;
+            const u64x4 v0 = ldg_stream256(p), v1 = ldg_stream256(p + 32), v2 = ldg_stream256(p + 64);
+            bc[0] = v0.x; um[0] = v0.y; bc[1] = v0.w; um[1] = v1.x;
+            bc[2] = v1.z; um[2] = v1.w; bc[3] = v2.y; um[3] = v2.z;
+        } else {
+            const uint8_t *p = reinterpret_cast<const uint8_t *>(sub) + lane * 64;
+            const u64x4 v0 = ldg_stream256(p), v1 = ldg_stream256(p + 32);
+            bc[0] = v0.x; um[0] = v0.y; bc[1] = v0.z; um[1] = v0.w;
+            bc[2] = v1.x; um[2] = v1.y; bc[3] = v1.z; um[3] = v1.w;
+        }
+    }
+    // ragged sub-tile: element-wise; absent elements repeat the key (pb, pu) of the last element
+    // of the input, so the padding never starts a run and never breaks the order
+    __device__ __forceinline__ void load_partial(const uint64_t *sub, uint32_t lane, uint32_t count,
+                                                 uint64_t pb, uint64_t pu) {
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            const uint32_t i = 4 * lane + q;
+            if (i < count) {
+                pb = ldg_stream64(sub + (uint64_t)i * STRIDE);
+                pu = ldg_stream64(sub + (uint64_t)i * STRIDE + 1);
+            }
+            bc[q] = pb;
+            um[q] = pu;
+        }
+    }
 };
 
 // STRIDE = u64 words per element (3: Record, 2: (barcode, umi) pair).
-template <int STRIDE>
-__global__ void __launch_bounds__(kBlockThreads) k_segments(const SegArgs a) {
-    extern __shared__ __align__(16) uint64_t tile[];  // kSegTile * STRIDE words
-    __shared__ uint32_t cnt_b[kSegPerThread][kWarpsPerBlock], cnt_p[kSegPerThread][kWarpsPerBlock];
-    __shared__ uint64_t s_prev[2];
-    __shared__ uint64_t s_tile, s_head_base;
-    const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+//
+// Every WARP is an independent worker: it claims the next tile (ordered ids from one atomic
+// counter, so a tile only ever waits on tiles whose warps are already running), streams its
+// 16 sub-tiles with the next one in flight and publishes the tile's head / pair counts.  The
+// look-back for the tile's global offsets does not stall the warp: it is polled, one
+// non-blocking step per sub-tile, while the warp already streams its NEXT tile (the masks of
+// two tiles are parked in shared memory), and only forced to completion before a third tile
+// would start.  No block barrier anywhere.
+template <int STRIDE, int kSegSubs>
+__global__ void __launch_bounds__(kBlockThreads, 4) k_segments(const SegArgs a) {
+    constexpr int kSegTile = kSegSub * kSegSubs;
+    // per (warp, buffer, sub-tile): each lane's head/pair masks and the packed counts before the
+    // sub-tile; parked so the sub-tile loop stays rolled and a finished tile can wait for its
+    // offsets while the next one streams
+    __shared__ uint32_t s_mask[kWarpsPerBlock][2][kSegSubs][32], s_run[kWarpsPerBlock][2][kSegSubs];
+    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    const uint32_t lt = (1u << lane) - 1u;
     volatile unsigned long long *v_flag = a.counters + 2;
+    volatile unsigned long long *desc = reinterpret_cast<volatile unsigned long long *>(a.desc);
+    // key of the last element of the input: the padding of the ragged final sub-tile
+    const uint64_t endb = a.src[(a.n - 1) * STRIDE], endu = a.src[(a.n - 1) * STRIDE + 1];
 
-    for (;;) {
-        if (tid == 0) s_tile = atomicAdd(a.counters, 1ull);
-        __syncthreads();
-        const uint64_t t = s_tile;
-        if (t >= a.n_tiles) break;
-        const uint64_t first = t * kSegTile;
-        const uint32_t count = (uint32_t)min((uint64_t)kSegTile, a.n - first);
+    // the tile whose look-back is still open (all fields warp-uniform)
+    bool p_active = false;
+    uint64_t p_t = 0, p_exb = 0, p_exp = 0;
+    int64_t p_j = 0;
+    uint32_t p_tot = 0, p_buf = 0;
 
-        // ---- stage the tile (coalesced 16-byte loads; the tile start is 16-byte aligned) ----
-        {
-            const uint32_t words = count * STRIDE;
-            const uint4 *g4 = reinterpret_cast<const uint4 *>(a.src + first * STRIDE);
-            uint4 *s4 = reinterpret_cast<uint4 *>(tile);
-            const uint32_t n16 = words / 2;
-            for (uint32_t i = tid; i < n16; i += kBlockThreads) s4[i] = ldg_stream(g4 + i);
-            if ((words & 1u) && tid == 0) tile[words - 1] = ldg_stream64(a.src + first * STRIDE + words - 1);
-            if (tid == 0 && first > 0) {
-                s_prev[0] = ldg_stream64(a.src + (first - 1) * STRIDE);
-                s_prev[1] = ldg_stream64(a.src + (first - 1) * STRIDE + 1);
-            }
-        }
-        __syncthreads();
-
-        // ---- flags: record i = tid + 256 q (24/16-byte stride: conflict-free 64-bit loads) ----
-        uint32_t hb = 0, hp = 0;  // bit q: record q of this thread is a head / starts a new pair
-        uint32_t bad = 0;
-#pragma unroll
-        for (int q = 0; q < kSegPerThread; q++) {
-            const uint32_t i = tid + kBlockThreads * q;
-            uint32_t is_b = 0, is_p = 0;
-            if (i < count) {
-                const uint64_t bc = tile[i * STRIDE], um = tile[i * STRIDE + 1];
-                if (i == 0 && first == 0) {
-                    is_b = is_p = 1;
-                } else {
-                    const uint64_t pb = i ? tile[(i - 1) * STRIDE] : s_prev[0];
-                    const uint64_t pu = i ? tile[(i - 1) * STRIDE + 1] : s_prev[1];
-                    is_b = bc != pb;
-                    is_p = is_b | (um != pu);
-                    bad |= (pb > bc) | ((pb == bc) & (pu > um));
+    // One look-back attempt for the open tile: consume published windows of 32 predecessors until
+    // an inclusive prefix is met.  Non-blocking mode gives up at the first window that is not
+    // fully published yet.  Returns true when the tile's exclusive offsets are final.
+    auto lookback = [&](bool blocking) -> bool {
+        uint32_t spins = 0;
+        for (;;) {
+            const int64_t mine_t = p_j - lane;  // lane l inspects tile j - l
+            const uint64_t d0 = mine_t >= 0 ? desc[2 * mine_t] : kStatusPrefix;
+            const uint64_t d1 = mine_t >= 0 ? desc[2 * mine_t + 1] : kStatusPrefix;
+            // a descriptor is usable when both words carry the same status
+            const uint32_t s0 = (uint32_t)(d0 >> 62), s1 = (uint32_t)(d1 >> 62);
+            const uint32_t st = s0 == s1 ? s0 : 0u;
+            const uint32_t inval = __ballot_sync(0xffffffffu, st == 0);
+            const uint32_t pref = __ballot_sync(0xffffffffu, st == 2);
+            // lanes up to and including the first inclusive prefix must be published
+            const uint32_t upto = pref ? ((2u << (__ffs(pref) - 1)) - 1u) : 0xffffffffu;
+            if (inval & upto) {  // warp-uniform
+                if (!blocking) return false;
+                // stop waiting when the order check failed elsewhere (results are void then) or,
+                // as a watchdog, after ~4 M polls; the vote keeps the decision uniform even if
+                // lanes observe the flag at different times
+                const bool timeout = ++spins > (1u << 22);
+                if (__any_sync(0xffffffffu, *v_flag != 0ull) || timeout) {
+                    if (timeout && lane == 0) atomicOr(a.counters + 2, 2ull);
+                    return true;
                 }
+                __nanosleep(64);  // leave the issue slots to the streaming warps
+                continue;
             }
-            const uint32_t mb = __ballot_sync(0xffffffffu, is_b), mp = __ballot_sync(0xffffffffu, is_p);
-            if (lane == 0) {
-                cnt_b[q][warp] = __popc(mb);
-                cnt_p[q][warp] = __popc(mp);
-            }
-            hb |= is_b << q;
-            hp |= is_p << q;
+            const bool take = (upto >> lane) & 1u;
+            p_exb += warp_sum64(take ? (d0 & kValueMask) : 0ull);
+            p_exp += warp_sum64(take ? (d1 & kValueMask) : 0ull);
+            if (pref) return true;
+            p_j -= 32;
         }
-        if (__any_sync(0xffffffffu, bad) && lane == 0) atomicOr(a.counters + 2, 1ull);
-        __syncthreads();
+    };
 
-        // ---- warp 0: scan the 64 (q, warp) counts in record order, then the look-back ----
-        if (warp == 0) {
-            uint32_t *fb = &cnt_b[0][0], *fp = &cnt_p[0][0];
-            uint32_t b0 = fb[2 * lane], b1 = fb[2 * lane + 1], p0 = fp[2 * lane], p1 = fp[2 * lane + 1];
-            uint32_t sb = b0 + b1, sp = p0 + p1;
+    // Close the open tile: publish its inclusive prefix and write the row stubs of its heads
+    // {barcode, start, distinct pairs before it}.  Ranks inside a sub-tile are rebuilt from the
+    // parked masks with ballots, only for sub-tiles that contain a head (heads are rare).
+    auto finish = [&]() {
+        const uint64_t tot_b = p_tot & 0xFFFFu, tot_p = p_tot >> 16;
+        if (lane == 0) {
+            if (p_t > 0) {
+                desc[2 * p_t] = kStatusPrefix | (p_exb + tot_b);
+                desc[2 * p_t + 1] = kStatusPrefix | (p_exp + tot_p);
+            }
+            if (p_t == a.n_tiles - 1) {
+                a.counters[1] = p_exb + tot_b;  // total rows
+                a.counters[3] = p_exp + tot_p;  // total distinct pairs
+            }
+        }
+        if (tot_b) {
+            const uint64_t wfirst = p_t * kSegTile;
+#pragma unroll 1
+            for (int s = 0; s < kSegSubs; s++) {
+                const uint32_t m = s_mask[warp][p_buf][s][lane], hb = m & 0xFu, hp = m >> 4;
+                if (!__any_sync(0xffffffffu, hb)) continue;
+                uint32_t below = s_run[warp][p_buf][s];
 #pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                uint32_t vb = __shfl_up_sync(0xffffffffu, sb, o), vp = __shfl_up_sync(0xffffffffu, sp, o);
-                if (lane >= o) { sb += vb; sp += vp; }
-            }
-            const uint32_t tot_b = __shfl_sync(0xffffffffu, sb, 31), tot_p = __shfl_sync(0xffffffffu, sp, 31);
-            fb[2 * lane] = sb - b0 - b1; fb[2 * lane + 1] = sb - b1;  // exclusive prefixes
-            fp[2 * lane] = sp - p0 - p1; fp[2 * lane + 1] = sp - p1;
-
-            volatile uint64_t *desc = a.desc;
-            if (lane == 0) {
-                a.tile_pairs[t] = tot_p;
-                desc[t] = (t == 0 ? kStatusPrefix : kStatusAgg) | tot_b;
-            }
-            uint64_t exclusive = 0;
-            if (t > 0) {
-                int64_t j = (int64_t)t - 1;  // nearest predecessor; lane l inspects tile j - l
-                for (;;) {
-                    const int64_t mine = j - lane;
-                    uint64_t d;
-                    uint32_t need, spins = 0;
-                    do {
-                        d = mine >= 0 ? desc[mine] : kStatusPrefix;
-                        const uint32_t inval = __ballot_sync(0xffffffffu, (d >> 62) == 0);
-                        const uint32_t pref = __ballot_sync(0xffffffffu, (d >> 62) == 2);
-                        // lanes up to and including the first inclusive prefix must be published
-                        const uint32_t upto = pref ? ((2u << (__ffs(pref) - 1)) - 1u) : 0xffffffffu;
-                        need = inval & upto;  // warp-uniform
-                        if (need) {
-                            // stop waiting when the order check failed elsewhere (results are void
-                            // then) or, as a watchdog, after ~4 M polls; the vote keeps the exit
-                            // decision uniform even if lanes observe the flag at different times
-                            const bool timeout = ++spins > (1u << 22);
-                            if (__any_sync(0xffffffffu, *v_flag != 0ull) || timeout) {
-                                if (timeout && lane == 0) atomicOr(a.counters + 2, 2ull);
-                                need = 0;
-                            }
+                for (int q = 0; q < 4; q++) {
+                    const uint32_t vb = __ballot_sync(0xffffffffu, (hb >> q) & 1u), vp = __ballot_sync(0xffffffffu, (hp >> q) & 1u);
+                    below += __popc(vb & lt) | (__popc(vp & lt) << 16);
+                }
+#pragma unroll
+                for (int q = 0; q < 4; q++) {
+                    if ((hb >> q) & 1u) {
+                        const uint32_t lower = (1u << q) - 1u;
+                        const uint64_t row = p_exb + (below & 0xFFFFu) + __popc(hb & lower);
+                        if (row < a.capacity) {
+                            // the barcode is re-read (an L2 hit) rather than kept in registers
+                            const uint64_t pos = wfirst + (uint64_t)s * kSegSub + 4 * lane + q;
+                            uint64_t *dst = a.tmp_rows + 3 * row;
+                            dst[0] = a.src[pos * STRIDE];
+                            dst[1] = pos;
+                            dst[2] = p_exp + (below >> 16) + __popc(hp & lower);
                         }
-                    } while (need);
-                    const uint32_t pref = __ballot_sync(0xffffffffu, (d >> 62) == 2);
-                    const uint32_t upto = pref ? ((2u << (__ffs(pref) - 1)) - 1u) : 0xffffffffu;
-                    uint64_t v = ((upto >> lane) & 1u) ? (d & kValueMask) : 0ull;
-                    exclusive += warp_sum64(v);
-                    if (pref) break;
-                    j -= 32;
+                    }
                 }
-                if (lane == 0) desc[t] = kStatusPrefix | (exclusive + tot_b);
-            }
-            if (lane == 0) {
-                s_head_base = exclusive;
-                if (t == a.n_tiles - 1) a.counters[1] = exclusive + tot_b;  // total rows
             }
         }
-        __syncthreads();
+        p_active = false;
+    };
 
-        // ---- heads write their row stub ----
-        const uint64_t head_base = s_head_base;
+    auto claim = [&]() -> uint64_t {  // tile ids are claimed in order
+        uint64_t t = 0;
+        if (lane == 0) t = atomicAdd(a.counters, 1ull);
+        return __shfl_sync(0xffffffffu, t, 0);
+    };
+    auto load_sub = [&](Keys4<STRIDE> &k, uint64_t tile, int s) {
+        const uint64_t sfirst = tile * kSegTile + (uint64_t)s * kSegSub;
+        if (sfirst + kSegSub <= a.n) {
+            k.load(a.src + sfirst * STRIDE, lane);
+        } else {  // ragged end of the input
+            const uint32_t count = sfirst < a.n ? (uint32_t)(a.n - sfirst) : 0u;
+            k.load_partial(a.src + sfirst * STRIDE, lane, count, endb, endu);
+        }
+    };
+    // key of the element in front of a tile (what lane 0's first element is compared with)
+    auto load_front = [&](uint64_t tile, uint64_t &fb, uint64_t &fu) {
+        fb = fu = 0;
+        if (tile > 0) {
+            fb = ldg_stream64(a.src + (tile * kSegTile - 1) * STRIDE);
+            fu = ldg_stream64(a.src + (tile * kSegTile - 1) * STRIDE + 1);
+        }
+    };
+
+    uint64_t t = claim();
+    if (t >= a.n_tiles) return;
+    // The sub-tile stream is continuous across tiles: the next tile is claimed two sub-tiles
+    // before the current one ends and its first sub-tile (and front key) are prefetched during
+    // the last one, so a tile switch costs no exposed latency.
+    Keys4<STRIDE> nxt;
+    uint64_t nfb, nfu;
+    load_sub(nxt, t, 0);
+    load_front(t, nfb, nfu);
+    uint32_t buf = 0;
+    for (;;) {
+        const uint64_t wfirst = t * kSegTile;  // first element of the tile
+        // lb/lu: every lane's copy of "the last key of the previous sub-tile of lane 31"; only
+        // lane 31's copy is ever consumed (by lane 0, through the rotate below).  Before the
+        // first sub-tile it is the key of the element in front of the tile.
+        uint64_t lb = nfb, lu = nfu;
+        uint64_t t_next = a.n_tiles;
+        // flags: element q of lane l in sub-tile s is tile element 128 s + 4 l + q
+        uint32_t run = 0, bad = 0;  // run: heads | pairs << 16 so far in the tile
+#pragma unroll 1
+        for (int s = 0; s < kSegSubs; s++) {
+            const Keys4<STRIDE> k = nxt;
+            if (s + 1 < kSegSubs) {
+                load_sub(nxt, t, s + 1);
+            } else if (t_next < a.n_tiles) {
+                load_sub(nxt, t_next, 0);
+                load_front(t_next, nfb, nfu);
+            }
+            if (s == kSegSubs - 2) t_next = claim();
+            // predecessor of the lane's first element = last element of lane l-1; lane 0 wraps
+            // to lane 31, which offers the previous sub-tile's last key instead of its own
+            const uint64_t ob = lane == 31 ? lb : k.bc[3], ou = lane == 31 ? lu : k.um[3];
+            uint64_t qb = __shfl_sync(0xffffffffu, ob, (lane + 31) & 31u), qu = __shfl_sync(0xffffffffu, ou, (lane + 31) & 31u);
+            lb = k.bc[3];
+            lu = k.um[3];
+            uint32_t mb = 0, mp = 0;
 #pragma unroll
-        for (int q = 0; q < kSegPerThread; q++) {
-            const uint32_t is_b = (hb >> q) & 1u, is_p = (hp >> q) & 1u;
-            const uint32_t mb = __ballot_sync(0xffffffffu, is_b), mp = __ballot_sync(0xffffffffu, is_p);
-            if (is_b) {
-                const uint32_t lt = (1u << lane) - 1u;
-                const uint64_t row = head_base + cnt_b[q][warp] + __popc(mb & lt);
-                if (row < a.capacity) {
-                    const uint32_t i = tid + kBlockThreads * q;
-                    uint64_t *dst = a.tmp_rows + 3 * row;
-                    dst[0] = tile[i * STRIDE];
-                    dst[1] = first + i;
-                    dst[2] = cnt_p[q][warp] + __popc(mp & lt);
-                }
+            for (int q = 0; q < 4; q++) {
+                const uint64_t cb = k.bc[q], cu = k.um[q];
+                const uint32_t is_b = cb != qb, is_p = is_b | (cu != qu);
+                bad |= (qb > cb) | ((qb == cb) & (qu > cu));
+                mb |= is_b << q;
+                mp |= is_p << q;
+                qb = cb; qu = cu;
             }
+            if (s == 0 && lane == 0 && wfirst == 0) { mb |= 1u; mp |= 1u; }  // the very first element
+            s_mask[warp][buf][s][lane] = mb | (mp << 4);
+            if (lane == 0) s_run[warp][buf][s] = run;  // heads | pairs << 16 before this sub-tile
+            run += __reduce_add_sync(0xffffffffu, __popc(mb) | (__popc(mp) << 16));
+            // the previous tile's offsets, if still open: one non-blocking look-back step
+            if (p_active && lookback(false)) finish();
         }
-        __syncthreads();  // the tile and the count arrays are reused by the next iteration
+        // (padding repeats a key and a missing predecessor reads as (0, 0): neither can look
+        // like an order violation)
+        if (__any_sync(0xffffffffu, bad) && lane == 0) atomicOr(a.counters + 2, 1ull);
+
+        // ---- publish this tile's counts first (successors only need the aggregate) ----
+        if (lane == 0) {
+            const uint64_t st = t == 0 ? kStatusPrefix : kStatusAgg;
+            desc[2 * t] = st | (uint64_t)(run & 0xFFFFu);
+            desc[2 * t + 1] = st | (uint64_t)(run >> 16);
+        }
+        // at most one tile stays open per warp: force the older one before taking its place
+        if (p_active) {
+            lookback(true);
+            finish();
+        }
+        __syncwarp();
+        p_active = true;
+        p_t = t; p_tot = run; p_buf = buf; p_exb = 0; p_exp = 0; p_j = (int64_t)t - 1;
+        if (t == 0) finish();  // no predecessors: offsets are zero
+        buf ^= 1u;
+        if (t_next >= a.n_tiles) break;
+        t = t_next;
+    }
+    if (p_active) {
+        lookback(true);
+        finish();
     }
 }
 
-// exclusive scan of tile_pairs -> tile_prefix (u64); totals[3] = number of distinct pairs
-__global__ void __launch_bounds__(1024) k_scan_tiles(const uint32_t *__restrict__ tile_pairs,
-                                                     uint64_t *__restrict__ tile_prefix, uint64_t n_tiles,
-                                                     unsigned long long *counters) {
-    __shared__ uint64_t part[1024];
-    const uint32_t tid = threadIdx.x;
-    const uint64_t per = (n_tiles + 1023) / 1024;
-    const uint64_t lo = min(n_tiles, tid * per), hi = min(n_tiles, lo + per);
-    uint64_t s = 0;
-    for (uint64_t i = lo; i < hi; i++) s += tile_pairs[i];
-    part[tid] = s;
-    __syncthreads();
-    for (int o = 1; o < 1024; o <<= 1) {  // Hillis-Steele inclusive scan
-        uint64_t v = tid >= (uint32_t)o ? part[tid - o] : 0;
-        __syncthreads();
-        part[tid] += v;
-        __syncthreads();
-    }
-    uint64_t run = part[tid] - s;
-    for (uint64_t i = lo; i < hi; i++) {
-        tile_prefix[i] = run;
-        run += tile_pairs[i];
-    }
-    if (tid == 1023) counters[3] = part[1023];
-}
-
+// row r: n_records = start[r+1] - start[r], n_distinct_umi = pairs_before[r+1] - pairs_before[r]
 __global__ void __launch_bounds__(kBlockThreads)
-k_finalize_rows(const uint64_t *__restrict__ tmp_rows, const uint64_t *__restrict__ tile_prefix,
-                uint64_t n_rows, uint64_t n, const unsigned long long *__restrict__ counters,
-                ibu_barcode_row_t *__restrict__ rows) {
+k_finalize_rows(const uint64_t *__restrict__ tmp_rows, uint64_t n_rows, uint64_t n,
+                const unsigned long long *__restrict__ counters, ibu_barcode_row_t *__restrict__ rows) {
     const uint64_t total_pairs = counters[3];
     for (uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; r < n_rows;
          r += (uint64_t)gridDim.x * blockDim.x) {
-        const uint64_t bc = tmp_rows[3 * r], start = tmp_rows[3 * r + 1], lp = tmp_rows[3 * r + 2];
-        const uint64_t g = tile_prefix[start / kSegTile] + lp;
+        const uint64_t bc = tmp_rows[3 * r], start = tmp_rows[3 * r + 1], g = tmp_rows[3 * r + 2];
         uint64_t next_start = n, next_g = total_pairs;
         if (r + 1 < n_rows) {
             next_start = tmp_rows[3 * r + 4];
-            next_g = tile_prefix[next_start / kSegTile] + tmp_rows[3 * r + 5];
+            next_g = tmp_rows[3 * r + 5];
         }
         rows[r].barcode = bc;
         rows[r].n_records = next_start - start;
@@ -377,63 +463,122 @@ k_radix_scatter(const uint64_t *__restrict__ in, uint64_t *__restrict__ out, uin
     }
 }
 
+// Scratch for one call: carved from the context's grow-only arena, falling back to cudaMalloc
+// (freed on scope exit) when the arena is too small, e.g. for the exact-capacity retry.
 struct Scratch {
-    std::vector<void *> ptrs;
+    ibu_gpu_ctx *ctx;
+    std::vector<void *> owned;
+    explicit Scratch(ibu_gpu_ctx *c) : ctx(c) {}
     ~Scratch() {
-        for (void *p : ptrs) cudaFree(p);
+        for (void *p : owned) cudaFree(p);
     }
     template <class T>
     cudaError_t alloc(T **out, size_t bytes) {
+        bytes = (bytes + 255) & ~(size_t)255;
+        if (bytes == 0) bytes = 256;
+        if (ctx->arena_off + bytes <= ctx->arena_cap) {
+            *out = (T *)((uint8_t *)ctx->arena_base + ctx->arena_off);
+            ctx->arena_off += bytes;
+            return cudaSuccess;
+        }
         void *p = nullptr;
-        cudaError_t e = cudaMalloc(&p, bytes ? bytes : 256);
-        if (e == cudaSuccess) ptrs.push_back(p);
+        cudaError_t e = cudaMalloc(&p, bytes);
+        if (e == cudaSuccess) owned.push_back(p);
         *out = (T *)p;
         return e;
     }
-    void release(void *p) {  // hand ownership to the caller
-        ptrs.erase(std::remove(ptrs.begin(), ptrs.end(), p), ptrs.end());
-    }
 };
+
+// Make the arena at least `bytes` large and empty.  Only called while nothing carved from it
+// is live (start of a call / between the sorted probe and the sort path).
+static cudaError_t arena_reset(ibu_gpu_ctx *ctx, size_t bytes) {
+    ctx->arena_off = 0;
+    if (ctx->arena_cap >= bytes) return cudaSuccess;
+    if (ctx->arena_base) cudaFree(ctx->arena_base);
+    ctx->arena_base = nullptr;
+    ctx->arena_cap = 0;
+    cudaError_t e = cudaMalloc(&ctx->arena_base, bytes);
+    if (e == cudaSuccess) ctx->arena_cap = bytes;
+    return e;
+}
+
+static uint64_t seg_capacity(uint64_t n) { return std::min<uint64_t>(n, 8ull << 20); }
+static size_t seg_scratch_bytes(uint64_t n) {
+    const uint64_t n_tiles = (n + kSegSubsDefault * kSegSub - 1) / (kSegSubsDefault * kSegSub);
+    return n_tiles * 16 + seg_capacity(n) * 24 + 8 * 256;
+}
+static size_t sort_scratch_bytes(uint64_t n) {
+    const uint64_t n_tiles = (n + 2047) / 2048;
+    return n * 32 + n_tiles * 1024 + 8 * 256 + 4096;
+}
 
 // Runs the segment pass over `src` (stride 3 or 2).  On success *rows_out (device, owned by the
 // caller) holds *n_rows rows.  *unsorted is set when the order check failed (no rows then).
+struct Trace {  // IBU_B200_TRACE=1: host-side phase timing on stderr (tuning only)
+    bool on = getenv("IBU_B200_TRACE") != nullptr;
+    std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
+    void mark(const char *what) {
+        if (!on) return;
+        auto t1 = std::chrono::steady_clock::now();
+        fprintf(stderr, "[ibu trace] %-28s %8.3f ms\n", what, std::chrono::duration<double, std::milli>(t1 - t0).count());
+        t0 = t1;
+    }
+};
+
 static int segment_pass(ibu_gpu_ctx *ctx, const uint64_t *src, int stride, uint64_t n, cudaStream_t s,
                         ibu_barcode_row_t **rows_out, uint64_t *n_rows, uint64_t *n_pairs, bool *unsorted,
                         ibu_error_t *err) {
+    Trace tr;
     *rows_out = nullptr;
     *n_rows = *n_pairs = 0;
     *unsorted = false;
-    const uint64_t n_tiles = (n + kSegTile - 1) / kSegTile;
-    Scratch sc;
-    uint64_t *desc, *tile_prefix, *tmp_rows;
-    uint32_t *tile_pairs;
+    const int subs = kSegSubsDefault;
+    const uint64_t tile = (uint64_t)kSegSub * subs;
+    const uint64_t n_tiles = (n + tile - 1) / tile;
+    Scratch sc(ctx);
+    ulonglong2 *desc;
+    uint64_t *tmp_rows;
     unsigned long long *counters;
-    IBU_CUDA(sc.alloc(&desc, n_tiles * 8));
-    IBU_CUDA(sc.alloc(&tile_prefix, n_tiles * 8));
-    IBU_CUDA(sc.alloc(&tile_pairs, n_tiles * 4));
+    IBU_CUDA(sc.alloc(&desc, n_tiles * 16));
     IBU_CUDA(sc.alloc(&counters, 4 * 8));
-    const size_t smem = (size_t)kSegTile * stride * 8;
-    auto kern = stride == 3 ? k_segments<3> : k_segments<2>;
-    IBU_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const size_t smem = 0;
+    auto kern = stride == 3 ? k_segments<3, kSegSubsDefault> : k_segments<2, kSegSubsDefault>;
     int per_sm = 0;
     IBU_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kBlockThreads, smem));
-    // every CTA must be resident: a waiting tile spins on descriptors of earlier tiles
+    // tile ids are claimed in order at run time, so a waiting tile only ever waits on tiles
+    // that are already running; the grid is one resident wave
     const int grid = (int)std::min<uint64_t>((uint64_t)ctx->sm_count * std::max(per_sm, 1), n_tiles);
 
-    uint64_t capacity = std::min<uint64_t>(n, 8ull << 20);  // optimistic: <= 8 Mi distinct barcodes
+    uint64_t capacity = seg_capacity(n);  // optimistic: <= 8 Mi distinct barcodes
     for (int attempt = 0; attempt < 2; attempt++) {
         IBU_CUDA(sc.alloc(&tmp_rows, capacity * 24));
-        IBU_CUDA(cudaMemsetAsync(desc, 0, n_tiles * 8, s));
+        IBU_CUDA(cudaMemsetAsync(desc, 0, n_tiles * 16, s));
         IBU_CUDA(cudaMemsetAsync(counters, 0, 4 * 8, s));
-        SegArgs a{src, n, n_tiles, desc, tile_pairs, tmp_rows, capacity, counters};
+        SegArgs a{src, n, n_tiles, desc, tmp_rows, capacity, counters};
+        cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+        if (tr.on) {
+            cudaEventCreate(&ev0);
+            cudaEventCreate(&ev1);
+            cudaEventRecord(ev0, s);
+        }
         kern<<<grid, kBlockThreads, smem, s>>>(a);
         g_launches.fetch_add(1, std::memory_order_relaxed);
         IBU_CUDA(cudaGetLastError());
-        k_scan_tiles<<<1, 1024, 0, s>>>(tile_pairs, tile_prefix, n_tiles, counters);
-        g_launches.fetch_add(1, std::memory_order_relaxed);
+        if (tr.on) {
+            cudaEventRecord(ev1, s);
+            cudaEventSynchronize(ev1);
+            float ms = 0;
+            cudaEventElapsedTime(&ms, ev0, ev1);
+            fprintf(stderr, "[ibu trace] k_segments<%d> grid %d: %.3f ms = %.0f GB/s\n", stride, grid, ms,
+                    (double)n * stride * 8 / ms / 1e6);
+            cudaEventDestroy(ev0);
+            cudaEventDestroy(ev1);
+        }
         unsigned long long h[4];
+        tr.mark("seg: setup+launch");
         IBU_CUDA(cudaMemcpyAsync(h, counters, sizeof(h), cudaMemcpyDeviceToHost, s));
         IBU_CUDA(cudaStreamSynchronize(s));
+        tr.mark("seg: k_segments sync");
         if (h[2] & 2ull)
             return set_error(err, IBU_ERR_CUDA, 0, 0, 0, "barcode_count: look-back watchdog expired");
         if (h[2]) {
@@ -444,17 +589,21 @@ static int segment_pass(ibu_gpu_ctx *ctx, const uint64_t *src, int stride, uint6
             capacity = h[1];
             continue;
         }
-        ibu_barcode_row_t *rows;
-        IBU_CUDA(sc.alloc(&rows, h[1] * sizeof(ibu_barcode_row_t)));
+        ibu_barcode_row_t *rows = nullptr;  // owned by the caller (ibu_gpu_table_free)
+        IBU_CUDA(cudaMalloc((void **)&rows, h[1] ? h[1] * sizeof(ibu_barcode_row_t) : 256));
         if (h[1]) {
             const uint64_t blocks = (h[1] + kBlockThreads - 1) / kBlockThreads;
             k_finalize_rows<<<(int)std::min<uint64_t>(blocks, (uint64_t)ctx->sm_count * 8), kBlockThreads, 0, s>>>(
-                tmp_rows, tile_prefix, h[1], n, counters, rows);
+                tmp_rows, h[1], n, counters, rows);
             g_launches.fetch_add(1, std::memory_order_relaxed);
-            IBU_CUDA(cudaGetLastError());
-            IBU_CUDA(cudaStreamSynchronize(s));
+            cudaError_t e = cudaGetLastError();
+            if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+            if (e != cudaSuccess) {
+                cudaFree(rows);
+                return cuda_fail(err, e, "k_finalize_rows");
+            }
         }
-        sc.release(rows);
+        tr.mark("seg: rows malloc+finalize");
         *rows_out = rows;
         *n_rows = h[1];
         *n_pairs = h[3];
@@ -516,8 +665,8 @@ int ibu_gpu_barcode_count(ibu_gpu_ctx_t *ctx, const ibu_record_t *d_records, uin
     clear_error(err);
     if (!ctx || !table || (!d_records && n)) return set_error(err, IBU_ERR_ARG, 0, 0, 0, "null argument");
     if (mode < 0 || mode > 2) return set_error(err, IBU_ERR_ARG, 0, mode, 0, "mode must be 0, 1 or 2");
-    if (((uintptr_t)d_records & 15u) != 0)
-        return set_error(err, IBU_ERR_ARG, 0, 0, 0, "d_records must be 16-byte aligned");
+    if (((uintptr_t)d_records & 31u) != 0)
+        return set_error(err, IBU_ERR_ARG, 0, 0, 0, "d_records must be 32-byte aligned");
     memset(table, 0, sizeof(*table));
     table->n_records = n;
     if (n == 0) {
@@ -525,18 +674,21 @@ int ibu_gpu_barcode_count(ibu_gpu_ctx_t *ctx, const ibu_record_t *d_records, uin
         return IBU_OK;
     }
     DeviceGuard guard(ctx->device);
+    std::lock_guard<std::mutex> lock(ctx->arena_mutex);  // one table build per context at a time
     cudaStream_t s = pick_stream(ctx, stream);
     const uint64_t *src = reinterpret_cast<const uint64_t *>(d_records);
     ibu_barcode_row_t *rows = nullptr;
     uint64_t n_rows = 0, n_pairs = 0;
     bool unsorted = mode == 2;
     if (mode != 2) {
+        IBU_CUDA(arena_reset(ctx, seg_scratch_bytes(n)));
         if (int rc = segment_pass(ctx, src, 3, n, s, &rows, &n_rows, &n_pairs, &unsorted, err)) return rc;
         if (!unsorted) table->input_was_sorted = 1;
     }
     if (unsorted) {
         if (mode == 1) return IBU_OK;  // caller required sorted input: input_was_sorted = 0, no rows
-        Scratch sc;
+        IBU_CUDA(arena_reset(ctx, sort_scratch_bytes(n) + seg_scratch_bytes(n)));
+        Scratch sc(ctx);
         uint64_t *sorted = nullptr;
         if (int rc = sort_pairs(ctx, src, n, s, sc, &sorted, err)) return rc;
         bool still_unsorted = false;

@@ -50,3 +50,5 @@ struct ibu_mmap_reader {
     size_t len;
 };
 const uint8_t *ibu_mmap_base(const ibu_mmap_reader *r);  // start of the mapping (header included)
+size_t ibu_mmap_bytes(const ibu_mmap_reader *r);        // size of the mapping
+int ibu_mmap_fd(const ibu_mmap_reader *r);              // descriptor of the mapped file (for pread staging)

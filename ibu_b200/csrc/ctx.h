@@ -2,6 +2,7 @@
 #pragma once
 #include <atomic>
 #include <cuda_runtime.h>
+#include <mutex>
 #include <vector>
 
 #include "common.h"
@@ -25,6 +26,11 @@ struct ibu_gpu_ctx {
     ibu_gpu_config_t cfg{};
     std::vector<ibu_chunk_slot> slots;
     int variant = 0;  // kernel variant override (IBU_B200_VARIANT env; tuning only)
+    // grow-only device scratch of the blocking table builder (K4): cudaMalloc/cudaFree per call
+    // would cost more than the streaming pass itself
+    std::mutex arena_mutex;
+    void *arena_base = nullptr;
+    size_t arena_cap = 0, arena_off = 0;
 };
 
 namespace ibu {

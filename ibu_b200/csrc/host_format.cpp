@@ -21,10 +21,13 @@ using ibu::set_error;
 struct ibu_mmap_shared {
     const uint8_t *base;
     size_t bytes;
+    int fd;  // kept open: the staging pipeline may pread() instead of touching the mapping
     std::atomic<long> refs;
 };
 
 const uint8_t *ibu_mmap_base(const ibu_mmap_reader *r) { return r->shared->base; }
+size_t ibu_mmap_bytes(const ibu_mmap_reader *r) { return r->shared->bytes; }
+int ibu_mmap_fd(const ibu_mmap_reader *r) { return r->shared->fd; }
 
 namespace {
 
@@ -128,8 +131,10 @@ int ibu_mmap_open(const char *path, ibu_mmap_reader_t **out, ibu_error_t *err) {
     }
     void *p = mmap(nullptr, bytes, PROT_READ, MAP_PRIVATE, fd, 0);
     int e = errno;
-    ::close(fd);
-    if (p == MAP_FAILED) return io_error(err, e, "mmap", path);
+    if (p == MAP_FAILED) {
+        ::close(fd);
+        return io_error(err, e, "mmap", path);
+    }
 
     ibu_header_t header;
     memcpy(&header, p, sizeof(header));
@@ -139,12 +144,14 @@ int ibu_mmap_open(const char *path, ibu_mmap_reader_t **out, ibu_error_t *err) {
                        "Invalid map size - not a multiple of record size");
     if (rc != IBU_OK) {
         munmap(p, bytes);
+        ::close(fd);
         return rc;
     }
-    auto *shared = new (std::nothrow) ibu_mmap_shared{(const uint8_t *)p, bytes, {1}};
+    auto *shared = new (std::nothrow) ibu_mmap_shared{(const uint8_t *)p, bytes, fd, {1}};
     auto *r = new (std::nothrow) ibu_mmap_reader{shared, header, (bytes - IBU_HEADER_SIZE) / IBU_RECORD_SIZE};
     if (!shared || !r) {
         munmap(p, bytes);
+        ::close(fd);
         delete shared;
         delete r;
         return set_error(err, IBU_ERR_NOMEM, 0, 0, 0, "out of memory");
@@ -164,6 +171,7 @@ void ibu_mmap_close(ibu_mmap_reader_t *r) {
     if (!r) return;
     if (r->shared->refs.fetch_sub(1, std::memory_order_acq_rel) == 1) {
         munmap((void *)r->shared->base, r->shared->bytes);
+        ::close(r->shared->fd);
         delete r->shared;
     }
     delete r;

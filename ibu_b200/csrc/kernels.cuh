@@ -45,6 +45,18 @@ __device__ __forceinline__ void stg_stream(uint4 *p, uint4 v) {
                  "r"(v.y), "r"(v.z), "r"(v.w)
                  : "memory");
 }
+// store-policy experiments (tuning only): 0 L1::no_allocate, 1 .cs, 2 default (.wb), 3 .cg
+template <int POL>
+__device__ __forceinline__ void stg_pol(uint4 *p, uint4 v) {
+    if constexpr (POL == 1)
+        asm volatile("st.global.cs.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+    else if constexpr (POL == 2)
+        asm volatile("st.global.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+    else if constexpr (POL == 3)
+        asm volatile("st.global.cg.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+    else
+        stg_stream(p, v);
+}
 __device__ __forceinline__ void stg_stream256(void *p, uint4 lo, uint4 hi) {
     asm volatile("st.global.L1::no_allocate.v8.u32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p),
                  "r"(lo.x), "r"(lo.y), "r"(lo.z), "r"(lo.w), "r"(hi.x), "r"(hi.y), "r"(hi.z),

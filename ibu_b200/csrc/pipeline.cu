@@ -9,6 +9,7 @@
 // mmap / user buffer), (3) enqueues H2D -> kernel -> D2H on the slot's stream.  With >= 2 slots
 // the copy engines, the SMs and the host memcpy of the next chunk all overlap.
 #include <algorithm>
+#include <atomic>
 #include <cerrno>
 #include <cstdlib>
 #include <fcntl.h>
@@ -50,6 +51,42 @@ void parallel_memcpy(void *dst, const void *src, size_t bytes, unsigned threads)
     for (auto &t : pool) t.join();
 }
 
+// The same fan-out with pread(2): file bytes land in pinned memory with one kernel copy and
+// without populating page tables for the mapping.
+bool parallel_pread(void *dst, int fd, uint64_t file_off, size_t bytes, unsigned threads) {
+    if (threads < 1) threads = 1;
+    size_t per = align_up((bytes + threads - 1) / threads, 1 << 20);
+    std::atomic<bool> ok{true};
+    auto work = [&](size_t off, size_t len) {
+        uint8_t *p = (uint8_t *)dst + off;
+        uint64_t fo = file_off + off;
+        while (len) {
+            ssize_t got = ::pread(fd, p, len, (off_t)fo);
+            if (got < 0 && errno == EINTR) continue;
+            if (got <= 0) {
+                ok = false;
+                return;
+            }
+            p += got;
+            fo += (uint64_t)got;
+            len -= (size_t)got;
+        }
+    };
+    std::vector<std::thread> pool;
+    for (unsigned i = 0; i < threads; i++) {
+        size_t off = (size_t)i * per;
+        if (off >= bytes) break;
+        size_t len = std::min(per, bytes - off);
+        if (i + 1 == threads || off + per >= bytes) {
+            work(off, len);  // the calling thread takes the last piece
+            break;
+        }
+        pool.emplace_back(work, off, len);
+    }
+    for (auto &t : pool) t.join();
+    return ok;
+}
+
 int ensure(void **p, size_t *have, size_t want, bool host, ibu_error_t *err) {
     if (*have >= want) return IBU_OK;
     if (*p) {
@@ -79,7 +116,7 @@ void merge(ibu_reduce_result_t &t, const ibu_reduce_result_t &c) {
 unsigned copy_threads(const ibu_gpu_ctx *ctx) {
     if (ctx->cfg.copy_threads) return ctx->cfg.copy_threads;
     unsigned hc = std::thread::hardware_concurrency();
-    return std::max(1u, std::min(16u, hc / 2));
+    return std::max(1u, std::min(32u, hc));  // staging is a DRAM-bandwidth job: use the cores
 }
 
 // What one chunk moves: inputs (host -> device) and outputs (device -> host) as byte spans
@@ -90,6 +127,8 @@ struct Span {
     size_t bytes = 0;
     size_t d_off = 0;             // offset in slot.d_in / slot.d_out
     bool pinned = false;          // host side is pinned: DMA straight from / to it
+    int fd = -1;                  // inputs only: stage with pread(fd, file_off) instead of memcpy
+    uint64_t file_off = 0;
 };
 
 struct ChunkPlan {
@@ -143,7 +182,12 @@ int run_chunks_impl(ibu_gpu_ctx *ctx, uint64_t n_chunks, PlanFn plan_of, Enqueue
             if (!sp.bytes) continue;
             const void *src = sp.h_src;
             if (!sp.pinned) {
-                parallel_memcpy((uint8_t *)slot.h_in + sp.d_off, sp.h_src, sp.bytes, threads);
+                if (sp.fd >= 0) {
+                    if (!parallel_pread((uint8_t *)slot.h_in + sp.d_off, sp.fd, sp.file_off, sp.bytes, threads))
+                        return set_error(err, IBU_ERR_IO, errno, 0, 0, "I/O error: pread failed while staging");
+                } else {
+                    parallel_memcpy((uint8_t *)slot.h_in + sp.d_off, sp.h_src, sp.bytes, threads);
+                }
                 src = (uint8_t *)slot.h_in + sp.d_off;
             }
             IBU_CUDA(cudaMemcpyAsync((uint8_t *)slot.d_in + sp.d_off, src, sp.bytes,
@@ -185,7 +229,8 @@ uint64_t chunk_records(const ibu_gpu_ctx *ctx) {
 
 int process_host_records(ibu_gpu_ctx *ctx, const ibu_record_t *h_records, uint64_t n, uint32_t bc_len,
                          uint32_t umi_len, uint64_t first_record, ibu_reduce_result_t *h_result,
-                         ibu_chunk_cb on_chunk, void *user, ibu_error_t *err) {
+                         ibu_chunk_cb on_chunk, void *user, ibu_error_t *err, int fd = -1,
+                         uint64_t file_off = 0) {
     DeviceGuard guard(ctx->device);
     memset(h_result, 0, sizeof(*h_result));
     if (n == 0) return IBU_OK;  // an empty range never calls on_batch_complete (mmap.rs:502-519)
@@ -206,6 +251,8 @@ int process_host_records(ibu_gpu_ctx *ctx, const ibu_record_t *h_records, uint64
             p.in[0].h_src = h_records + start;
             p.in[0].bytes = cnt * IBU_RECORD_SIZE;
             p.in[0].pinned = pinned;
+            p.in[0].fd = fd;
+            p.in[0].file_off = file_off + start * IBU_RECORD_SIZE;
             p.d_in_bytes = align_up(chunk * IBU_RECORD_SIZE);
             p.d_out_bytes = kAlign;
             return p;
@@ -296,6 +343,7 @@ void ibu_gpu_ctx_destroy(ibu_gpu_ctx_t *ctx) {
         cudaStreamSynchronize(ctx->stream);
         cudaStreamDestroy(ctx->stream);
     }
+    if (ctx->arena_base) cudaFree(ctx->arena_base);
     delete ctx;
 }
 
@@ -374,6 +422,18 @@ void ibu_host_unregister(void *h_ptr) {
     if (h_ptr && cudaHostUnregister(h_ptr) != cudaSuccess) cudaGetLastError();
 }
 
+int ibu_mmap_pin(ibu_mmap_reader_t *reader, ibu_error_t *err) {
+    clear_error(err);
+    if (!reader) return set_error(err, IBU_ERR_ARG, 0, 0, 0, "null reader");
+    IBU_CUDA(cudaHostRegister((void *)ibu_mmap_base(reader), ibu_mmap_bytes(reader),
+                              cudaHostRegisterPortable | cudaHostRegisterReadOnly));
+    return IBU_OK;
+}
+
+void ibu_mmap_unpin(ibu_mmap_reader_t *reader) {
+    if (reader && cudaHostUnregister((void *)ibu_mmap_base(reader)) != cudaSuccess) cudaGetLastError();
+}
+
 // ---- GPU counterpart of process_parallel -------------------------------------------------
 
 int ibu_gpu_process_host(ibu_gpu_ctx_t *ctx, const ibu_record_t *h_records, uint64_t n, uint32_t bc_len,
@@ -395,8 +455,13 @@ int ibu_gpu_process_mmap(ibu_gpu_ctx_t *ctx, const ibu_mmap_reader_t *reader, ui
                          "Invalid index (%llu) - Must be less than %zu", (unsigned long long)end, reader->len);
     const ibu_record_t *recs =
         (const ibu_record_t *)(ibu_mmap_base(reader) + IBU_HEADER_SIZE) + start;
+    // pageable source: stage with pread from the reader's descriptor (IBU_B200_STAGE=mmap forces
+    // memcpy out of the mapping instead; a pinned mapping is DMA'd directly either way)
+    const char *mode = getenv("IBU_B200_STAGE");
+    const int fd = (mode && !strcmp(mode, "mmap")) ? -1 : ibu_mmap_fd(reader);
     return process_host_records(ctx, recs, end - start, reader->header.bc_len, reader->header.umi_len,
-                                start, h_result, on_chunk, user, err);
+                                start, h_result, on_chunk, user, err, fd,
+                                IBU_HEADER_SIZE + start * IBU_RECORD_SIZE);
 }
 
 // ---- device path of load_to_vec -----------------------------------------------------------
@@ -428,7 +493,6 @@ int ibu_gpu_load_to_device(ibu_gpu_ctx_t *ctx, const char *path, uint64_t start,
     }
     int rc = IBU_OK;
     if (count) {
-        const uint8_t *src = ibu_mmap_base(reader) + IBU_HEADER_SIZE + start * IBU_RECORD_SIZE;
         const uint64_t chunk = chunk_records(ctx);
         const uint64_t n_chunks = (count + chunk - 1) / chunk;
         const unsigned threads = copy_threads(ctx);
@@ -443,7 +507,11 @@ int ibu_gpu_load_to_device(ibu_gpu_ctx_t *ctx, const char *path, uint64_t start,
                 break;
             }
             if ((rc = ensure(&slot.h_in, &slot.h_in_bytes, align_up(chunk * IBU_RECORD_SIZE), true, err))) break;
-            parallel_memcpy(slot.h_in, src + off, bytes, threads);
+            if (!parallel_pread(slot.h_in, ibu_mmap_fd(reader), IBU_HEADER_SIZE + start * IBU_RECORD_SIZE + off,
+                                bytes, threads)) {
+                rc = set_error(err, IBU_ERR_IO, errno, 0, 0, "I/O error: pread failed while loading");
+                break;
+            }
             e = cudaMemcpyAsync((uint8_t *)dev + off, slot.h_in, bytes, cudaMemcpyHostToDevice, slot.stream);
             if (e == cudaSuccess) e = cudaEventRecord(slot.done, slot.stream);
             if (e != cudaSuccess) rc = cuda_fail(err, e, "cudaMemcpyAsync");

@@ -271,7 +271,9 @@ enum {
     IBU_GEN_CLEAN = 0,     /* barcode/umi masked to bc_len/umi_len, index = i */
     IBU_GEN_DIRTY = 1,     /* as CLEAN, `param` ppm of records carry an unmasked word */
     IBU_GEN_PATTERN = 2,   /* (i % 1e6, 31 i % 1e6, i): examples/parallel.rs:65-69 */
-    IBU_GEN_WHITELIST = 3  /* `param` distinct barcodes, 4^min(umi_len,6)... umis; unsorted */
+    IBU_GEN_WHITELIST = 3, /* param: low 32 bits = #distinct barcodes, high 32 = umi space; unsorted */
+    IBU_GEN_SORTED = 4     /* param: low 32 bits = records per barcode, high 32 = records per umi;
+                              sorted by Record's Ord: (i / rpb, (i % rpb) / dup, i) */
 };
 int ibu_gpu_generate_records_async(ibu_gpu_ctx_t *ctx, ibu_record_t *d_records,
                                    uint64_t first, uint64_t n, uint32_t bc_len,
@@ -297,6 +299,12 @@ typedef int (*ibu_chunk_cb)(void *user, uint64_t chunk_start, uint64_t chunk_n,
 int ibu_gpu_process_mmap(ibu_gpu_ctx_t *ctx, const ibu_mmap_reader_t *reader, uint64_t start,
                          uint64_t end, ibu_reduce_result_t *h_result, ibu_chunk_cb on_chunk,
                          void *user, ibu_error_t *err);
+/* Optional: page-lock the reader's mapping (cudaHostRegister, read-only) so that
+ * ibu_gpu_process_mmap DMAs straight out of the page cache instead of staging through
+ * pinned bounce buffers.  Fails with IBU_ERR_CUDA where the driver refuses file-backed
+ * mappings; the staged path then still applies. */
+int ibu_mmap_pin(ibu_mmap_reader_t *reader, ibu_error_t *err);
+void ibu_mmap_unpin(ibu_mmap_reader_t *reader);
 /* Same over a host array (pinned: copied directly; pageable: staged). */
 int ibu_gpu_process_host(ibu_gpu_ctx_t *ctx, const ibu_record_t *h_records, uint64_t n,
                          uint32_t bc_len, uint32_t umi_len, ibu_reduce_result_t *h_result,

@@ -684,6 +684,12 @@ static inline orc_record_t gen_record(uint64_t i, uint32_t bc_len, uint32_t umi_
         }
         case 2:  // PATTERN (examples/parallel.rs:65-69, examples/roundtrip.rs:34-38)
             return {i % 1000000ull, (i * 31ull) % 1000000ull, i};
+        case 4: {  // SORTED: low 32 bits of param = records per barcode, high 32 = records per umi
+            uint64_t rpb = param & 0xFFFFFFFFull, dup = param >> 32;
+            if (rpb == 0) rpb = 1000;
+            if (dup == 0) dup = 1;
+            return {(i / rpb) & mb, ((i % rpb) / dup) & mu, i};
+        }
         case 3: {  // WHITELIST: low 32 bits of param = #barcodes, high 32 bits = umi space
             uint64_t nb = param & 0xFFFFFFFFull, us = param >> 32;
             if (nb == 0) nb = 1000;  // examples/random.rs default --barcodes

@@ -171,6 +171,9 @@ def generate_records(first: int, n: int, bc_len: int, umi_len: int, mode: int, p
         nb = nb or 1000
         out["barcode"] = splitmix64((rb % U64(nb)) ^ U64(seed) ^ U64(0xB)) & mb
         out["umi"] = ((ru % U64(us)) if us else ru) & mu
+    elif mode == 4:
+        rpb, dup = (param & 0xFFFFFFFF) or 1000, (param >> 32) or 1
+        out["barcode"], out["umi"] = (i // U64(rpb)) & mb, ((i % U64(rpb)) // U64(dup)) & mu
     else:
         raise ValueError(mode)
     return out

@@ -176,7 +176,7 @@ def test_pack_every_byte_value(ctx):
 
 
 # ---- generators ---------------------------------------------------------------------------
-@pytest.mark.parametrize("mode,param", [(0, 0), (1, 100_000), (2, 0), (3, (4096 << 32) | 10_000)])
+@pytest.mark.parametrize("mode,param", [(0, 0), (1, 100_000), (2, 0), (3, (4096 << 32) | 10_000), (4, (5 << 32) | 1000)])
 @pytest.mark.parametrize("bc,umi", [(16, 12), (32, 32), (3, 9)])
 def test_device_generators_match_oracle(ctx, mode, param, bc, umi):
     n = 100_003
@@ -305,3 +305,17 @@ def test_barcode_table_capacity_retry(ctx):
     want = on.barcode_table(recs)
     assert info["input_was_sorted"] and len(rows) > (8 << 20)
     assert np.array_equal(rows, want)
+
+
+def test_barcode_table_sorted_full_size_closed_form(ctx):
+    """10^8 sorted records (1000 per barcode, 5 per umi): 10^5 rows x 1000 records x 200 UMIs,
+    streamed in one pass (24 B/record)."""
+    n = 100_000_000
+    d = Dev(ctx, 24 * n)
+    ctx.generate_records_async(d, 0, n, 16, 12, ibu.GEN_SORTED, (5 << 32) | 1000, 0)
+    ctx.synchronize()
+    rows, info = ctx.barcode_count(d, n, mode=1)
+    d.free()
+    assert info["input_was_sorted"] and len(rows) == 100_000 and info["n_distinct_pairs"] == 20_000_000
+    assert np.array_equal(rows["barcode"], np.arange(100_000, dtype=U64))
+    assert np.all(rows["n_records"] == 1000) and np.all(rows["n_distinct_umi"] == 200)

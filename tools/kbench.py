@@ -72,6 +72,8 @@ def main():
             report(f"K2 unpack bc{bc}/umi{umi}", 24 + bc + umi,
                    lambda: ctx.unpack_async(recs, n, bc, umi, b, u, None, res, stream))
             if (bc, umi) == (16, 12):
+                report(f"K2 unpack bc{bc}/umi{umi} noresult", 24 + bc + umi,
+                       lambda: ctx.unpack_async(recs, n, bc, umi, b, u, None, None, stream))
                 fl = u8(n)
                 report(f"K2 unpack bc{bc}/umi{umi} +flags", 25 + bc + umi,
                        lambda: ctx.unpack_async(recs, n, bc, umi, b, u, fl, res, stream))
@@ -85,6 +87,27 @@ def main():
                        lambda: ctx.pack_async(b, u, n, bc, umi, back, d_index=idx, d_result=res, stream=stream))
                 del idx
             del recs, b, u, back
+        # K4: sorted streaming path (blocking API: wall clock, includes scratch allocation and
+        # the table's D2H) and the unsorted sort-then-segment path
+        if not args.only or "K4" in args.only:
+            import time
+            recs = u8(24 * n)
+            for label, mode, param, m in [("K4 barcode_count sorted (1000/barcode, 5/umi)", ibu.GEN_SORTED, (5 << 32) | 1000, 1),
+                                          ("K4 barcode_count unsorted whitelist 1M barcodes", ibu.GEN_WHITELIST, (4096 << 32) | 1_000_000, 0),
+                                          ("K4 barcode_count unsorted pattern", ibu.GEN_PATTERN, 0, 0)]:
+                ctx.generate_records_async(recs, 0, n, 16, 12, mode, param, 3, stream)
+                stream.synchronize()
+                ts = []
+                for _ in range(5):
+                    t0 = time.perf_counter()
+                    rows, info = ctx.barcode_count(recs, n, m, stream)
+                    ts.append((time.perf_counter() - t0) * 1e3)
+                ts.sort()
+                print(json.dumps(dict(kernel=label, records=n, alg_bytes_per_record=24, ms_mean=sum(ts) / len(ts),
+                                      ms_best=ts[0], achieved_gbs=24 * n / ts[0] / 1e6, frac=24 * n / ts[0] / 1e6 / pk,
+                                      rows=len(rows), sorted=info["input_was_sorted"], timing="wall clock of the blocking call")),
+                      flush=True)
+            del recs
         # torch's own device copy of the same footprint as a same-run peak probe
         a, c = u8(2_600_000_000), u8(2_600_000_000)
         if not args.only:
