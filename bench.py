@@ -165,7 +165,9 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=dev)
 
     n = N_RECORDS
-    ctx = ibu.GpuContext(local, chunk_records=4 << 20, n_slots=3)
+    chunk = int(os.environ.get("IBU_BENCH_CHUNK", 4 << 20))
+    slots = int(os.environ.get("IBU_BENCH_SLOTS", 3))
+    ctx = ibu.GpuContext(local, chunk_records=chunk, n_slots=slots)
     stream = torch.cuda.Stream(device=dev)
     peak, peak_kind = hbm_peak()
 
@@ -261,10 +263,10 @@ def run_ours(args):
                          "kernel_ms": kern_mean, "frac_of_nominal_8TBs": achieved / 8000.0},
             "cpu_baseline": None,
             "e2e": {"value": world * n / e2e_s, "unit": "records/s", "h2d_bytes_per_step": n * 24,
-                    "d2h_bytes_per_step": n * (BC_LEN + UMI_LEN) + 64 * ((n + (4 << 20) - 1) // (4 << 20)),
+                    "d2h_bytes_per_step": n * (BC_LEN + UMI_LEN) + 64 * ((n + chunk - 1) // chunk),
                     "ms_per_step": e2e_s * 1e3, "steps": e2e_steps,
                     "link_gbs": (n * 24 + n * (BC_LEN + UMI_LEN)) / e2e_s / 1e9,
-                    "api": "ibu_gpu_unpack_host (pinned host in/out, 4 Mi-record chunks, 3 slots)"},
+                    "api": f"ibu_gpu_unpack_host (pinned host in/out, {chunk}-record chunks, {slots} slots)"},
             "gpu_launches": launches, "gpu_launches_e2e": launches_e2e,
             "clocks": clocks,
             "counters": {"n_records": int(counters[0]), "n_bad_barcode": int(counters[5]),

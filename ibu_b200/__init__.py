@@ -33,6 +33,7 @@ RECORD_DTYPE = np.dtype([("barcode", "<u8"), ("umi", "<u8"), ("index", "<u8")])
 ROW_DTYPE = np.dtype([("barcode", "<u8"), ("n_records", "<u8"), ("n_distinct_umi", "<u8")])
 
 GEN_CLEAN, GEN_DIRTY, GEN_PATTERN, GEN_WHITELIST, GEN_SORTED = 0, 1, 2, 3, 4
+COUNT_WEIGHTED = 8
 
 
 # ---- errors (src/error.rs:56-128) ---------------------------------------------------------
@@ -331,6 +332,20 @@ class GpuContext:
         finally:
             lib.ibu_gpu_table_free(self._h, C.byref(table))
         return rows, info
+
+    def pair_table(self, d_records, n, weighted: bool = False, stream=None):
+        """Distinct (barcode, umi) pairs with multiplicities as device records: (ptr, n_pairs).
+        Release with .free(ptr)."""
+        p, cnt, err = C.c_void_p(), C.c_uint64(), _lib.Error()
+        _check(lib.ibu_gpu_pair_table(self._h, _ptr(d_records), n, int(weighted), C.byref(p), C.byref(cnt),
+                                      _stream(stream), C.byref(err)), err)
+        return int(p.value or 0), int(cnt.value)
+
+    def sort_records(self, d_records, n, d_sorted, stream=None):
+        """Device sort by Record's Ord (barcode, umi, index) into d_sorted."""
+        err = _lib.Error()
+        _check(lib.ibu_gpu_sort_records(self._h, _ptr(d_records), n, _ptr(d_sorted), _stream(stream),
+                                        C.byref(err)), err)
 
     # -- host-buffer (end-to-end) paths
     def process_host(self, h_records: np.ndarray, bc_len: int, umi_len: int, on_chunk=None) -> ReduceResult:

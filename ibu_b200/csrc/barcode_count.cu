@@ -92,7 +92,9 @@ struct Keys4 {
 // non-blocking step per sub-tile, while the warp already streams its NEXT tile (the masks of
 // two tiles are parked in shared memory), and only forced to completion before a third tile
 // would start.  No block barrier anywhere.
-template <int STRIDE, int kSegSubs>
+// PAIRS: rows are distinct (barcode, umi) pairs instead of barcodes (the stub's third word then
+// carries the umi): the de-duplicated pair table that shards exchange for an exact merge.
+template <int STRIDE, int kSegSubs, bool PAIRS>
 __global__ void __launch_bounds__(kBlockThreads, 4) k_segments(const SegArgs a) {
     constexpr int kSegTile = kSegSub * kSegSubs;
     // per (warp, buffer, sub-tile): each lane's head/pair masks and the packed counts before the
@@ -187,7 +189,7 @@ __global__ void __launch_bounds__(kBlockThreads, 4) k_segments(const SegArgs a) 
                             uint64_t *dst = a.tmp_rows + 3 * row;
                             dst[0] = a.src[pos * STRIDE];
                             dst[1] = pos;
-                            dst[2] = p_exp + (below >> 16) + __popc(hp & lower);
+                            dst[2] = PAIRS ? a.src[pos * STRIDE + 1] : p_exp + (below >> 16) + __popc(hp & lower);
                         }
                     }
                 }
@@ -265,6 +267,7 @@ __global__ void __launch_bounds__(kBlockThreads, 4) k_segments(const SegArgs a) 
                 qb = cb; qu = cu;
             }
             if (s == 0 && lane == 0 && wfirst == 0) { mb |= 1u; mp |= 1u; }  // the very first element
+            if (PAIRS) mb = mp;
             s_mask[warp][buf][s][lane] = mb | (mp << 4);
             if (lane == 0) s_run[warp][buf][s] = run;  // heads | pairs << 16 before this sub-tile
             run += __reduce_add_sync(0xffffffffu, __popc(mb) | (__popc(mp) << 16));
@@ -300,10 +303,11 @@ __global__ void __launch_bounds__(kBlockThreads, 4) k_segments(const SegArgs a) 
     }
 }
 
-// row r: n_records = start[r+1] - start[r], n_distinct_umi = pairs_before[r+1] - pairs_before[r]
+// row r: n_records = start[r+1] - start[r], n_distinct_umi = pairs_before[r+1] - pairs_before[r];
+// pair mode: row r = {barcode, umi, multiplicity}
 __global__ void __launch_bounds__(kBlockThreads)
 k_finalize_rows(const uint64_t *__restrict__ tmp_rows, uint64_t n_rows, uint64_t n,
-                const unsigned long long *__restrict__ counters, ibu_barcode_row_t *__restrict__ rows) {
+                const unsigned long long *__restrict__ counters, uint64_t *__restrict__ rows, int pair_mode) {
     const uint64_t total_pairs = counters[3];
     for (uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; r < n_rows;
          r += (uint64_t)gridDim.x * blockDim.x) {
@@ -313,41 +317,83 @@ k_finalize_rows(const uint64_t *__restrict__ tmp_rows, uint64_t n_rows, uint64_t
             next_start = tmp_rows[3 * r + 4];
             next_g = tmp_rows[3 * r + 5];
         }
-        rows[r].barcode = bc;
-        rows[r].n_records = next_start - start;
-        rows[r].n_distinct_umi = next_g - g;
+        rows[3 * r] = bc;
+        rows[3 * r + 1] = pair_mode ? g : next_start - start;
+        rows[3 * r + 2] = pair_mode ? next_start - start : next_g - g;
     }
 }
 
-// ============================================================ unsorted path: LSD radix sort
-constexpr int kSortTile = 2048;                              // pairs per CTA tile
+// ============================================================ LSD radix sort (unsorted inputs)
+// Elements are STRIDE u64 words (2: (barcode, umi) pair, 3: Record); one pass sorts stably by
+// one 8-bit digit of one key word.  Digits on which every key agrees are skipped, so clean
+// bc16/umi12 data needs 4 + 3 passes, not 16.
+constexpr int kSortTile = 2048;                              // elements per CTA tile
 constexpr int kSortItems = kSortTile / kBlockThreads;        // 8 per thread
 
-// records -> (barcode, umi) pairs, plus OR / AND of every word (which bits vary at all)
+template <int STRIDE>
+struct Elem {
+    uint64_t w[STRIDE];
+};
+template <int STRIDE>
+__device__ __forceinline__ Elem<STRIDE> load_elem(const uint64_t *base, uint64_t i) {
+    Elem<STRIDE> e;
+    if constexpr (STRIDE == 2) {
+        const ulonglong2 v = reinterpret_cast<const ulonglong2 *>(base)[i];
+        e.w[0] = v.x; e.w[1] = v.y;
+    } else {
+#pragma unroll
+        for (int k = 0; k < STRIDE; k++) e.w[k] = base[i * STRIDE + k];
+    }
+    return e;
+}
+template <int STRIDE>
+__device__ __forceinline__ void store_elem(uint64_t *base, uint64_t i, const Elem<STRIDE> &e) {
+    if constexpr (STRIDE == 2) {
+        reinterpret_cast<ulonglong2 *>(base)[i] = make_ulonglong2(e.w[0], e.w[1]);
+    } else {
+#pragma unroll
+        for (int k = 0; k < STRIDE; k++) base[i * STRIDE + k] = e.w[k];
+    }
+}
+
+// records -> (barcode, umi) pairs (optional), plus OR / AND of every key word: masks[2k] |= w_k,
+// masks[2k+1] &= w_k (which bits vary at all)
+template <int WORDS>
 __global__ void __launch_bounds__(kBlockThreads)
-k_extract_pairs(const uint64_t *__restrict__ recs, uint64_t n, uint64_t *__restrict__ pairs,
-                unsigned long long *__restrict__ masks /* or_b, and_b, or_u, and_u */) {
-    uint64_t ob = 0, ab = ~0ull, ou = 0, au = ~0ull;
+k_key_masks(const uint64_t *__restrict__ recs, uint64_t n, uint64_t *__restrict__ pairs,
+            unsigned long long *__restrict__ masks) {
+    uint64_t o[WORDS], a[WORDS];
+#pragma unroll
+    for (int k = 0; k < WORDS; k++) { o[k] = 0; a[k] = ~0ull; }
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
          i += (uint64_t)gridDim.x * blockDim.x) {
-        const uint64_t b = ldg_stream64(recs + 3 * i), u = ldg_stream64(recs + 3 * i + 1);
-        ob |= b; ab &= b; ou |= u; au &= u;
-        reinterpret_cast<ulonglong2 *>(pairs)[i] = make_ulonglong2(b, u);
+        uint64_t w[WORDS];
+#pragma unroll
+        for (int k = 0; k < WORDS; k++) {
+            w[k] = ldg_stream64(recs + 3 * i + k);
+            o[k] |= w[k];
+            a[k] &= w[k];
+        }
+        if (pairs) reinterpret_cast<ulonglong2 *>(pairs)[i] = make_ulonglong2(w[0], w[1]);
     }
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        ob |= __shfl_xor_sync(0xffffffffu, ob, o); ab &= __shfl_xor_sync(0xffffffffu, ab, o);
-        ou |= __shfl_xor_sync(0xffffffffu, ou, o); au &= __shfl_xor_sync(0xffffffffu, au, o);
-    }
-    if ((threadIdx.x & 31u) == 0) {
-        atomicOr(masks + 0, ob); atomicAnd(masks + 1, ab);
-        atomicOr(masks + 2, ou); atomicAnd(masks + 3, au);
+    for (int k = 0; k < WORDS; k++) {
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+            o[k] |= __shfl_xor_sync(0xffffffffu, o[k], off);
+            a[k] &= __shfl_xor_sync(0xffffffffu, a[k], off);
+        }
+        if ((threadIdx.x & 31u) == 0) {
+            atomicOr(masks + 2 * k, o[k]);
+            atomicAnd(masks + 2 * k + 1, a[k]);
+        }
     }
 }
 
 // per-tile digit histogram, stored digit-major: hist[d * n_tiles + tile]
+template <int STRIDE>
 __global__ void __launch_bounds__(kBlockThreads)
-k_radix_hist(const uint64_t *__restrict__ pairs, uint64_t n, uint32_t word, uint32_t shift,
+k_radix_hist(const uint64_t *__restrict__ in, uint64_t n, uint32_t word, uint32_t shift,
              uint32_t *__restrict__ hist, uint64_t n_tiles) {
     __shared__ uint32_t h[256];
     const uint64_t tile_id = blockIdx.x;
@@ -356,7 +402,7 @@ k_radix_hist(const uint64_t *__restrict__ pairs, uint64_t n, uint32_t word, uint
     const uint64_t first = tile_id * kSortTile;
     const uint32_t count = (uint32_t)min((uint64_t)kSortTile, n - first);
     for (uint32_t i = threadIdx.x; i < count; i += kBlockThreads) {
-        const uint64_t key = pairs[2 * (first + i) + (word ? 0 : 1)];  // (barcode, umi): word 0 = umi
+        const uint64_t key = in[(first + i) * STRIDE + word];
         atomicAdd(&h[(key >> shift) & 0xFFu], 1u);
     }
     __syncthreads();
@@ -381,8 +427,8 @@ k_radix_scan(uint32_t *__restrict__ hist, uint64_t n_tiles, uint64_t *__restrict
         part[tid] += v;
         __syncthreads();
     }
-    // a tile's offset within one digit never exceeds n < 2^32 * tiles; keep 32 bits per entry by
-    // storing offsets relative to the digit (the digit base is added from digit_total)
+    // offsets are kept relative to the digit (32 bits suffice for n < 2^32); the digit base is
+    // added from digit_total by the scatter kernel
     uint64_t run = part[tid] - s;
     for (uint64_t i = lo; i < hi; i++) {
         const uint32_t c = row[i];
@@ -393,6 +439,7 @@ k_radix_scan(uint32_t *__restrict__ hist, uint64_t n_tiles, uint64_t *__restrict
 }
 
 // stable scatter of one tile by one 8-bit digit
+template <int STRIDE>
 __global__ void __launch_bounds__(kBlockThreads)
 k_radix_scatter(const uint64_t *__restrict__ in, uint64_t *__restrict__ out, uint64_t n, uint32_t word,
                 uint32_t shift, const uint32_t *__restrict__ hist, const uint64_t *__restrict__ digit_total,
@@ -421,17 +468,15 @@ k_radix_scatter(const uint64_t *__restrict__ in, uint64_t *__restrict__ out, uin
     const uint64_t first = tile_id * kSortTile;
     const uint32_t count = (uint32_t)min((uint64_t)kSortTile, n - first);
     // warp w owns elements [w*256, w*256+256) of the tile; item k of lane l is element w*256 + 32k + l
-    ulonglong2 el[kSortItems];
+    Elem<STRIDE> el[kSortItems];
     uint32_t rank[kSortItems];
     uint32_t dig[kSortItems];
 #pragma unroll
     for (int k = 0; k < kSortItems; k++) {
         const uint32_t i = warp * (kSortTile / kWarpsPerBlock) + 32 * k + lane;
         const bool live = i < count;
-        if (live) el[k] = reinterpret_cast<const ulonglong2 *>(in)[first + i];
-        const uint64_t key = live ? (word ? el[k].x : el[k].y) : 0;
-        // pairs are stored (barcode, umi): word 1 = barcode = .x, word 0 = umi = .y
-        const uint32_t d = live ? (uint32_t)((key >> shift) & 0xFFu) : 0x100u;  // 0x100: no element
+        if (live) el[k] = load_elem<STRIDE>(in, first + i);
+        const uint32_t d = live ? (uint32_t)((el[k].w[word] >> shift) & 0xFFu) : 0x100u;  // 0x100: no element
         dig[k] = d;
         const uint32_t peers = __match_any_sync(0xffffffffu, d);
         const uint32_t leader = __ffs(peers) - 1;
@@ -458,8 +503,24 @@ k_radix_scatter(const uint64_t *__restrict__ in, uint64_t *__restrict__ out, uin
     for (int k = 0; k < kSortItems; k++) {
         if (dig[k] < 0x100u) {
             const uint64_t pos = base[dig[k]] + warp_cnt[warp][dig[k]] + rank[k];
-            reinterpret_cast<ulonglong2 *>(out)[pos] = el[k];
+            store_elem<STRIDE>(out, pos, el[k]);
         }
+    }
+}
+
+// weighted tables (merging per-shard pair tables): a row's count is the sum of the `index`
+// words (multiplicities) of the records in its run instead of the run length.  One warp per row.
+__global__ void __launch_bounds__(kBlockThreads)
+k_sum_weights(const uint64_t *__restrict__ tmp_rows, uint64_t n_rows, uint64_t n,
+              const uint64_t *__restrict__ src, uint64_t *__restrict__ rows, int count_word) {
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint64_t warps = (uint64_t)gridDim.x * kWarpsPerBlock;
+    for (uint64_t r = (uint64_t)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5); r < n_rows; r += warps) {
+        const uint64_t start = tmp_rows[3 * r + 1], end = r + 1 < n_rows ? tmp_rows[3 * r + 4] : n;
+        uint64_t s = 0;
+        for (uint64_t i = start + lane; i < end; i += 32) s += src[3 * i + 2];
+        s = warp_sum64(s);
+        if (lane == 0) rows[3 * r + count_word] = s;
     }
 }
 
@@ -507,10 +568,6 @@ static size_t seg_scratch_bytes(uint64_t n) {
     const uint64_t n_tiles = (n + kSegSubsDefault * kSegSub - 1) / (kSegSubsDefault * kSegSub);
     return n_tiles * 16 + seg_capacity(n) * 24 + 8 * 256;
 }
-static size_t sort_scratch_bytes(uint64_t n) {
-    const uint64_t n_tiles = (n + 2047) / 2048;
-    return n * 32 + n_tiles * 1024 + 8 * 256 + 4096;
-}
 
 // Runs the segment pass over `src` (stride 3 or 2).  On success *rows_out (device, owned by the
 // caller) holds *n_rows rows.  *unsorted is set when the order check failed (no rows then).
@@ -525,15 +582,18 @@ struct Trace {  // IBU_B200_TRACE=1: host-side phase timing on stderr (tuning on
     }
 };
 
+// Runs the segment pass over `src` (stride 3 or 2).  On success *rows_out (device, cudaMalloc'ed,
+// owned by the caller) holds *n_rows rows of 3 u64: barcode rows {barcode, n_records,
+// n_distinct_umi} or, in pair mode, {barcode, umi, multiplicity}.  `weighted` (stride 3 only):
+// counts are sums of the records' index words.  *unsorted is set when the order check failed.
 static int segment_pass(ibu_gpu_ctx *ctx, const uint64_t *src, int stride, uint64_t n, cudaStream_t s,
-                        ibu_barcode_row_t **rows_out, uint64_t *n_rows, uint64_t *n_pairs, bool *unsorted,
-                        ibu_error_t *err) {
+                        bool pair_mode, bool weighted, uint64_t **rows_out, uint64_t *n_rows, uint64_t *n_pairs,
+                        bool *unsorted, ibu_error_t *err) {
     Trace tr;
     *rows_out = nullptr;
     *n_rows = *n_pairs = 0;
     *unsorted = false;
-    const int subs = kSegSubsDefault;
-    const uint64_t tile = (uint64_t)kSegSub * subs;
+    const uint64_t tile = (uint64_t)kSegSub * kSegSubsDefault;
     const uint64_t n_tiles = (n + tile - 1) / tile;
     Scratch sc(ctx);
     ulonglong2 *desc;
@@ -541,15 +601,18 @@ static int segment_pass(ibu_gpu_ctx *ctx, const uint64_t *src, int stride, uint6
     unsigned long long *counters;
     IBU_CUDA(sc.alloc(&desc, n_tiles * 16));
     IBU_CUDA(sc.alloc(&counters, 4 * 8));
-    const size_t smem = 0;
-    auto kern = stride == 3 ? k_segments<3, kSegSubsDefault> : k_segments<2, kSegSubsDefault>;
+    void (*kern)(const SegArgs) =
+        stride == 3 ? (pair_mode ? k_segments<3, kSegSubsDefault, true> : k_segments<3, kSegSubsDefault, false>)
+                    : (pair_mode ? k_segments<2, kSegSubsDefault, true> : k_segments<2, kSegSubsDefault, false>);
     int per_sm = 0;
-    IBU_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kBlockThreads, smem));
+    IBU_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kBlockThreads, 0));
     // tile ids are claimed in order at run time, so a waiting tile only ever waits on tiles
-    // that are already running; the grid is one resident wave
-    const int grid = (int)std::min<uint64_t>((uint64_t)ctx->sm_count * std::max(per_sm, 1), n_tiles);
+    // whose warps are already running; the grid is one resident wave
+    const uint64_t tiles_per_cta = kWarpsPerBlock;
+    const int grid = (int)std::min<uint64_t>((uint64_t)ctx->sm_count * std::max(per_sm, 1),
+                                             (n_tiles + tiles_per_cta - 1) / tiles_per_cta);
 
-    uint64_t capacity = seg_capacity(n);  // optimistic: <= 8 Mi distinct barcodes
+    uint64_t capacity = seg_capacity(n);  // optimistic: <= 8 Mi rows
     for (int attempt = 0; attempt < 2; attempt++) {
         IBU_CUDA(sc.alloc(&tmp_rows, capacity * 24));
         IBU_CUDA(cudaMemsetAsync(desc, 0, n_tiles * 16, s));
@@ -561,7 +624,7 @@ static int segment_pass(ibu_gpu_ctx *ctx, const uint64_t *src, int stride, uint6
             cudaEventCreate(&ev1);
             cudaEventRecord(ev0, s);
         }
-        kern<<<grid, kBlockThreads, smem, s>>>(a);
+        kern<<<grid, kBlockThreads, 0, s>>>(a);
         g_launches.fetch_add(1, std::memory_order_relaxed);
         IBU_CUDA(cudaGetLastError());
         if (tr.on) {
@@ -585,17 +648,23 @@ static int segment_pass(ibu_gpu_ctx *ctx, const uint64_t *src, int stride, uint6
             *unsorted = true;
             return IBU_OK;
         }
-        if (h[1] > capacity) {  // more distinct barcodes than the optimistic table: exact re-run
+        if (h[1] > capacity) {  // more rows than the optimistic table: exact re-run
             capacity = h[1];
             continue;
         }
-        ibu_barcode_row_t *rows = nullptr;  // owned by the caller (ibu_gpu_table_free)
-        IBU_CUDA(cudaMalloc((void **)&rows, h[1] ? h[1] * sizeof(ibu_barcode_row_t) : 256));
+        uint64_t *rows = nullptr;  // owned by the caller (ibu_gpu_table_free / ibu_gpu_free)
+        IBU_CUDA(cudaMalloc((void **)&rows, h[1] ? h[1] * 24 : 256));
         if (h[1]) {
             const uint64_t blocks = (h[1] + kBlockThreads - 1) / kBlockThreads;
-            k_finalize_rows<<<(int)std::min<uint64_t>(blocks, (uint64_t)ctx->sm_count * 8), kBlockThreads, 0, s>>>(
-                tmp_rows, h[1], n, counters, rows);
+            const int fgrid = (int)std::min<uint64_t>(blocks, (uint64_t)ctx->sm_count * 8);
+            k_finalize_rows<<<fgrid, kBlockThreads, 0, s>>>(tmp_rows, h[1], n, counters, rows, pair_mode ? 1 : 0);
             g_launches.fetch_add(1, std::memory_order_relaxed);
+            if (weighted) {
+                const uint64_t wblocks = (h[1] + kWarpsPerBlock - 1) / kWarpsPerBlock;
+                k_sum_weights<<<(int)std::min<uint64_t>(wblocks, (uint64_t)ctx->sm_count * 8), kBlockThreads, 0, s>>>(
+                    tmp_rows, h[1], n, src, rows, pair_mode ? 2 : 1);
+                g_launches.fetch_add(1, std::memory_order_relaxed);
+            }
             cudaError_t e = cudaGetLastError();
             if (e == cudaSuccess) e = cudaStreamSynchronize(s);
             if (e != cudaSuccess) {
@@ -606,51 +675,134 @@ static int segment_pass(ibu_gpu_ctx *ctx, const uint64_t *src, int stride, uint6
         tr.mark("seg: rows malloc+finalize");
         *rows_out = rows;
         *n_rows = h[1];
-        *n_pairs = h[3];
+        *n_pairs = pair_mode ? h[1] : h[3];
         return IBU_OK;
     }
     return set_error(err, IBU_ERR_CUDA, 0, 0, 0, "barcode table capacity retry failed");
 }
 
-// LSD radix sort of (barcode, umi) pairs over the bits that vary; returns the sorted buffer.
-static int sort_pairs(ibu_gpu_ctx *ctx, const uint64_t *recs, uint64_t n, cudaStream_t s, Scratch &sc,
-                      uint64_t **sorted, ibu_error_t *err) {
-    if (n >= (1ull << 32))  // per-digit tile offsets are kept in 32 bits
-        return set_error(err, IBU_ERR_ARG, 0, n, 0, "unsorted barcode_count supports fewer than 2^32 records per call");
-    const uint64_t n_tiles = (n + kSortTile - 1) / kSortTile;
-    uint64_t *buf[2], *digit_total;
-    uint32_t *hist;
+// OR/AND masks of the first WORDS words of every record (and, optionally, the (barcode, umi)
+// pairs extracted to `pairs`): vary[k] = bits of word k on which the records disagree.
+template <int WORDS>
+static int key_masks(ibu_gpu_ctx *ctx, const uint64_t *recs, uint64_t n, uint64_t *pairs, cudaStream_t s,
+                     Scratch &sc, uint64_t vary[3], ibu_error_t *err) {
     unsigned long long *masks;
-    IBU_CUDA(sc.alloc(&buf[0], n * 16));
-    IBU_CUDA(sc.alloc(&buf[1], n * 16));
-    IBU_CUDA(sc.alloc(&hist, 256 * n_tiles * 4));
-    IBU_CUDA(sc.alloc(&digit_total, 256 * 8));
-    IBU_CUDA(sc.alloc(&masks, 4 * 8));
-    const unsigned long long init[4] = {0ull, ~0ull, 0ull, ~0ull};
+    IBU_CUDA(sc.alloc(&masks, 6 * 8));
+    const unsigned long long init[6] = {0ull, ~0ull, 0ull, ~0ull, 0ull, ~0ull};
     IBU_CUDA(cudaMemcpyAsync(masks, init, sizeof(init), cudaMemcpyHostToDevice, s));
     const uint64_t blocks = (n + kBlockThreads - 1) / kBlockThreads;
-    k_extract_pairs<<<(int)std::min<uint64_t>(blocks, (uint64_t)ctx->sm_count * 8), kBlockThreads, 0, s>>>(
-        recs, n, buf[0], masks);
+    k_key_masks<WORDS><<<(int)std::min<uint64_t>(blocks, (uint64_t)ctx->sm_count * 8), kBlockThreads, 0, s>>>(
+        recs, n, pairs, masks);
     g_launches.fetch_add(1, std::memory_order_relaxed);
     IBU_CUDA(cudaGetLastError());
-    unsigned long long m[4];
+    unsigned long long m[6];
     IBU_CUDA(cudaMemcpyAsync(m, masks, sizeof(m), cudaMemcpyDeviceToHost, s));
     IBU_CUDA(cudaStreamSynchronize(s));
-    const uint64_t vary[2] = {m[2] ^ m[3], m[0] ^ m[1]};  // word 0 = umi (minor key), word 1 = barcode
-    int cur = 0;
-    for (uint32_t word = 0; word < 2; word++) {
+    for (int k = 0; k < 3; k++) vary[k] = k < WORDS ? (m[2 * k] ^ m[2 * k + 1]) : 0;
+    return IBU_OK;
+}
+
+static int count_passes(const uint64_t vary[3], const int *key_order, int n_keys) {
+    int p = 0;
+    for (int k = 0; k < n_keys; k++)
+        for (uint32_t shift = 0; shift < 64; shift += 8)
+            if ((vary[key_order[k]] >> shift) & 0xFFull) p++;
+    return p;
+}
+
+// LSD radix sort of n elements of STRIDE words.  key_order lists the key words from the least
+// to the most significant.  `in` is only read; passes ping-pong between `first_dst` and `other`
+// (the first pass writes first_dst).  *result is where the sorted elements end up (`in` itself
+// when no digit varies).
+template <int STRIDE>
+static int radix_sort(ibu_gpu_ctx *ctx, const uint64_t *in, uint64_t *first_dst, uint64_t *other, uint64_t n,
+                      const uint64_t vary[3], const int *key_order, int n_keys, cudaStream_t s, Scratch &sc,
+                      const uint64_t **result, ibu_error_t *err) {
+    if (n >= (1ull << 32))  // per-digit tile offsets are kept in 32 bits
+        return set_error(err, IBU_ERR_ARG, 0, n, 0, "device sort supports fewer than 2^32 elements per call");
+    const uint64_t n_tiles = (n + kSortTile - 1) / kSortTile;
+    uint64_t *digit_total;
+    uint32_t *hist;
+    IBU_CUDA(sc.alloc(&hist, 256 * n_tiles * 4));
+    IBU_CUDA(sc.alloc(&digit_total, 256 * 8));
+    const uint64_t *src = in;
+    uint64_t *dst = first_dst, *spare = other;
+    for (int k = 0; k < n_keys; k++) {
+        const uint32_t word = (uint32_t)key_order[k];
         for (uint32_t shift = 0; shift < 64; shift += 8) {
             if (((vary[word] >> shift) & 0xFFull) == 0) continue;  // every key agrees on this digit
-            k_radix_hist<<<(int)n_tiles, kBlockThreads, 0, s>>>(buf[cur], n, word, shift, hist, n_tiles);
+            k_radix_hist<STRIDE><<<(int)n_tiles, kBlockThreads, 0, s>>>(src, n, word, shift, hist, n_tiles);
             k_radix_scan<<<256, kBlockThreads, 0, s>>>(hist, n_tiles, digit_total);
-            k_radix_scatter<<<(int)n_tiles, kBlockThreads, 0, s>>>(buf[cur], buf[cur ^ 1], n, word, shift, hist,
-                                                                    digit_total, n_tiles);
+            k_radix_scatter<STRIDE><<<(int)n_tiles, kBlockThreads, 0, s>>>(src, dst, n, word, shift, hist,
+                                                                             digit_total, n_tiles);
             g_launches.fetch_add(3, std::memory_order_relaxed);
             IBU_CUDA(cudaGetLastError());
-            cur ^= 1;
+            src = dst;
+            std::swap(dst, spare);
         }
     }
-    *sorted = buf[cur];
+    *result = src;
+    return IBU_OK;
+}
+
+// Table of an unsorted input: sort by (barcode, umi), then the streaming segment pass.
+static int unsorted_table(ibu_gpu_ctx *ctx, const uint64_t *recs, uint64_t n, cudaStream_t s, bool pair_mode,
+                          bool weighted, uint64_t **rows, uint64_t *n_rows, uint64_t *n_pairs, ibu_error_t *err) {
+    Scratch sc(ctx);
+    static const int order[2] = {1, 0};  // umi is the minor key, barcode the major one
+    uint64_t vary[3];
+    const uint64_t *sorted = nullptr;
+    int stride;
+    if (!weighted) {  // only the keys are needed: sort 16-byte (barcode, umi) pairs
+        uint64_t *a, *b;
+        IBU_CUDA(sc.alloc(&a, n * 16));
+        IBU_CUDA(sc.alloc(&b, n * 16));
+        if (int rc = key_masks<2>(ctx, recs, n, a, s, sc, vary, err)) return rc;
+        if (int rc = radix_sort<2>(ctx, a, b, a, n, vary, order, 2, s, sc, &sorted, err)) return rc;
+        stride = 2;
+    } else {  // the multiplicity (index word) travels with its key: sort whole records
+        uint64_t *a, *b;
+        IBU_CUDA(sc.alloc(&a, n * 24));
+        IBU_CUDA(sc.alloc(&b, n * 24));
+        if (int rc = key_masks<2>(ctx, recs, n, nullptr, s, sc, vary, err)) return rc;
+        if (int rc = radix_sort<3>(ctx, recs, a, b, n, vary, order, 2, s, sc, &sorted, err)) return rc;
+        stride = 3;
+    }
+    bool still_unsorted = false;
+    if (int rc = segment_pass(ctx, sorted, stride, n, s, pair_mode, weighted, rows, n_rows, n_pairs,
+                              &still_unsorted, err))
+        return rc;
+    if (still_unsorted)
+        return set_error(err, IBU_ERR_CUDA, 0, 0, 0, "internal error: radix sort left the keys unsorted");
+    return IBU_OK;
+}
+
+static size_t sort_scratch_bytes(uint64_t n, int elem_bytes) {
+    const uint64_t n_tiles = (n + kSortTile - 1) / kSortTile;
+    return n * 2 * elem_bytes + n_tiles * 1024 + 16 * 256;
+}
+
+// Shared driver of ibu_gpu_barcode_count / ibu_gpu_pair_table.
+static int build_table(ibu_gpu_ctx *ctx, const ibu_record_t *d_records, uint64_t n, int mode, bool pair_mode,
+                       bool weighted, cudaStream_t s, uint64_t **rows, uint64_t *n_rows, uint64_t *n_pairs,
+                       bool *was_sorted, ibu_error_t *err) {
+    *rows = nullptr;
+    *n_rows = *n_pairs = 0;
+    *was_sorted = false;
+    const uint64_t *src = reinterpret_cast<const uint64_t *>(d_records);
+    std::lock_guard<std::mutex> lock(ctx->arena_mutex);  // one table build per context at a time
+    bool unsorted = mode == 2;
+    if (mode != 2) {
+        IBU_CUDA(arena_reset(ctx, seg_scratch_bytes(n)));
+        if (int rc = segment_pass(ctx, src, 3, n, s, pair_mode, weighted, rows, n_rows, n_pairs, &unsorted, err))
+            return rc;
+        *was_sorted = !unsorted;
+    }
+    if (unsorted) {
+        if (mode == 1) return IBU_OK;  // caller required sorted input: was_sorted = false, no rows
+        IBU_CUDA(arena_reset(ctx, sort_scratch_bytes(n, weighted ? 24 : 16) + seg_scratch_bytes(n)));
+        return unsorted_table(ctx, src, n, s, pair_mode, weighted, rows, n_rows, n_pairs, err);
+    }
     return IBU_OK;
 }
 
@@ -664,6 +816,8 @@ int ibu_gpu_barcode_count(ibu_gpu_ctx_t *ctx, const ibu_record_t *d_records, uin
                           ibu_barcode_table_t *table, void *stream, ibu_error_t *err) {
     clear_error(err);
     if (!ctx || !table || (!d_records && n)) return set_error(err, IBU_ERR_ARG, 0, 0, 0, "null argument");
+    const bool weighted = (mode & IBU_COUNT_WEIGHTED) != 0;
+    mode &= ~IBU_COUNT_WEIGHTED;
     if (mode < 0 || mode > 2) return set_error(err, IBU_ERR_ARG, 0, mode, 0, "mode must be 0, 1 or 2");
     if (((uintptr_t)d_records & 31u) != 0)
         return set_error(err, IBU_ERR_ARG, 0, 0, 0, "d_records must be 32-byte aligned");
@@ -674,30 +828,15 @@ int ibu_gpu_barcode_count(ibu_gpu_ctx_t *ctx, const ibu_record_t *d_records, uin
         return IBU_OK;
     }
     DeviceGuard guard(ctx->device);
-    std::lock_guard<std::mutex> lock(ctx->arena_mutex);  // one table build per context at a time
-    cudaStream_t s = pick_stream(ctx, stream);
-    const uint64_t *src = reinterpret_cast<const uint64_t *>(d_records);
-    ibu_barcode_row_t *rows = nullptr;
-    uint64_t n_rows = 0, n_pairs = 0;
-    bool unsorted = mode == 2;
-    if (mode != 2) {
-        IBU_CUDA(arena_reset(ctx, seg_scratch_bytes(n)));
-        if (int rc = segment_pass(ctx, src, 3, n, s, &rows, &n_rows, &n_pairs, &unsorted, err)) return rc;
-        if (!unsorted) table->input_was_sorted = 1;
-    }
-    if (unsorted) {
-        if (mode == 1) return IBU_OK;  // caller required sorted input: input_was_sorted = 0, no rows
-        IBU_CUDA(arena_reset(ctx, sort_scratch_bytes(n) + seg_scratch_bytes(n)));
-        Scratch sc(ctx);
-        uint64_t *sorted = nullptr;
-        if (int rc = sort_pairs(ctx, src, n, s, sc, &sorted, err)) return rc;
-        bool still_unsorted = false;
-        if (int rc = segment_pass(ctx, sorted, 2, n, s, &rows, &n_rows, &n_pairs, &still_unsorted, err)) return rc;
-        if (still_unsorted) return set_error(err, IBU_ERR_CUDA, 0, 0, 0, "internal error: radix sort left the pairs unsorted");
-    }
-    table->d_rows = rows;
+    uint64_t *rows = nullptr, n_rows = 0, n_pairs = 0;
+    bool was_sorted = false;
+    if (int rc = build_table(ctx, d_records, n, mode, false, weighted, pick_stream(ctx, stream), &rows, &n_rows,
+                             &n_pairs, &was_sorted, err))
+        return rc;
+    table->d_rows = reinterpret_cast<ibu_barcode_row_t *>(rows);
     table->n_rows = n_rows;
     table->n_distinct_pairs = n_pairs;
+    table->input_was_sorted = was_sorted ? 1 : 0;
     return IBU_OK;
 }
 
@@ -706,6 +845,55 @@ void ibu_gpu_table_free(ibu_gpu_ctx_t *ctx, ibu_barcode_table_t *table) {
     if (table->d_rows) ibu_gpu_free(ctx, table->d_rows);
     table->d_rows = nullptr;
     table->n_rows = 0;
+}
+
+int ibu_gpu_pair_table(ibu_gpu_ctx_t *ctx, const ibu_record_t *d_records, uint64_t n, int weighted,
+                       ibu_record_t **d_pairs, uint64_t *n_pairs, void *stream, ibu_error_t *err) {
+    clear_error(err);
+    if (!ctx || !d_pairs || !n_pairs || (!d_records && n)) return set_error(err, IBU_ERR_ARG, 0, 0, 0, "null argument");
+    if (((uintptr_t)d_records & 31u) != 0)
+        return set_error(err, IBU_ERR_ARG, 0, 0, 0, "d_records must be 32-byte aligned");
+    *d_pairs = nullptr;
+    *n_pairs = 0;
+    if (n == 0) return IBU_OK;
+    DeviceGuard guard(ctx->device);
+    uint64_t *rows = nullptr, n_rows = 0, np = 0;
+    bool was_sorted = false;
+    if (int rc = build_table(ctx, d_records, n, 0, true, weighted != 0, pick_stream(ctx, stream), &rows, &n_rows,
+                             &np, &was_sorted, err))
+        return rc;
+    *d_pairs = reinterpret_cast<ibu_record_t *>(rows);
+    *n_pairs = n_rows;
+    return IBU_OK;
+}
+
+int ibu_gpu_sort_records(ibu_gpu_ctx_t *ctx, const ibu_record_t *d_records, uint64_t n, ibu_record_t *d_sorted,
+                         void *stream, ibu_error_t *err) {
+    clear_error(err);
+    if (!ctx || (n && (!d_records || !d_sorted))) return set_error(err, IBU_ERR_ARG, 0, 0, 0, "null argument");
+    if (n == 0) return IBU_OK;
+    if (d_records == d_sorted) return set_error(err, IBU_ERR_ARG, 0, 0, 0, "d_sorted must not alias d_records");
+    DeviceGuard guard(ctx->device);
+    cudaStream_t s = pick_stream(ctx, stream);
+    std::lock_guard<std::mutex> lock(ctx->arena_mutex);
+    IBU_CUDA(arena_reset(ctx, n * 24 + ((n + kSortTile - 1) / kSortTile) * 1024 + 16 * 256));
+    Scratch sc(ctx);
+    uint64_t *spare;
+    IBU_CUDA(sc.alloc(&spare, n * 24));
+    const uint64_t *src = reinterpret_cast<const uint64_t *>(d_records);
+    uint64_t *dst = reinterpret_cast<uint64_t *>(d_sorted);
+    uint64_t vary[3];
+    if (int rc = key_masks<3>(ctx, src, n, nullptr, s, sc, vary, err)) return rc;
+    static const int order[3] = {2, 1, 0};  // Record's Ord: barcode, then umi, then index (record.rs:58)
+    const int passes = count_passes(vary, order, 3);
+    const uint64_t *result = nullptr;
+    // an odd number of passes must start into d_sorted to end there
+    if (int rc = radix_sort<3>(ctx, src, (passes & 1) ? dst : spare, (passes & 1) ? spare : dst, n, vary, order, 3,
+                               s, sc, &result, err))
+        return rc;
+    if (result != dst) IBU_CUDA(cudaMemcpyAsync(dst, result, n * 24, cudaMemcpyDeviceToDevice, s));
+    IBU_CUDA(cudaStreamSynchronize(s));
+    return IBU_OK;
 }
 
 }  // extern "C"

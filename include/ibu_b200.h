@@ -263,6 +263,25 @@ int ibu_gpu_barcode_count(ibu_gpu_ctx_t *ctx, const ibu_record_t *d_records, uin
                           ibu_error_t *err);
 void ibu_gpu_table_free(ibu_gpu_ctx_t *ctx, ibu_barcode_table_t *table);
 
+/* OR into `mode` of ibu_gpu_barcode_count: the records are a (barcode, umi, multiplicity) pair
+ * table (index = how many records the pair stands for), e.g. the concatenation of several
+ * shards' ibu_gpu_pair_table outputs; n_records sums the multiplicities. */
+#define IBU_COUNT_WEIGHTED 8
+
+/* De-duplicated (barcode, umi) pairs of a record range with their multiplicities, sorted by
+ * (barcode, umi): rows are ibu_record_t {barcode, umi, index = count}.  This is what shards
+ * exchange to merge distinct-UMI counts exactly (they are not additive across shards).
+ * weighted != 0: the input's index words are multiplicities already.  *d_pairs is released
+ * with ibu_gpu_free.  Blocking. */
+int ibu_gpu_pair_table(ibu_gpu_ctx_t *ctx, const ibu_record_t *d_records, uint64_t n, int weighted,
+                       ibu_record_t **d_pairs, uint64_t *n_pairs, void *stream, ibu_error_t *err);
+
+/* Device sort by Record's Ord (src/constructs/record.rs:29-32,58): barcode, then umi, then
+ * index.  d_sorted (n records) must not alias d_records.  Blocking.  After it, a header with
+ * set_sorted (header.rs:111-113) is truthful and ibu_gpu_barcode_count streams in one pass. */
+int ibu_gpu_sort_records(ibu_gpu_ctx_t *ctx, const ibu_record_t *d_records, uint64_t n,
+                         ibu_record_t *d_sorted, void *stream, ibu_error_t *err);
+
 /* ------------------------------------------------ synthetic data (benches) */
 
 /* Counter-based generators (splitmix64 of seed and record number) shared by the

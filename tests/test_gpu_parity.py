@@ -319,3 +319,81 @@ def test_barcode_table_sorted_full_size_closed_form(ctx):
     assert info["input_was_sorted"] and len(rows) == 100_000 and info["n_distinct_pairs"] == 20_000_000
     assert np.array_equal(rows["barcode"], np.arange(100_000, dtype=U64))
     assert np.all(rows["n_records"] == 1000) and np.all(rows["n_distinct_umi"] == 200)
+
+
+# ---- device sort by Record's Ord, pair tables, weighted merge ----------------------------------
+def gpu_sort(ctx, recs):
+    n = len(recs)
+    d, o = Dev(ctx, recs.nbytes, recs), Dev(ctx, 24 * n)
+    ctx.sort_records(d, n, o)
+    out = o.get(ibu.RECORD_DTYPE, n)
+    d.free(), o.free()
+    return out
+
+
+@pytest.mark.parametrize("n", [0, 1, 2, 2047, 2048, 2049, 100_003, 3_000_005])
+@pytest.mark.parametrize("bc,umi,mode,param", [(16, 12, 3, (64 << 32) | 1000), (16, 12, 1, 500_000), (32, 32, 0, 0),
+                                               (16, 12, 2, 0), (16, 12, 4, (5 << 32) | 1000), (3, 2, 0, 0)])
+def test_sort_records_matches_record_ord(ctx, n, bc, umi, mode, param):
+    """record.rs:29-32,58: lexicographic (barcode, umi, index)."""
+    recs = oc.generate_records(0, n, bc, umi, mode, param, 31)
+    if n > 10:
+        recs["index"] = recs["index"][::-1].copy()  # index must be sorted as the third key, not kept
+    got = gpu_sort(ctx, recs)
+    assert np.array_equal(got, sort_records(recs))
+    if n:
+        assert np.array_equal(gpu_sort(ctx, got), got)  # idempotent
+        rows, info = gpu_table(ctx, got, mode=1)        # and the sorted fast path accepts it
+        assert info["input_was_sorted"] and np.array_equal(rows, on.barcode_table(recs))
+
+
+def np_pair_table(recs, weighted=False):
+    order = np.lexsort((recs["umi"], recs["barcode"]))
+    b, u, w = recs["barcode"][order], recs["umi"][order], recs["index"][order]
+    head = np.ones(len(b), bool)
+    head[1:] = (b[1:] != b[:-1]) | (u[1:] != u[:-1])
+    seg = np.cumsum(head) - 1
+    out = np.zeros(int(head.sum()), ibu.RECORD_DTYPE)
+    out["barcode"], out["umi"] = b[head], u[head]
+    out["index"] = np.bincount(seg, weights=w.astype(np.float64) if weighted else None).astype(U64) if len(b) else 0
+    return out
+
+
+@pytest.mark.parametrize("n", [1, 2049, 100_003, 2_000_003])
+@pytest.mark.parametrize("mode,param,pre_sorted", [(3, (64 << 32) | 1000, False), (3, (8 << 32) | 50, True), (2, 0, False),
+                                                   (4, (5 << 32) | 1000, True)])
+def test_pair_table(ctx, n, mode, param, pre_sorted):
+    recs = oc.generate_records(0, n, 16, 12, mode, param, 32)
+    if pre_sorted:
+        recs = sort_records(recs)
+    d = Dev(ctx, recs.nbytes, recs)
+    ptr, n_pairs = ctx.pair_table(d, n)
+    got = np.zeros(n_pairs, ibu.RECORD_DTYPE)
+    ctx.d2h(got, ptr)
+    ctx.free(ptr), d.free()
+    want = np_pair_table(recs)
+    assert np.array_equal(got, want) and int(got["index"].sum()) == n
+
+
+@pytest.mark.parametrize("world", [2, 3, 8])
+def test_weighted_merge_of_shard_pair_tables_is_exact(ctx, world):
+    """distinct-UMI counts are not additive across shards; exchanging the shards'
+    de-duplicated (barcode, umi, count) tables and counting them weighted is exact."""
+    n = 1_000_003
+    recs = oc.generate_records(0, n, 16, 12, 3, (32 << 32) | 5000, 33)  # unsorted, heavy duplication
+    shards = []
+    for r in range(world):
+        s, e = ibu.shard_range(n, r, world)
+        d = Dev(ctx, 24 * (e - s), recs[s:e])
+        ptr, k = ctx.pair_table(d, e - s)
+        part = np.zeros(k, ibu.RECORD_DTYPE)
+        ctx.d2h(part, ptr)
+        ctx.free(ptr), d.free()
+        shards.append(part)
+    merged = np.concatenate(shards)  # what an all-gather / all-to-all of the pair tables delivers
+    assert len(merged) < n
+    d = Dev(ctx, merged.nbytes, merged)
+    rows, info = ctx.barcode_count(d, len(merged), ibu.COUNT_WEIGHTED)
+    d.free()
+    assert np.array_equal(rows, on.barcode_table(recs))
+    assert int(rows["n_records"].sum()) == n
