@@ -341,6 +341,17 @@ class GpuContext:
                                       _stream(stream), C.byref(err)), err)
         return int(p.value or 0), int(cnt.value)
 
+    def partition_by_owner(self, d_pairs, n, world: int, d_out, stream=None) -> list[int]:
+        """Group pair-table rows by owner(barcode) = splitmix64(barcode) % world; returns bucket sizes."""
+        counts, err = (C.c_uint64 * world)(), _lib.Error()
+        _check(lib.ibu_gpu_partition_by_owner(self._h, _ptr(d_pairs), n, world, _ptr(d_out), counts, _stream(stream),
+                                              C.byref(err)), err)
+        return [int(c) for c in counts]
+
+    def memcpy(self, dst, src, nbytes: int):
+        err = _lib.Error()
+        _check(lib.ibu_gpu_memcpy(self._h, _ptr(dst), _ptr(src), nbytes, C.byref(err)), err)
+
     def sort_records(self, d_records, n, d_sorted, stream=None):
         """Device sort by Record's Ord (barcode, umi, index) into d_sorted."""
         err = _lib.Error()

@@ -508,6 +508,43 @@ k_radix_scatter(const uint64_t *__restrict__ in, uint64_t *__restrict__ out, uin
     }
 }
 
+// ---- owner partition of a pair table (the send side of the multi-GPU exchange) ----
+// owner(barcode) = splitmix64(barcode) % world: every barcode's pairs meet on one rank.
+__device__ __forceinline__ uint32_t owner_of(uint64_t barcode, uint32_t world) {
+    return (uint32_t)(splitmix64(barcode) % world);
+}
+
+__global__ void __launch_bounds__(kBlockThreads)
+k_owner_count(const uint64_t *__restrict__ recs, uint64_t n, uint32_t world, unsigned long long *__restrict__ counts) {
+    __shared__ uint32_t h[256];
+    h[threadIdx.x] = 0;
+    __syncthreads();
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x)
+        atomicAdd(&h[owner_of(recs[3 * i], world)], 1u);
+    __syncthreads();
+    if (threadIdx.x < world && h[threadIdx.x]) atomicAdd(counts + threadIdx.x, (unsigned long long)h[threadIdx.x]);
+}
+
+__global__ void __launch_bounds__(kBlockThreads)
+k_owner_scatter(const uint64_t *__restrict__ recs, uint64_t n, uint32_t world,
+                unsigned long long *__restrict__ cursor /* preset to the bucket offsets */, uint64_t *__restrict__ out) {
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint64_t step = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t base = (uint64_t)blockIdx.x * blockDim.x; base < n; base += step) {  // warp-uniform trip count
+        const uint64_t i = base + threadIdx.x;
+        const bool live = i < n;
+        uint64_t b = 0, u = 0, c = 0;
+        if (live) { b = recs[3 * i]; u = recs[3 * i + 1]; c = recs[3 * i + 2]; }
+        const uint32_t o = live ? owner_of(b, world) : 0xFFFFFFFFu;
+        const uint32_t peers = __match_any_sync(0xffffffffu, o);  // one atomic per owner per warp
+        const uint32_t leader = __ffs(peers) - 1;
+        unsigned long long pos = 0;
+        if (live && lane == leader) pos = atomicAdd(cursor + o, (unsigned long long)__popc(peers));
+        pos = __shfl_sync(0xffffffffu, pos, leader) + __popc(peers & ((1u << lane) - 1u));
+        if (live) { out[3 * pos] = b; out[3 * pos + 1] = u; out[3 * pos + 2] = c; }
+    }
+}
+
 // weighted tables (merging per-shard pair tables): a row's count is the sum of the `index`
 // words (multiplicities) of the records in its run instead of the run length.  One warp per row.
 __global__ void __launch_bounds__(kBlockThreads)
@@ -894,6 +931,42 @@ int ibu_gpu_sort_records(ibu_gpu_ctx_t *ctx, const ibu_record_t *d_records, uint
     if (result != dst) IBU_CUDA(cudaMemcpyAsync(dst, result, n * 24, cudaMemcpyDeviceToDevice, s));
     IBU_CUDA(cudaStreamSynchronize(s));
     return IBU_OK;
+}
+
+int ibu_gpu_partition_by_owner(ibu_gpu_ctx_t *ctx, const ibu_record_t *d_pairs, uint64_t n, uint32_t world,
+                               ibu_record_t *d_out, uint64_t *h_counts, void *stream, ibu_error_t *err) {
+    clear_error(err);
+    if (!ctx || !h_counts || (n && (!d_pairs || !d_out))) return set_error(err, IBU_ERR_ARG, 0, 0, 0, "null argument");
+    if (world == 0 || world > 256) return set_error(err, IBU_ERR_ARG, 0, world, 0, "world must be 1..256");
+    for (uint32_t r = 0; r < world; r++) h_counts[r] = 0;
+    if (n == 0) return IBU_OK;
+    DeviceGuard guard(ctx->device);
+    cudaStream_t s = pick_stream(ctx, stream);
+    unsigned long long *d_counts = nullptr;
+    IBU_CUDA(cudaMalloc((void **)&d_counts, 256 * 8));
+    int rc = IBU_OK;
+    do {
+        cudaError_t e = cudaMemsetAsync(d_counts, 0, 256 * 8, s);
+        const uint64_t blocks = (n + kBlockThreads - 1) / kBlockThreads;
+        const int grid = (int)std::min<uint64_t>(blocks, (uint64_t)ctx->sm_count * 8);
+        const uint64_t *src = reinterpret_cast<const uint64_t *>(d_pairs);
+        k_owner_count<<<grid, kBlockThreads, 0, s>>>(src, n, world, d_counts);
+        g_launches.fetch_add(1, std::memory_order_relaxed);
+        unsigned long long h[256];
+        if (e == cudaSuccess) e = cudaMemcpyAsync(h, d_counts, world * 8, cudaMemcpyDeviceToHost, s);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+        if (e != cudaSuccess) { rc = cuda_fail(err, e, "k_owner_count"); break; }
+        unsigned long long off[256], run = 0;
+        for (uint32_t r = 0; r < world; r++) { h_counts[r] = h[r]; off[r] = run; run += h[r]; }
+        e = cudaMemcpyAsync(d_counts, off, world * 8, cudaMemcpyHostToDevice, s);
+        k_owner_scatter<<<grid, kBlockThreads, 0, s>>>(src, n, world, d_counts, reinterpret_cast<uint64_t *>(d_out));
+        g_launches.fetch_add(1, std::memory_order_relaxed);
+        if (e == cudaSuccess) e = cudaGetLastError();
+        if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+        if (e != cudaSuccess) rc = cuda_fail(err, e, "k_owner_scatter");
+    } while (0);
+    cudaFree(d_counts);
+    return rc;
 }
 
 }  // extern "C"

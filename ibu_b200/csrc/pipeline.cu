@@ -391,6 +391,15 @@ int ibu_gpu_memcpy_d2h(ibu_gpu_ctx_t *ctx, void *h_dst, const void *d_src, size_
     return IBU_OK;
 }
 
+int ibu_gpu_memcpy(ibu_gpu_ctx_t *ctx, void *dst, const void *src, size_t bytes, ibu_error_t *err) {
+    clear_error(err);
+    if (!ctx) return set_error(err, IBU_ERR_ARG, 0, 0, 0, "null context");
+    DeviceGuard guard(ctx->device);
+    IBU_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDefault, ctx->stream));
+    IBU_CUDA(cudaStreamSynchronize(ctx->stream));
+    return IBU_OK;
+}
+
 int ibu_gpu_memset(ibu_gpu_ctx_t *ctx, void *d_dst, int value, size_t bytes, ibu_error_t *err) {
     clear_error(err);
     if (!ctx) return set_error(err, IBU_ERR_ARG, 0, 0, 0, "null context");

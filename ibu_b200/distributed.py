@@ -89,3 +89,56 @@ def gather_tables(rows: np.ndarray, boundary=None, group=None):
     tables = [g[0] for g in got]
     bounds = [g[1] for g in got]
     return merge_tables_host(tables, bounds if any(b is not None for b in bounds) else None)
+
+
+def owner_of(barcode, world: int) -> np.ndarray:
+    """owner(barcode) = splitmix64(barcode) % world — the rank on which a barcode's pairs meet
+    (host restatement of the device function in barcode_count.cu, for tests and planning)."""
+    x = np.asarray(barcode, dtype=np.uint64)
+    with np.errstate(over="ignore"):
+        z = x + np.uint64(0x9E3779B97F4A7C15)
+        z = (z ^ (z >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+        z = (z ^ (z >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+        z = z ^ (z >> np.uint64(31))
+    return (z % np.uint64(world)).astype(np.int64)
+
+
+def exact_barcode_table(ctx, d_records, n: int, device, group=None) -> np.ndarray:
+    """Per-barcode table of the WHOLE job from per-rank record shards, exact for any input order
+    (the path's one real exchange step):
+
+      1. each rank de-duplicates its shard into a (barcode, umi, count) pair table   [device]
+      2. rows are grouped by owner(barcode) and exchanged with ONE all-to-all        [NCCL]
+      3. each owner counts the pairs it received, weighted                           [device]
+      4. the owners' disjoint row sets are all-gathered and ordered by barcode       [small]
+
+    Every rank returns the same table."""
+    import torch
+    import torch.distributed as dist
+
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    ptr, k = ctx.pair_table(d_records, n)
+    send = torch.empty((max(k, 1), 3), dtype=torch.int64, device=device)
+    try:
+        counts = ctx.partition_by_owner(ptr, k, world, send) if k else [0] * world
+    finally:
+        if ptr:
+            ctx.free(ptr)
+    in_split = torch.tensor(counts, dtype=torch.int64, device=device)
+    out_split = torch.empty_like(in_split)
+    dist.all_to_all_single(out_split, in_split, group=group)  # how many rows each peer sends me
+    recv_counts = [int(c) for c in out_split.cpu()]
+    recv = torch.empty((max(sum(recv_counts), 1), 3), dtype=torch.int64, device=device)
+    dist.all_to_all_single(recv[: sum(recv_counts)], send[:k], recv_counts, counts, group=group)
+    torch.cuda.synchronize(device)
+    m = sum(recv_counts)
+    if m:
+        from . import COUNT_WEIGHTED
+
+        rows, _ = ctx.barcode_count(recv, m, COUNT_WEIGHTED)
+    else:
+        rows = np.zeros(0, ROW_DTYPE)
+    got = [None] * world
+    dist.all_gather_object(got, rows, group=group)
+    cat = np.concatenate([g for g in got if len(g)]) if any(len(g) for g in got) else np.zeros(0, ROW_DTYPE)
+    return cat[np.argsort(cat["barcode"], kind="stable")]

@@ -180,6 +180,8 @@ int ibu_gpu_memcpy_h2d(ibu_gpu_ctx_t *ctx, void *d_dst, const void *h_src, size_
 int ibu_gpu_memcpy_d2h(ibu_gpu_ctx_t *ctx, void *h_dst, const void *d_src, size_t bytes,
                        ibu_error_t *err);
 int ibu_gpu_memset(ibu_gpu_ctx_t *ctx, void *d_dst, int value, size_t bytes, ibu_error_t *err);
+/* any direction (device<->device included), blocking */
+int ibu_gpu_memcpy(ibu_gpu_ctx_t *ctx, void *dst, const void *src, size_t bytes, ibu_error_t *err);
 int ibu_host_alloc(size_t bytes, void **h_out, ibu_error_t *err); /* pinned */
 void ibu_host_free(void *h_ptr);
 int ibu_host_register(void *h_ptr, size_t bytes, int read_only, ibu_error_t *err);
@@ -275,6 +277,14 @@ void ibu_gpu_table_free(ibu_gpu_ctx_t *ctx, ibu_barcode_table_t *table);
  * with ibu_gpu_free.  Blocking. */
 int ibu_gpu_pair_table(ibu_gpu_ctx_t *ctx, const ibu_record_t *d_records, uint64_t n, int weighted,
                        ibu_record_t **d_pairs, uint64_t *n_pairs, void *stream, ibu_error_t *err);
+
+/* Send side of the multi-GPU pair exchange: groups the rows of a pair table by
+ * owner(barcode) = splitmix64(barcode) % world into d_out (bucket r = rows owned by rank r,
+ * buckets in rank order, order inside a bucket unspecified) and returns the bucket sizes in
+ * h_counts[world] — the split sizes of the all-to-all.  Blocking. */
+int ibu_gpu_partition_by_owner(ibu_gpu_ctx_t *ctx, const ibu_record_t *d_pairs, uint64_t n,
+                               uint32_t world, ibu_record_t *d_out, uint64_t *h_counts, void *stream,
+                               ibu_error_t *err);
 
 /* Device sort by Record's Ord (src/constructs/record.rs:29-32,58): barcode, then umi, then
  * index.  d_sorted (n records) must not alias d_records.  Blocking.  After it, a header with

@@ -397,3 +397,37 @@ def test_weighted_merge_of_shard_pair_tables_is_exact(ctx, world):
     d.free()
     assert np.array_equal(rows, on.barcode_table(recs))
     assert int(rows["n_records"].sum()) == n
+
+
+def test_partition_by_owner_and_emulated_all_to_all(ctx):
+    """The exchange of ibu_b200.distributed.exact_barcode_table emulated on one GPU: per-shard pair
+    tables -> owner buckets -> every owner counts what it would receive -> concatenated rows."""
+    from ibu_b200 import distributed as ibd
+
+    n, world = 600_011, 4
+    recs = oc.generate_records(0, n, 16, 12, 3, (32 << 32) | 3000, 34)
+    inbox = [[] for _ in range(world)]
+    for r in range(world):
+        s, e = ibu.shard_range(n, r, world)
+        d = Dev(ctx, 24 * (e - s), recs[s:e])
+        ptr, k = ctx.pair_table(d, e - s)
+        out = Dev(ctx, 24 * k)
+        counts = ctx.partition_by_owner(ptr, k, world, out)
+        buckets = out.get(ibu.RECORD_DTYPE, k)
+        ctx.free(ptr), d.free(), out.free()
+        assert sum(counts) == k
+        off = 0
+        for o, c in enumerate(counts):
+            part = buckets[off:off + c]
+            assert np.all(ibd.owner_of(part["barcode"], world) == o)
+            inbox[o].append(part)
+            off += c
+    tables = []
+    for o in range(world):
+        got = np.concatenate(inbox[o])
+        d = Dev(ctx, got.nbytes, got)
+        rows, _ = ctx.barcode_count(d, len(got), ibu.COUNT_WEIGHTED)
+        d.free()
+        tables.append(rows)
+    cat = np.concatenate(tables)
+    assert np.array_equal(cat[np.argsort(cat["barcode"])], on.barcode_table(recs))
