@@ -589,6 +589,11 @@ class Writer:
         err = _lib.Error()
         _check(lib.ibu_writer_write_batch(self._h, _ptr(recs), len(recs), C.byref(err)), err)
 
+    def write_device(self, ctx: "GpuContext", d_records, n: int):
+        """write_batch fed from HBM: pipelined D2H through pinned buffers, then the file."""
+        err = _lib.Error()
+        _check(lib.ibu_gpu_write_records(ctx._h, self._h, _ptr(d_records), n, C.byref(err)), err)
+
     def write_iter(self, it):
         for b, u, i in it:
             self.write_record(int(b), int(u), int(i))

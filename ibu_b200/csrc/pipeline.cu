@@ -540,6 +540,42 @@ int ibu_gpu_load_to_device(ibu_gpu_ctx_t *ctx, const char *path, uint64_t start,
     return IBU_OK;
 }
 
+// ---- Writer device path ----------------------------------------------------------------------
+
+int ibu_gpu_write_records(ibu_gpu_ctx_t *ctx, ibu_writer_t *writer, const ibu_record_t *d_records, uint64_t n,
+                          ibu_error_t *err) {
+    clear_error(err);
+    if (!ctx || !writer || (!d_records && n)) return set_error(err, IBU_ERR_ARG, 0, 0, 0, "null argument");
+    if (n == 0) return IBU_OK;
+    DeviceGuard guard(ctx->device);
+    const uint64_t chunk = chunk_records(ctx);
+    const uint64_t n_chunks = (n + chunk - 1) / chunk;
+    const size_t n_slots = ctx->slots.size();
+    int rc = IBU_OK;
+    auto flush = [&](uint64_t c) -> int {  // chunk c has landed in its slot: append it to the file
+        ibu_chunk_slot &slot = ctx->slots[c % n_slots];
+        cudaError_t e = cudaEventSynchronize(slot.done);
+        if (e != cudaSuccess) return cuda_fail(err, e, "cudaEventSynchronize");
+        const uint64_t cnt = std::min(chunk, n - c * chunk);
+        return ibu_writer_write_batch(writer, (const ibu_record_t *)slot.h_out, cnt, err);
+    };
+    for (uint64_t c = 0; c < n_chunks && rc == IBU_OK; c++) {
+        ibu_chunk_slot &slot = ctx->slots[c % n_slots];
+        if (c >= n_slots && (rc = flush(c - n_slots)) != IBU_OK) break;  // file order = chunk order
+        if ((rc = ensure(&slot.h_out, &slot.h_out_bytes, align_up(chunk * IBU_RECORD_SIZE), true, err))) break;
+        const uint64_t cnt = std::min(chunk, n - c * chunk);
+        cudaError_t e = cudaMemcpyAsync(slot.h_out, d_records + c * chunk, cnt * IBU_RECORD_SIZE,
+                                        cudaMemcpyDeviceToHost, slot.stream);
+        if (e == cudaSuccess) e = cudaEventRecord(slot.done, slot.stream);
+        if (e != cudaSuccess) rc = cuda_fail(err, e, "cudaMemcpyAsync");
+    }
+    for (uint64_t c = n_chunks > n_slots ? n_chunks - n_slots : 0; c < n_chunks && rc == IBU_OK; c++) rc = flush(c);
+    if (rc != IBU_OK)
+        for (auto &slot : ctx->slots)
+            if (cudaStreamSynchronize(slot.stream) != cudaSuccess) cudaGetLastError();
+    return rc;
+}
+
 // ---- host -> host unpack / pack through the GPU --------------------------------------------
 
 int ibu_gpu_unpack_host(ibu_gpu_ctx_t *ctx, const ibu_record_t *h_records, uint64_t n, uint32_t bc_len,

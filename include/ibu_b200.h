@@ -346,6 +346,13 @@ int ibu_gpu_load_to_device(ibu_gpu_ctx_t *ctx, const char *path, uint64_t start,
                            ibu_header_t *header, ibu_record_t **d_records, uint64_t *n,
                            ibu_error_t *err);
 
+/* Writer device path (src/io/writer.rs:315-351 write_batch fed from HBM): device-resident
+ * records are brought back through the pinned slot buffers (D2H on alternating streams) and
+ * appended with ibu_writer_write_batch semantics while the next chunk is in flight.  With
+ * ibu_gpu_sort_records this turns any file into a truthfully `sorted` one. */
+int ibu_gpu_write_records(ibu_gpu_ctx_t *ctx, ibu_writer_t *writer, const ibu_record_t *d_records,
+                          uint64_t n, ibu_error_t *err);
+
 /* End-to-end unpack: host records -> host ASCII, pipelined H2D / K2 / D2H. */
 int ibu_gpu_unpack_host(ibu_gpu_ctx_t *ctx, const ibu_record_t *h_records, uint64_t n,
                         uint32_t bc_len, uint32_t umi_len, uint8_t *h_bc_ascii,

@@ -152,3 +152,29 @@ def test_unpack_host_and_pack_host(ctx, bc, umi, pinned):
     del src, gb, gu, gf
     for b in bufs:
         b.free()
+
+
+@pytest.mark.parametrize("n", [0, 5, (1 << 18) * 3 + 17])
+def test_sort_on_device_and_write_sorted_file(ctx, tmp_path, n):
+    """'Next' row 1+2 of SURVEY §8f: load_to_device -> sort by Record's Ord -> Writer device path
+    with a truthful set_sorted header; the file equals the oracle's sorted file byte for byte and
+    its table streams through the sorted fast path."""
+    src, dst = str(tmp_path / "in.ibu"), str(tmp_path / "sorted.ibu")
+    recs = oc.generate_records(0, n, 16, 12, 3, (16 << 32) | 700, 41)
+    write(src, recs)
+    h, d = ibu.load_to_device(ctx, src)
+    out = ctx.malloc(max(24 * n, 1))
+    ctx.sort_records(d, n, out)
+    hs = ibu.Header(h.bc_len, h.umi_len)
+    hs.set_sorted()
+    with ibu.Writer(dst, hs) as w:
+        w.write_device(ctx, out, n)
+        assert w.records_written() == n
+    want = recs[np.lexsort((recs["index"], recs["umi"], recs["barcode"]))]
+    assert open(dst, "rb").read() == on.file_bytes(16, 12, want, sorted_=True)
+    if n:
+        rows, info = ctx.barcode_count(out, n, 1)
+        assert info["input_was_sorted"] and np.array_equal(rows, on.barcode_table(recs))
+    ctx.free(out)
+    d.free()
+    assert ibu.MmapReader(dst).header().sorted()
