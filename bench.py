@@ -221,6 +221,33 @@ def run_ours(args):
     local_counters = res.cpu().numpy().astype(np.uint64)
     counters = merged.cpu().numpy().astype(np.uint64) if world > 1 else local_counters
 
+    # ---- link probe: what the host<->device link gives a plain pinned copy on this box ----
+    def link_probe(nbytes=1 << 30):
+        h_a = torch.empty(nbytes, dtype=torch.uint8, pin_memory=True)
+        h_b = torch.empty(nbytes, dtype=torch.uint8, pin_memory=True)
+        d_a = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        d_b = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        s1, s2 = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
+
+        def run(h2d, d2h):
+            best = 1e9
+            for _ in range(3):
+                torch.cuda.synchronize()
+                t0 = time.perf_counter()
+                if h2d:
+                    with torch.cuda.stream(s1):
+                        d_a.copy_(h_a, non_blocking=True)
+                if d2h:
+                    with torch.cuda.stream(s2):
+                        h_b.copy_(d_b, non_blocking=True)
+                torch.cuda.synchronize()
+                best = min(best, time.perf_counter() - t0)
+            return nbytes * (int(h2d) + int(d2h)) / best / 1e9
+
+        return {"h2d_gbs": run(True, False), "d2h_gbs": run(False, True), "bidir_gbs": run(True, True)}
+
+    link = link_probe()
+
     # ---- e2e: host buffers through the C ABI, H2D + K2 + D2H inside the timed region ----
     e2e_steps = max(1, min(args.steps, 5))
     pin_in = ibu.PinnedBuffer(n * 24)
@@ -266,6 +293,9 @@ def run_ours(args):
                     "d2h_bytes_per_step": n * (BC_LEN + UMI_LEN) + 64 * ((n + chunk - 1) // chunk),
                     "ms_per_step": e2e_s * 1e3, "steps": e2e_steps,
                     "link_gbs": (n * 24 + n * (BC_LEN + UMI_LEN)) / e2e_s / 1e9,
+                    "link_probe": link,
+                    "frac_of_link": (n * 24 + n * (BC_LEN + UMI_LEN)) / e2e_s / 1e9 / link["bidir_gbs"],
+                    "d2h_frac_of_link": n * (BC_LEN + UMI_LEN) / e2e_s / 1e9 / link["d2h_gbs"],
                     "api": f"ibu_gpu_unpack_host (pinned host in/out, {chunk}-record chunks, {slots} slots)"},
             "gpu_launches": launches, "gpu_launches_e2e": launches_e2e,
             "clocks": clocks,

@@ -25,7 +25,6 @@ struct ibu_gpu_ctx {
     cudaStream_t stream = nullptr;  // default stream of the context (non-blocking)
     ibu_gpu_config_t cfg{};
     std::vector<ibu_chunk_slot> slots;
-    int variant = 0;  // kernel variant override (IBU_B200_VARIANT env; tuning only)
     // grow-only device scratch of the blocking table builder (K4): cudaMalloc/cudaFree per call
     // would cost more than the streaming pass itself
     std::mutex arena_mutex;

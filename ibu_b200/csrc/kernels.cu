@@ -135,7 +135,6 @@ struct UnpackArgs {
     uint32_t bc_len, umi_len;
     uint32_t warp_smem_bytes;  // per-warp shared memory: input tile + staged outputs
     uint32_t bc_stage_off, umi_stage_off;
-    uint32_t blocked;          // tuning: 1 = each warp owns a contiguous run of tiles
 };
 
 template <int L>
@@ -150,7 +149,7 @@ struct LenOf<0> {
 // Emit one decoded row.  L = 32 / 16: straight from registers with a 256 / 128-bit store
 // (a warp covers 1024 / 512 contiguous bytes).  Otherwise the row is staged in shared memory
 // and the whole tile (128 x len bytes, 16-byte aligned in the output) is copied out afterwards.
-template <int L, int POL = 0>
+template <int L>
 __device__ __forceinline__ void emit_row(uint64_t w, uint32_t len, uint8_t *gout, uint64_t rec,
                                          uint8_t *stage, uint32_t r) {
     uint32_t asc[8];
@@ -160,7 +159,7 @@ __device__ __forceinline__ void emit_row(uint64_t w, uint32_t len, uint8_t *gout
                       make_uint4(asc[4], asc[5], asc[6], asc[7]));
     } else if (L == 16) {
         decode_word<4>(w, asc);
-        stg_pol<POL>(reinterpret_cast<uint4 *>(gout) + rec, make_uint4(asc[0], asc[1], asc[2], asc[3]));
+        stg_stream(reinterpret_cast<uint4 *>(gout) + rec, make_uint4(asc[0], asc[1], asc[2], asc[3]));
     } else if (L > 0) {  // compile-time length, multiple of 4: word stores into the stage
         static_assert(L % 4 == 0, "compile-time staged lengths are multiples of 4");
         decode_word<L / 4>(w, asc);
@@ -190,17 +189,17 @@ __device__ __forceinline__ void emit_row(uint64_t w, uint32_t len, uint8_t *gout
     }
 }
 
-template <int L, int POL = 0>
+template <int L>
 __device__ __forceinline__ void copy_out_stage(uint32_t len, uint8_t *gout, uint64_t tile,
                                                const uint8_t *stage, uint32_t lane) {
     if (L == 32 || L == 16) return;  // rows were stored directly
     const uint32_t n16 = 8 * len;    // 128 rows x len bytes / 16
     uint4 *dst = reinterpret_cast<uint4 *>(gout) + tile * n16;
     const uint4 *src = reinterpret_cast<const uint4 *>(stage);
-    for (uint32_t i = lane; i < n16; i += 32) stg_pol<POL>(dst + i, src[i]);
+    for (uint32_t i = lane; i < n16; i += 32) stg_stream(dst + i, src[i]);
 }
 
-template <int BC, int UMI, int POL = 0>
+template <int BC, int UMI>
 __global__ void __launch_bounds__(kBlockThreads) k_unpack(const UnpackArgs a) {
     extern __shared__ __align__(16) uint8_t smem[];
     const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
@@ -217,23 +216,17 @@ __global__ void __launch_bounds__(kBlockThreads) k_unpack(const UnpackArgs a) {
     const uint4 *g4 = reinterpret_cast<const uint4 *>(a.recs);
 
     uint4 pre[6];  // software prefetch: the next tile is in flight while this one is decoded
-    uint64_t t = gwarp, t_step = total_warps, t_end = n_tiles;
-    if (a.blocked) {
-        const uint64_t per = (n_tiles + total_warps - 1) / total_warps;
-        t = gwarp * per;
-        t_step = 1;
-        t_end = min(n_tiles, t + per);
-    }
-    if (t < t_end) {
+    uint64_t t = gwarp;
+    if (t < n_tiles) {
 #pragma unroll
         for (int k = 0; k < 6; k++) pre[k] = ldg_stream(g4 + t * kTileU4 + lane + 32 * k);
     }
-    while (t < t_end) {
+    while (t < n_tiles) {
 #pragma unroll
         for (int k = 0; k < 6; k++) in4[lane + 32 * k] = pre[k];
         __syncwarp();
-        const uint64_t t_next = t + t_step;
-        if (t_next < t_end) {
+        const uint64_t t_next = t + total_warps;
+        if (t_next < n_tiles) {
 #pragma unroll
             for (int k = 0; k < 6; k++) pre[k] = ldg_stream(g4 + t_next * kTileU4 + lane + 32 * k);
         }
@@ -243,15 +236,15 @@ __global__ void __launch_bounds__(kBlockThreads) k_unpack(const UnpackArgs a) {
             // 64-bit shared loads at a 24-byte stride: conflict-free per half-warp
             const uint64_t bc = in64[3 * r], umi = in64[3 * r + 1];
             const uint64_t rec = t * kTileRecords + r;
-            emit_row<BC, POL>(bc, bc_len, a.bc_out, rec, bc_stage, r);
-            emit_row<UMI, POL>(umi, umi_len, a.umi_out, rec, umi_stage, r);
+            emit_row<BC>(bc, bc_len, a.bc_out, rec, bc_stage, r);
+            emit_row<UMI>(umi, umi_len, a.umi_out, rec, umi_stage, r);
             const uint32_t bb = (bc & a.bc_hi) != 0ull, bu = (umi & a.umi_hi) != 0ull;
             n_bb += bb; n_bu += bu; n_br += (bb | bu);
             if (a.flags) a.flags[rec] = (uint8_t)(bb | (bu << 1));
         }
         __syncwarp();
-        copy_out_stage<BC, POL>(bc_len, a.bc_out, t, bc_stage, lane);
-        copy_out_stage<UMI, POL>(umi_len, a.umi_out, t, umi_stage, lane);
+        copy_out_stage<BC>(bc_len, a.bc_out, t, bc_stage, lane);
+        copy_out_stage<UMI>(umi_len, a.umi_out, t, umi_stage, lane);
         __syncwarp();
         t = t_next;
     }
@@ -264,121 +257,6 @@ __global__ void __launch_bounds__(kBlockThreads) k_unpack(const UnpackArgs a) {
                 a.bc_out[rec * bc_len + i] = (uint8_t)(kAcgt >> (8 * ((bc >> (2 * i)) & 3u)));
             for (uint32_t i = 0; i < umi_len; i++)
                 a.umi_out[rec * umi_len + i] = (uint8_t)(kAcgt >> (8 * ((umi >> (2 * i)) & 3u)));
-            const uint32_t bb = (bc & a.bc_hi) != 0ull, bu = (umi & a.umi_hi) != 0ull;
-            n_bb += bb; n_bu += bu; n_br += (bb | bu);
-            if (a.flags) a.flags[rec] = (uint8_t)(bb | (bu << 1));
-        }
-    }
-
-    if (a.res) {
-        n_bb = __reduce_add_sync(0xffffffffu, n_bb);
-        n_bu = __reduce_add_sync(0xffffffffu, n_bu);
-        n_br = __reduce_add_sync(0xffffffffu, n_br);
-        unsigned long long *out = reinterpret_cast<unsigned long long *>(a.res);
-        if (lane == 0) {
-            if (n_bb) atomicAdd(out + 5, (unsigned long long)n_bb);
-            if (n_bu) atomicAdd(out + 6, (unsigned long long)n_bu);
-            if (n_br) atomicAdd(out + 7, (unsigned long long)n_br);
-            if (gwarp == 0) atomicAdd(out, (unsigned long long)a.n);
-        }
-    }
-}
-
-// ---------------------------------------------------------------------------- K2, variant r4
-// No shared-memory transpose of the input: lane l owns the 4 consecutive records 4l..4l+3 of
-// the tile = 96 contiguous bytes = three 32-byte units, fetched with three LDG.E.256 (every
-// access is a whole 32-byte sector; a warp instruction covers every third sector of the 3 KB
-// tile).  The 12 words land in registers with a static record layout.  16-base rows leave as
-// 2 x STG.256 (64 contiguous bytes per lane), 32-base rows as 4 x STG.256; 12-base rows are
-// staged (3 x STS.128 per lane, conflict-free at a 48-byte stride) and copied out coalesced.
-template <int L>
-__device__ __forceinline__ void emit4(const uint64_t (&w)[4], uint8_t *gout, uint64_t rec0,
-                                      uint8_t *stage, uint32_t lane) {
-    uint32_t a[8], b[8];
-    if constexpr (L == 16) {
-#pragma unroll
-        for (int p = 0; p < 2; p++) {
-            decode_word<4>(w[2 * p], a);
-            decode_word<4>(w[2 * p + 1], b);
-            stg_stream256(gout + (rec0 + 2 * p) * 16, make_uint4(a[0], a[1], a[2], a[3]),
-                          make_uint4(b[0], b[1], b[2], b[3]));
-        }
-    } else if constexpr (L == 32) {
-#pragma unroll
-        for (int q = 0; q < 4; q++) {
-            decode_word<8>(w[q], a);
-            stg_stream256(gout + (rec0 + q) * 32, make_uint4(a[0], a[1], a[2], a[3]),
-                          make_uint4(a[4], a[5], a[6], a[7]));
-        }
-    } else {
-        static_assert(L == 12, "r4 variant: lengths 12, 16, 32");
-        uint32_t o[12];
-#pragma unroll
-        for (int q = 0; q < 4; q++) {
-            decode_word<3>(w[q], a);
-            o[3 * q] = a[0]; o[3 * q + 1] = a[1]; o[3 * q + 2] = a[2];
-        }
-        uint4 *s4 = reinterpret_cast<uint4 *>(stage) + 3 * lane;
-        s4[0] = make_uint4(o[0], o[1], o[2], o[3]);
-        s4[1] = make_uint4(o[4], o[5], o[6], o[7]);
-        s4[2] = make_uint4(o[8], o[9], o[10], o[11]);
-    }
-}
-
-template <int BC, int UMI>
-__global__ void __launch_bounds__(kBlockThreads) k_unpack_r4(const UnpackArgs a) {
-    extern __shared__ __align__(16) uint8_t smem[];
-    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
-    const uint64_t gwarp = (uint64_t)blockIdx.x * kWarpsPerBlock + warp;
-    const uint64_t total_warps = (uint64_t)gridDim.x * kWarpsPerBlock;
-    uint8_t *wsm = smem + warp * a.warp_smem_bytes;
-    uint8_t *bc_stage = wsm + a.bc_stage_off, *umi_stage = wsm + a.umi_stage_off;
-    constexpr bool kStaged = (BC == 12) || (UMI == 12);
-
-    uint32_t n_bb = 0, n_bu = 0, n_br = 0;
-    const uint64_t n_tiles = a.n / kTileRecords;
-    u64x4 pre[3];
-    uint64_t t = gwarp;
-    if (t < n_tiles) {
-#pragma unroll
-        for (int k = 0; k < 3; k++) pre[k] = ldg_stream256(a.recs + t * kTileBytes + lane * 96 + 32 * k);
-    }
-    while (t < n_tiles) {
-        const u64x4 v0 = pre[0], v1 = pre[1], v2 = pre[2];
-        const uint64_t t_next = t + total_warps;
-        if (t_next < n_tiles) {
-#pragma unroll
-            for (int k = 0; k < 3; k++) pre[k] = ldg_stream256(a.recs + t_next * kTileBytes + lane * 96 + 32 * k);
-        }
-        const uint64_t bc[4] = {v0.x, v0.w, v1.z, v2.y}, um[4] = {v0.y, v1.x, v1.w, v2.z};
-        const uint64_t rec0 = t * kTileRecords + 4 * lane;
-        emit4<BC>(bc, a.bc_out, rec0, bc_stage, lane);
-        emit4<UMI>(um, a.umi_out, rec0, umi_stage, lane);
-        uint32_t fl = 0;
-#pragma unroll
-        for (int q = 0; q < 4; q++) {
-            const uint32_t bb = (bc[q] & a.bc_hi) != 0ull, bu = (um[q] & a.umi_hi) != 0ull;
-            n_bb += bb; n_bu += bu; n_br += (bb | bu);
-            fl |= (bb | (bu << 1)) << (8 * q);
-        }
-        if (a.flags) *reinterpret_cast<uint32_t *>(a.flags + rec0) = fl;
-        if (kStaged) {
-            __syncwarp();
-            copy_out_stage<BC>(BC, a.bc_out, t, bc_stage, lane);
-            copy_out_stage<UMI>(UMI, a.umi_out, t, umi_stage, lane);
-            __syncwarp();
-        }
-        t = t_next;
-    }
-
-    if (gwarp == total_warps - 1) {  // ragged tail: plain per-record code
-        const uint64_t *r64 = reinterpret_cast<const uint64_t *>(a.recs);
-        for (uint64_t rec = n_tiles * kTileRecords + lane; rec < a.n; rec += 32) {
-            const uint64_t bc = ldg_stream64(r64 + 3 * rec), umi = ldg_stream64(r64 + 3 * rec + 1);
-            for (uint32_t i = 0; i < BC; i++)
-                a.bc_out[rec * BC + i] = (uint8_t)(kAcgt >> (8 * ((bc >> (2 * i)) & 3u)));
-            for (uint32_t i = 0; i < UMI; i++)
-                a.umi_out[rec * UMI + i] = (uint8_t)(kAcgt >> (8 * ((umi >> (2 * i)) & 3u)));
             const uint32_t bb = (bc & a.bc_hi) != 0ull, bu = (umi & a.umi_hi) != 0ull;
             n_bb += bb; n_bu += bu; n_br += (bb | bu);
             if (a.flags) a.flags[rec] = (uint8_t)(bb | (bu << 1));
@@ -675,7 +553,7 @@ static int grid_for(ibu_gpu_ctx *ctx, const void *kernel, size_t smem, uint64_t 
 
 static bool aligned(const void *p, size_t a) { return ((uintptr_t)p & (a - 1)) == 0; }
 
-template <int BC, int UMI, int POL = 0>
+template <int BC, int UMI>
 static int launch_unpack(ibu_gpu_ctx *ctx, UnpackArgs &a, cudaStream_t s, ibu_error_t *err) {
     // per-warp shared memory: input tile, then the staged outputs that are not stored directly
     uint32_t off = kTileBytes;
@@ -685,29 +563,8 @@ static int launch_unpack(ibu_gpu_ctx *ctx, UnpackArgs &a, cudaStream_t s, ibu_er
     if (!(UMI == 32 || UMI == 16)) off += (kTileRecords * a.umi_len + 15u) & ~15u;
     a.warp_smem_bytes = off;
     const size_t smem = (size_t)off * kWarpsPerBlock;
-    auto kern = k_unpack<BC, UMI, POL>;
+    auto kern = k_unpack<BC, UMI>;
     IBU_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    int grid = grid_for(ctx, (const void *)kern, smem, a.n / kTileRecords, err);
-    if (grid < 0) return -grid;
-    const int cap = (ctx->variant >> 8) & 0xF;  // tuning: CTAs per SM
-    if (cap && grid > cap * ctx->sm_count) grid = cap * ctx->sm_count;
-    a.blocked = (ctx->variant >> 12) & 1;
-    kern<<<grid, kBlockThreads, smem, s>>>(a);
-    g_launches.fetch_add(1, std::memory_order_relaxed);
-    IBU_CUDA(cudaGetLastError());
-    return IBU_OK;
-}
-
-template <int BC, int UMI>
-static int launch_unpack_r4(ibu_gpu_ctx *ctx, UnpackArgs &a, cudaStream_t s, ibu_error_t *err) {
-    uint32_t off = 0;
-    a.bc_stage_off = off;
-    if (BC == 12) off += kTileRecords * 12;
-    a.umi_stage_off = off;
-    if (UMI == 12) off += kTileRecords * 12;
-    a.warp_smem_bytes = off;
-    const size_t smem = (size_t)off * kWarpsPerBlock;
-    auto kern = k_unpack_r4<BC, UMI>;
     int grid = grid_for(ctx, (const void *)kern, smem, a.n / kTileRecords, err);
     if (grid < 0) return -grid;
     kern<<<grid, kBlockThreads, smem, s>>>(a);
@@ -800,20 +657,6 @@ int ibu_gpu_unpack_async(ibu_gpu_ctx_t *ctx, const ibu_record_t *d_records, uint
     const int bm = (bc_len == 32 && aligned(d_bc_ascii, 32)) ? 32 : bc_len == 16 ? 16 : 0;
     const int um = (umi_len == 32 && aligned(d_umi_ascii, 32)) ? 32
                    : umi_len == 16 ? 16 : umi_len == 12 ? 12 : 0;
-    // r4 variant (records consumed from registers): 32-byte aligned pointers, lengths 12/16/32
-    const int pol = (ctx->variant >> 4) & 0xF;
-    if (pol && bm == 16 && um == 12) {
-        if (pol == 1) return launch_unpack<16, 12, 1>(ctx, a, s, err);
-        if (pol == 2) return launch_unpack<16, 12, 2>(ctx, a, s, err);
-        if (pol == 3) return launch_unpack<16, 12, 3>(ctx, a, s, err);
-    }
-    const bool r4_ok = (ctx->variant & 0xF) == 1 && aligned(d_records, 32) && aligned(d_bc_ascii, 32) &&
-                       aligned(d_umi_ascii, 32) && (!d_flags || aligned(d_flags, 4));
-#define IBU_UNPACK_R4(B, U) \
-    if (r4_ok && bc_len == B && umi_len == U) return launch_unpack_r4<B, U>(ctx, a, s, err);
-    IBU_UNPACK_R4(16, 12) IBU_UNPACK_R4(16, 16) IBU_UNPACK_R4(32, 32) IBU_UNPACK_R4(16, 32) IBU_UNPACK_R4(32, 16)
-    IBU_UNPACK_R4(32, 12)
-#undef IBU_UNPACK_R4
 #define IBU_UNPACK_CASE(B, U) \
     if (bm == B && um == U) return launch_unpack<B, U>(ctx, a, s, err);
     IBU_UNPACK_CASE(16, 12) IBU_UNPACK_CASE(16, 16) IBU_UNPACK_CASE(16, 32) IBU_UNPACK_CASE(16, 0)

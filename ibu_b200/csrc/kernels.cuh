@@ -40,22 +40,12 @@ __device__ __forceinline__ uint64_t ldg_stream64(const uint64_t *p) {
     asm("ld.global.nc.L1::no_allocate.u64 %0, [%1];" : "=l"(r) : "l"(p));
     return r;
 }
+// (plain write-back stores: measured 1.4 % faster on K2 than L1::no_allocate / .cs, A/B in one
+// process, 80 launches each)
 __device__ __forceinline__ void stg_stream(uint4 *p, uint4 v) {
-    asm volatile("st.global.L1::no_allocate.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x),
+    asm volatile("st.global.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x),
                  "r"(v.y), "r"(v.z), "r"(v.w)
                  : "memory");
-}
-// store-policy experiments (tuning only): 0 L1::no_allocate, 1 .cs, 2 default (.wb), 3 .cg
-template <int POL>
-__device__ __forceinline__ void stg_pol(uint4 *p, uint4 v) {
-    if constexpr (POL == 1)
-        asm volatile("st.global.cs.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
-    else if constexpr (POL == 2)
-        asm volatile("st.global.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
-    else if constexpr (POL == 3)
-        asm volatile("st.global.cg.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
-    else
-        stg_stream(p, v);
 }
 __device__ __forceinline__ void stg_stream256(void *p, uint4 lo, uint4 hi) {
     asm volatile("st.global.L1::no_allocate.v8.u32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p),

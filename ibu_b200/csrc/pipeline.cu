@@ -305,7 +305,6 @@ int ibu_gpu_ctx_create(int device, const ibu_gpu_config_t *cfg, ibu_gpu_ctx_t **
     ctx->device = device;
     ctx->sm_count = prop.multiProcessorCount;
     if (cfg) ctx->cfg = *cfg;
-    if (const char *v = getenv("IBU_B200_VARIANT")) ctx->variant = atoi(v);
     cudaError_t e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
     const uint32_t n_slots = ctx->cfg.n_slots ? ctx->cfg.n_slots : 3;
     ctx->slots.resize(n_slots);
