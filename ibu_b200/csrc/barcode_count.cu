@@ -28,6 +28,17 @@
 
 namespace ibu {
 
+struct Trace {  // IBU_B200_TRACE=1: host-side phase timing on stderr (tuning only)
+    bool on = getenv("IBU_B200_TRACE") != nullptr;
+    std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
+    void mark(const char *what) {
+        if (!on) return;
+        auto t1 = std::chrono::steady_clock::now();
+        fprintf(stderr, "[ibu trace] %-28s %8.3f ms\n", what, std::chrono::duration<double, std::milli>(t1 - t0).count());
+        t0 = t1;
+    }
+};
+
 constexpr int kSegSub = 128;                     // records per sub-tile (4 per lane)
 // sub-tiles per (warp) tile: 16 = 2048 records.  Measured on B200 at 10^8 records: 4 -> 1.20 ms,
 // 8 -> 0.66 ms, 16 -> 0.44 ms (short tiles leave the deferred look-back too little slack).
@@ -223,6 +234,7 @@ __global__ void __launch_bounds__(kBlockThreads, 4) k_segments(const SegArgs a) 
 
     uint64_t t = claim();
     if (t >= a.n_tiles) return;
+    // (once any warp has seen an order violation the pass is void: everybody stops claiming)
     // The sub-tile stream is continuous across tiles: the next tile is claimed two sub-tiles
     // before the current one ends and its first sub-tile (and front key) are prefetched during
     // the last one, so a tile switch costs no exposed latency.
@@ -294,7 +306,7 @@ __global__ void __launch_bounds__(kBlockThreads, 4) k_segments(const SegArgs a) 
         p_t = t; p_tot = run; p_buf = buf; p_exb = 0; p_exp = 0; p_j = (int64_t)t - 1;
         if (t == 0) finish();  // no predecessors: offsets are zero
         buf ^= 1u;
-        if (t_next >= a.n_tiles) break;
+        if (t_next >= a.n_tiles || *v_flag != 0ull) break;
         t = t_next;
     }
     if (p_active) {
@@ -508,6 +520,116 @@ k_radix_scatter(const uint64_t *__restrict__ in, uint64_t *__restrict__ out, uin
     }
 }
 
+// ============================================================ hash aggregation (unsorted inputs)
+// Unsorted records are first folded into distinct (barcode, umi, multiplicity) pairs with an
+// open-addressing table in HBM/L2 (linear probing, 32-byte slots {barcode, umi, count, pad},
+// 128-bit CAS to claim a slot).  Duplicate-heavy data (the common case: PCR duplicates, the
+// reference's own example pattern) shrinks by the duplication factor before anything is
+// sorted; the few distinct pairs are then sorted and counted weighted.  All-distinct data is
+// detected on a sample and goes straight to the radix sort instead.
+#define kHashEmpty 0xFFFFFFFFFFFFFFFFull
+constexpr uint32_t kHashMaxProbe = 256;
+
+struct HashArgs {
+    const uint64_t *recs;
+    uint64_t n;
+    uint64_t *table;   // (mask + 1) slots of 4 u64, memset to 0xFF (count is stored minus one)
+    uint64_t mask;
+    unsigned long long *ctr;  // [0] slots claimed, [1] overflow flag, [2] weight of the all-ones key
+    int weighted;
+};
+
+__device__ __forceinline__ void cas128(uint64_t *addr, uint64_t c0, uint64_t c1, uint64_t s0, uint64_t s1,
+                                       uint64_t &o0, uint64_t &o1) {
+    asm volatile(
+        "{\n\t.reg .b128 c, s, d;\n\t"
+        "mov.b128 c, {%2, %3};\n\t"
+        "mov.b128 s, {%4, %5};\n\t"
+        "atom.global.relaxed.gpu.cas.b128 d, [%6], c, s;\n\t"
+        "mov.b128 {%0, %1}, d;\n\t}"
+        : "=l"(o0), "=l"(o1)
+        : "l"(c0), "l"(c1), "l"(s0), "l"(s1), "l"(addr)
+        : "memory");
+}
+
+__device__ __forceinline__ void hash_insert(const HashArgs &a, uint64_t bc, uint64_t um, uint64_t w, uint32_t &fresh) {
+    if (bc == kHashEmpty && um == kHashEmpty) {  // the one key that collides with the empty marker
+        atomicAdd(a.ctr + 2, (unsigned long long)w);
+        return;
+    }
+    uint64_t slot = splitmix64(bc ^ splitmix64(um)) & a.mask;
+    for (uint32_t probe = 0; probe < kHashMaxProbe; probe++, slot = (slot + 1) & a.mask) {
+        uint64_t *s = a.table + 4 * slot;
+        uint64_t k0, k1;
+        asm volatile("ld.volatile.global.v2.u64 {%0, %1}, [%2];" : "=l"(k0), "=l"(k1) : "l"(s));
+        if (k0 != bc || k1 != um) {
+            // a half that reads as "empty" is either an empty slot, a torn view of a slot being
+            // claimed, or a key with an all-ones word: the CAS is the authoritative read
+            if (k0 != kHashEmpty && k1 != kHashEmpty) continue;  // another key lives here
+            cas128(s, kHashEmpty, kHashEmpty, bc, um, k0, k1);
+            if (k0 == kHashEmpty && k1 == kHashEmpty) fresh++;   // claimed
+            else if (k0 != bc || k1 != um) continue;             // lost the race to another key
+        }
+        atomicAdd(reinterpret_cast<unsigned long long *>(s + 2), (unsigned long long)w);
+        return;
+    }
+    atomicOr(a.ctr + 1, 1ull);  // table too full
+}
+
+__global__ void __launch_bounds__(kBlockThreads) k_hash_insert(const HashArgs a) {
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint64_t gwarp = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint64_t total_warps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+    const uint64_t n_tiles = a.n / kSegSub;
+    uint32_t fresh = 0;
+    for (uint64_t t = gwarp; t < n_tiles; t += total_warps) {  // lane l owns records 4l..4l+3 of the tile
+        const uint8_t *p = reinterpret_cast<const uint8_t *>(a.recs) + t * (kSegSub * 24) + lane * 96;
+        const u64x4 v0 = ldg_stream256(p), v1 = ldg_stream256(p + 32), v2 = ldg_stream256(p + 64);
+        hash_insert(a, v0.x, v0.y, a.weighted ? v0.z : 1ull, fresh);
+        hash_insert(a, v0.w, v1.x, a.weighted ? v1.y : 1ull, fresh);
+        hash_insert(a, v1.z, v1.w, a.weighted ? v2.x : 1ull, fresh);
+        hash_insert(a, v2.y, v2.z, a.weighted ? v2.w : 1ull, fresh);
+    }
+    if (gwarp == 0)  // ragged tail
+        for (uint64_t i = n_tiles * kSegSub + lane; i < a.n; i += 32)
+            hash_insert(a, a.recs[3 * i], a.recs[3 * i + 1], a.weighted ? a.recs[3 * i + 2] : 1ull, fresh);
+    fresh = __reduce_add_sync(0xffffffffu, fresh);
+    if (lane == 0 && fresh) atomicAdd(a.ctr, (unsigned long long)fresh);
+}
+
+// occupied slots -> dense (barcode, umi, count) records, order unspecified
+__global__ void __launch_bounds__(kBlockThreads)
+k_hash_compact(const uint64_t *__restrict__ table, uint64_t slots, uint64_t *__restrict__ out,
+               unsigned long long *__restrict__ cursor) {
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint64_t step = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t base = (uint64_t)blockIdx.x * blockDim.x; base < slots; base += step) {  // warp-uniform trips
+        const uint64_t i = base + threadIdx.x;
+        u64x4 v{kHashEmpty, kHashEmpty, 0, 0};
+        if (i < slots) v = ldg_stream256(table + 4 * i);
+        const bool live = !(v.x == kHashEmpty && v.y == kHashEmpty);
+        const uint32_t m = __ballot_sync(0xffffffffu, live);
+        if (!m) continue;
+        unsigned long long pos = 0;
+        if (lane == 0) pos = atomicAdd(cursor, (unsigned long long)__popc(m));
+        pos = __shfl_sync(0xffffffffu, pos, 0) + __popc(m & ((1u << lane) - 1u));
+        if (live) { out[3 * pos] = v.x; out[3 * pos + 1] = v.y; out[3 * pos + 2] = v.z + 1ull; }
+    }
+}
+
+// growth: every pair of the old table is re-inserted, with its count as the weight
+__global__ void __launch_bounds__(kBlockThreads)
+k_hash_rehash(const uint64_t *__restrict__ old_table, uint64_t old_slots, const HashArgs a) {
+    uint32_t fresh = 0;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < old_slots;
+         i += (uint64_t)gridDim.x * blockDim.x) {
+        const u64x4 v = ldg_stream256(old_table + 4 * i);
+        if (!(v.x == kHashEmpty && v.y == kHashEmpty)) hash_insert(a, v.x, v.y, v.z + 1ull, fresh);
+    }
+    fresh = __reduce_add_sync(0xffffffffu, fresh);
+    if ((threadIdx.x & 31u) == 0 && fresh) atomicAdd(a.ctr, (unsigned long long)fresh);
+}
+
 // ---- owner partition of a pair table (the send side of the multi-GPU exchange) ----
 // owner(barcode) = splitmix64(barcode) % world: every barcode's pairs meet on one rank.
 __device__ __forceinline__ uint32_t owner_of(uint64_t barcode, uint32_t world) {
@@ -608,16 +730,6 @@ static size_t seg_scratch_bytes(uint64_t n) {
 
 // Runs the segment pass over `src` (stride 3 or 2).  On success *rows_out (device, owned by the
 // caller) holds *n_rows rows.  *unsorted is set when the order check failed (no rows then).
-struct Trace {  // IBU_B200_TRACE=1: host-side phase timing on stderr (tuning only)
-    bool on = getenv("IBU_B200_TRACE") != nullptr;
-    std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
-    void mark(const char *what) {
-        if (!on) return;
-        auto t1 = std::chrono::steady_clock::now();
-        fprintf(stderr, "[ibu trace] %-28s %8.3f ms\n", what, std::chrono::duration<double, std::milli>(t1 - t0).count());
-        t0 = t1;
-    }
-};
 
 // Runs the segment pass over `src` (stride 3 or 2).  On success *rows_out (device, cudaMalloc'ed,
 // owned by the caller) holds *n_rows rows of 3 u64: barcode rows {barcode, n_records,
@@ -689,8 +801,10 @@ static int segment_pass(ibu_gpu_ctx *ctx, const uint64_t *src, int stride, uint6
             capacity = h[1];
             continue;
         }
-        uint64_t *rows = nullptr;  // owned by the caller (ibu_gpu_table_free / ibu_gpu_free)
-        IBU_CUDA(cudaMalloc((void **)&rows, h[1] ? h[1] * 24 : 256));
+        // owned by the caller (ibu_gpu_table_free / ibu_gpu_free); from the stream-ordered pool,
+        // whose cached blocks make this allocation cheap after the first call
+        uint64_t *rows = nullptr;
+        IBU_CUDA(cudaMallocAsync((void **)&rows, h[1] ? h[1] * 24 : 256, s));
         if (h[1]) {
             const uint64_t blocks = (h[1] + kBlockThreads - 1) / kBlockThreads;
             const int fgrid = (int)std::min<uint64_t>(blocks, (uint64_t)ctx->sm_count * 8);
@@ -814,6 +928,111 @@ static int unsorted_table(ibu_gpu_ctx *ctx, const uint64_t *recs, uint64_t n, cu
     return IBU_OK;
 }
 
+
+static uint64_t pow2_ceil(uint64_t v) {
+    uint64_t p = 1;
+    while (p < v) p <<= 1;
+    return p;
+}
+
+// Distinct (barcode, umi, multiplicity) pairs of an unsorted input by hash aggregation.
+// Records are inserted a chunk at a time; the table starts at 8 Mi slots (256 MiB) and is
+// re-hashed into one four times larger whenever it passes 0.7 load, so duplicate-heavy data
+// never pays for a table sized for the worst case.  *use_sort is set (and nothing else
+// produced) when the first 4 Mi records are close to all-distinct — aggregation would only add a pass —
+// or a table would not fit: the caller then sorts the input directly.
+static int hash_aggregate(ibu_gpu_ctx *ctx, const uint64_t *recs, uint64_t n, bool weighted, cudaStream_t s,
+                          Scratch &sc, uint64_t **pairs, uint64_t *n_pairs, bool *use_sort, ibu_error_t *err) {
+    Trace tr;
+    *use_sort = false;
+    *pairs = nullptr;
+    *n_pairs = 0;
+    unsigned long long *ctr;  // [0] slots claimed, [1] overflow flag, [2] weight of the all-ones key
+    IBU_CUDA(sc.alloc(&ctr, 4 * 8));
+    // 8 Mi slots = 256 MiB to start with: the hot part of a low-cardinality table then stays
+    // inside L2 and TLB reach (a 1 GiB start measured 40 % slower on the reference pattern)
+    uint64_t slots = std::max<uint64_t>(1024, std::min<uint64_t>(pow2_ceil(2 * n), 8ull << 20));
+    uint64_t *table;
+    IBU_CUDA(sc.alloc(&table, slots * 32));
+    IBU_CUDA(cudaMemsetAsync(table, 0xFF, slots * 32, s));
+    IBU_CUDA(cudaMemsetAsync(ctr, 0, 4 * 8, s));
+    const int max_grid = ctx->sm_count * 8;
+    const uint64_t decide_at = 4ull << 20;  // records after which hash-vs-sort is decided
+    uint64_t chunk = 2ull << 20;            // records per launch; grows while few keys are new
+    unsigned long long h[3] = {0, 0, 0}, claimed_before = 0;
+    bool decided = false;
+    for (uint64_t pos = 0; pos < n;) {
+        const uint64_t cnt = std::min(chunk, n - pos);
+        HashArgs a{recs + 3 * pos, cnt, table, slots - 1, ctr, weighted ? 1 : 0};
+        const uint64_t blocks = (cnt / kSegSub + kWarpsPerBlock) / kWarpsPerBlock;
+        k_hash_insert<<<(int)std::min<uint64_t>(blocks, max_grid), kBlockThreads, 0, s>>>(a);
+        g_launches.fetch_add(1, std::memory_order_relaxed);
+        IBU_CUDA(cudaGetLastError());
+        IBU_CUDA(cudaMemcpyAsync(h, ctr, sizeof(h), cudaMemcpyDeviceToHost, s));
+        IBU_CUDA(cudaStreamSynchronize(s));
+        tr.mark("hash: insert chunk");
+        pos += cnt;
+        const uint64_t fresh = h[0] - claimed_before;
+        claimed_before = h[0];
+        if (h[1]) {  // probe limit hit: the table could not keep up
+            *use_sort = true;
+            return IBU_OK;
+        }
+        if (!decided && pos >= decide_at) {
+            decided = true;
+            if (pos < n && h[0] > pos / 10 * 4) {  // (nearly) all-distinct so far
+                *use_sort = true;
+                return IBU_OK;
+            }
+        }
+        if (pos >= n) break;
+        if (h[0] > slots / 10 * 7) {  // past 0.7 load: grow x4 and re-hash what is there
+            const uint64_t bigger = slots * 4;
+            if (bigger > (1ull << 31)) {
+                *use_sort = true;
+                return IBU_OK;
+            }
+            uint64_t *next;
+            IBU_CUDA(sc.alloc(&next, bigger * 32));
+            IBU_CUDA(cudaMemsetAsync(next, 0xFF, bigger * 32, s));
+            IBU_CUDA(cudaMemsetAsync(ctr, 0, 2 * 8, s));  // claimed + overflow; the all-ones weight stays
+            HashArgs b{nullptr, 0, next, bigger - 1, ctr, 1};
+            k_hash_rehash<<<max_grid, kBlockThreads, 0, s>>>(table, slots, b);
+            g_launches.fetch_add(1, std::memory_order_relaxed);
+            IBU_CUDA(cudaGetLastError());
+            table = next;
+            slots = bigger;
+        }
+        // a chunk may add at most a quarter of the table while keys are still mostly new; once
+        // they are mostly repeats the launches get longer (fewer host round trips)
+        if (fresh < cnt / 8) chunk = std::min<uint64_t>(chunk * 2, 64ull << 20);
+        else if (fresh > cnt / 2) chunk = std::max<uint64_t>(1ull << 20, std::min<uint64_t>(chunk, slots / 8));
+        chunk &= ~3ull;  // chunk starts stay 32-byte aligned
+    }
+    if (h[0] > slots / 10 * 9) {  // the last chunk overfilled the table: probes were long, not wrong
+        // (correct but slow; nothing to do)
+    }
+    // compact the occupied slots (plus the all-ones key, if it occurred) into pair records
+    const uint64_t k = h[0] + (h[2] ? 1 : 0);
+    uint64_t *out;
+    IBU_CUDA(sc.alloc(&out, (k ? k : 1) * 24));
+    IBU_CUDA(cudaMemsetAsync(ctr, 0, 8, s));
+    const uint64_t blocks = (slots + kBlockThreads - 1) / kBlockThreads;
+    k_hash_compact<<<(int)std::min<uint64_t>(blocks, (uint64_t)ctx->sm_count * 16), kBlockThreads, 0, s>>>(
+        table, slots, out, ctr);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    IBU_CUDA(cudaGetLastError());
+    if (h[2]) {
+        const unsigned long long special[3] = {kHashEmpty, kHashEmpty, h[2]};
+        IBU_CUDA(cudaMemcpyAsync(out + 3 * h[0], special, sizeof(special), cudaMemcpyHostToDevice, s));
+    }
+    IBU_CUDA(cudaStreamSynchronize(s));
+    tr.mark("hash: compact");
+    *pairs = out;
+    *n_pairs = k;
+    return IBU_OK;
+}
+
 static size_t sort_scratch_bytes(uint64_t n, int elem_bytes) {
     const uint64_t n_tiles = (n + kSortTile - 1) / kSortTile;
     return n * 2 * elem_bytes + n_tiles * 1024 + 16 * 256;
@@ -830,13 +1049,33 @@ static int build_table(ibu_gpu_ctx *ctx, const ibu_record_t *d_records, uint64_t
     std::lock_guard<std::mutex> lock(ctx->arena_mutex);  // one table build per context at a time
     bool unsorted = mode == 2;
     if (mode != 2) {
+        Trace tr;
         IBU_CUDA(arena_reset(ctx, seg_scratch_bytes(n)));
         if (int rc = segment_pass(ctx, src, 3, n, s, pair_mode, weighted, rows, n_rows, n_pairs, &unsorted, err))
             return rc;
         *was_sorted = !unsorted;
+        tr.mark("table: sorted probe total");
     }
     if (unsorted) {
         if (mode == 1) return IBU_OK;  // caller required sorted input: was_sorted = false, no rows
+        // duplicate-heavy inputs: fold to distinct pairs first, then sort/count only those
+        // room for the first table (256 MiB), the compacted pairs and their sort; a larger
+        // full-size table falls back to a one-off allocation inside Scratch
+        IBU_CUDA(arena_reset(ctx, (768ull << 20) + seg_scratch_bytes(std::min<uint64_t>(n, 8ull << 20))));
+        Trace tr;
+        tr.mark("table: arena");
+        bool use_sort = getenv("IBU_B200_NO_HASH") != nullptr;
+        if (!use_sort) {
+            Scratch sc(ctx);
+            uint64_t *pairs = nullptr, k = 0;
+            if (int rc = hash_aggregate(ctx, src, n, weighted, s, sc, &pairs, &k, &use_sort, err)) return rc;
+            tr.mark("table: hash aggregate total");
+            if (!use_sort) {  // the pairs live in `sc` (arena or fallback allocations) until we return
+                int rc = unsorted_table(ctx, pairs, k, s, pair_mode, true, rows, n_rows, n_pairs, err);
+                tr.mark("table: sort+count of pairs");
+                return rc;
+            }
+        }
         IBU_CUDA(arena_reset(ctx, sort_scratch_bytes(n, weighted ? 24 : 16) + seg_scratch_bytes(n)));
         return unsorted_table(ctx, src, n, s, pair_mode, weighted, rows, n_rows, n_pairs, err);
     }
@@ -879,7 +1118,10 @@ int ibu_gpu_barcode_count(ibu_gpu_ctx_t *ctx, const ibu_record_t *d_records, uin
 
 void ibu_gpu_table_free(ibu_gpu_ctx_t *ctx, ibu_barcode_table_t *table) {
     if (!ctx || !table) return;
-    if (table->d_rows) ibu_gpu_free(ctx, table->d_rows);
+    if (table->d_rows) {
+        DeviceGuard guard(ctx->device);
+        if (cudaFreeAsync(table->d_rows, ctx->stream) != cudaSuccess) cudaGetLastError();
+    }
     table->d_rows = nullptr;
     table->n_rows = 0;
 }

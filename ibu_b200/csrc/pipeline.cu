@@ -305,6 +305,14 @@ int ibu_gpu_ctx_create(int device, const ibu_gpu_config_t *cfg, ibu_gpu_ctx_t **
     ctx->device = device;
     ctx->sm_count = prop.multiProcessorCount;
     if (cfg) ctx->cfg = *cfg;
+    {   // keep freed blocks of the stream-ordered pool cached (result tables come from it)
+        cudaMemPool_t pool;
+        if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+            uint64_t keep = UINT64_MAX;
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+        }
+        cudaGetLastError();
+    }
     cudaError_t e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
     const uint32_t n_slots = ctx->cfg.n_slots ? ctx->cfg.n_slots : 3;
     ctx->slots.resize(n_slots);
