@@ -12,7 +12,6 @@ constexpr int kTileRecords = 128;                       // records per warp tile
 constexpr int kTileBytes = kTileRecords * 24;           // 3072
 constexpr int kTileU4 = kTileBytes / 16;                // 192 x 16 B
 constexpr int kTileU8 = kTileBytes / 32;                // 96 x 32 B
-constexpr int kPackTileRows = 64;                       // rows per warp tile (pack)
 constexpr uint32_t kAcgt = 0x54474341u;                 // "ACGT" as PRMT lookup table
 
 struct alignas(32) u64x4 {
