@@ -178,6 +178,13 @@ __device__ __forceinline__ void emit_row(uint64_t w, uint32_t len, uint8_t *gout
 #pragma unroll
             for (int g = 0; g < 8; g++)
                 if (g < ng) s32[g] = asc[g];
+        } else if ((len & 1u) == 0) {  // even lengths (e.g. 10-base UMIs): rows are 2-byte aligned
+            uint16_t *s16 = reinterpret_cast<uint16_t *>(stage) + r * (len >> 1);
+#pragma unroll
+            for (int g = 0; g < 8; g++)
+#pragma unroll
+                for (int b = 0; b < 2; b++)
+                    if (4 * g + 2 * b < len) s16[2 * g + b] = (uint16_t)(asc[g] >> (16 * b));
         } else {
             uint8_t *s8 = stage + r * len;
 #pragma unroll
@@ -298,10 +305,11 @@ struct RowRegs;
 template <int Q>
 struct RowRegs<32, Q> {
     u64x4 v[Q];
-    __device__ __forceinline__ void load(const uint8_t *g, uint64_t tile, uint32_t lane) {
+    __device__ __forceinline__ void load(const uint8_t *g, uint64_t tile, uint32_t lane, uint32_t) {
 #pragma unroll
         for (int q = 0; q < Q; q++) v[q] = ldg_stream256(g + (tile * (32 * Q) + lane + 32 * q) * 32);
     }
+    __device__ __forceinline__ void park(uint8_t *, uint32_t, uint32_t) const {}
     __device__ __forceinline__ void get(int q, uint4 &lo, uint4 &hi) const {
         lo = make_uint4((uint32_t)v[q].x, (uint32_t)(v[q].x >> 32), (uint32_t)v[q].y, (uint32_t)(v[q].y >> 32));
         hi = make_uint4((uint32_t)v[q].z, (uint32_t)(v[q].z >> 32), (uint32_t)v[q].w, (uint32_t)(v[q].w >> 32));
@@ -310,32 +318,40 @@ struct RowRegs<32, Q> {
 template <int Q>
 struct RowRegs<16, Q> {
     uint4 v[Q];
-    __device__ __forceinline__ void load(const uint8_t *g, uint64_t tile, uint32_t lane) {
+    __device__ __forceinline__ void load(const uint8_t *g, uint64_t tile, uint32_t lane, uint32_t) {
 #pragma unroll
         for (int q = 0; q < Q; q++)
             v[q] = ldg_stream(reinterpret_cast<const uint4 *>(g) + tile * (32 * Q) + lane + 32 * q);
     }
+    __device__ __forceinline__ void park(uint8_t *, uint32_t, uint32_t) const {}
     __device__ __forceinline__ void get(int q, uint4 &lo, uint4 &hi) const {
         lo = v[q];
         hi = make_uint4(0x41414141u, 0x41414141u, 0x41414141u, 0x41414141u);
     }
 };
+// Rows of any other length travel through shared memory: the 32 Q-row tile (32 Q x len bytes,
+// 16-byte aligned in the input, at most 2 Q 16-byte pieces per lane) is prefetched into
+// registers one tile ahead like the direct rows, then parked in the warp's stage.
 template <int Q>
 struct RowRegs<0, Q> {
-    __device__ __forceinline__ void load(const uint8_t *, uint64_t, uint32_t) {}
+    uint4 v[2 * Q];
+    __device__ __forceinline__ void load(const uint8_t *g, uint64_t tile, uint32_t lane, uint32_t len) {
+        const uint32_t n16 = 2 * Q * len;
+        const uint4 *src = reinterpret_cast<const uint4 *>(g) + tile * n16;
+#pragma unroll
+        for (int k = 0; k < 2 * Q; k++)
+            if (lane + 32 * k < n16) v[k] = ldg_stream(src + lane + 32 * k);
+    }
+    __device__ __forceinline__ void park(uint8_t *stage, uint32_t lane, uint32_t len) const {
+        const uint32_t n16 = 2 * Q * len;
+        uint4 *dst = reinterpret_cast<uint4 *>(stage);
+#pragma unroll
+        for (int k = 0; k < 2 * Q; k++)
+            if (lane + 32 * k < n16) dst[lane + 32 * k] = v[k];
+    }
 };
 template <int Q>
 struct RowRegs<12, Q> : RowRegs<0, Q> {};  // 12-byte rows are staged too, with a compile-time length
-
-// copy a 32 Q-row tile (32 Q x len bytes, 16-byte aligned in the input) into shared memory
-template <int Q>
-__device__ __forceinline__ void stage_rows(const uint8_t *g, uint64_t tile, uint32_t len,
-                                           uint8_t *stage, uint32_t lane) {
-    const uint32_t n16 = 2 * Q * len;
-    const uint4 *src = reinterpret_cast<const uint4 *>(g) + tile * n16;
-    uint4 *dst = reinterpret_cast<uint4 *>(stage);
-    for (uint32_t i = lane; i < n16; i += 32) dst[i] = ldg_stream(src + i);
-}
 
 // gather one staged row into two 16-byte halves, padded with 'A' (code 0, valid)
 template <int L>
@@ -356,15 +372,29 @@ __device__ __forceinline__ void staged_row(const uint8_t *stage, uint32_t r, uin
 #pragma unroll
         for (int g = 0; g < 8; g++)
             if (4u * g < len) w[g] = r32[g];
-    } else {
+    } else if ((len & 1u) == 0) {  // even lengths: 2-byte aligned rows, halfword loads
+        const uint16_t *r16 = reinterpret_cast<const uint16_t *>(row);
 #pragma unroll
         for (int g = 0; g < 8; g++) {
             if (4u * g < len) {
-                uint32_t v = 0x41414141u;
+                const uint32_t lo16 = r16[2 * g];
+                const uint32_t hi16 = (4u * g + 2 < len) ? (uint32_t)r16[2 * g + 1] : 0x4141u;
+                w[g] = lo16 | (hi16 << 16);
+            }
+        }
+    } else {  // odd lengths, rows start at any byte: aligned words + funnel shift, tail padded with 'A'
+        const uint32_t o = r * len, sh = (o & 3u) * 8u;
+        const uint32_t *r32 = reinterpret_cast<const uint32_t *>(stage) + (o >> 2);
+        uint32_t cur = r32[0];
 #pragma unroll
-                for (int b = 0; b < 4; b++)
-                    if (4u * g + b < len) v = (v & ~(0xFFu << (8 * b))) | ((uint32_t)row[4 * g + b] << (8 * b));
+        for (int g = 0; g < 8; g++) {
+            if (4u * g < len) {
+                const uint32_t nxt = r32[g + 1];  // (the stage has 16 spare bytes behind the tile)
+                uint32_t v = __funnelshift_r(cur, nxt, sh);
+                const uint32_t rem = len - 4u * g;
+                if (rem < 4u) v = (v & ((1u << (8u * rem)) - 1u)) | (0x41414141u << (8u * rem));
                 w[g] = v;
+                cur = nxt;
             }
         }
     }
@@ -400,13 +430,13 @@ __global__ void __launch_bounds__(kBlockThreads) k_pack(const PackArgs a) {
     RowRegs<UMI, Q> umi_rows;
     uint64_t t = gwarp;
     if (t < n_tiles) {
-        bc_rows.load(a.bc_in, t, lane);
-        umi_rows.load(a.umi_in, t, lane);
+        bc_rows.load(a.bc_in, t, lane, bc_len);
+        umi_rows.load(a.umi_in, t, lane, umi_len);
     }
     while (t < n_tiles) {
         constexpr bool kStageBc = (BC == 0 || BC == 12), kStageUmi = (UMI == 0 || UMI == 12);
-        if (kStageBc) stage_rows<Q>(a.bc_in, t, bc_len, bc_stage, lane);
-        if (kStageUmi) stage_rows<Q>(a.umi_in, t, umi_len, umi_stage, lane);
+        bc_rows.park(bc_stage, lane, bc_len);
+        umi_rows.park(umi_stage, lane, umi_len);
         if (kStageBc || kStageUmi) __syncwarp();
         uint4 bl[Q], bh[Q], ul[Q], uh[Q];
 #pragma unroll
@@ -418,8 +448,8 @@ __global__ void __launch_bounds__(kBlockThreads) k_pack(const PackArgs a) {
         }
         const uint64_t t_next = t + total_warps;
         if (t_next < n_tiles) {  // prefetch while this tile is encoded
-            bc_rows.load(a.bc_in, t_next, lane);
-            umi_rows.load(a.umi_in, t_next, lane);
+            bc_rows.load(a.bc_in, t_next, lane, bc_len);
+            umi_rows.load(a.umi_in, t_next, lane, umi_len);
         }
 #pragma unroll
         for (int q = 0; q < Q; q++) {
@@ -585,9 +615,9 @@ static int launch_pack(ibu_gpu_ctx *ctx, PackArgs &a, cudaStream_t s, ibu_error_
     constexpr uint32_t kRows = 32 * Q;
     uint32_t off = kRows * 24;
     a.bc_stage_off = off;
-    if (BC == 0 || BC == 12) off += (kRows * a.bc_len + 15u) & ~15u;
+    if (BC == 0 || BC == 12) off += ((kRows * a.bc_len + 15u) & ~15u) + 16u;  // +16: funnel-shift over-read
     a.umi_stage_off = off;
-    if (UMI == 0 || UMI == 12) off += (kRows * a.umi_len + 15u) & ~15u;
+    if (UMI == 0 || UMI == 12) off += ((kRows * a.umi_len + 15u) & ~15u) + 16u;
     a.warp_smem_bytes = off;
     const size_t smem = (size_t)off * kWarpsPerBlock;
     auto kern = k_pack<BC, UMI, Q>;

@@ -108,7 +108,7 @@ def gpu_unpack(ctx, recs, bc, umi, flags=True):
 
 @pytest.mark.parametrize("n", SIZES)
 @pytest.mark.parametrize("bc,umi", [(16, 12), (16, 16), (32, 32), (12, 8), (5, 3), (32, 12), (1, 1), (20, 10), (31, 32),
-                                    (16, 32), (28, 16)])
+                                    (16, 32), (28, 16), (16, 10), (30, 2), (18, 26)])
 def test_unpack(ctx, n, bc, umi):
     recs = oc.generate_records(0, n, bc, umi, 1, 100_000, 99)
     gb, gu, gf, gr = gpu_unpack(ctx, recs, bc, umi)
@@ -151,7 +151,8 @@ def gpu_pack(ctx, bc_rows, umi_rows, index=None, index_base=0):
 
 
 @pytest.mark.parametrize("n", SIZES)
-@pytest.mark.parametrize("bc,umi", [(32, 32), (16, 16), (16, 12), (32, 16), (16, 32), (5, 3), (1, 1), (31, 7), (20, 28)])
+@pytest.mark.parametrize("bc,umi", [(32, 32), (16, 16), (16, 12), (32, 16), (16, 32), (5, 3), (1, 1), (31, 7), (20, 28),
+                                    (16, 10), (30, 2), (18, 26), (12, 12)])
 def test_pack(ctx, n, bc, umi):
     b = oc.generate_ascii(3, n, bc, 30_000, 200_000, 7)
     u = oc.generate_ascii(3, n, umi, 30_000, 200_000, 8)

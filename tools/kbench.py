@@ -64,7 +64,7 @@ def main():
 
     with torch.cuda.stream(stream):
         res = torch.zeros(8, dtype=torch.int64, device=dev)
-        for bc, umi in [(16, 12), (32, 32), (16, 16), (20, 10)]:
+        for bc, umi in [(16, 12), (32, 32), (16, 16), (16, 10), (20, 10), (15, 9)]:
             recs, b, u = u8(24 * n), u8(bc * n), u8(umi * n)
             ctx.generate_records_async(recs, 0, n, bc, umi, ibu.GEN_DIRTY, 10_000, 1, stream)
             if (bc, umi) == (16, 12):
