@@ -160,12 +160,17 @@ __device__ __forceinline__ void emit_row(uint64_t w, uint32_t len, uint8_t *gout
     } else if (L == 16) {
         decode_word<4>(w, asc);
         stg_stream(reinterpret_cast<uint4 *>(gout) + rec, make_uint4(asc[0], asc[1], asc[2], asc[3]));
-    } else if (L > 0) {  // compile-time length, multiple of 4: word stores into the stage
-        static_assert(L % 4 == 0, "compile-time staged lengths are multiples of 4");
+    } else if (L > 0 && L % 4 == 0) {  // compile-time length, multiple of 4: word stores into the stage
         decode_word<L / 4>(w, asc);
         uint32_t *s32 = reinterpret_cast<uint32_t *>(stage) + r * (L / 4);
 #pragma unroll
         for (int g = 0; g < L / 4; g++) s32[g] = asc[g];
+    } else if (L > 0) {  // compile-time even length (10-base UMIs): halfword stores
+        static_assert(L % 2 == 0, "compile-time staged lengths are even");
+        decode_word<(L + 3) / 4>(w, asc);
+        uint16_t *s16 = reinterpret_cast<uint16_t *>(stage) + r * (L / 2);
+#pragma unroll
+        for (int h = 0; h < L / 2; h++) s16[h] = (uint16_t)(asc[h / 2] >> (16 * (h & 1)));
     } else {  // runtime length
         const uint32_t ng = (len + 3) >> 2;
         const uint32_t lo = (uint32_t)w, hi = (uint32_t)(w >> 32);
@@ -351,7 +356,9 @@ struct RowRegs<0, Q> {
     }
 };
 template <int Q>
-struct RowRegs<12, Q> : RowRegs<0, Q> {};  // 12-byte rows are staged too, with a compile-time length
+struct RowRegs<12, Q> : RowRegs<0, Q> {};  // 12- and 10-byte rows are staged too, with a compile-time length
+template <int Q>
+struct RowRegs<10, Q> : RowRegs<0, Q> {};
 
 // gather one staged row into two 16-byte halves, padded with 'A' (code 0, valid)
 template <int L>
@@ -360,6 +367,13 @@ __device__ __forceinline__ void staged_row(const uint8_t *stage, uint32_t r, uin
     if constexpr (L == 12) {  // word stride 3: conflict-free
         const uint32_t *r32 = reinterpret_cast<const uint32_t *>(stage) + 3 * r;
         lo = make_uint4(r32[0], r32[1], r32[2], 0x41414141u);
+        hi = make_uint4(0x41414141u, 0x41414141u, 0x41414141u, 0x41414141u);
+        return;
+    }
+    if constexpr (L == 10) {  // halfword stride 5
+        const uint16_t *r16 = reinterpret_cast<const uint16_t *>(stage) + 5 * r;
+        lo = make_uint4(r16[0] | ((uint32_t)r16[1] << 16), r16[2] | ((uint32_t)r16[3] << 16),
+                        r16[4] | 0x41410000u, 0x41414141u);
         hi = make_uint4(0x41414141u, 0x41414141u, 0x41414141u, 0x41414141u);
         return;
     }
@@ -434,7 +448,7 @@ __global__ void __launch_bounds__(kBlockThreads) k_pack(const PackArgs a) {
         umi_rows.load(a.umi_in, t, lane, umi_len);
     }
     while (t < n_tiles) {
-        constexpr bool kStageBc = (BC == 0 || BC == 12), kStageUmi = (UMI == 0 || UMI == 12);
+        constexpr bool kStageBc = (BC != 16 && BC != 32), kStageUmi = (UMI != 16 && UMI != 32);
         bc_rows.park(bc_stage, lane, bc_len);
         umi_rows.park(umi_stage, lane, umi_len);
         if (kStageBc || kStageUmi) __syncwarp();
@@ -615,9 +629,9 @@ static int launch_pack(ibu_gpu_ctx *ctx, PackArgs &a, cudaStream_t s, ibu_error_
     constexpr uint32_t kRows = 32 * Q;
     uint32_t off = kRows * 24;
     a.bc_stage_off = off;
-    if (BC == 0 || BC == 12) off += ((kRows * a.bc_len + 15u) & ~15u) + 16u;  // +16: funnel-shift over-read
+    if (BC != 16 && BC != 32) off += ((kRows * a.bc_len + 15u) & ~15u) + 16u;  // +16: funnel-shift over-read
     a.umi_stage_off = off;
-    if (UMI == 0 || UMI == 12) off += ((kRows * a.umi_len + 15u) & ~15u) + 16u;
+    if (UMI != 16 && UMI != 32) off += ((kRows * a.umi_len + 15u) & ~15u) + 16u;
     a.warp_smem_bytes = off;
     const size_t smem = (size_t)off * kWarpsPerBlock;
     auto kern = k_pack<BC, UMI, Q>;
@@ -694,10 +708,11 @@ int ibu_gpu_unpack_async(ibu_gpu_ctx_t *ctx, const ibu_record_t *d_records, uint
     // compile-time staged, 0 = runtime-length staged
     const int bm = (bc_len == 32 && aligned(d_bc_ascii, 32)) ? 32 : bc_len == 16 ? 16 : 0;
     const int um = (umi_len == 32 && aligned(d_umi_ascii, 32)) ? 32
-                   : umi_len == 16 ? 16 : umi_len == 12 ? 12 : 0;
+                   : umi_len == 16 ? 16 : umi_len == 12 ? 12 : umi_len == 10 ? 10 : 0;
 #define IBU_UNPACK_CASE(B, U) \
     if (bm == B && um == U) return launch_unpack<B, U>(ctx, a, s, err);
     IBU_UNPACK_CASE(16, 12) IBU_UNPACK_CASE(16, 16) IBU_UNPACK_CASE(16, 32) IBU_UNPACK_CASE(16, 0)
+    IBU_UNPACK_CASE(16, 10) IBU_UNPACK_CASE(32, 10) IBU_UNPACK_CASE(0, 10)
     IBU_UNPACK_CASE(32, 12) IBU_UNPACK_CASE(32, 16) IBU_UNPACK_CASE(32, 32) IBU_UNPACK_CASE(32, 0)
     IBU_UNPACK_CASE(0, 12) IBU_UNPACK_CASE(0, 16) IBU_UNPACK_CASE(0, 32) IBU_UNPACK_CASE(0, 0)
 #undef IBU_UNPACK_CASE
@@ -730,12 +745,13 @@ int ibu_gpu_pack_async(ibu_gpu_ctx_t *ctx, const uint8_t *d_bc_ascii, const uint
     a.bc_len = bc_len;
     a.umi_len = umi_len;
     const int bm = (bc_len == 32 && aligned(d_bc_ascii, 32)) ? 32 : bc_len == 16 ? 16 : 0;
-    const int um = (umi_len == 32 && aligned(d_umi_ascii, 32)) ? 32 : umi_len == 16 ? 16 : umi_len == 12 ? 12 : 0;
+    const int um = (umi_len == 32 && aligned(d_umi_ascii, 32)) ? 32
+                   : umi_len == 16 ? 16 : umi_len == 12 ? 12 : umi_len == 10 ? 10 : 0;
 #define IBU_PACK_CASE(B, U) \
     if (bm == B && um == U) return launch_pack<B, U>(ctx, a, s, err);
     IBU_PACK_CASE(32, 32) IBU_PACK_CASE(32, 16) IBU_PACK_CASE(32, 12) IBU_PACK_CASE(32, 0)
     IBU_PACK_CASE(16, 32) IBU_PACK_CASE(16, 16) IBU_PACK_CASE(16, 12) IBU_PACK_CASE(16, 0)
-    IBU_PACK_CASE(0, 12)
+    IBU_PACK_CASE(0, 12) IBU_PACK_CASE(16, 10) IBU_PACK_CASE(32, 10) IBU_PACK_CASE(0, 10)
     IBU_PACK_CASE(0, 32) IBU_PACK_CASE(0, 16) IBU_PACK_CASE(0, 0)
 #undef IBU_PACK_CASE
     return set_error(err, IBU_ERR_ARG, 0, 0, 0, "no pack kernel for this shape");
