@@ -27,6 +27,7 @@ struct ibu_gpu_ctx {
     std::vector<ibu_chunk_slot> slots;
     // grow-only device scratch of the blocking table builder (K4): cudaMalloc/cudaFree per call
     // would cost more than the streaming pass itself
+    std::mutex pipe_mutex;  // the chunk slots serve one host-buffer call at a time
     std::mutex arena_mutex;
     void *arena_base = nullptr;
     size_t arena_cap = 0, arena_off = 0;

@@ -10,6 +10,8 @@
 // AoS records are transposed to per-lane records through shared memory (K2) or consumed in
 // place with a lane-static field rotation (K1), decode/encode is branch-free SWAR with the
 // ACGT table held in a register (PRMT).  No tensor cores: nothing here is a contraction.
+#include <algorithm>
+
 #include "ctx.h"
 #include "kernels.cuh"
 
@@ -38,9 +40,13 @@ struct ReduceAcc {
         bm |= bit__ << (SLOT);                        \
     } while (0)
 
+// `head` records in front of the 32-byte aligned body (a record pointer is only 8-byte aligned
+// in general, e.g. a slice of a larger array) are handled with the ragged tail.
 __global__ void __launch_bounds__(kBlockThreads)
-k_validate_reduce(const uint8_t *__restrict__ recs, uint64_t n, uint64_t bc_hi, uint64_t umi_hi,
-                  ibu_reduce_result_t *__restrict__ res) {
+k_validate_reduce(const uint8_t *__restrict__ recs_all, uint64_t n_all, uint32_t head, uint64_t bc_hi,
+                  uint64_t umi_hi, ibu_reduce_result_t *__restrict__ res) {
+    const uint8_t *recs = recs_all + (uint64_t)head * 24;
+    const uint64_t n = n_all - head;
     const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
     const uint64_t gwarp = (uint64_t)blockIdx.x * kWarpsPerBlock + warp;
     const uint64_t total_warps = (uint64_t)gridDim.x * kWarpsPerBlock;
@@ -85,9 +91,11 @@ k_validate_reduce(const uint8_t *__restrict__ recs, uint64_t n, uint64_t bc_hi, 
     uint64_t n_bu = c == 0 ? acc.b1 : c == 1 ? acc.b0 : acc.b2;
     uint64_t x = acc.x, n_both = both;
 
-    if (gwarp == 0) {  // ragged tail (< 128 records), one record per lane per step
-        const uint64_t *r64 = reinterpret_cast<const uint64_t *>(recs);
-        for (uint64_t r = n_tiles * kTileRecords + lane; r < n; r += 32) {
+    if (gwarp == 0) {  // head + ragged tail (< 4 + 128 records), one record per lane per step
+        const uint64_t *r64 = reinterpret_cast<const uint64_t *>(recs_all);
+        const uint64_t tail0 = head + n_tiles * kTileRecords;
+        for (uint64_t k = lane; k < head + (n_all - tail0); k += 32) {
+            const uint64_t r = k < head ? k : tail0 + (k - head);
             uint64_t b = ldg_stream64(r64 + 3 * r), u = ldg_stream64(r64 + 3 * r + 1),
                      i = ldg_stream64(r64 + 3 * r + 2);
             s_bc += b; s_umi += u; s_idx += i; x ^= b ^ u ^ i;
@@ -122,7 +130,7 @@ k_validate_reduce(const uint8_t *__restrict__ recs, uint64_t n, uint64_t bc_hi, 
         }
     }
     if (blockIdx.x == 0 && threadIdx.x == 0)
-        atomicAdd(reinterpret_cast<unsigned long long *>(res), (unsigned long long)n);  // n_records
+        atomicAdd(reinterpret_cast<unsigned long long *>(res), (unsigned long long)n_all);  // n_records
 }
 
 // ============================================================================ K2
@@ -667,13 +675,15 @@ int ibu_gpu_validate_reduce_async(ibu_gpu_ctx_t *ctx, const ibu_record_t *d_reco
     clear_error(err);
     if (!ctx || !d_result || (!d_records && n)) return set_error(err, IBU_ERR_ARG, 0, 0, 0, "null argument");
     if (int rc = check_lens(bc_len, umi_len, err)) return rc;
-    if (!aligned(d_records, 32)) return set_error(err, IBU_ERR_ARG, 0, 0, 0, "d_records must be 32-byte aligned");
+    if (!aligned(d_records, 8)) return set_error(err, IBU_ERR_ARG, 0, 0, 0, "d_records must be 8-byte aligned");
     DeviceGuard guard(ctx->device);
     cudaStream_t s = pick_stream(ctx, stream);
     IBU_CUDA(cudaMemsetAsync(d_result, 0, sizeof(*d_result), s));
-    int grid = grid_for(ctx, (const void *)k_validate_reduce, 0, n / kTileRecords, err);
+    // records until the next 32-byte boundary: 24 h = -p (mod 32)  <=>  h = (p / 8) mod 4
+    const uint32_t head = (uint32_t)std::min<uint64_t>(n, ((uintptr_t)d_records >> 3) & 3u);
+    int grid = grid_for(ctx, (const void *)k_validate_reduce, 0, (n - head) / kTileRecords, err);
     if (grid < 0) return -grid;
-    k_validate_reduce<<<grid, kBlockThreads, 0, s>>>((const uint8_t *)d_records, n, high_mask(bc_len),
+    k_validate_reduce<<<grid, kBlockThreads, 0, s>>>((const uint8_t *)d_records, n, head, high_mask(bc_len),
                                                      high_mask(umi_len), d_result);
     g_launches.fetch_add(1, std::memory_order_relaxed);
     IBU_CUDA(cudaGetLastError());

@@ -232,6 +232,7 @@ int process_host_records(ibu_gpu_ctx *ctx, const ibu_record_t *h_records, uint64
                          ibu_chunk_cb on_chunk, void *user, ibu_error_t *err, int fd = -1,
                          uint64_t file_off = 0) {
     DeviceGuard guard(ctx->device);
+    std::lock_guard<std::mutex> lock(ctx->pipe_mutex);
     memset(h_result, 0, sizeof(*h_result));
     if (n == 0) return IBU_OK;  // an empty range never calls on_batch_complete (mmap.rs:502-519)
     const uint64_t chunk = chunk_records(ctx);
@@ -500,6 +501,7 @@ int ibu_gpu_load_to_device(ibu_gpu_ctx_t *ctx, const char *path, uint64_t start,
         return rc;
     }
     DeviceGuard guard(ctx->device);
+    std::lock_guard<std::mutex> lock(ctx->pipe_mutex);
     const uint64_t count = end - start;
     void *dev = nullptr;
     cudaError_t e = cudaMalloc(&dev, count ? count * IBU_RECORD_SIZE : kAlign);
@@ -555,6 +557,7 @@ int ibu_gpu_write_records(ibu_gpu_ctx_t *ctx, ibu_writer_t *writer, const ibu_re
     if (!ctx || !writer || (!d_records && n)) return set_error(err, IBU_ERR_ARG, 0, 0, 0, "null argument");
     if (n == 0) return IBU_OK;
     DeviceGuard guard(ctx->device);
+    std::lock_guard<std::mutex> lock(ctx->pipe_mutex);
     const uint64_t chunk = chunk_records(ctx);
     const uint64_t n_chunks = (n + chunk - 1) / chunk;
     const size_t n_slots = ctx->slots.size();
@@ -595,6 +598,7 @@ int ibu_gpu_unpack_host(ibu_gpu_ctx_t *ctx, const ibu_record_t *h_records, uint6
     if (h_result) *h_result = total;
     if (n == 0) return IBU_OK;
     DeviceGuard guard(ctx->device);
+    std::lock_guard<std::mutex> lock(ctx->pipe_mutex);
     const uint64_t chunk = chunk_records(ctx);
     const uint64_t n_chunks = (n + chunk - 1) / chunk;
     const bool pin_in = is_pinned(h_records), pin_bc = is_pinned(h_bc_ascii), pin_umi = is_pinned(h_umi_ascii),
@@ -643,6 +647,7 @@ int ibu_gpu_pack_host(ibu_gpu_ctx_t *ctx, const uint8_t *h_bc_ascii, const uint8
     if (h_result) *h_result = total;
     if (n == 0) return IBU_OK;
     DeviceGuard guard(ctx->device);
+    std::lock_guard<std::mutex> lock(ctx->pipe_mutex);
     const uint64_t chunk = chunk_records(ctx);
     const uint64_t n_chunks = (n + chunk - 1) / chunk;
     const bool pin_bc = is_pinned(h_bc_ascii), pin_umi = is_pinned(h_umi_ascii),

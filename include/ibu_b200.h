@@ -209,8 +209,8 @@ typedef struct ibu_reduce_result {
     uint64_t n_bad_records;
 } ibu_reduce_result_t;
 
-/* K1: validate + reduce over device-resident records.  d_records must be
- * 16-byte aligned.  *d_result (device) is OVERWRITTEN with this pass's values. */
+/* K1: validate + reduce over device-resident records (any 8-byte aligned record
+ * pointer, e.g. a slice).  *d_result (device) is OVERWRITTEN with this pass's values. */
 int ibu_gpu_validate_reduce_async(ibu_gpu_ctx_t *ctx, const ibu_record_t *d_records,
                                   uint64_t n, uint32_t bc_len, uint32_t umi_len,
                                   ibu_reduce_result_t *d_result, void *stream,
