@@ -387,6 +387,48 @@ class GpuContext:
         return recs, ReduceResult(res.as_dict())
 
 
+class GpuStream:
+    """Streaming ingest: the reference's `Reader<R>` (src/io/reader.rs:152-306) feeding the GPU.
+    Push the bytes of an .ibu stream in pieces of any size; `finish()` returns the reduction."""
+
+    def __init__(self, ctx: GpuContext):
+        self._h = C.c_void_p()
+        err = _lib.Error()
+        _check(lib.ibu_gpu_stream_open(ctx._h, C.byref(self._h), C.byref(err)), err)
+
+    def push(self, data):
+        buf = np.frombuffer(data, dtype=np.uint8) if not isinstance(data, np.ndarray) else data.view(np.uint8).reshape(-1)
+        err = _lib.Error()
+        _check(lib.ibu_gpu_stream_push(self._h, _ptr(np.ascontiguousarray(buf)), buf.size, C.byref(err)), err)
+
+    def header(self) -> Header:
+        h, err = _lib.Header(), _lib.Error()
+        _check(lib.ibu_gpu_stream_header(self._h, C.byref(h), C.byref(err)), err)
+        return Header._wrap(h)
+
+    def finish(self) -> ReduceResult:
+        res, err = _lib.ReduceResult(), _lib.Error()
+        _check(lib.ibu_gpu_stream_finish(self._h, C.byref(res), C.byref(err)), err)
+        return ReduceResult(res.as_dict())
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib.ibu_gpu_stream_close(self._h)
+            self._h = C.c_void_p()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 def _as_records(a) -> np.ndarray:
     if isinstance(a, np.ndarray) and a.dtype == RECORD_DTYPE and a.flags.c_contiguous:
         return a

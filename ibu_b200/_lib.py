@@ -111,6 +111,11 @@ SIGNATURES = {
     "ibu_mmap_unpin": (None, [_vp]),
     "ibu_gpu_process_mmap": (_int, [_vp, _vp, _u64, _u64, _P(ReduceResult), CHUNK_CB, _vp, _err]),
     "ibu_gpu_process_host": (_int, [_vp, _vp, _u64, _u32, _u32, _P(ReduceResult), CHUNK_CB, _vp, _err]),
+    "ibu_gpu_stream_open": (_int, [_vp, _P(_vp), _err]),
+    "ibu_gpu_stream_push": (_int, [_vp, _vp, _sz, _err]),
+    "ibu_gpu_stream_header": (_int, [_vp, _P(Header), _err]),
+    "ibu_gpu_stream_finish": (_int, [_vp, _P(ReduceResult), _err]),
+    "ibu_gpu_stream_close": (None, [_vp]),
     "ibu_gpu_load_to_device": (_int, [_vp, C.c_char_p, _u64, _u64, _P(Header), _P(_vp), _P(_u64), _err]),
     "ibu_gpu_write_records": (_int, [_vp, _vp, _vp, _u64, _err]),
     "ibu_gpu_unpack_host": (_int, [_vp, _vp, _u64, _u32, _u32, _vp, _vp, _vp, _P(ReduceResult), _err]),

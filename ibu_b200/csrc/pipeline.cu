@@ -13,6 +13,7 @@
 #include <cerrno>
 #include <cstdlib>
 #include <fcntl.h>
+#include <mutex>
 #include <thread>
 #include <unistd.h>
 
@@ -479,6 +480,165 @@ int ibu_gpu_process_mmap(ibu_gpu_ctx_t *ctx, const ibu_mmap_reader_t *reader, ui
     return process_host_records(ctx, recs, end - start, reader->header.bc_len, reader->header.umi_len,
                                 start, h_result, on_chunk, user, err, fd,
                                 IBU_HEADER_SIZE + start * IBU_RECORD_SIZE);
+}
+
+// ---- streaming ingest ----------------------------------------------------------------------
+
+struct ibu_gpu_stream {
+    ibu_gpu_ctx *ctx = nullptr;
+    std::unique_lock<std::mutex> lock;  // the context's slots are ours until close
+    uint8_t header_bytes[IBU_HEADER_SIZE];
+    size_t header_have = 0;
+    ibu_header_t header{};
+    uint64_t chunk_bytes = 0;
+    size_t slot = 0, fill = 0;        // slot being filled, bytes already in its pinned buffer
+    std::vector<char> busy;           // slot has a chunk in flight
+    uint64_t records_submitted = 0;
+    ibu_reduce_result_t total{};
+    bool failed = false;
+};
+
+namespace {
+
+int stream_drain(ibu_gpu_stream *st, size_t s, ibu_error_t *err) {
+    if (!st->busy[s]) return IBU_OK;
+    ibu_chunk_slot &slot = st->ctx->slots[s];
+    IBU_CUDA(cudaEventSynchronize(slot.done));
+    merge(st->total, *slot.h_result);
+    st->busy[s] = 0;
+    return IBU_OK;
+}
+
+// enqueue the records gathered in the current slot and move on to the next one
+int stream_submit(ibu_gpu_stream *st, ibu_error_t *err) {
+    ibu_gpu_ctx *ctx = st->ctx;
+    ibu_chunk_slot &slot = ctx->slots[st->slot];
+    const uint64_t n = st->fill / IBU_RECORD_SIZE;
+    if (n) {
+        if (int rc = ensure(&slot.d_in, &slot.d_in_bytes, align_up(st->chunk_bytes), false, err)) return rc;
+        IBU_CUDA(cudaMemcpyAsync(slot.d_in, slot.h_in, n * IBU_RECORD_SIZE, cudaMemcpyHostToDevice, slot.stream));
+        if (int rc = ibu_gpu_validate_reduce_async(ctx, (const ibu_record_t *)slot.d_in, n, st->header.bc_len,
+                                                   st->header.umi_len, slot.d_result, slot.stream, err))
+            return rc;
+        IBU_CUDA(cudaMemcpyAsync(slot.h_result, slot.d_result, sizeof(ibu_reduce_result_t), cudaMemcpyDeviceToHost,
+                                 slot.stream));
+        IBU_CUDA(cudaEventRecord(slot.done, slot.stream));
+        st->busy[st->slot] = 1;
+        st->records_submitted += n;
+    }
+    // the bytes of an incomplete record move to the front of the next slot's buffer
+    const size_t rest = st->fill - n * IBU_RECORD_SIZE;
+    const size_t next = (st->slot + 1) % ctx->slots.size();
+    if (int rc = stream_drain(st, next, err)) return rc;
+    ibu_chunk_slot &ns = ctx->slots[next];
+    if (int rc = ensure(&ns.h_in, &ns.h_in_bytes, align_up(st->chunk_bytes), true, err)) return rc;
+    if (rest) memcpy(ns.h_in, (uint8_t *)slot.h_in + n * IBU_RECORD_SIZE, rest);
+    st->slot = next;
+    st->fill = rest;
+    return IBU_OK;
+}
+
+}  // namespace
+
+int ibu_gpu_stream_open(ibu_gpu_ctx_t *ctx, ibu_gpu_stream_t **out, ibu_error_t *err) {
+    clear_error(err);
+    if (!ctx || !out) return set_error(err, IBU_ERR_ARG, 0, 0, 0, "null argument");
+    *out = nullptr;
+    std::unique_lock<std::mutex> lock(ctx->pipe_mutex, std::try_to_lock);
+    if (!lock.owns_lock())
+        return set_error(err, IBU_ERR_ARG, 0, 0, 0, "context busy: another stream or host-buffer call is active");
+    auto *st = new (std::nothrow) ibu_gpu_stream;
+    if (!st) return set_error(err, IBU_ERR_NOMEM, 0, 0, 0, "out of memory");
+    st->ctx = ctx;
+    st->lock = std::move(lock);
+    st->chunk_bytes = chunk_records(ctx) * IBU_RECORD_SIZE;
+    st->busy.assign(ctx->slots.size(), 0);
+    DeviceGuard guard(ctx->device);
+    ibu_chunk_slot &slot = ctx->slots[0];
+    if (int rc = ensure(&slot.h_in, &slot.h_in_bytes, align_up(st->chunk_bytes), true, err)) {
+        delete st;
+        return rc;
+    }
+    *out = st;
+    return IBU_OK;
+}
+
+int ibu_gpu_stream_push(ibu_gpu_stream_t *st, const void *bytes, size_t len, ibu_error_t *err) {
+    clear_error(err);
+    if (!st || (!bytes && len)) return set_error(err, IBU_ERR_ARG, 0, 0, 0, "null argument");
+    if (st->failed) return set_error(err, IBU_ERR_ARG, 0, 0, 0, "stream already failed");
+    DeviceGuard guard(st->ctx->device);
+    const uint8_t *p = (const uint8_t *)bytes;
+    if (st->header_have < IBU_HEADER_SIZE) {  // Reader::new: read_exact(32), then validate
+        const size_t take = std::min(len, (size_t)IBU_HEADER_SIZE - st->header_have);
+        memcpy(st->header_bytes + st->header_have, p, take);
+        st->header_have += take;
+        p += take;
+        len -= take;
+        if (st->header_have < IBU_HEADER_SIZE) return IBU_OK;
+        memcpy(&st->header, st->header_bytes, IBU_HEADER_SIZE);
+        if (int rc = ibu_header_validate(&st->header, err)) {
+            st->failed = true;
+            return rc;
+        }
+    }
+    const unsigned threads = copy_threads(st->ctx);
+    while (len) {
+        ibu_chunk_slot &slot = st->ctx->slots[st->slot];
+        const size_t take = std::min<size_t>(len, st->chunk_bytes - st->fill);
+        parallel_memcpy((uint8_t *)slot.h_in + st->fill, p, take, threads);
+        st->fill += take;
+        p += take;
+        len -= take;
+        if (st->fill == st->chunk_bytes) {
+            if (int rc = stream_submit(st, err)) {
+                st->failed = true;
+                return rc;
+            }
+        }
+    }
+    return IBU_OK;
+}
+
+int ibu_gpu_stream_header(const ibu_gpu_stream_t *st, ibu_header_t *header, ibu_error_t *err) {
+    clear_error(err);
+    if (!st || !header) return set_error(err, IBU_ERR_ARG, 0, 0, 0, "null argument");
+    if (st->header_have < IBU_HEADER_SIZE || st->failed)
+        return set_error(err, IBU_ERR_ARG, 0, 0, 0, "no valid header yet");
+    *header = st->header;
+    return IBU_OK;
+}
+
+int ibu_gpu_stream_finish(ibu_gpu_stream_t *st, ibu_reduce_result_t *h_result, ibu_error_t *err) {
+    clear_error(err);
+    if (!st || !h_result) return set_error(err, IBU_ERR_ARG, 0, 0, 0, "null argument");
+    memset(h_result, 0, sizeof(*h_result));
+    if (st->failed) return set_error(err, IBU_ERR_ARG, 0, 0, 0, "stream already failed");
+    if (st->header_have < IBU_HEADER_SIZE)  // read_exact on a short stream: UnexpectedEof
+        return set_error(err, IBU_ERR_IO, EIO, st->header_have, 0, "I/O error: stream ended inside the 32-byte header");
+    DeviceGuard guard(st->ctx->device);
+    const size_t rest = st->fill % IBU_RECORD_SIZE;
+    int rc = stream_submit(st, err);
+    for (size_t s = 0; s < st->busy.size() && rc == IBU_OK; s++) rc = stream_drain(st, s, err);
+    st->failed = true;  // finished: no more pushes
+    if (rc != IBU_OK) return rc;
+    *h_result = st->total;
+    if (rest) {
+        const uint64_t pos = IBU_HEADER_SIZE + st->records_submitted * IBU_RECORD_SIZE;
+        return set_error(err, IBU_ERR_TRUNCATED_RECORD, 0, pos, 0, "Truncated record at position %llu",
+                         (unsigned long long)pos);
+    }
+    return IBU_OK;
+}
+
+void ibu_gpu_stream_close(ibu_gpu_stream_t *st) {
+    if (!st) return;
+    {
+        DeviceGuard guard(st->ctx->device);
+        for (auto &slot : st->ctx->slots)
+            if (cudaStreamSynchronize(slot.stream) != cudaSuccess) cudaGetLastError();
+    }
+    delete st;  // releases the context's pipeline lock
 }
 
 // ---- device path of load_to_vec -----------------------------------------------------------

@@ -339,6 +339,23 @@ int ibu_gpu_process_host(ibu_gpu_ctx_t *ctx, const ibu_record_t *h_records, uint
                          uint32_t bc_len, uint32_t umi_len, ibu_reduce_result_t *h_result,
                          ibu_chunk_cb on_chunk, void *user, ibu_error_t *err);
 
+/* Streaming ingest — the Reader<R> of src/io/reader.rs feeding the GPU.
+ * The bytes of an .ibu stream (header first) are pushed in pieces of any size, from any source
+ * (stdin, a decompressor, a socket): the first 32 bytes are parsed and validated like
+ * Reader::new (reader.rs:152-176); record bytes are gathered into pinned chunks and each full
+ * chunk goes H2D -> K1 on the next slot's stream while the caller keeps pushing.  One stream
+ * (or host-buffer call) per context at a time: open fails with IBU_ERR_ARG while another is
+ * active.  finish() flushes the last partial chunk and returns the merged result; trailing
+ * bytes that do not make a whole record give IBU_ERR_TRUNCATED_RECORD with a = byte position
+ * of the incomplete record (reader.rs:232-237), a stream shorter than a header IBU_ERR_IO. */
+typedef struct ibu_gpu_stream ibu_gpu_stream_t;
+int ibu_gpu_stream_open(ibu_gpu_ctx_t *ctx, ibu_gpu_stream_t **out, ibu_error_t *err);
+int ibu_gpu_stream_push(ibu_gpu_stream_t *st, const void *bytes, size_t len, ibu_error_t *err);
+/* valid once 32 bytes have been pushed; returns IBU_ERR_ARG before that */
+int ibu_gpu_stream_header(const ibu_gpu_stream_t *st, ibu_header_t *header, ibu_error_t *err);
+int ibu_gpu_stream_finish(ibu_gpu_stream_t *st, ibu_reduce_result_t *h_result, ibu_error_t *err);
+void ibu_gpu_stream_close(ibu_gpu_stream_t *st);
+
 /* Device path of load_to_vec (src/io/reader.rs:510-535): header validated, size
  * checked, records [start,end) of the file land in one device allocation
  * (*d_records, release with ibu_gpu_free).  end = UINT64_MAX means "to the end". */

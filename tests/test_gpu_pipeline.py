@@ -178,3 +178,49 @@ def test_sort_on_device_and_write_sorted_file(ctx, tmp_path, n):
     ctx.free(out)
     d.free()
     assert ibu.MmapReader(dst).header().sorted()
+
+
+# ---- streaming ingest: the Reader<R> semantics (reader.rs:152-306) on the GPU path --------------------
+@pytest.mark.parametrize("n", [0, 1, 1000, (1 << 18), (1 << 18) * 2 + 12345])
+@pytest.mark.parametrize("piece", [1 << 20, 4097, 24 * 1000 + 7])
+def test_stream_ingest_matches_oracle(ctx, n, piece):
+    recs = oc.generate_records(0, n, 16, 12, 1, 30_000, 51)
+    data = on.file_bytes(16, 12, recs)
+    with ibu.GpuStream(ctx) as st:
+        for off in range(0, len(data), piece):  # pieces cut anywhere: mid-header, mid-record
+            st.push(data[off:off + piece])
+        assert st.header().as_bytes() == data[:32]
+        got = st.finish()
+    assert got == oc.reduce_records(recs, 16, 12)
+
+
+def test_stream_ingest_errors(ctx):
+    good = on.file_bytes(16, 12, oc.generate_records(0, 10, 16, 12, 0, 0, 52))
+    with ibu.GpuStream(ctx) as st:  # reader.rs:618-636: truncated record
+        st.push(good[:-5])
+        with pytest.raises(ibu.TruncatedRecord) as e:
+            st.finish()
+        assert e.value.pos == 32 + 24 * 9
+    with pytest.raises(oc.OracleError) as oe:  # the oracle reports the same position for 1 record - 5 bytes
+        oc.stream_first(good[:32 + 24 - 5])
+    assert oe.value.variant == "TruncatedRecord" and oe.value.a == 32
+    with ibu.GpuStream(ctx) as st:
+        st.push(good[:32 + 24 - 5])
+        with pytest.raises(ibu.TruncatedRecord) as e:
+            st.finish()
+        assert e.value.pos == 32
+    bad = bytearray(good)
+    bad[0] = 0
+    with ibu.GpuStream(ctx) as st:  # Reader::new validates the header first
+        with pytest.raises(ibu.InvalidMagicNumber):
+            st.push(bytes(bad))
+    with ibu.GpuStream(ctx) as st:  # shorter than a header: read_exact fails
+        st.push(good[:20])
+        with pytest.raises(ibu.Io):
+            st.finish()
+    with ibu.GpuStream(ctx) as st:  # one stream per context at a time
+        with pytest.raises(ibu.ArgError):
+            ibu.GpuStream(ctx)
+        st.push(good)
+        assert st.finish()["n_records"] == 10
+    assert ctx.process_host(np.frombuffer(good[32:], ibu.RECORD_DTYPE), 16, 12)["n_records"] == 10  # lock released
