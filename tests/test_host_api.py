@@ -182,3 +182,78 @@ def test_gpu_entry_points_fail_loudly_without_a_device():
         pytest.skip("a GPU is present")
     with pytest.raises(ibu.CudaError):
         ibu.GpuContext(0)
+
+
+# ---- the reference's own writer / error tests, asked of the product library -----------------------
+def test_writer_reference_tests(tmp_path):  # writer.rs:629-760
+    p = str(tmp_path / "w.ibu")
+    w = ibu.Writer(p, ibu.Header(16, 12))  # test_writer_creation: header written immediately
+    assert w.records_written() == 0 and os.path.getsize(p) == 32
+    w.write_record(0x1234, 0x5678, 42)  # test_single_record_write
+    assert w.records_written() == 1 and os.path.getsize(p) == 32  # still buffered
+    w.finish()
+    assert os.path.getsize(p) == 32 + 24
+    w.write_batch(pattern(3))  # test_batch_write
+    assert w.records_written() == 4
+    w.close()
+    assert os.path.getsize(p) == 32 + 4 * 24
+    q = str(tmp_path / "h.bin")
+    w = ibu.Writer(q, None)  # test_writer_headless
+    assert w.records_written() == 0 and os.path.getsize(q) == 0
+    w.close()
+    w = ibu.Writer(p, ibu.Header(16, 12))  # test_buffer_flushing: 48 Ki records fill the buffer exactly
+    full = 48 * 1024
+    w.write_iter((i, 0, 0) for i in range(full))
+    assert os.path.getsize(p) == 32  # not flushed yet
+    w.write_record(999, 0, 0)  # one more record triggers the flush
+    assert os.path.getsize(p) == 32 + full * 24
+    w.write_batch(pattern(100_000))  # test_large_batch_direct_write: bypasses the buffer, after flushing it
+    assert w.records_written() == full + 1 + 100_000
+    assert os.path.getsize(p) == 32 + (full + 1 + 100_000) * 24
+    w.close()
+    w = ibu.Writer(p, ibu.Header(20, 10))  # test_writer_roundtrip
+    r = ibu.records(2)
+    r[0], r[1] = (0x12345, 0x67890, 100), (0xABCDE, 0xF0123, 200)
+    w.write_batch(r)
+    w.close()  # Drop flushes (writer.rs:519-523)
+    h, got = ibu.load_to_vec(p)
+    assert (h.bc_len, h.umi_len) == (20, 10) and np.array_equal(got, r)
+    bad = ibu.Header(0, 99)  # Writer::new does not validate the header (writer.rs:129-133)
+    with ibu.Writer(p, bad):
+        pass
+    with pytest.raises(ibu.InvalidBarcodeLength):
+        ibu.MmapReader(p)
+
+
+def test_error_display_messages(tmp_path):  # error.rs:179-260: Display strings carry the payload
+    raw = bytearray(ibu.Header(16, 12).as_bytes())
+    raw[0:4] = (0x12345678).to_bytes(4, "little")
+    with pytest.raises(ibu.IbuError) as e:
+        ibu.Header.from_bytes(bytes(raw)).validate()
+    assert "0x21554249" in str(e.value) and "0x12345678" in str(e.value)
+    raw = bytearray(ibu.Header(16, 12).as_bytes())
+    raw[4:8] = (1).to_bytes(4, "little")
+    with pytest.raises(ibu.IbuError) as e:
+        ibu.Header.from_bytes(bytes(raw)).validate()
+    assert "expected (2)" in str(e.value) and "found (1)" in str(e.value)
+    with pytest.raises(ibu.IbuError) as e:
+        ibu.Header(33, 12).validate()
+    assert "33" in str(e.value) and "1-32" in str(e.value)
+    with pytest.raises(ibu.IbuError) as e:
+        ibu.Header(16, 0).validate()
+    assert "0" in str(e.value) and "1-32" in str(e.value)
+    p = str(tmp_path / "x.ibu")
+    with ibu.Writer(p, ibu.Header(16, 12)) as w:
+        w.write_batch(pattern(50))
+    with open(p, "r+b") as f:
+        f.truncate(32 + 24 * 50 - 1)
+    with pytest.raises(ibu.IbuError) as e:
+        ibu.MmapReader(p)
+    assert "not a multiple" in str(e.value)
+    with open(p, "r+b") as f:
+        f.truncate(32 + 24 * 50 - 24)
+    with pytest.raises(ibu.IbuError) as e:
+        ibu.MmapReader(p).slice(0, 100)
+    assert "100" in str(e.value) and "49" in str(e.value)
+    for code, text in [(1, "I/O error"), (8, "not a multiple"), (10, "Processing error")]:
+        assert text in _lib.lib.ibu_strerror(code).decode()
