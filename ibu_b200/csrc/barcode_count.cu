@@ -551,6 +551,10 @@ k_radix_scatter(const uint64_t *__restrict__ in, uint64_t *__restrict__ out, uin
 // detected on a sample and goes straight to the radix sort instead.
 #define kHashEmpty 0xFFFFFFFFFFFFFFFFull
 constexpr uint32_t kHashMaxProbe = 256;
+// start size / growth factor: 1-8 Mi slots and x2 / x4 all measured within 10 % of each other on
+// 10^9 records (the insert rate is bound by L2 transactions: one 16-byte read + one RED per record)
+constexpr uint64_t kHashStartSlots = 8ull << 20;
+constexpr uint64_t kHashGrowth = 4;
 
 struct HashArgs {
     const uint64_t *recs;
@@ -975,7 +979,7 @@ static int hash_aggregate(ibu_gpu_ctx *ctx, const uint64_t *recs, uint64_t n, bo
     IBU_CUDA(sc.alloc(&ctr, 4 * 8));
     // 8 Mi slots = 256 MiB to start with: the hot part of a low-cardinality table then stays
     // inside L2 and TLB reach (a 1 GiB start measured 40 % slower on the reference pattern)
-    uint64_t slots = std::max<uint64_t>(1024, std::min<uint64_t>(pow2_ceil(2 * n), 8ull << 20));
+    uint64_t slots = std::max<uint64_t>(1024, std::min<uint64_t>(pow2_ceil(2 * n), kHashStartSlots));
     uint64_t *table;
     IBU_CUDA(sc.alloc(&table, slots * 32));
     IBU_CUDA(cudaMemsetAsync(table, 0xFF, slots * 32, s));
@@ -1011,7 +1015,7 @@ static int hash_aggregate(ibu_gpu_ctx *ctx, const uint64_t *recs, uint64_t n, bo
         }
         if (pos >= n) break;
         if (h[0] > slots / 10 * 7) {  // past 0.7 load: grow x4 and re-hash what is there
-            const uint64_t bigger = slots * 4;
+            const uint64_t bigger = slots * kHashGrowth;
             if (bigger > (1ull << 31)) {
                 *use_sort = true;
                 return IBU_OK;

@@ -6,7 +6,8 @@
 //   generators             synthetic inputs shared with the oracle
 //
 // All three are HBM-bound streamers: every global access is a 128/256-bit fully coalesced
-// vector access of read-once / write-once data (L1 no-allocate, L2 evict-first), the 24-byte
+// vector access of read-once / write-once data (loads: L1 no-allocate, L2 evict-first on the
+// 256-bit ones; stores: plain write-back, measured fastest), the 24-byte
 // AoS records are transposed to per-lane records through shared memory (K2) or consumed in
 // place with a lane-static field rotation (K1), decode/encode is branch-free SWAR with the
 // ACGT table held in a register (PRMT).  No tensor cores: nothing here is a contraction.

@@ -256,10 +256,15 @@ typedef struct ibu_barcode_table {
     uint32_t reserved;
 } ibu_barcode_table_t;
 
-/* Blocking (the table size is data dependent).  mode: 0 = auto (verify
- * sortedness on device, stream if sorted else sort-then-segment),
- * 1 = require sorted (IBU_ERR_ARG-free: returns input_was_sorted = 0 and no rows
- * if the data is not sorted), 2 = force the unsorted path. */
+/* Blocking (the table size is data dependent).  d_records must be 32-byte aligned.
+ * mode 0 = auto: one streaming pass that also verifies the (barcode, umi) order
+ *          (the header's `sorted` flag is advisory: examples/parallel.rs:52-53 sets it on
+ *          unsorted data); if the order does not hold, the records are hash-aggregated
+ *          into distinct pairs (or radix sorted when nearly all pairs are distinct) and
+ *          the pairs are counted;
+ * mode 1 = streaming pass only: unsorted input is not an error, it returns
+ *          input_was_sorted = 0 and no rows;
+ * mode 2 = skip the streaming attempt. */
 int ibu_gpu_barcode_count(ibu_gpu_ctx_t *ctx, const ibu_record_t *d_records, uint64_t n,
                           int mode, ibu_barcode_table_t *table, void *stream,
                           ibu_error_t *err);

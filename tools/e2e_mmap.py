@@ -74,10 +74,20 @@ def main():
     t0 = time.perf_counter()
     hd, d = ibu.load_to_device(ctx, path)
     t_dev = time.perf_counter() - t0
+    for rep in range(2):  # configs[3]: per-barcode record / distinct-UMI table of the loaded file
+        t0 = time.perf_counter()
+        rows, info = ctx.barcode_count(d, len(d))
+        t_tab = time.perf_counter() - t0
+    print(json.dumps(dict(stage="gpu barcode_count of the loaded file", sec=t_tab, grec_s=n / t_tab / 1e9,
+                          rows=len(rows), pairs=info["n_distinct_pairs"], sorted=info["input_was_sorted"],
+                          closed_form_ok=bool(len(rows) == min(n, 1_000_000) and int(rows["n_records"].sum()) == n
+                                              and bool((rows["n_distinct_umi"] == 1).all())))), flush=True)
     d.free()
-    t0 = time.perf_counter()
-    hv, v = ibu.load_to_vec(path)
-    t_vec = time.perf_counter() - t0
+    t_vec = float("nan")
+    if n <= 200_000_000:
+        t0 = time.perf_counter()
+        hv, v = ibu.load_to_vec(path)
+        t_vec = time.perf_counter() - t0
     print(json.dumps(dict(stage="load_to_device vs load_to_vec", dev_sec=t_dev, dev_gb_s=24 * n / t_dev / 1e9,
                           vec_sec=t_vec, vec_gb_s=24 * n / t_vec / 1e9)), flush=True)
     ctx.close()
