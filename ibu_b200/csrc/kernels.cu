@@ -1,7 +1,7 @@
 // kernels.cu — sm_100a kernels of the bulk record path and their stream-ordered launchers.
 //
 //   K1 k_validate_reduce   24 B/record read            built-in reductions of process_parallel
-//   K2 k_unpack            24 + bc_len + umi_len B     2-bit -> ASCII + validation
+//   K2 k_unpack            24 + bc_len + umi_len B     2-bit -> ASCII + validation + K1's reductions
 //   K3 k_pack              bc_len + umi_len + 24 B     ASCII -> Record + validation
 //   generators             synthetic inputs shared with the oracle
 //
@@ -12,6 +12,7 @@
 // place with a lane-static field rotation (K1), decode/encode is branch-free SWAR with the
 // ACGT table held in a register (PRMT).  No tensor cores: nothing here is a contraction.
 #include <algorithm>
+#include <cstdlib>
 
 #include "ctx.h"
 #include "kernels.cuh"
@@ -220,7 +221,7 @@ __device__ __forceinline__ void copy_out_stage(uint32_t len, uint8_t *gout, uint
     for (uint32_t i = lane; i < n16; i += 32) stg_stream(dst + i, src[i]);
 }
 
-template <int BC, int UMI>
+template <int BC, int UMI, bool SUMS>
 __global__ void __launch_bounds__(kBlockThreads) k_unpack(const UnpackArgs a) {
     extern __shared__ __align__(16) uint8_t smem[];
     const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
@@ -233,6 +234,7 @@ __global__ void __launch_bounds__(kBlockThreads) k_unpack(const UnpackArgs a) {
     const uint32_t bc_len = LenOf<BC>::get(a.bc_len), umi_len = LenOf<UMI>::get(a.umi_len);
 
     uint32_t n_bb = 0, n_bu = 0, n_br = 0;
+    uint64_t s_bc = 0, s_umi = 0, s_idx = 0, x_all = 0;
     const uint64_t n_tiles = a.n / kTileRecords;
     const uint4 *g4 = reinterpret_cast<const uint4 *>(a.recs);
 
@@ -262,6 +264,10 @@ __global__ void __launch_bounds__(kBlockThreads) k_unpack(const UnpackArgs a) {
             const uint32_t bb = (bc & a.bc_hi) != 0ull, bu = (umi & a.umi_hi) != 0ull;
             n_bb += bb; n_bu += bu; n_br += (bb | bu);
             if (a.flags) a.flags[rec] = (uint8_t)(bb | (bu << 1));
+            if (SUMS) {  // the reference processors' sums / checksum ride along (the tile is on chip)
+                const uint64_t idx = in64[3 * r + 2];
+                s_bc += bc; s_umi += umi; s_idx += idx; x_all ^= bc ^ umi ^ idx;
+            }
         }
         __syncwarp();
         copy_out_stage<BC>(bc_len, a.bc_out, t, bc_stage, lane);
@@ -281,6 +287,10 @@ __global__ void __launch_bounds__(kBlockThreads) k_unpack(const UnpackArgs a) {
             const uint32_t bb = (bc & a.bc_hi) != 0ull, bu = (umi & a.umi_hi) != 0ull;
             n_bb += bb; n_bu += bu; n_br += (bb | bu);
             if (a.flags) a.flags[rec] = (uint8_t)(bb | (bu << 1));
+            if (SUMS) {
+                const uint64_t idx = ldg_stream64(r64 + 3 * rec + 2);
+                s_bc += bc; s_umi += umi; s_idx += idx; x_all ^= bc ^ umi ^ idx;
+            }
         }
     }
 
@@ -294,6 +304,21 @@ __global__ void __launch_bounds__(kBlockThreads) k_unpack(const UnpackArgs a) {
             if (n_bu) atomicAdd(out + 6, (unsigned long long)n_bu);
             if (n_br) atomicAdd(out + 7, (unsigned long long)n_br);
             if (gwarp == 0) atomicAdd(out, (unsigned long long)a.n);
+        }
+        if (SUMS) {  // warp -> block -> one atomic per word per CTA
+            __shared__ uint64_t red[kWarpsPerBlock][4];
+            s_bc = warp_sum64(s_bc); s_umi = warp_sum64(s_umi); s_idx = warp_sum64(s_idx);
+            x_all = warp_xor64(x_all);
+            if (lane == 0) { red[warp][0] = s_bc; red[warp][1] = s_umi; red[warp][2] = s_idx; red[warp][3] = x_all; }
+            __syncthreads();
+            if (threadIdx.x < 4) {
+                uint64_t v = 0;
+                for (int w = 0; w < kWarpsPerBlock; w++) {
+                    if (threadIdx.x == 3) v ^= red[w][3]; else v += red[w][threadIdx.x];
+                }
+                if (threadIdx.x == 3) atomicXor(out + 4, (unsigned long long)v);
+                else atomicAdd(out + 1 + threadIdx.x, (unsigned long long)v);
+            }
         }
     }
 }
@@ -620,7 +645,8 @@ static int launch_unpack(ibu_gpu_ctx *ctx, UnpackArgs &a, cudaStream_t s, ibu_er
     if (!(UMI == 32 || UMI == 16)) off += (kTileRecords * a.umi_len + 15u) & ~15u;
     a.warp_smem_bytes = off;
     const size_t smem = (size_t)off * kWarpsPerBlock;
-    auto kern = k_unpack<BC, UMI>;
+    // with a result block the pass also carries K1's sums / checksum (measured cost: 0.2 %)
+    auto kern = a.res ? k_unpack<BC, UMI, true> : k_unpack<BC, UMI, false>;
     IBU_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int grid = grid_for(ctx, (const void *)kern, smem, a.n / kTileRecords, err);
     if (grid < 0) return -grid;

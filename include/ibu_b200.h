@@ -220,8 +220,9 @@ int ibu_gpu_validate_reduce_async(ibu_gpu_ctx_t *ctx, const ibu_record_t *d_reco
  * [2i,2i+1], A=0 C=1 G=2 T=3; src/constructs/record.rs:19-27) fused with
  * validation.  d_bc_ascii is [n][bc_len], d_umi_ascii is [n][umi_len], dense,
  * no terminators, 16-byte aligned bases.  d_flags (nullable) gets one byte per
- * record: bit0 = bad barcode, bit1 = bad umi.  d_result (nullable) is overwritten
- * (sums/xor are NOT computed by this kernel and are written as 0). */
+ * record: bit0 = bad barcode, bit1 = bad umi.  d_result (nullable) is overwritten with
+ * the full reduction of K1 (count, sums, xor, invalid-word counters): decode + validate +
+ * count is ONE pass over the records. */
 int ibu_gpu_unpack_async(ibu_gpu_ctx_t *ctx, const ibu_record_t *d_records, uint64_t n,
                          uint32_t bc_len, uint32_t umi_len, uint8_t *d_bc_ascii,
                          uint8_t *d_umi_ascii, uint8_t *d_flags,

@@ -116,6 +116,7 @@ def test_unpack(ctx, n, bc, umi):
     assert np.array_equal(gb, ob) and np.array_equal(gu, ou) and np.array_equal(gf, of)
     for k in ("n_records", "n_bad_barcode", "n_bad_umi", "n_bad_records"):
         assert gr[k] == orr[k], k
+    assert gr == oc.reduce_records(recs, bc, umi)  # the unpack pass also carries K1's reductions
 
 
 def test_unpack_without_flags_and_result(ctx):

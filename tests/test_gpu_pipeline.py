@@ -141,6 +141,7 @@ def test_unpack_host_and_pack_host(ctx, bc, umi, pinned):
     assert np.array_equal(gb, ob) and np.array_equal(gu, ou) and np.array_equal(gf, of)
     for k in ("n_records", "n_bad_barcode", "n_bad_umi", "n_bad_records"):
         assert res[k] == ores[k]
+    assert res == oc.reduce_records(recs, bc, umi)  # sums / xor ride along, merged across chunks
     # pack the decoded rows back: masked originals, explicit index array
     idx = np.ascontiguousarray(recs["index"])
     back, pres = ctx.pack_host(gb, gu, index=idx)
