@@ -98,7 +98,7 @@ class ClockSampler:
                 "power_w_max": max(pw) if pw else None, "samples": len(rows), "reasons": reasons}
 
 
-def cpu_reference_rate(n_sample: int, steps: int, warmup: int):
+def cpu_reference_rate(n_sample: int, steps: int, warmup: int, threads: int = 0):
     """The oracle port of process_parallel + per-record 2-bit decode + validation on all host
     cores (threads = 0 -> num_cpus, mmap.rs:292-296), host memory to host memory."""
     import numpy as np
@@ -113,7 +113,7 @@ def cpu_reference_rate(n_sample: int, steps: int, warmup: int):
     times = []
     for i in range(warmup + steps):
         t0 = time.perf_counter()
-        oc.unpack_records(recs, BC_LEN, UMI_LEN, 0, bc, umi, fl)
+        oc.unpack_records(recs, BC_LEN, UMI_LEN, threads, bc, umi, fl)
         if i >= warmup:
             times.append(time.perf_counter() - t0)
     return n_sample / (sum(times) / len(times)), cores, sum(times) / len(times)
@@ -305,8 +305,10 @@ def run_ours(args):
         if world == 1 and not args.no_cpu:
             n_sample = pick_cpu_sample(8.0)
             rate, cores, sec = cpu_reference_rate(n_sample, 2, 1)
+            one, _, _ = cpu_reference_rate(4_000_000, 1, 1, threads=1)
             line["cpu_baseline"] = {"value": rate, "unit": "records/s", "cores": cores, "kind": "port",
-                                    "sample": f"{n_sample} of {n} records, 2 timed passes, all {cores} host threads"}
+                                    "sample": f"{n_sample} of {n} records, 2 timed passes, all {cores} host threads",
+                                    "value_1_thread": one}
         print(json.dumps(line))
     del h_recs, h_bc, h_umi
     for p in (pin_in, pin_bc, pin_umi):
