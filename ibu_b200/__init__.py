@@ -318,6 +318,19 @@ class GpuContext:
         _check(lib.ibu_gpu_generate_ascii_async(self._h, _ptr(d_ascii), first_row, n_rows, length, dirty_ppm,
                                                 lower_ppm, seed, _stream(stream), C.byref(err)), err)
 
+    def barcode_count_device(self, d_records, n, mode: int = 0, stream=None):
+        """Per-barcode table left on the device: (table struct, info).  Release the rows with
+        `lib.ibu_gpu_table_free` (or use `barcode_count`, which copies them to the host)."""
+        table, err = _lib.BarcodeTable(), _lib.Error()
+        _check(lib.ibu_gpu_barcode_count(self._h, _ptr(d_records), n, mode, C.byref(table), _stream(stream),
+                                         C.byref(err)), err)
+        info = dict(n_rows=int(table.n_rows), n_records=int(table.n_records),
+                    n_distinct_pairs=int(table.n_distinct_pairs), input_was_sorted=bool(table.input_was_sorted))
+        return table, info
+
+    def table_free(self, table):
+        lib.ibu_gpu_table_free(self._h, C.byref(table))
+
     def barcode_count(self, d_records, n, mode: int = 0, stream=None):
         """Per-barcode table (parallel.rs:79-98 + distinct UMIs): (rows[ROW_DTYPE], info dict)."""
         table, err = _lib.BarcodeTable(), _lib.Error()

@@ -132,13 +132,35 @@ def exact_barcode_table(ctx, d_records, n: int, device, group=None) -> np.ndarra
     dist.all_to_all_single(recv[: sum(recv_counts)], send[:k], recv_counts, counts, group=group)
     torch.cuda.synchronize(device)
     m = sum(recv_counts)
-    if m:
-        from . import COUNT_WEIGHTED
+    from . import COUNT_WEIGHTED
 
-        rows, _ = ctx.barcode_count(recv, m, COUNT_WEIGHTED)
-    else:
-        rows = np.zeros(0, ROW_DTYPE)
-    got = [None] * world
-    dist.all_gather_object(got, rows, group=group)
-    cat = np.concatenate([g for g in got if len(g)]) if any(len(g) for g in got) else np.zeros(0, ROW_DTYPE)
-    return cat[np.argsort(cat["barcode"], kind="stable")]
+    # 3. the owner counts what it received; its rows stay on the device
+    mine = torch.empty((0, 3), dtype=torch.int64, device=device)
+    if m:
+        table, _ = ctx.barcode_count_device(recv, m, COUNT_WEIGHTED)
+        try:
+            mine = torch.empty((int(table.n_rows), 3), dtype=torch.int64, device=device)
+            if table.n_rows:
+                ctx.memcpy(mine, int(table.d_rows), int(table.n_rows) * 24)
+        finally:
+            ctx.table_free(table)
+    # 4. all-gather the owners' disjoint row sets (padded to the longest) and put them in barcode
+    #    order with the device sort (rows are 24-byte records led by the barcode)
+    sizes = torch.tensor([mine.shape[0]], dtype=torch.int64, device=device)
+    all_sizes = [torch.empty_like(sizes) for _ in range(world)]
+    dist.all_gather(all_sizes, sizes, group=group)
+    counts_rows = [int(x.item()) for x in all_sizes]
+    longest = max(max(counts_rows), 1)
+    padded = torch.zeros((longest, 3), dtype=torch.int64, device=device)
+    padded[: mine.shape[0]] = mine
+    parts = [torch.empty_like(padded) for _ in range(world)]
+    dist.all_gather(parts, padded, group=group)
+    cat = torch.cat([p[:c] for p, c in zip(parts, counts_rows)]) if sum(counts_rows) else mine
+    total = int(cat.shape[0])
+    out = np.zeros(total, ROW_DTYPE)
+    if total:
+        ordered = torch.empty_like(cat)
+        torch.cuda.synchronize(device)
+        ctx.sort_records(cat, total, ordered)
+        ctx.d2h(out, ordered)
+    return out
