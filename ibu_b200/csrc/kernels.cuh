@@ -52,13 +52,9 @@ __device__ __forceinline__ void stg_stream256(void *p, uint4 lo, uint4 hi) {
                  "r"(hi.w)
                  : "memory");
 }
-__device__ __forceinline__ void stg_stream64(uint2 *p, uint2 v) {
-    asm volatile("st.global.L1::no_allocate.v2.u32 [%0], {%1,%2};" ::"l"(p), "r"(v.x), "r"(v.y)
-                 : "memory");
-}
 
 // ---- 2-bit -> ASCII, branch-free, LUT in a register (record.rs:19-27; base i at bits 2i..2i+1) ----
-// 8 bases (16 bits: byte `lo_sel` picks which half of w32) -> two u32 of ASCII.
+// 8 bases (16 bits: HALF picks the low or high half of w32) -> two u32 of ASCII.
 template <int HALF>
 __device__ __forceinline__ void decode8(uint32_t w32, uint32_t &a0, uint32_t &a1) {
     // spread the two source bytes to bytes 0 and 2, then nibbles, then 2-bit fields -> PRMT selectors

@@ -1,3 +1,6 @@
+#!/usr/bin/env python
+"""k4_probe.py N MODE GEN [PARAM] — time ibu_gpu_barcode_count on N generated records
+(IBU_B200_TRACE=1 prints the phases and the k_segments kernel time).  Tuning tool."""
 import sys, time, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
