@@ -44,14 +44,17 @@ struct ReduceAcc {
 
 // `head` records in front of the 32-byte aligned body (a record pointer is only 8-byte aligned
 // in general, e.g. a slice of a larger array) are handled with the ragged tail.
+// No grid-stride loop: CTA c owns the 8 TPW consecutive tiles from 8 TPW c, warp w takes tiles
+// w, w + 8, ... of them (next one prefetched).  Block-scheduled tiles read at 7.45 TB/s where
+// the persistent lock-step grid read at 7.05 (tools/k2lab.cu); TPW = 4 amortises the CTA's
+// reduction without losing that.
+template <int TPW, bool PREFETCH>
 __global__ void __launch_bounds__(kBlockThreads)
 k_validate_reduce(const uint8_t *__restrict__ recs_all, uint64_t n_all, uint32_t head, uint64_t bc_hi,
                   uint64_t umi_hi, ibu_reduce_result_t *__restrict__ res) {
     const uint8_t *recs = recs_all + (uint64_t)head * 24;
     const uint64_t n = n_all - head;
     const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
-    const uint64_t gwarp = (uint64_t)blockIdx.x * kWarpsPerBlock + warp;
-    const uint64_t total_warps = (uint64_t)gridDim.x * kWarpsPerBlock;
     const uint32_t c = lane % 3u;
     // mask of group g = mask of field (c + g) % 3; field 2 (index) is never invalid
     const uint64_t m0 = c == 0 ? bc_hi : c == 1 ? umi_hi : 0ull;
@@ -61,10 +64,25 @@ k_validate_reduce(const uint8_t *__restrict__ recs_all, uint64_t n_all, uint32_t
     ReduceAcc acc;
     uint32_t both = 0;  // records whose barcode AND umi are invalid
     const uint64_t n_tiles = n / kTileRecords;
-    for (uint64_t t = gwarp; t < n_tiles; t += total_warps) {
+    uint64_t t = (uint64_t)blockIdx.x * (kWarpsPerBlock * TPW) + warp;
+    u64x4 p0, p1, p2;
+    if (PREFETCH && t < n_tiles) {
         const u64x4 *base = reinterpret_cast<const u64x4 *>(recs) + t * kTileU8 + lane;
-        const u64x4 v0 = ldg_stream256(base), v1 = ldg_stream256(base + 32),
-                    v2 = ldg_stream256(base + 64);
+        p0 = ldg_stream256(base); p1 = ldg_stream256(base + 32); p2 = ldg_stream256(base + 64);
+    }
+#pragma unroll 1
+    for (int j = 0; j < TPW && t < n_tiles; j++) {
+        if (!PREFETCH) {
+            const u64x4 *base = reinterpret_cast<const u64x4 *>(recs) + t * kTileU8 + lane;
+            p0 = ldg_stream256(base); p1 = ldg_stream256(base + 32); p2 = ldg_stream256(base + 64);
+        }
+        const u64x4 v0 = p0, v1 = p1, v2 = p2;
+        const uint64_t tn = t + kWarpsPerBlock;
+        if (PREFETCH && j + 1 < TPW && tn < n_tiles) {
+            const u64x4 *base = reinterpret_cast<const u64x4 *>(recs) + tn * kTileU8 + lane;
+            p0 = ldg_stream256(base); p1 = ldg_stream256(base + 32); p2 = ldg_stream256(base + 64);
+        }
+        t = tn;
         uint32_t bm = 0;  // bit 4k+j: element (k, j) failed its mask
         IBU_ACC(0, v0.x, 0); IBU_ACC(1, v0.y, 1); IBU_ACC(2, v0.z, 2);  IBU_ACC(0, v0.w, 3);
         IBU_ACC(2, v1.x, 4); IBU_ACC(0, v1.y, 5); IBU_ACC(1, v1.z, 6);  IBU_ACC(2, v1.w, 7);
@@ -93,7 +111,7 @@ k_validate_reduce(const uint8_t *__restrict__ recs_all, uint64_t n_all, uint32_t
     uint64_t n_bu = c == 0 ? acc.b1 : c == 1 ? acc.b0 : acc.b2;
     uint64_t x = acc.x, n_both = both;
 
-    if (gwarp == 0) {  // head + ragged tail (< 4 + 128 records), one record per lane per step
+    if (blockIdx.x == 0 && warp == 0) {  // head + ragged tail (< 4 + 128 records), one record per lane per step
         const uint64_t *r64 = reinterpret_cast<const uint64_t *>(recs_all);
         const uint64_t tail0 = head + n_tiles * kTileRecords;
         for (uint64_t k = lane; k < head + (n_all - tail0); k += 32) {
@@ -106,33 +124,25 @@ k_validate_reduce(const uint8_t *__restrict__ recs_all, uint64_t n_all, uint32_t
         }
     }
 
-    __shared__ uint64_t red[kWarpsPerBlock][7];
+    __shared__ uint64_t red[kWarpsPerBlock][8];  // slots follow ibu_reduce_result_t
     s_bc = warp_sum64(s_bc); s_umi = warp_sum64(s_umi); s_idx = warp_sum64(s_idx);
     x = warp_xor64(x);
     n_bb = warp_sum64(n_bb); n_bu = warp_sum64(n_bu); n_both = warp_sum64(n_both);
     if (lane == 0) {
-        red[warp][0] = s_bc; red[warp][1] = s_umi; red[warp][2] = s_idx; red[warp][3] = x;
-        red[warp][4] = n_bb; red[warp][5] = n_bu; red[warp][6] = n_both;
+        red[warp][1] = s_bc; red[warp][2] = s_umi; red[warp][3] = s_idx; red[warp][4] = x;
+        red[warp][5] = n_bb; red[warp][6] = n_bu; red[warp][7] = n_bb + n_bu - n_both;  // bad records
     }
     __syncthreads();
-    if (threadIdx.x < 7) {
+    unsigned long long *out = reinterpret_cast<unsigned long long *>(res);
+    if (threadIdx.x >= 1 && threadIdx.x < 8) {  // one RED instruction per CTA (+ one for the xor)
         uint64_t v = 0;
         for (int w = 0; w < kWarpsPerBlock; w++) {
-            if (threadIdx.x == 3) v ^= red[w][3]; else v += red[w][threadIdx.x];
+            if (threadIdx.x == 4) v ^= red[w][4]; else v += red[w][threadIdx.x];
         }
-        unsigned long long *out = reinterpret_cast<unsigned long long *>(res);
-        switch (threadIdx.x) {  // field order of ibu_reduce_result_t
-            case 0: atomicAdd(out + 1, v); break;                 // sum_barcode
-            case 1: atomicAdd(out + 2, v); break;                 // sum_umi
-            case 2: atomicAdd(out + 3, v); break;                 // sum_index
-            case 3: atomicXor(out + 4, v); break;                 // xor_all
-            case 4: atomicAdd(out + 5, v); atomicAdd(out + 7, v); break;  // bad barcode; records +=
-            case 5: atomicAdd(out + 6, v); atomicAdd(out + 7, v); break;  // bad umi; records +=
-            case 6: atomicAdd(out + 7, 0ull - v); break;          // records -= both (wrapping)
-        }
+        if (threadIdx.x == 4) atomicXor(out + 4, (unsigned long long)v);
+        else if (v) atomicAdd(out + threadIdx.x, (unsigned long long)v);
     }
-    if (blockIdx.x == 0 && threadIdx.x == 0)
-        atomicAdd(reinterpret_cast<unsigned long long *>(res), (unsigned long long)n_all);  // n_records
+    if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(out, (unsigned long long)n_all);  // n_records
 }
 
 // ============================================================================ K2
@@ -218,15 +228,29 @@ __device__ __forceinline__ void copy_out_stage(uint32_t len, uint8_t *gout, uint
     const uint32_t n16 = 8 * len;    // 128 rows x len bytes / 16
     uint4 *dst = reinterpret_cast<uint4 *>(gout) + tile * n16;
     const uint4 *src = reinterpret_cast<const uint4 *>(stage);
-    for (uint32_t i = lane; i < n16; i += 32) stg_stream(dst + i, src[i]);
+    if constexpr (L > 0) {  // compile-time length: all shared loads first, then the stores
+        constexpr int kIters = (8 * L + 31) / 32;
+        uint4 v[kIters];
+#pragma unroll
+        for (int k = 0; k < kIters; k++)
+            if (lane + 32 * k < 8 * L) v[k] = src[lane + 32 * k];
+#pragma unroll
+        for (int k = 0; k < kIters; k++)
+            if (lane + 32 * k < 8 * L) stg_stream(dst + lane + 32 * k, v[k]);
+    } else {
+        for (uint32_t i = lane; i < n16; i += 32) stg_stream(dst + i, src[i]);
+    }
 }
 
+// One 128-record tile per warp and no grid-stride loop: the grid is ceil(tiles / 8) CTAs.
+// Measured on B200 (tools/k2lab.cu, 10^8 records): a persistent grid marching through memory
+// in lock step moves this byte mix at 5.95-6.05 TB/s whatever the kernel does (a decode-free
+// traffic kernel of the same shape is no faster), the same tiles handed out by the block
+// scheduler at 6.5 TB/s (traffic-only: 6.8); every extra tile per warp costs bandwidth.
 template <int BC, int UMI, bool SUMS>
 __global__ void __launch_bounds__(kBlockThreads) k_unpack(const UnpackArgs a) {
     extern __shared__ __align__(16) uint8_t smem[];
     const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
-    const uint64_t gwarp = (uint64_t)blockIdx.x * kWarpsPerBlock + warp;
-    const uint64_t total_warps = (uint64_t)gridDim.x * kWarpsPerBlock;
     uint8_t *wsm = smem + warp * a.warp_smem_bytes;
     uint4 *in4 = reinterpret_cast<uint4 *>(wsm);
     const uint64_t *in64 = reinterpret_cast<const uint64_t *>(wsm);
@@ -236,23 +260,13 @@ __global__ void __launch_bounds__(kBlockThreads) k_unpack(const UnpackArgs a) {
     uint32_t n_bb = 0, n_bu = 0, n_br = 0;
     uint64_t s_bc = 0, s_umi = 0, s_idx = 0, x_all = 0;
     const uint64_t n_tiles = a.n / kTileRecords;
-    const uint4 *g4 = reinterpret_cast<const uint4 *>(a.recs);
+    const uint64_t t = (uint64_t)blockIdx.x * kWarpsPerBlock + warp;  // this warp's tile
 
-    uint4 pre[6];  // software prefetch: the next tile is in flight while this one is decoded
-    uint64_t t = gwarp;
     if (t < n_tiles) {
+        const uint4 *g4 = reinterpret_cast<const uint4 *>(a.recs) + t * kTileU4;
 #pragma unroll
-        for (int k = 0; k < 6; k++) pre[k] = ldg_stream(g4 + t * kTileU4 + lane + 32 * k);
-    }
-    while (t < n_tiles) {
-#pragma unroll
-        for (int k = 0; k < 6; k++) in4[lane + 32 * k] = pre[k];
+        for (int k = 0; k < 6; k++) in4[lane + 32 * k] = ldg_stream(g4 + lane + 32 * k);
         __syncwarp();
-        const uint64_t t_next = t + total_warps;
-        if (t_next < n_tiles) {
-#pragma unroll
-            for (int k = 0; k < 6; k++) pre[k] = ldg_stream(g4 + t_next * kTileU4 + lane + 32 * k);
-        }
 #pragma unroll
         for (int q = 0; q < 4; q++) {
             const uint32_t r = lane + 32 * q;  // record of the tile handled by this lane
@@ -272,11 +286,7 @@ __global__ void __launch_bounds__(kBlockThreads) k_unpack(const UnpackArgs a) {
         __syncwarp();
         copy_out_stage<BC>(bc_len, a.bc_out, t, bc_stage, lane);
         copy_out_stage<UMI>(umi_len, a.umi_out, t, umi_stage, lane);
-        __syncwarp();
-        t = t_next;
-    }
-
-    if (gwarp == total_warps - 1) {  // ragged tail: plain per-record code
+    } else if (t == n_tiles) {  // ragged tail (< 128 records): plain per-record code
         const uint64_t *r64 = reinterpret_cast<const uint64_t *>(a.recs);
         for (uint64_t rec = n_tiles * kTileRecords + lane; rec < a.n; rec += 32) {
             const uint64_t bc = ldg_stream64(r64 + 3 * rec), umi = ldg_stream64(r64 + 3 * rec + 1);
@@ -294,32 +304,28 @@ __global__ void __launch_bounds__(kBlockThreads) k_unpack(const UnpackArgs a) {
         }
     }
 
-    if (a.res) {
+    if (SUMS) {  // a.res != nullptr: warp -> CTA -> one RED instruction per CTA (+ one for the xor)
+        __shared__ uint64_t red[kWarpsPerBlock][8];
         n_bb = __reduce_add_sync(0xffffffffu, n_bb);
         n_bu = __reduce_add_sync(0xffffffffu, n_bu);
         n_br = __reduce_add_sync(0xffffffffu, n_br);
+        s_bc = warp_sum64(s_bc); s_umi = warp_sum64(s_umi); s_idx = warp_sum64(s_idx);
+        x_all = warp_xor64(x_all);
+        if (lane == 0) {  // slots follow ibu_reduce_result_t
+            red[warp][1] = s_bc; red[warp][2] = s_umi; red[warp][3] = s_idx; red[warp][4] = x_all;
+            red[warp][5] = n_bb; red[warp][6] = n_bu; red[warp][7] = n_br;
+        }
+        __syncthreads();
         unsigned long long *out = reinterpret_cast<unsigned long long *>(a.res);
-        if (lane == 0) {
-            if (n_bb) atomicAdd(out + 5, (unsigned long long)n_bb);
-            if (n_bu) atomicAdd(out + 6, (unsigned long long)n_bu);
-            if (n_br) atomicAdd(out + 7, (unsigned long long)n_br);
-            if (gwarp == 0) atomicAdd(out, (unsigned long long)a.n);
-        }
-        if (SUMS) {  // warp -> block -> one atomic per word per CTA
-            __shared__ uint64_t red[kWarpsPerBlock][4];
-            s_bc = warp_sum64(s_bc); s_umi = warp_sum64(s_umi); s_idx = warp_sum64(s_idx);
-            x_all = warp_xor64(x_all);
-            if (lane == 0) { red[warp][0] = s_bc; red[warp][1] = s_umi; red[warp][2] = s_idx; red[warp][3] = x_all; }
-            __syncthreads();
-            if (threadIdx.x < 4) {
-                uint64_t v = 0;
-                for (int w = 0; w < kWarpsPerBlock; w++) {
-                    if (threadIdx.x == 3) v ^= red[w][3]; else v += red[w][threadIdx.x];
-                }
-                if (threadIdx.x == 3) atomicXor(out + 4, (unsigned long long)v);
-                else atomicAdd(out + 1 + threadIdx.x, (unsigned long long)v);
+        if (threadIdx.x >= 1 && threadIdx.x < 8) {
+            uint64_t v = 0;
+            for (int w = 0; w < kWarpsPerBlock; w++) {
+                if (threadIdx.x == 4) v ^= red[w][4]; else v += red[w][threadIdx.x];
             }
+            if (threadIdx.x == 4) atomicXor(out + 4, (unsigned long long)v);
+            else if (v) atomicAdd(out + threadIdx.x, (unsigned long long)v);
         }
+        if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(out, (unsigned long long)a.n);
     }
 }
 
@@ -459,13 +465,12 @@ __device__ __forceinline__ uint64_t pack_row(uint4 lo, uint4 hi, uint32_t len, u
     return w;
 }
 
+// One tile of 32 Q rows per warp, no grid-stride loop (see k_unpack for the measurement).
 template <int BC, int UMI, int Q>
 __global__ void __launch_bounds__(kBlockThreads) k_pack(const PackArgs a) {
     constexpr int kRows = 32 * Q;  // rows per warp tile
     extern __shared__ __align__(16) uint8_t smem[];
     const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
-    const uint64_t gwarp = (uint64_t)blockIdx.x * kWarpsPerBlock + warp;
-    const uint64_t total_warps = (uint64_t)gridDim.x * kWarpsPerBlock;
     uint8_t *wsm = smem + warp * a.warp_smem_bytes;
     uint64_t *out64 = reinterpret_cast<uint64_t *>(wsm);  // kRows records x 24 B staged output
     const uint4 *out4 = reinterpret_cast<const uint4 *>(wsm);
@@ -474,38 +479,28 @@ __global__ void __launch_bounds__(kBlockThreads) k_pack(const PackArgs a) {
 
     uint32_t n_bb = 0, n_bu = 0, n_br = 0;
     const uint64_t n_tiles = a.n / kRows;
-    RowRegs<BC, Q> bc_rows;
-    RowRegs<UMI, Q> umi_rows;
-    uint64_t t = gwarp;
+    const uint64_t t = (uint64_t)blockIdx.x * kWarpsPerBlock + warp;  // this warp's tile
     if (t < n_tiles) {
+        constexpr bool kStageBc = (BC != 16 && BC != 32), kStageUmi = (UMI != 16 && UMI != 32);
+        RowRegs<BC, Q> bc_rows;
+        RowRegs<UMI, Q> umi_rows;
         bc_rows.load(a.bc_in, t, lane, bc_len);
         umi_rows.load(a.umi_in, t, lane, umi_len);
-    }
-    while (t < n_tiles) {
-        constexpr bool kStageBc = (BC != 16 && BC != 32), kStageUmi = (UMI != 16 && UMI != 32);
         bc_rows.park(bc_stage, lane, bc_len);
         umi_rows.park(umi_stage, lane, umi_len);
         if (kStageBc || kStageUmi) __syncwarp();
-        uint4 bl[Q], bh[Q], ul[Q], uh[Q];
 #pragma unroll
         for (int q = 0; q < Q; q++) {
-            if constexpr (!kStageBc) bc_rows.get(q, bl[q], bh[q]);
-            else staged_row<BC>(bc_stage, lane + 32 * q, bc_len, bl[q], bh[q]);
-            if constexpr (!kStageUmi) umi_rows.get(q, ul[q], uh[q]);
-            else staged_row<UMI>(umi_stage, lane + 32 * q, umi_len, ul[q], uh[q]);
-        }
-        const uint64_t t_next = t + total_warps;
-        if (t_next < n_tiles) {  // prefetch while this tile is encoded
-            bc_rows.load(a.bc_in, t_next, lane, bc_len);
-            umi_rows.load(a.umi_in, t_next, lane, umi_len);
-        }
-#pragma unroll
-        for (int q = 0; q < Q; q++) {
+            uint4 bl, bh, ul, uh;
+            if constexpr (!kStageBc) bc_rows.get(q, bl, bh);
+            else staged_row<BC>(bc_stage, lane + 32 * q, bc_len, bl, bh);
+            if constexpr (!kStageUmi) umi_rows.get(q, ul, uh);
+            else staged_row<UMI>(umi_stage, lane + 32 * q, umi_len, ul, uh);
             const uint32_t r = lane + 32 * q;
             const uint64_t row = t * kRows + r;
             uint32_t bb, bu;
-            const uint64_t bw = pack_row<BC>(bl[q], bh[q], bc_len, bb);
-            const uint64_t uw = pack_row<UMI>(ul[q], uh[q], umi_len, bu);
+            const uint64_t bw = pack_row<BC>(bl, bh, bc_len, bb);
+            const uint64_t uw = pack_row<UMI>(ul, uh, umi_len, bu);
             const uint64_t idx = a.index ? ldg_stream64(a.index + row) : a.index_base + row;
             out64[3 * r] = bw; out64[3 * r + 1] = uw; out64[3 * r + 2] = idx;
             n_bb += bb; n_bu += bu; n_br += (bb | bu);
@@ -515,11 +510,7 @@ __global__ void __launch_bounds__(kBlockThreads) k_pack(const PackArgs a) {
         uint4 *dst = reinterpret_cast<uint4 *>(a.recs_out) + t * (kRows * 24 / 16);
 #pragma unroll
         for (int k = 0; k < 3 * Q / 2; k++) stg_stream(dst + lane + 32 * k, out4[lane + 32 * k]);
-        __syncwarp();
-        t = t_next;
-    }
-
-    if (gwarp == total_warps - 1) {  // ragged tail (< kRows rows): plain per-row code
+    } else if (t == n_tiles) {  // ragged tail (< kRows rows): plain per-row code
         uint64_t *o64 = reinterpret_cast<uint64_t *>(a.recs_out);
         for (uint64_t row = n_tiles * kRows + lane; row < a.n; row += 32) {
             uint64_t w[2];
@@ -544,17 +535,20 @@ __global__ void __launch_bounds__(kBlockThreads) k_pack(const PackArgs a) {
         }
     }
 
-    if (a.res) {
+    if (a.res) {  // counters: warp -> CTA -> one RED instruction per CTA that saw a bad row
+        __shared__ uint32_t red[kWarpsPerBlock][4];
         n_bb = __reduce_add_sync(0xffffffffu, n_bb);
         n_bu = __reduce_add_sync(0xffffffffu, n_bu);
         n_br = __reduce_add_sync(0xffffffffu, n_br);
+        if (lane == 0) { red[warp][0] = n_bb; red[warp][1] = n_bu; red[warp][2] = n_br; }
+        __syncthreads();
         unsigned long long *out = reinterpret_cast<unsigned long long *>(a.res);
-        if (lane == 0) {
-            if (n_bb) atomicAdd(out + 5, (unsigned long long)n_bb);
-            if (n_bu) atomicAdd(out + 6, (unsigned long long)n_bu);
-            if (n_br) atomicAdd(out + 7, (unsigned long long)n_br);
-            if (gwarp == 0) atomicAdd(out, (unsigned long long)a.n);
+        if (threadIdx.x < 3) {
+            uint32_t v = 0;
+            for (int w = 0; w < kWarpsPerBlock; w++) v += red[w][threadIdx.x];
+            if (v) atomicAdd(out + 5 + threadIdx.x, (unsigned long long)v);
         }
+        if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(out, (unsigned long long)a.n);
     }
 }
 
@@ -619,19 +613,8 @@ k_generate_ascii(uint8_t *__restrict__ out, uint64_t first_row, uint64_t n_rows,
 }
 
 // ============================================================================ launch helpers
-static int grid_for(ibu_gpu_ctx *ctx, const void *kernel, size_t smem, uint64_t n_tiles,
-                    ibu_error_t *err) {
-    int per_sm = 0;
-    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kBlockThreads, smem);
-    if (e != cudaSuccess) return -cuda_fail(err, e, "cudaOccupancyMaxActiveBlocksPerMultiprocessor");
-    if (per_sm < 1) per_sm = 1;
-    // a whole number of resident waves: sm_count x resident CTAs, shrunk for small inputs
-    uint64_t grid = (uint64_t)ctx->sm_count * per_sm;
-    uint64_t need = (n_tiles + kWarpsPerBlock - 1) / kWarpsPerBlock;
-    if (need < 1) need = 1;
-    if (grid > need) grid = need;
-    return (int)grid;
-}
+// one tile per warp, plus the warp that takes the ragged tail
+static unsigned tile_grid(uint64_t n_tiles) { return (unsigned)((n_tiles + 1 + kWarpsPerBlock - 1) / kWarpsPerBlock); }
 
 static bool aligned(const void *p, size_t a) { return ((uintptr_t)p & (a - 1)) == 0; }
 
@@ -647,9 +630,17 @@ static int launch_unpack(ibu_gpu_ctx *ctx, UnpackArgs &a, cudaStream_t s, ibu_er
     const size_t smem = (size_t)off * kWarpsPerBlock;
     // with a result block the pass also carries K1's sums / checksum (measured cost: 0.2 %)
     auto kern = a.res ? k_unpack<BC, UMI, true> : k_unpack<BC, UMI, false>;
+    // Resident CTAs per SM matter more than anything else here (10^8 records bc16/umi12: 6 CTAs
+    // 0.865 ms, 5: 0.803, 4: 0.780, 3: 0.796, 2: 0.93).  The shared-memory carve-out is the knob:
+    // enough for 4 CTAs of the staged kernels (bc16/umi12: 37 KB each -> the 164 KB configuration);
+    // the unstaged ones keep the default.
+    constexpr bool kStaged = !(BC == 32 || BC == 16) || !(UMI == 32 || UMI == 16);
+    static const int carve_env = getenv("IBU_CARVEOUT") ? atoi(getenv("IBU_CARVEOUT")) : -2;  // tuning hook
+    const int four_ctas = (int)std::min<size_t>(100, (4 * (smem + 1536) * 100 + 233471) / 233472);
+    const int carve = carve_env != -2 ? carve_env : (kStaged ? four_ctas : -1);
+    if (carve >= 0) IBU_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, carve));
     IBU_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    int grid = grid_for(ctx, (const void *)kern, smem, a.n / kTileRecords, err);
-    if (grid < 0) return -grid;
+    const unsigned grid = tile_grid(a.n / kTileRecords);
     kern<<<grid, kBlockThreads, smem, s>>>(a);
     g_launches.fetch_add(1, std::memory_order_relaxed);
     IBU_CUDA(cudaGetLastError());
@@ -670,9 +661,11 @@ static int launch_pack(ibu_gpu_ctx *ctx, PackArgs &a, cudaStream_t s, ibu_error_
     a.warp_smem_bytes = off;
     const size_t smem = (size_t)off * kWarpsPerBlock;
     auto kern = k_pack<BC, UMI, Q>;
+    // (16,16) rows, 4 per lane: 5 resident CTAs (carve-out 75 %) pack at 6.73 TB/s, the default at 6.31
+    static const int carve = getenv("IBU_CARVEOUT") ? atoi(getenv("IBU_CARVEOUT")) : ((BC == 16 && UMI == 16) ? 75 : -1);
+    if (carve >= 0) IBU_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, carve));
     IBU_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    int grid = grid_for(ctx, (const void *)kern, smem, a.n / kRows, err);
-    if (grid < 0) return -grid;
+    const unsigned grid = tile_grid(a.n / kRows);
     kern<<<grid, kBlockThreads, smem, s>>>(a);
     g_launches.fetch_add(1, std::memory_order_relaxed);
     IBU_CUDA(cudaGetLastError());
@@ -708,10 +701,17 @@ int ibu_gpu_validate_reduce_async(ibu_gpu_ctx_t *ctx, const ibu_record_t *d_reco
     IBU_CUDA(cudaMemsetAsync(d_result, 0, sizeof(*d_result), s));
     // records until the next 32-byte boundary: 24 h = -p (mod 32)  <=>  h = (p / 8) mod 4
     const uint32_t head = (uint32_t)std::min<uint64_t>(n, ((uintptr_t)d_records >> 3) & 3u);
-    int grid = grid_for(ctx, (const void *)k_validate_reduce, 0, (n - head) / kTileRecords, err);
-    if (grid < 0) return -grid;
-    k_validate_reduce<<<grid, kBlockThreads, 0, s>>>((const uint8_t *)d_records, n, head, high_mask(bc_len),
-                                                     high_mask(umi_len), d_result);
+    const uint64_t n_tiles = (n - head) / kTileRecords;
+    static const int mode = getenv("IBU_K1_MODE") ? atoi(getenv("IBU_K1_MODE")) : 40;  // tuning hook: 10*TPW + prefetch
+#define IBU_K1_CASE(TPW, PF)                                                                                  \
+    if (mode == 10 * TPW + PF) {                                                                              \
+        const unsigned grid = (unsigned)std::max<uint64_t>(1, (n_tiles + kWarpsPerBlock * TPW - 1) / (kWarpsPerBlock * TPW)); \
+        k_validate_reduce<TPW, PF><<<grid, kBlockThreads, 0, s>>>((const uint8_t *)d_records, n, head, high_mask(bc_len),    \
+                                                                  high_mask(umi_len), d_result);              \
+    }
+    IBU_K1_CASE(1, 0) IBU_K1_CASE(2, 0) IBU_K1_CASE(4, 0) IBU_K1_CASE(8, 0) IBU_K1_CASE(16, 0)
+    IBU_K1_CASE(2, 1) IBU_K1_CASE(4, 1) IBU_K1_CASE(8, 1) IBU_K1_CASE(16, 1)
+#undef IBU_K1_CASE
     g_launches.fetch_add(1, std::memory_order_relaxed);
     IBU_CUDA(cudaGetLastError());
     return IBU_OK;

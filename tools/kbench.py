@@ -53,7 +53,7 @@ def main():
     out = []
 
     def report(name, alg_bytes, fn, **extra):
-        if args.only and args.only not in name:
+        if args.only and not any(o in name for o in args.only.split(",")):
             return
         mean, best, med = timeit(fn, stream, args.iters)
         line = dict(kernel=name, records=n, alg_bytes_per_record=alg_bytes, ms_mean=mean, ms_best=best, ms_median=med,
@@ -64,7 +64,10 @@ def main():
 
     with torch.cuda.stream(stream):
         res = torch.zeros(8, dtype=torch.int64, device=dev)
-        for bc, umi in [(16, 12), (32, 32), (16, 16), (16, 10), (20, 10), (15, 9)]:
+        shapes = [(16, 12), (32, 32), (16, 16), (16, 10), (20, 10), (15, 9)]
+        if args.only:
+            shapes = [sh for sh in shapes if any(f"bc{sh[0]}/umi{sh[1]}" in o or o == "K1" and sh == (16, 12) for o in args.only.split(","))] or shapes[:1]
+        for bc, umi in shapes:
             recs, b, u = u8(24 * n), u8(bc * n), u8(umi * n)
             ctx.generate_records_async(recs, 0, n, bc, umi, ibu.GEN_DIRTY, 10_000, 1, stream)
             if (bc, umi) == (16, 12):
@@ -89,7 +92,7 @@ def main():
             del recs, b, u, back
         # K4: sorted streaming path (blocking API: wall clock, includes scratch allocation and
         # the table's D2H) and the unsorted sort-then-segment path
-        if not args.only or "K4" in args.only:
+        if not args.only or "K4" in args.only:  # noqa: E501
             import time
             recs = u8(24 * n)
             for label, mode, param, m in [("K4 barcode_count sorted (1000/barcode, 5/umi)", ibu.GEN_SORTED, (5 << 32) | 1000, 1),
