@@ -96,6 +96,7 @@ SIGNATURES = {
     "ibu_host_free": (None, [_vp]),
     "ibu_host_register": (_int, [_vp, _sz, _int, _err]),
     "ibu_host_unregister": (None, [_vp]),
+    "ibu_host_stream_copy": (None, [_vp, _vp, _sz, _u32]),
     "ibu_gpu_validate_reduce_async": (_int, [_vp, _vp, _u64, _u32, _u32, _vp, _vp, _err]),
     "ibu_gpu_unpack_async": (_int, [_vp, _vp, _u64, _u32, _u32, _vp, _vp, _vp, _vp, _vp, _err]),
     "ibu_gpu_pack_async": (_int, [_vp, _vp, _vp, _vp, _u64, _u64, _u32, _u32, _vp, _vp, _vp, _vp, _err]),

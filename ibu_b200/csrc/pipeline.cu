@@ -13,7 +13,11 @@
 #include <cerrno>
 #include <cstdlib>
 #include <fcntl.h>
+#if defined(__SSE2__)
+#include <emmintrin.h>
+#endif
 #include <mutex>
+#include <sys/mman.h>
 #include <thread>
 #include <unistd.h>
 
@@ -36,9 +40,39 @@ bool is_pinned(const void *p) {
     return attr.type == cudaMemoryTypeHost;
 }
 
+// Copy with non-temporal stores.  A staging buffer is written once and next read by the DMA
+// engine: ordinary stores would first read each destination line for ownership, i.e. three
+// DRAM transfers per byte instead of two, and the staging copy is bound by host DRAM
+// bandwidth (B200 box, 16 threads, H2D running: memcpy / pread 38-39 GB/s, this 46-48 GB/s;
+// profiles/r1_probe_pin*.jsonl).
+void stream_copy(void *dst, const void *src, size_t bytes) {
+#if defined(__SSE2__)
+    uint8_t *d = (uint8_t *)dst;
+    const uint8_t *s = (const uint8_t *)src;
+    const size_t head = std::min(bytes, (size_t)(-(uintptr_t)d & 15u));
+    if (head) {
+        memcpy(d, s, head);
+        d += head; s += head; bytes -= head;
+    }
+    const size_t n64 = bytes / 64;
+    for (size_t i = 0; i < n64; i++, d += 64, s += 64) {
+        const __m128i a = _mm_loadu_si128((const __m128i *)s), b = _mm_loadu_si128((const __m128i *)(s + 16)),
+                      c = _mm_loadu_si128((const __m128i *)(s + 32)), e = _mm_loadu_si128((const __m128i *)(s + 48));
+        _mm_stream_si128((__m128i *)d, a);
+        _mm_stream_si128((__m128i *)(d + 16), b);
+        _mm_stream_si128((__m128i *)(d + 32), c);
+        _mm_stream_si128((__m128i *)(d + 48), e);
+    }
+    _mm_sfence();
+    if (bytes % 64) memcpy(d, s, bytes % 64);
+#else
+    memcpy(dst, src, bytes);
+#endif
+}
+
 void parallel_memcpy(void *dst, const void *src, size_t bytes, unsigned threads) {
     if (threads <= 1 || bytes < (8u << 20)) {
-        memcpy(dst, src, bytes);
+        stream_copy(dst, src, bytes);
         return;
     }
     size_t per = align_up(bytes / threads, 4096);
@@ -47,27 +81,31 @@ void parallel_memcpy(void *dst, const void *src, size_t bytes, unsigned threads)
         size_t off = (size_t)i * per;
         if (off >= bytes) break;
         size_t len = std::min(per, bytes - off);
-        pool.emplace_back([=] { memcpy((uint8_t *)dst + off, (const uint8_t *)src + off, len); });
+        pool.emplace_back([=] { stream_copy((uint8_t *)dst + off, (const uint8_t *)src + off, len); });
     }
     for (auto &t : pool) t.join();
 }
 
-// The same fan-out with pread(2): file bytes land in pinned memory with one kernel copy and
-// without populating page tables for the mapping.
+// The same fan-out with pread(2): no page tables are populated for the mapping and an I/O error
+// is a return code, not a SIGBUS.  Each thread reads 64 KB pieces into a cache-resident bounce
+// buffer and streams them on (pread straight into the pinned buffer is the 38 GB/s case above).
 bool parallel_pread(void *dst, int fd, uint64_t file_off, size_t bytes, unsigned threads) {
     if (threads < 1) threads = 1;
     size_t per = align_up((bytes + threads - 1) / threads, 1 << 20);
     std::atomic<bool> ok{true};
     auto work = [&](size_t off, size_t len) {
+        constexpr size_t kBounce = 64u << 10;
+        alignas(64) uint8_t bounce[kBounce];
         uint8_t *p = (uint8_t *)dst + off;
         uint64_t fo = file_off + off;
         while (len) {
-            ssize_t got = ::pread(fd, p, len, (off_t)fo);
+            ssize_t got = ::pread(fd, bounce, std::min(len, kBounce), (off_t)fo);
             if (got < 0 && errno == EINTR) continue;
             if (got <= 0) {
                 ok = false;
                 return;
             }
+            stream_copy(p, bounce, (size_t)got);
             p += got;
             fo += (uint64_t)got;
             len -= (size_t)got;
@@ -440,11 +478,27 @@ void ibu_host_unregister(void *h_ptr) {
     if (h_ptr && cudaHostUnregister(h_ptr) != cudaSuccess) cudaGetLastError();
 }
 
+void ibu_host_stream_copy(void *dst, const void *src, size_t bytes, unsigned threads) {
+    if (!bytes || !dst || !src) return;
+    if (threads == 0) threads = std::max(1u, std::thread::hardware_concurrency());
+    parallel_memcpy(dst, src, bytes, threads);
+}
+
 int ibu_mmap_pin(ibu_mmap_reader_t *reader, ibu_error_t *err) {
     clear_error(err);
     if (!reader) return set_error(err, IBU_ERR_ARG, 0, 0, 0, "null reader");
-    IBU_CUDA(cudaHostRegister((void *)ibu_mmap_base(reader), ibu_mmap_bytes(reader),
-                              cudaHostRegisterPortable | cudaHostRegisterReadOnly));
+    // The driver refuses to page-lock a mapping without write permission (cudaErrorInvalidValue,
+    // read-only flag or not) but takes a private file mapping that has it, and with the read-only
+    // flag it pins the page-cache pages themselves, no copy-on-write (tools/probe_pin.cu).  The
+    // mapping is MAP_PRIVATE, so the permission never reaches the file; it is dropped again once
+    // the pages are locked.
+    void *base = (void *)ibu_mmap_base(reader);
+    const size_t bytes = ibu_mmap_bytes(reader);
+    if (mprotect(base, bytes, PROT_READ | PROT_WRITE) != 0)
+        return set_error(err, IBU_ERR_IO, errno, 0, 0, "I/O error: mprotect of the mapping failed");
+    cudaError_t e = cudaHostRegister(base, bytes, cudaHostRegisterPortable | cudaHostRegisterReadOnly);
+    mprotect(base, bytes, PROT_READ);
+    if (e != cudaSuccess) return cuda_fail(err, e, "cudaHostRegister(mmap)");
     return IBU_OK;
 }
 

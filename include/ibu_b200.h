@@ -186,6 +186,10 @@ int ibu_host_alloc(size_t bytes, void **h_out, ibu_error_t *err); /* pinned */
 void ibu_host_free(void *h_ptr);
 int ibu_host_register(void *h_ptr, size_t bytes, int read_only, ibu_error_t *err);
 void ibu_host_unregister(void *h_ptr);
+/* Host utility: copy with non-temporal stores on `threads` threads (0 = all cores) — what the
+ * pipelines use to fill pinned staging buffers (no read-for-ownership of the destination).
+ * Any alignment, any size. */
+void ibu_host_stream_copy(void *dst, const void *src, size_t bytes, unsigned threads);
 
 /* ---------------------------------------------------------- device kernels */
 
@@ -335,9 +339,11 @@ int ibu_gpu_process_mmap(ibu_gpu_ctx_t *ctx, const ibu_mmap_reader_t *reader, ui
                          uint64_t end, ibu_reduce_result_t *h_result, ibu_chunk_cb on_chunk,
                          void *user, ibu_error_t *err);
 /* Optional: page-lock the reader's mapping (cudaHostRegister, read-only) so that
- * ibu_gpu_process_mmap DMAs straight out of the page cache instead of staging through
- * pinned bounce buffers.  Fails with IBU_ERR_CUDA where the driver refuses file-backed
- * mappings; the staged path then still applies. */
+ * ibu_gpu_process_mmap DMAs straight out of the page cache at the link rate instead of staging
+ * through pinned bounce buffers.  Locking costs about 0.1-0.5 s per GB (it faults every page
+ * in), so it pays when the same reader is processed more than once; a single pass is faster
+ * staged.  Fails with IBU_ERR_CUDA / IBU_ERR_IO where the driver or the kernel refuses; the
+ * staged path then still applies. */
 int ibu_mmap_pin(ibu_mmap_reader_t *reader, ibu_error_t *err);
 void ibu_mmap_unpin(ibu_mmap_reader_t *reader);
 /* Same over a host array (pinned: copied directly; pageable: staged). */

@@ -52,6 +52,26 @@ def test_process_gpu_reference_kat(ctx, tmp_ibu):  # mmap.rs:454-481
     assert got["n_records"] == 10_000 and got.count_sum == 299_970_000
 
 
+def test_process_gpu_from_a_pinned_mapping(ctx, tmp_ibu):
+    """ibu_mmap_pin: the mapping itself is page-locked (read-only) and DMA'd without staging; the
+    results, slices and clones of the reader are unchanged, and unpin returns to the staged path."""
+    n = 600_001
+    recs = oc.generate_records(0, n, 16, 12, 1, 30_000, 11)
+    write(tmp_ibu, recs)
+    want, _ = oc.MmapReader(tmp_ibu).process_parallel_reduce(0)
+    reader = ibu.MmapReader(tmp_ibu)
+    staged = reader.process_gpu(ctx)
+    reader.pin()
+    try:
+        assert reader.process_gpu(ctx) == want == staged
+        assert reader.process_gpu(ctx, 12_345, 500_000) == oc.reduce_records(recs[12_345:500_000], 16, 12)
+        assert np.array_equal(reader.slice(7, 1000), recs[7:1000])
+        assert reader.clone().process_gpu(ctx) == want
+    finally:
+        reader.unpin()
+    assert reader.process_gpu(ctx) == want
+
+
 def test_process_gpu_shards_merge_to_whole(ctx, tmp_ibu):
     """Range sharding (mmap.rs:297-307 with n = #GPUs): shard results merge to the file's."""
     n = 777_777

@@ -40,6 +40,19 @@ def test_abi_exports_every_declared_symbol():
     assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
 
 
+def test_host_stream_copy_any_alignment_and_size():
+    """The non-temporal staging copy (head to 16-byte alignment, 64-byte body, tail) is exact."""
+    rng = np.random.default_rng(7)
+    src = rng.integers(0, 256, 40 << 20, dtype=np.uint8)
+    dst = np.zeros(src.size + 256, np.uint8)
+    for so, do, n, thr in [(0, 0, 0, 1), (1, 3, 1, 1), (5, 9, 63, 1), (3, 1, 64, 1), (7, 16, 4097, 2), (0, 5, 1 << 20, 3),
+                           (11, 13, (33 << 20) + 77, 4), (0, 0, 40 << 20, 0)]:
+        dst[:] = 0xEE
+        _lib.lib.ibu_host_stream_copy(dst.ctypes.data + do, src.ctypes.data + so, n, thr)
+        assert np.array_equal(dst[do:do + n], src[so:so + n]), (so, do, n, thr)
+        assert (dst[:do] == 0xEE).all() and (dst[do + n:do + n + 64] == 0xEE).all(), (so, do, n, thr)
+
+
 def test_struct_layouts():
     assert C.sizeof(_lib.Header) == 32 and C.sizeof(_lib.Record) == 24
     assert C.sizeof(_lib.ReduceResult) == 64 and C.sizeof(_lib.Error) == 256
