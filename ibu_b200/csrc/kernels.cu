@@ -466,8 +466,8 @@ __device__ __forceinline__ uint64_t pack_row(uint4 lo, uint4 hi, uint32_t len, u
 }
 
 // One tile of 32 Q rows per warp, no grid-stride loop (see k_unpack for the measurement).
-template <int BC, int UMI, int Q>
-__global__ void __launch_bounds__(kBlockThreads) k_pack(const PackArgs a) {
+template <int BC, int UMI, int Q, int MINB = 1>
+__global__ void __launch_bounds__(kBlockThreads, MINB) k_pack(const PackArgs a) {
     constexpr int kRows = 32 * Q;  // rows per warp tile
     extern __shared__ __align__(16) uint8_t smem[];
     const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
@@ -616,6 +616,18 @@ k_generate_ascii(uint8_t *__restrict__ out, uint64_t first_row, uint64_t n_rows,
 // one tile per warp, plus the warp that takes the ragged tail
 static unsigned tile_grid(uint64_t n_tiles) { return (unsigned)((n_tiles + 1 + kWarpsPerBlock - 1) / kWarpsPerBlock); }
 
+// Shared-memory carve-out (percent of 228 KB, -1 = driver default) for a streaming kernel.  It
+// fixes both the number of resident CTAs and what is left as L1, and these kernels are sensitive
+// to the pair: unpack bc16/umi12 on 10^8 records runs in 0.865 ms at the default (6 CTAs, 28 KB
+// L1), 0.803 at 75 % (5 CTAs), 0.780 at 64 % (4 CTAs, 92 KB L1), 0.796 at 50 % (3 CTAs); padding the
+// request to get 4 CTAs WITHOUT enlarging L1 gives 0.876.  profiles/r1_carveout_sweep*.txt.
+static int set_carveout(const void *kern, int carve, ibu_error_t *err) {
+    static const int env = getenv("IBU_CARVEOUT") ? atoi(getenv("IBU_CARVEOUT")) : -2;  // tuning hook
+    if (env != -2) carve = env;
+    if (carve >= 0) IBU_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, carve));
+    return IBU_OK;
+}
+
 static bool aligned(const void *p, size_t a) { return ((uintptr_t)p & (a - 1)) == 0; }
 
 template <int BC, int UMI>
@@ -630,15 +642,10 @@ static int launch_unpack(ibu_gpu_ctx *ctx, UnpackArgs &a, cudaStream_t s, ibu_er
     const size_t smem = (size_t)off * kWarpsPerBlock;
     // with a result block the pass also carries K1's sums / checksum (measured cost: 0.2 %)
     auto kern = a.res ? k_unpack<BC, UMI, true> : k_unpack<BC, UMI, false>;
-    // Resident CTAs per SM matter more than anything else here (10^8 records bc16/umi12: 6 CTAs
-    // 0.865 ms, 5: 0.803, 4: 0.780, 3: 0.796, 2: 0.93).  The shared-memory carve-out is the knob:
-    // enough for 4 CTAs of the staged kernels (bc16/umi12: 37 KB each -> the 164 KB configuration);
-    // the unstaged ones keep the default.
     constexpr bool kStaged = !(BC == 32 || BC == 16) || !(UMI == 32 || UMI == 16);
-    static const int carve_env = getenv("IBU_CARVEOUT") ? atoi(getenv("IBU_CARVEOUT")) : -2;  // tuning hook
+    // staged kernels: the smallest configuration that holds 4 CTAs (bc16/umi12: 37 KB each -> 164 KB)
     const int four_ctas = (int)std::min<size_t>(100, (4 * (smem + 1536) * 100 + 233471) / 233472);
-    const int carve = carve_env != -2 ? carve_env : (kStaged ? four_ctas : -1);
-    if (carve >= 0) IBU_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, carve));
+    if (int rc = set_carveout((const void *)kern, kStaged ? four_ctas : -1, err)) return rc;
     IBU_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const unsigned grid = tile_grid(a.n / kTileRecords);
     kern<<<grid, kBlockThreads, smem, s>>>(a);
@@ -647,12 +654,9 @@ static int launch_unpack(ibu_gpu_ctx *ctx, UnpackArgs &a, cudaStream_t s, ibu_er
     return IBU_OK;
 }
 
-template <int BC, int UMI>
-static int launch_pack(ibu_gpu_ctx *ctx, PackArgs &a, cudaStream_t s, ibu_error_t *err) {
-    // rows per lane: 4 when both inputs are 16-byte rows loaded straight into registers
-    // (measured: 0.99 -> 0.91 ms per 10^8 rows); staged inputs do better with 2
-    constexpr int Q = (BC == 16 && UMI == 16) ? 4 : 2;
-    constexpr uint32_t kRows = 32 * Q;
+template <int BC, int UMI, int Q, int MINB>
+static int launch_pack_q(ibu_gpu_ctx *ctx, PackArgs &a, cudaStream_t s, ibu_error_t *err) {
+    constexpr uint32_t kRows = 32 * Q;  // rows per warp tile, Q per lane
     uint32_t off = kRows * 24;
     a.bc_stage_off = off;
     if (BC != 16 && BC != 32) off += ((kRows * a.bc_len + 15u) & ~15u) + 16u;  // +16: funnel-shift over-read
@@ -660,16 +664,25 @@ static int launch_pack(ibu_gpu_ctx *ctx, PackArgs &a, cudaStream_t s, ibu_error_
     if (UMI != 16 && UMI != 32) off += ((kRows * a.umi_len + 15u) & ~15u) + 16u;
     a.warp_smem_bytes = off;
     const size_t smem = (size_t)off * kWarpsPerBlock;
-    auto kern = k_pack<BC, UMI, Q>;
-    // (16,16) rows, 4 per lane: 5 resident CTAs (carve-out 75 %) pack at 6.73 TB/s, the default at 6.31
-    static const int carve = getenv("IBU_CARVEOUT") ? atoi(getenv("IBU_CARVEOUT")) : ((BC == 16 && UMI == 16) ? 75 : -1);
-    if (carve >= 0) IBU_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, carve));
+    auto kern = k_pack<BC, UMI, Q, MINB>;
+    if (int rc = set_carveout((const void *)kern, -1, err)) return rc;
     IBU_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const unsigned grid = tile_grid(a.n / kRows);
     kern<<<grid, kBlockThreads, smem, s>>>(a);
     g_launches.fetch_add(1, std::memory_order_relaxed);
     IBU_CUDA(cudaGetLastError());
     return IBU_OK;
+}
+
+// 4 rows per lane (128-row warp tiles) and at most 64 registers (4 resident CTAs): measured best
+// or equal for every shape on 10^8 rows — bc32/umi32 7.07 TB/s, bc16/umi12 6.93, bc16/umi16 6.91,
+// bc16/umi10 6.92 (2 rows per lane with the compiler's default allocation: 6.91 / 6.39 / 6.75 /
+// 6.19; profiles/r1_k3_variants.txt).
+template <int BC, int UMI>
+static int launch_pack(ibu_gpu_ctx *ctx, PackArgs &a, cudaStream_t s, ibu_error_t *err) {
+    // (a 32-byte row next to a runtime-length one needs a few more registers: 3 resident CTAs)
+    constexpr int kMinB = ((BC == 0 && UMI == 32) || (BC == 32 && UMI == 0)) ? 3 : 4;
+    return launch_pack_q<BC, UMI, 4, kMinB>(ctx, a, s, err);
 }
 
 static int check_lens(uint32_t bc_len, uint32_t umi_len, ibu_error_t *err) {

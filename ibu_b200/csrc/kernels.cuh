@@ -76,21 +76,25 @@ __device__ __forceinline__ void decode_word(uint64_t w, uint32_t (&asc)[8]) {
 }
 
 // ---- ASCII -> 2-bit, SWAR.  16 input bytes -> 32 bits; `bad` accumulates mismatch bits ----
-// code = c' ^ (c' >> 1), c' = (c >> 1) & 3 maps A/a C/c G/g T/t to 0 1 2 3; validity by
-// re-expanding the code through the ACGT table and comparing with the case-folded input.
-__device__ __forceinline__ uint32_t pack4(uint32_t w, uint32_t &bad) {
-    uint32_t c = (w >> 1) & 0x03030303u;
-    uint32_t code = c ^ ((w >> 2) & 0x01010101u);
-    uint32_t g = (code * 0x01041040u) >> 24;  // b0 | b1<<2 | b2<<4 | b3<<6 (no carries)
-    uint32_t t = (g | (g << 4)) & 0x0F0Fu;
-    t = (t | (t << 2)) & 0x3333u;
-    uint32_t expect = __byte_perm(kAcgt, 0, t);
-    bad |= (w & 0xDFDFDFDFu) ^ expect;
-    return g;
+// code = c' ^ (c' >> 1), c' = (c >> 1) & 3 maps A/a C/c G/g T/t to 0 1 2 3.  Validity without a
+// table: bits 1-2 of a byte are its code by construction and bit 5 is the case, so only bits
+// {7,6,4,3,0} remain to be checked; they must read 0x41, or 0x50 for T (c' = 2: bit 2 set, bit 1
+// clear): ((c & 0xD9) ^ (T ? 0x11 : 0)) == 0x41  <=>  (c & 0xDF) in {A, C, G, T}  (exhaustive
+// over all 256 byte values: tests/test_oracle_kat.py).  The four codes of a 32-bit group
+// gather into the top byte of one multiply (no carries); pack16 collects four top bytes with
+// three PRMTs.
+__device__ __forceinline__ uint32_t pack4_top(uint32_t w, uint32_t &bad) {
+    const uint32_t s1 = w >> 1, s2 = w >> 2;
+    const uint32_t code = (s1 & 0x03030303u) ^ (s2 & 0x01010101u);
+    const uint32_t t = s2 & ~s1 & 0x01010101u;  // 1 in every byte that claims to be T
+    bad |= ((w & 0xD9D9D9D9u) ^ (t * 0x11u)) ^ 0x41414141u;
+    return code * 0x01041040u;  // top byte = b0 | b1<<2 | b2<<4 | b3<<6
 }
 __device__ __forceinline__ uint32_t pack16(uint4 v, uint32_t &bad) {
-    uint32_t g0 = pack4(v.x, bad), g1 = pack4(v.y, bad), g2 = pack4(v.z, bad), g3 = pack4(v.w, bad);
-    return g0 | (g1 << 8) | (g2 << 16) | (g3 << 24);
+    const uint32_t p0 = pack4_top(v.x, bad), p1 = pack4_top(v.y, bad), p2 = pack4_top(v.z, bad),
+                   p3 = pack4_top(v.w, bad);
+    // bytes 3 of p0..p3 -> bytes 0..3
+    return __byte_perm(__byte_perm(p0, p1, 0x0073), __byte_perm(p2, p3, 0x0073), 0x5410);
 }
 
 // ---- warp reductions ----

@@ -24,6 +24,26 @@ def test_codec_kats():  # record.rs:19-27 + bitnuc: first base in the least-sign
         assert oc.pack_word(bytes([c]))[0] == c1 ^ (c1 >> 1)
 
 
+def test_kernel_validity_identity_exhaustive():
+    """K3's table-free validity test (kernels.cuh pack4_top) against the oracle on every byte value
+    and on random 32-bit groups: ((c & 0xD9) ^ (T ? 0x11 : 0)) == 0x41, T = bit 2 & ~bit 1."""
+    for c in range(256):
+        t = (c >> 2) & ~(c >> 1) & 1
+        assert (((c & 0xD9) ^ (0x11 * t)) != 0x41) == oc.pack_word(bytes([c]))[1], c
+    rng = np.random.default_rng(5)
+    alphabet = np.frombuffer(b"ACGTacgtNn@BDEHPQSUVWXd`\x00\xff", np.uint8)
+    for _ in range(2000):
+        group = alphabet[rng.integers(0, len(alphabet), 4)]
+        w = int.from_bytes(group.tobytes(), "little")
+        s1, s2 = w >> 1, w >> 2
+        t = s2 & ~s1 & 0x01010101
+        bad = (((w & 0xD9D9D9D9) ^ (t * 0x11)) ^ 0x41414141) != 0
+        code = (s1 & 0x03030303) ^ (s2 & 0x01010101)
+        top = ((code * 0x01041040) & 0xFFFFFFFF) >> 24
+        want_w, want_bad = oc.pack_word(group.tobytes())
+        assert bad == want_bad and (want_bad or top == want_w), group
+
+
 @pytest.mark.parametrize("length", [1, 2, 5, 12, 16, 31, 32])
 def test_codec_roundtrip_cross(length):
     rng = np.random.default_rng(length)
