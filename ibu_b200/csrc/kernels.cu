@@ -45,10 +45,9 @@ struct ReduceAcc {
 // `head` records in front of the 32-byte aligned body (a record pointer is only 8-byte aligned
 // in general, e.g. a slice of a larger array) are handled with the ragged tail.
 // No grid-stride loop: CTA c owns the 8 TPW consecutive tiles from 8 TPW c, warp w takes tiles
-// w, w + 8, ... of them (next one prefetched).  Block-scheduled tiles read at 7.45 TB/s where
-// the persistent lock-step grid read at 7.05 (tools/k2lab.cu); TPW = 4 amortises the CTA's
-// reduction without losing that.
-template <int TPW, bool PREFETCH>
+// w, w + 8, ... of them.  TPW = 4 amortises the CTA's reduction (10^8 records: TPW 1 0.41 ms,
+// 2 0.346, 4 and 8 0.333; a register prefetch of the next tile costs occupancy: 0.36-0.49).
+template <int TPW>
 __global__ void __launch_bounds__(kBlockThreads)
 k_validate_reduce(const uint8_t *__restrict__ recs_all, uint64_t n_all, uint32_t head, uint64_t bc_hi,
                   uint64_t umi_hi, ibu_reduce_result_t *__restrict__ res) {
@@ -65,24 +64,10 @@ k_validate_reduce(const uint8_t *__restrict__ recs_all, uint64_t n_all, uint32_t
     uint32_t both = 0;  // records whose barcode AND umi are invalid
     const uint64_t n_tiles = n / kTileRecords;
     uint64_t t = (uint64_t)blockIdx.x * (kWarpsPerBlock * TPW) + warp;
-    u64x4 p0, p1, p2;
-    if (PREFETCH && t < n_tiles) {
-        const u64x4 *base = reinterpret_cast<const u64x4 *>(recs) + t * kTileU8 + lane;
-        p0 = ldg_stream256(base); p1 = ldg_stream256(base + 32); p2 = ldg_stream256(base + 64);
-    }
 #pragma unroll 1
-    for (int j = 0; j < TPW && t < n_tiles; j++) {
-        if (!PREFETCH) {
-            const u64x4 *base = reinterpret_cast<const u64x4 *>(recs) + t * kTileU8 + lane;
-            p0 = ldg_stream256(base); p1 = ldg_stream256(base + 32); p2 = ldg_stream256(base + 64);
-        }
-        const u64x4 v0 = p0, v1 = p1, v2 = p2;
-        const uint64_t tn = t + kWarpsPerBlock;
-        if (PREFETCH && j + 1 < TPW && tn < n_tiles) {
-            const u64x4 *base = reinterpret_cast<const u64x4 *>(recs) + tn * kTileU8 + lane;
-            p0 = ldg_stream256(base); p1 = ldg_stream256(base + 32); p2 = ldg_stream256(base + 64);
-        }
-        t = tn;
+    for (int j = 0; j < TPW && t < n_tiles; j++, t += kWarpsPerBlock) {
+        const u64x4 *base = reinterpret_cast<const u64x4 *>(recs) + t * kTileU8 + lane;
+        const u64x4 v0 = ldg_stream256(base), v1 = ldg_stream256(base + 32), v2 = ldg_stream256(base + 64);
         uint32_t bm = 0;  // bit 4k+j: element (k, j) failed its mask
         IBU_ACC(0, v0.x, 0); IBU_ACC(1, v0.y, 1); IBU_ACC(2, v0.z, 2);  IBU_ACC(0, v0.w, 3);
         IBU_ACC(2, v1.x, 4); IBU_ACC(0, v1.y, 5); IBU_ACC(1, v1.z, 6);  IBU_ACC(2, v1.w, 7);
@@ -715,16 +700,10 @@ int ibu_gpu_validate_reduce_async(ibu_gpu_ctx_t *ctx, const ibu_record_t *d_reco
     // records until the next 32-byte boundary: 24 h = -p (mod 32)  <=>  h = (p / 8) mod 4
     const uint32_t head = (uint32_t)std::min<uint64_t>(n, ((uintptr_t)d_records >> 3) & 3u);
     const uint64_t n_tiles = (n - head) / kTileRecords;
-    static const int mode = getenv("IBU_K1_MODE") ? atoi(getenv("IBU_K1_MODE")) : 40;  // tuning hook: 10*TPW + prefetch
-#define IBU_K1_CASE(TPW, PF)                                                                                  \
-    if (mode == 10 * TPW + PF) {                                                                              \
-        const unsigned grid = (unsigned)std::max<uint64_t>(1, (n_tiles + kWarpsPerBlock * TPW - 1) / (kWarpsPerBlock * TPW)); \
-        k_validate_reduce<TPW, PF><<<grid, kBlockThreads, 0, s>>>((const uint8_t *)d_records, n, head, high_mask(bc_len),    \
-                                                                  high_mask(umi_len), d_result);              \
-    }
-    IBU_K1_CASE(1, 0) IBU_K1_CASE(2, 0) IBU_K1_CASE(4, 0) IBU_K1_CASE(8, 0) IBU_K1_CASE(16, 0)
-    IBU_K1_CASE(2, 1) IBU_K1_CASE(4, 1) IBU_K1_CASE(8, 1) IBU_K1_CASE(16, 1)
-#undef IBU_K1_CASE
+    constexpr int kTpw = 4;  // tiles per warp: a CTA covers 4096 records
+    const unsigned grid = (unsigned)std::max<uint64_t>(1, (n_tiles + kWarpsPerBlock * kTpw - 1) / (kWarpsPerBlock * kTpw));
+    k_validate_reduce<kTpw><<<grid, kBlockThreads, 0, s>>>((const uint8_t *)d_records, n, head, high_mask(bc_len),
+                                                           high_mask(umi_len), d_result);
     g_launches.fetch_add(1, std::memory_order_relaxed);
     IBU_CUDA(cudaGetLastError());
     return IBU_OK;
