@@ -188,20 +188,36 @@ __device__ __forceinline__ void emit_row(uint64_t w, uint32_t len, uint8_t *gout
 #pragma unroll
             for (int g = 0; g < 8; g++)
                 if (g < ng) s32[g] = asc[g];
-        } else if ((len & 1u) == 0) {  // even lengths (e.g. 10-base UMIs): rows are 2-byte aligned
-            uint16_t *s16 = reinterpret_cast<uint16_t *>(stage) + r * (len >> 1);
-#pragma unroll
-            for (int g = 0; g < 8; g++)
-#pragma unroll
-                for (int b = 0; b < 2; b++)
-                    if (4 * g + 2 * b < len) s16[2 * g + b] = (uint16_t)(asc[g] >> (16 * b));
         } else {
-            uint8_t *s8 = stage + r * len;
+            // rows start at any byte: the row is shifted into place with funnel shifts and OR-ed
+            // into the stage (zeroed beforehand, zero_stage) word by word — neighbouring rows
+            // share boundary words, hence the shared-memory atomics.  <= 9 word operations per
+            // row instead of up to 32 byte stores.
+            const uint32_t o = r * len, sh = (o & 3u) * 8u, rem = len & 3u;
+            uint32_t *s32 = reinterpret_cast<uint32_t *>(stage) + (o >> 2);
+            const uint32_t span = (o & 3u) + len;  // bytes from the first touched word's start
+            uint32_t prev = 0;
 #pragma unroll
-            for (int g = 0; g < 8; g++)
-#pragma unroll
-                for (int b = 0; b < 4; b++)
-                    if (4 * g + b < len) s8[4 * g + b] = (uint8_t)(asc[g] >> (8 * b));
+            for (int g = 0; g < 9; g++) {
+                uint32_t cur = 0;
+                if (g < 8 && (uint32_t)g < ng) {
+                    cur = asc[g < 8 ? g : 0];
+                    if ((uint32_t)g == ng - 1) cur &= (1u << (8u * rem)) - 1u;  // rem is 1..3 here
+                }
+                if (4u * g < span) atomicOr(s32 + g, __funnelshift_l(prev, cur, sh));
+                prev = cur;
+            }
+        }
+    }
+}
+
+// zero a runtime-length stage whose rows are OR-ed in (len % 4 != 0); no-op otherwise
+template <int L>
+__device__ __forceinline__ void zero_stage(uint32_t len, uint8_t *stage, uint32_t lane) {
+    if constexpr (L == 0) {
+        if (len & 3u) {
+            uint4 *s4 = reinterpret_cast<uint4 *>(stage);
+            for (uint32_t i = lane; i < 8 * len; i += 32) s4[i] = make_uint4(0, 0, 0, 0);
         }
     }
 }
@@ -251,6 +267,8 @@ __global__ void __launch_bounds__(kBlockThreads) k_unpack(const UnpackArgs a) {
         const uint4 *g4 = reinterpret_cast<const uint4 *>(a.recs) + t * kTileU4;
 #pragma unroll
         for (int k = 0; k < 6; k++) in4[lane + 32 * k] = ldg_stream(g4 + lane + 32 * k);
+        zero_stage<BC>(bc_len, bc_stage, lane);
+        zero_stage<UMI>(umi_len, umi_stage, lane);
         __syncwarp();
 #pragma unroll
         for (int q = 0; q < 4; q++) {

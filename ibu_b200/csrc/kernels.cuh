@@ -98,15 +98,18 @@ __device__ __forceinline__ uint32_t pack16(uint4 v, uint32_t &bad) {
 }
 
 // ---- warp reductions ----
+// Wrapping 64-bit sum with three REDUX instead of a 5-level shuffle tree: the value is cut into
+// 22-bit limbs; 32 lanes x (2^22 - 1) < 2^27, so every limb sum is exact in 32 bits, and
+// s0 + s1 2^22 + s2 2^44 (mod 2^64) is the wrapping sum.
 __device__ __forceinline__ uint64_t warp_sum64(uint64_t v) {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    return v;
+    const uint32_t l0 = (uint32_t)v & 0x3FFFFFu, l1 = (uint32_t)(v >> 22) & 0x3FFFFFu, l2 = (uint32_t)(v >> 44);
+    const uint64_t s0 = __reduce_add_sync(0xffffffffu, l0), s1 = __reduce_add_sync(0xffffffffu, l1),
+                   s2 = __reduce_add_sync(0xffffffffu, l2);
+    return s0 + (s1 << 22) + (s2 << 44);
 }
 __device__ __forceinline__ uint64_t warp_xor64(uint64_t v) {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v ^= __shfl_xor_sync(0xffffffffu, v, o);
-    return v;
+    const uint32_t lo = __reduce_xor_sync(0xffffffffu, (uint32_t)v), hi = __reduce_xor_sync(0xffffffffu, (uint32_t)(v >> 32));
+    return ((uint64_t)hi << 32) | lo;
 }
 
 // counter-based generator shared with the oracle (DESIGN.md §Synthetic data)

@@ -136,6 +136,49 @@ def test_unpack_codec_kats(ctx):  # record.rs:19-27 + bitnuc order
     assert gf.tolist() == [0, 1, 2]
 
 
+@pytest.mark.parametrize("n", [1, 127, 128, 129, 1023, 1024, 1025, 128 * 8 * 5 + 3])
+@pytest.mark.parametrize("bc,umi", [(16, 12), (32, 32), (15, 9), (20, 10), (1, 32)])
+def test_kernels_stay_inside_their_buffers(ctx, n, bc, umi):
+    """One tile per warp, the grid rounded up to whole CTAs, one warp for the ragged tail: guard
+    zones around every output of K2 and K3 (and K2's input tail) must come back untouched."""
+    G = 4096  # guard bytes on both sides (keeps 16/32-byte alignment)
+    recs = oc.generate_records(0, n, bc, umi, 1, 200_000, 17)
+
+    def guarded(nbytes, payload=None):
+        host = np.full(G + nbytes + G, 0xA5, np.uint8)
+        if payload is not None:
+            host[G:G + nbytes] = np.frombuffer(payload.tobytes(), np.uint8)
+        return Dev(ctx, host.nbytes, host), host
+
+    def check(dev, nbytes):
+        back = dev.get(np.uint8, G + nbytes + G)
+        assert (back[:G] == 0xA5).all() and (back[G + nbytes:] == 0xA5).all()
+        return back[G:G + nbytes]
+
+    d_recs, _ = guarded(recs.nbytes, recs)
+    d_bc, _ = guarded(n * bc)
+    d_umi, _ = guarded(n * umi)
+    d_fl, _ = guarded(n)
+    res = Dev(ctx, 64)
+    ctx.unpack_async(d_recs.ptr + G, n, bc, umi, d_bc.ptr + G, d_umi.ptr + G, d_fl.ptr + G, res)
+    ctx.synchronize()
+    ob, ou, of, _ = oc.unpack_records(recs, bc, umi, 1)
+    gb, gu, gf = check(d_bc, n * bc), check(d_umi, n * umi), check(d_fl, n)
+    assert np.array_equal(gb.reshape(n, bc), ob) and np.array_equal(gu.reshape(n, umi), ou) and np.array_equal(gf, of)
+    # pack the rows back into a guarded record buffer
+    d_out, _ = guarded(n * 24)
+    ctx.pack_async(d_bc.ptr + G, d_umi.ptr + G, n, bc, umi, d_out.ptr + G, d_flags=d_fl.ptr + G, d_result=res)
+    ctx.synchronize()
+    back = check(d_out, n * 24).view(ibu.RECORD_DTYPE)
+    check(d_fl, n)
+    mask = lambda length: U64(2**64 - 1) if length == 32 else U64((1 << (2 * length)) - 1)  # noqa: E731
+    assert np.array_equal(back["barcode"], recs["barcode"] & mask(bc))
+    assert np.array_equal(back["umi"], recs["umi"] & mask(umi))
+    assert np.array_equal(back["index"], np.arange(n, dtype=U64))
+    for d in (d_recs, d_bc, d_umi, d_fl, d_out, res):
+        d.free()
+
+
 # ---- K3 -----------------------------------------------------------------------------------
 def gpu_pack(ctx, bc_rows, umi_rows, index=None, index_base=0):
     n, bc = bc_rows.shape
