@@ -19,6 +19,16 @@ struct ibu_chunk_slot {
     ibu_reduce_result_t *h_result = nullptr;  // pinned
 };
 
+// One entry of the result-scratch ring: 256 spread result blocks (256 x 8 u64, kept zeroed between
+// uses) that the warps of a K1/K2 launch RED into, and the event recorded after the launch's fold
+// kernel, which the next user of the entry waits on.
+struct ibu_result_scratch {
+    unsigned long long *blocks = nullptr;
+    cudaEvent_t folded = nullptr;
+};
+constexpr int kResultBlocks = 256;
+constexpr int kResultRing = 16;
+
 struct ibu_gpu_ctx {
     int device = 0;
     int sm_count = 0;
@@ -27,6 +37,8 @@ struct ibu_gpu_ctx {
     std::vector<ibu_chunk_slot> slots;
     // grow-only device scratch of the blocking table builder (K4): cudaMalloc/cudaFree per call
     // would cost more than the streaming pass itself
+    std::vector<ibu_result_scratch> result_ring;
+    std::atomic<uint32_t> result_next{0};
     std::mutex pipe_mutex;  // the chunk slots serve one host-buffer call at a time
     std::mutex arena_mutex;
     void *arena_base = nullptr;

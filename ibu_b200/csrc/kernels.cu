@@ -42,6 +42,57 @@ struct ReduceAcc {
         bm |= bit__ << (SLOT);                        \
     } while (0)
 
+// ---- result blocks ---------------------------------------------------------------------------
+// A warp adds its partial result to one of 256 zeroed result blocks (one RED instruction whose
+// lanes 1-7 carry the words of ibu_reduce_result_t, a second one for the xor word) and exits: no
+// block barrier, no CTA-level tail.  k_fold_result folds the blocks into the caller's result and
+// re-zeroes them.  Measured on unpack bc16/umi12, 10^8 records (tools/k2lab.cu): CTA reduction +
+// one RED per CTA into the result itself 0.797 ms, this 0.757 ms, no result at all 0.754 ms — and
+// 195 k CTAs RED-ing into ONE 64-byte block take 1.30 ms (same-address atomics serialise at
+// ~3 ns each), which is why the blocks are spread.
+__device__ __forceinline__ void red_spread(unsigned long long *blocks, uint32_t slot, uint32_t lane,
+                                           uint64_t s_bc, uint64_t s_umi, uint64_t s_idx, uint64_t x_all,
+                                           uint64_t n_bb, uint64_t n_bu, uint64_t n_br) {
+    const uint64_t v = lane == 1 ? s_bc : lane == 2 ? s_umi : lane == 3 ? s_idx : lane == 4 ? x_all
+                       : lane == 5 ? n_bb : lane == 6 ? n_bu : n_br;
+    unsigned long long *blk = blocks + 8 * (slot & (kResultBlocks - 1));
+    if (lane >= 1 && lane < 8 && v) {
+        if (lane == 4) atomicXor(blk + 4, (unsigned long long)v);
+        else atomicAdd(blk + lane, (unsigned long long)v);
+    }
+}
+
+// <<<1, 256>>>: thread t owns result block t
+__global__ void __launch_bounds__(kResultBlocks)
+k_fold_result(unsigned long long *__restrict__ blocks, ibu_reduce_result_t *__restrict__ res, uint64_t n_records) {
+    __shared__ uint64_t red[kResultBlocks / 32][8];
+    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    ulonglong2 *mine = reinterpret_cast<ulonglong2 *>(blocks + 8 * threadIdx.x);
+    uint64_t w[8];
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        const ulonglong2 v = mine[k];
+        w[2 * k] = v.x; w[2 * k + 1] = v.y;
+        mine[k] = make_ulonglong2(0ull, 0ull);
+    }
+#pragma unroll
+    for (int k = 1; k < 8; k++) {
+        const uint64_t r = k == 4 ? warp_xor64(w[k]) : warp_sum64(w[k]);
+        if (lane == 0) red[warp][k] = r;
+    }
+    __syncthreads();
+    if (threadIdx.x < 8) {
+        uint64_t v = n_records;  // word 0
+        if (threadIdx.x > 0) {
+            v = 0;
+            for (int q = 0; q < kResultBlocks / 32; q++) {
+                if (threadIdx.x == 4) v ^= red[q][4]; else v += red[q][threadIdx.x];
+            }
+        }
+        reinterpret_cast<uint64_t *>(res)[threadIdx.x] = v;
+    }
+}
+
 // `head` records in front of the 32-byte aligned body (a record pointer is only 8-byte aligned
 // in general, e.g. a slice of a larger array) are handled with the ragged tail.
 // No grid-stride loop: CTA c owns the 8 TPW consecutive tiles from 8 TPW c, warp w takes tiles
@@ -50,7 +101,7 @@ struct ReduceAcc {
 template <int TPW>
 __global__ void __launch_bounds__(kBlockThreads)
 k_validate_reduce(const uint8_t *__restrict__ recs_all, uint64_t n_all, uint32_t head, uint64_t bc_hi,
-                  uint64_t umi_hi, ibu_reduce_result_t *__restrict__ res) {
+                  uint64_t umi_hi, unsigned long long *__restrict__ blocks) {
     const uint8_t *recs = recs_all + (uint64_t)head * 24;
     const uint64_t n = n_all - head;
     const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
@@ -109,25 +160,11 @@ k_validate_reduce(const uint8_t *__restrict__ recs_all, uint64_t n_all, uint32_t
         }
     }
 
-    __shared__ uint64_t red[kWarpsPerBlock][8];  // slots follow ibu_reduce_result_t
     s_bc = warp_sum64(s_bc); s_umi = warp_sum64(s_umi); s_idx = warp_sum64(s_idx);
     x = warp_xor64(x);
     n_bb = warp_sum64(n_bb); n_bu = warp_sum64(n_bu); n_both = warp_sum64(n_both);
-    if (lane == 0) {
-        red[warp][1] = s_bc; red[warp][2] = s_umi; red[warp][3] = s_idx; red[warp][4] = x;
-        red[warp][5] = n_bb; red[warp][6] = n_bu; red[warp][7] = n_bb + n_bu - n_both;  // bad records
-    }
-    __syncthreads();
-    unsigned long long *out = reinterpret_cast<unsigned long long *>(res);
-    if (threadIdx.x >= 1 && threadIdx.x < 8) {  // one RED instruction per CTA (+ one for the xor)
-        uint64_t v = 0;
-        for (int w = 0; w < kWarpsPerBlock; w++) {
-            if (threadIdx.x == 4) v ^= red[w][4]; else v += red[w][threadIdx.x];
-        }
-        if (threadIdx.x == 4) atomicXor(out + 4, (unsigned long long)v);
-        else if (v) atomicAdd(out + threadIdx.x, (unsigned long long)v);
-    }
-    if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(out, (unsigned long long)n_all);  // n_records
+    red_spread(blocks, blockIdx.x * kWarpsPerBlock + warp, lane, s_bc, s_umi, s_idx, x, n_bb, n_bu,
+               n_bb + n_bu - n_both);
 }
 
 // ============================================================================ K2
@@ -136,7 +173,7 @@ struct UnpackArgs {
     uint64_t n;
     uint8_t *bc_out, *umi_out, *flags;
     uint64_t bc_hi, umi_hi;
-    ibu_reduce_result_t *res;
+    unsigned long long *res_blocks;  // 256 spread result blocks (SUMS) or nullptr
     uint32_t bc_len, umi_len;
     uint32_t warp_smem_bytes;  // per-warp shared memory: input tile + staged outputs
     uint32_t bc_stage_off, umi_stage_off;
@@ -307,28 +344,12 @@ __global__ void __launch_bounds__(kBlockThreads) k_unpack(const UnpackArgs a) {
         }
     }
 
-    if (SUMS) {  // a.res != nullptr: warp -> CTA -> one RED instruction per CTA (+ one for the xor)
-        __shared__ uint64_t red[kWarpsPerBlock][8];
-        n_bb = __reduce_add_sync(0xffffffffu, n_bb);
-        n_bu = __reduce_add_sync(0xffffffffu, n_bu);
-        n_br = __reduce_add_sync(0xffffffffu, n_br);
+    if (SUMS) {  // a result was asked for: warp-level reduction, then straight into a spread block
+        const uint64_t c_bb = __reduce_add_sync(0xffffffffu, n_bb), c_bu = __reduce_add_sync(0xffffffffu, n_bu),
+                       c_br = __reduce_add_sync(0xffffffffu, n_br);
         s_bc = warp_sum64(s_bc); s_umi = warp_sum64(s_umi); s_idx = warp_sum64(s_idx);
         x_all = warp_xor64(x_all);
-        if (lane == 0) {  // slots follow ibu_reduce_result_t
-            red[warp][1] = s_bc; red[warp][2] = s_umi; red[warp][3] = s_idx; red[warp][4] = x_all;
-            red[warp][5] = n_bb; red[warp][6] = n_bu; red[warp][7] = n_br;
-        }
-        __syncthreads();
-        unsigned long long *out = reinterpret_cast<unsigned long long *>(a.res);
-        if (threadIdx.x >= 1 && threadIdx.x < 8) {
-            uint64_t v = 0;
-            for (int w = 0; w < kWarpsPerBlock; w++) {
-                if (threadIdx.x == 4) v ^= red[w][4]; else v += red[w][threadIdx.x];
-            }
-            if (threadIdx.x == 4) atomicXor(out + 4, (unsigned long long)v);
-            else if (v) atomicAdd(out + threadIdx.x, (unsigned long long)v);
-        }
-        if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(out, (unsigned long long)a.n);
+        red_spread(a.res_blocks, blockIdx.x * kWarpsPerBlock + warp, lane, s_bc, s_umi, s_idx, x_all, c_bb, c_bu, c_br);
     }
 }
 
@@ -621,13 +642,31 @@ static unsigned tile_grid(uint64_t n_tiles) { return (unsigned)((n_tiles + 1 + k
 
 // Shared-memory carve-out (percent of 228 KB, -1 = driver default) for a streaming kernel.  It
 // fixes both the number of resident CTAs and what is left as L1, and these kernels are sensitive
-// to the pair: unpack bc16/umi12 on 10^8 records runs in 0.865 ms at the default (6 CTAs, 28 KB
-// L1), 0.803 at 75 % (5 CTAs), 0.780 at 64 % (4 CTAs, 92 KB L1), 0.796 at 50 % (3 CTAs); padding the
-// request to get 4 CTAs WITHOUT enlarging L1 gives 0.876.  profiles/r1_carveout_sweep*.txt.
+// to the pair: unpack bc16/umi12 on 10^8 records runs in 0.864 ms at the default (6 CTAs, 28 KB
+// L1), 0.766 at 75 % (5 CTAs), 0.763 at 64 % (4 CTAs, 92 KB L1), 0.800 at 50 % (3 CTAs); padding the
+// request to get 4 CTAs WITHOUT enlarging L1 gave 0.876.  profiles/r1_carveout_sweep*.txt.
 static int set_carveout(const void *kern, int carve, ibu_error_t *err) {
     static const int env = getenv("IBU_CARVEOUT") ? atoi(getenv("IBU_CARVEOUT")) : -2;  // tuning hook
     if (env != -2) carve = env;
     if (carve >= 0) IBU_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, carve));
+    return IBU_OK;
+}
+
+// Take the next entry of the context's result-scratch ring for a launch on stream s (the stream
+// first waits for the fold of the entry's previous user), and, after the kernel, fold it into
+// d_result on the same stream.
+static int result_acquire(ibu_gpu_ctx *ctx, cudaStream_t s, ibu_result_scratch **out, ibu_error_t *err) {
+    ibu_result_scratch &r = ctx->result_ring[ctx->result_next.fetch_add(1, std::memory_order_relaxed) % kResultRing];
+    IBU_CUDA(cudaStreamWaitEvent(s, r.folded, 0));
+    *out = &r;
+    return IBU_OK;
+}
+static int result_fold(ibu_result_scratch *r, ibu_reduce_result_t *d_result, uint64_t n, cudaStream_t s,
+                       ibu_error_t *err) {
+    k_fold_result<<<1, kResultBlocks, 0, s>>>(r->blocks, d_result, n);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    IBU_CUDA(cudaGetLastError());
+    IBU_CUDA(cudaEventRecord(r->folded, s));
     return IBU_OK;
 }
 
@@ -643,12 +682,15 @@ static int launch_unpack(ibu_gpu_ctx *ctx, UnpackArgs &a, cudaStream_t s, ibu_er
     if (!(UMI == 32 || UMI == 16)) off += (kTileRecords * a.umi_len + 15u) & ~15u;
     a.warp_smem_bytes = off;
     const size_t smem = (size_t)off * kWarpsPerBlock;
-    // with a result block the pass also carries K1's sums / checksum (measured cost: 0.2 %)
-    auto kern = a.res ? k_unpack<BC, UMI, true> : k_unpack<BC, UMI, false>;
+    // with a result block the pass also carries K1's sums / checksum
+    auto kern = a.res_blocks ? k_unpack<BC, UMI, true> : k_unpack<BC, UMI, false>;
     constexpr bool kStaged = !(BC == 32 || BC == 16) || !(UMI == 32 || UMI == 16);
-    // staged kernels: the smallest configuration that holds 4 CTAs (bc16/umi12: 37 KB each -> 164 KB)
-    const int four_ctas = (int)std::min<size_t>(100, (4 * (smem + 1536) * 100 + 233471) / 233472);
-    if (int rc = set_carveout((const void *)kern, kStaged ? four_ctas : -1, err)) return rc;
+    // staged kernels: the smallest configuration that holds 5 CTAs (bc16/umi12: 37 KB each -> 196 KB,
+    // 60 KB of L1).  With the barrier-free result tail 4 and 5 CTAs are equal for bc16/umi12
+    // (0.763 / 0.766 ms) and 5 is better for bc16/umi10 (0.776 vs 0.799); the default (6 CTAs,
+    // 28 KB L1) costs 13 % and 3 CTAs 5 %.
+    const int five_ctas = (int)std::min<size_t>(100, (5 * (smem + 1536) * 100 + 233471) / 233472);
+    if (int rc = set_carveout((const void *)kern, kStaged ? five_ctas : -1, err)) return rc;
     IBU_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const unsigned grid = tile_grid(a.n / kTileRecords);
     kern<<<grid, kBlockThreads, smem, s>>>(a);
@@ -714,17 +756,18 @@ int ibu_gpu_validate_reduce_async(ibu_gpu_ctx_t *ctx, const ibu_record_t *d_reco
     if (!aligned(d_records, 8)) return set_error(err, IBU_ERR_ARG, 0, 0, 0, "d_records must be 8-byte aligned");
     DeviceGuard guard(ctx->device);
     cudaStream_t s = pick_stream(ctx, stream);
-    IBU_CUDA(cudaMemsetAsync(d_result, 0, sizeof(*d_result), s));
+    ibu_result_scratch *scratch = nullptr;
+    if (int rc = result_acquire(ctx, s, &scratch, err)) return rc;
     // records until the next 32-byte boundary: 24 h = -p (mod 32)  <=>  h = (p / 8) mod 4
     const uint32_t head = (uint32_t)std::min<uint64_t>(n, ((uintptr_t)d_records >> 3) & 3u);
     const uint64_t n_tiles = (n - head) / kTileRecords;
     constexpr int kTpw = 4;  // tiles per warp: a CTA covers 4096 records
     const unsigned grid = (unsigned)std::max<uint64_t>(1, (n_tiles + kWarpsPerBlock * kTpw - 1) / (kWarpsPerBlock * kTpw));
     k_validate_reduce<kTpw><<<grid, kBlockThreads, 0, s>>>((const uint8_t *)d_records, n, head, high_mask(bc_len),
-                                                           high_mask(umi_len), d_result);
+                                                           high_mask(umi_len), scratch->blocks);
     g_launches.fetch_add(1, std::memory_order_relaxed);
     IBU_CUDA(cudaGetLastError());
-    return IBU_OK;
+    return result_fold(scratch, d_result, n, s, err);
 }
 
 int ibu_gpu_unpack_async(ibu_gpu_ctx_t *ctx, const ibu_record_t *d_records, uint64_t n,
@@ -739,7 +782,9 @@ int ibu_gpu_unpack_async(ibu_gpu_ctx_t *ctx, const ibu_record_t *d_records, uint
         return set_error(err, IBU_ERR_ARG, 0, 0, 0, "device pointers must be 16-byte aligned");
     DeviceGuard guard(ctx->device);
     cudaStream_t s = pick_stream(ctx, stream);
-    if (d_result) IBU_CUDA(cudaMemsetAsync(d_result, 0, sizeof(*d_result), s));
+    ibu_result_scratch *scratch = nullptr;
+    if (d_result)
+        if (int rc = result_acquire(ctx, s, &scratch, err)) return rc;
     UnpackArgs a{};
     a.recs = (const uint8_t *)d_records;
     a.n = n;
@@ -748,7 +793,7 @@ int ibu_gpu_unpack_async(ibu_gpu_ctx_t *ctx, const ibu_record_t *d_records, uint
     a.flags = d_flags;
     a.bc_hi = high_mask(bc_len);
     a.umi_hi = high_mask(umi_len);
-    a.res = d_result;
+    a.res_blocks = scratch ? scratch->blocks : nullptr;
     a.bc_len = bc_len;
     a.umi_len = umi_len;
     // store mode per output: 32 / 16 = direct vector store (needs that alignment), 12 =
@@ -756,14 +801,17 @@ int ibu_gpu_unpack_async(ibu_gpu_ctx_t *ctx, const ibu_record_t *d_records, uint
     const int bm = (bc_len == 32 && aligned(d_bc_ascii, 32)) ? 32 : bc_len == 16 ? 16 : 0;
     const int um = (umi_len == 32 && aligned(d_umi_ascii, 32)) ? 32
                    : umi_len == 16 ? 16 : umi_len == 12 ? 12 : umi_len == 10 ? 10 : 0;
+    int rc = -1;
 #define IBU_UNPACK_CASE(B, U) \
-    if (bm == B && um == U) return launch_unpack<B, U>(ctx, a, s, err);
+    if (bm == B && um == U) rc = launch_unpack<B, U>(ctx, a, s, err);
     IBU_UNPACK_CASE(16, 12) IBU_UNPACK_CASE(16, 16) IBU_UNPACK_CASE(16, 32) IBU_UNPACK_CASE(16, 0)
     IBU_UNPACK_CASE(16, 10) IBU_UNPACK_CASE(32, 10) IBU_UNPACK_CASE(0, 10)
     IBU_UNPACK_CASE(32, 12) IBU_UNPACK_CASE(32, 16) IBU_UNPACK_CASE(32, 32) IBU_UNPACK_CASE(32, 0)
     IBU_UNPACK_CASE(0, 12) IBU_UNPACK_CASE(0, 16) IBU_UNPACK_CASE(0, 32) IBU_UNPACK_CASE(0, 0)
 #undef IBU_UNPACK_CASE
-    return set_error(err, IBU_ERR_ARG, 0, 0, 0, "no unpack kernel for this shape");
+    if (rc < 0) return set_error(err, IBU_ERR_ARG, 0, 0, 0, "no unpack kernel for this shape");
+    if (rc != IBU_OK || !scratch) return rc;
+    return result_fold(scratch, d_result, n, s, err);
 }
 
 int ibu_gpu_pack_async(ibu_gpu_ctx_t *ctx, const uint8_t *d_bc_ascii, const uint8_t *d_umi_ascii,

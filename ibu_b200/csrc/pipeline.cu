@@ -362,6 +362,13 @@ int ibu_gpu_ctx_create(int device, const ibu_gpu_config_t *cfg, ibu_gpu_ctx_t **
         if (e == cudaSuccess) e = cudaMalloc((void **)&s.d_result, sizeof(ibu_reduce_result_t));
         if (e == cudaSuccess) e = cudaHostAlloc((void **)&s.h_result, sizeof(ibu_reduce_result_t), cudaHostAllocDefault);
     }
+    ctx->result_ring.resize(kResultRing);
+    for (auto &r : ctx->result_ring) {
+        const size_t bytes = (size_t)kResultBlocks * sizeof(ibu_reduce_result_t);
+        if (e == cudaSuccess) e = cudaMalloc((void **)&r.blocks, bytes);
+        if (e == cudaSuccess) e = cudaMemset(r.blocks, 0, bytes);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&r.folded, cudaEventDisableTiming);
+    }
     if (e != cudaSuccess) {
         ibu_gpu_ctx_destroy(ctx);
         return cuda_fail(err, e, "context creation");
@@ -389,6 +396,13 @@ void ibu_gpu_ctx_destroy(ibu_gpu_ctx_t *ctx) {
     if (ctx->stream) {
         cudaStreamSynchronize(ctx->stream);
         cudaStreamDestroy(ctx->stream);
+    }
+    for (auto &r : ctx->result_ring) {
+        if (r.folded) {
+            cudaEventSynchronize(r.folded);
+            cudaEventDestroy(r.folded);
+        }
+        if (r.blocks) cudaFree(r.blocks);
     }
     if (ctx->arena_base) cudaFree(ctx->arena_base);
     delete ctx;

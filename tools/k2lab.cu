@@ -297,12 +297,12 @@ k_unpack_tma(const uint8_t *__restrict__ recs, uint64_t n_tiles128, uint8_t *__r
 
 // Non-persistent K2: CTA c owns 8*TPW consecutive 128-record tiles; a warp takes one tile per
 // round (prefetching the next round's tile when TPW > 1).  No grid-stride loop.
-template <int TPW, int HINT>
-__global__ void __launch_bounds__(256)
+template <int TPW, int HINT, int WARPS = 8, int TAIL = 0>
+__global__ void __launch_bounds__(WARPS * 32)
 k_unpack_np(const uint8_t *__restrict__ recs, uint64_t n_tiles, uint8_t *__restrict__ bc_out,
             uint8_t *__restrict__ umi_out, uint64_t bc_hi, uint64_t umi_hi, unsigned long long *res) {
-    __shared__ __align__(16) uint8_t smem[8 * (3072 + 1536)];
-    __shared__ uint64_t red[8][8];
+    __shared__ __align__(16) uint8_t smem[WARPS * (3072 + 1536)];
+    __shared__ uint64_t red[WARPS][8];
     const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
     uint8_t *wsm = smem + warp * (3072 + 1536);
     uint4 *in4 = reinterpret_cast<uint4 *>(wsm);
@@ -311,7 +311,7 @@ k_unpack_np(const uint8_t *__restrict__ recs, uint64_t n_tiles, uint8_t *__restr
     const uint4 *g4 = reinterpret_cast<const uint4 *>(recs);
     uint32_t n_bb = 0, n_bu = 0, n_br = 0;
     uint64_t s_bc = 0, s_umi = 0, s_idx = 0, x_all = 0;
-    uint64_t t = 8ull * TPW * blockIdx.x + warp;
+    uint64_t t = (uint64_t)WARPS * TPW * blockIdx.x + warp;
     uint4 pre[6];
     if (t < n_tiles) {
 #pragma unroll
@@ -322,7 +322,7 @@ k_unpack_np(const uint8_t *__restrict__ recs, uint64_t n_tiles, uint8_t *__restr
 #pragma unroll
         for (int k = 0; k < 6; k++) in4[lane + 32 * k] = pre[k];
         __syncwarp();
-        const uint64_t tn = t + 8;
+        const uint64_t tn = t + WARPS;
         if (TPW > 1 && j + 1 < TPW && tn < n_tiles) {
 #pragma unroll
             for (int k = 0; k < 6; k++) pre[k] = ldg_stream(g4 + tn * 192 + lane + 32 * k);
@@ -347,10 +347,19 @@ k_unpack_np(const uint8_t *__restrict__ recs, uint64_t n_tiles, uint8_t *__restr
         if (TPW > 1) __syncwarp();
         t = tn;
     }
+    if (TAIL == 2) return;
     s_bc = warp_sum64(s_bc); s_umi = warp_sum64(s_umi); s_idx = warp_sum64(s_idx); x_all = warp_xor64(x_all);
     n_bb = __reduce_add_sync(0xffffffffu, n_bb);
     n_bu = __reduce_add_sync(0xffffffffu, n_bu);
     n_br = __reduce_add_sync(0xffffffffu, n_br);
+    if (TAIL == 1) {  // no barrier: every warp REDs into one of 256 spread result blocks (res[256][8])
+        const uint64_t v = lane == 1 ? s_bc : lane == 2 ? s_umi : lane == 3 ? s_idx : lane == 4 ? x_all
+                           : lane == 5 ? n_bb : lane == 6 ? n_bu : n_br;
+        unsigned long long *blk = res + 8 * ((blockIdx.x * WARPS + warp) & 255u);
+        if (lane == 4) atomicXor(blk + 4, (unsigned long long)v);
+        else if (lane >= 1 && lane < 8 && v) atomicAdd(blk + lane, (unsigned long long)v);
+        return;
+    }
     if (lane == 0) {
         red[warp][1] = s_bc; red[warp][2] = s_umi; red[warp][3] = s_idx; red[warp][4] = x_all;
         red[warp][5] = n_bb; red[warp][6] = n_bu; red[warp][7] = n_br;
@@ -358,7 +367,7 @@ k_unpack_np(const uint8_t *__restrict__ recs, uint64_t n_tiles, uint8_t *__restr
     __syncthreads();
     if (threadIdx.x >= 1 && threadIdx.x < 8) {
         uint64_t v = 0;
-        for (int w = 0; w < 8; w++) { if (threadIdx.x == 4) v ^= red[w][4]; else v += red[w][threadIdx.x]; }
+        for (int w = 0; w < WARPS; w++) { if (threadIdx.x == 4) v ^= red[w][4]; else v += red[w][threadIdx.x]; }
         if (threadIdx.x == 4) atomicXor(res + 4, (unsigned long long)v);
         else if (v) atomicAdd(res + threadIdx.x, (unsigned long long)v);
     }
@@ -470,6 +479,8 @@ int main(int argc, char **argv) {
 
     // pure traffic: K2's mix and 50/50 mixes on the same structures (buffers big enough for all)
     const uint64_t n_tiles = n / 128;
+    const bool only_k2 = argc > 3;
+    if (!only_k2) {
     uint4 *tin, *ta, *tb;
     CK(cudaMalloc(&tin, n_tiles * 512 * 8)); CK(cudaMalloc(&ta, n_tiles * 512 * 8)); CK(cudaMalloc(&tb, n_tiles * 512 * 4));
     CK(cudaMemsetAsync(tin, 1, n_tiles * 512 * 8, s));
@@ -504,33 +515,47 @@ int main(int argc, char **argv) {
     T.run("cudaMemsetAsync (write only)", 1.0 * copy16 * 16, [&] { cudaMemsetAsync(ta, 0, copy16 * 16, s); });
     T.run("cudaMemcpyAsync D2D", 2.0 * copy16 * 16, [&] { cudaMemcpyAsync(ta, tin, copy16 * 16, cudaMemcpyDeviceToDevice, s); });
     CK(cudaFree(tin)); CK(cudaFree(ta)); CK(cudaFree(tb));
+    }
 
     // non-persistent K2
-    auto run_np = [&](auto kern, const char *name, int tpw) {
+    unsigned long long *res_spread;
+    CK(cudaMalloc(&res_spread, 256 * 64));
+    auto run_np = [&](auto kern, const char *name, int tpw, int warps, int tail, int carve) {
         const uint64_t hi_bc = ~0ull << 32, hi_umi = ~0ull << 24;
-        const unsigned grid = (unsigned)((n / 128 + 8 * tpw - 1) / (8 * tpw));
-        CK(cudaMemsetAsync(bc2, 0, n * 16, s)); CK(cudaMemsetAsync(umi2, 0, n * 12, s)); CK(cudaMemsetAsync(res2, 0, 64, s));
-        kern<<<grid, 256, 0, s>>>(recs, n / 128, bc2, umi2, hi_bc, hi_umi, res2);
+        const unsigned grid = (unsigned)((n / 128 + warps * tpw - 1) / (warps * tpw));
+        if (carve >= 0) CK(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, carve));
+        unsigned long long *r = tail == 1 ? res_spread : res2;
+        CK(cudaMemsetAsync(bc2, 0, n * 16, s)); CK(cudaMemsetAsync(umi2, 0, n * 12, s)); CK(cudaMemsetAsync(r, 0, tail == 1 ? 256 * 64 : 64, s));
+        kern<<<grid, warps * 32, 0, s>>>(recs, n / 128, bc2, umi2, hi_bc, hi_umi, r);
         CK(cudaMemsetAsync(d_count, 0, 8, s));
         k_diff<<<sms * 8, 256, 0, s>>>((const uint4 *)bc2, (const uint4 *)bc, n, d_count);
         k_diff<<<sms * 8, 256, 0, s>>>((const uint4 *)umi2, (const uint4 *)umi, n * 12 / 16, d_count);
-        unsigned long long bad = 0, got[8];
+        unsigned long long bad = 0;
+        std::vector<unsigned long long> got(tail == 1 ? 2048 : 8);
         CK(cudaMemcpyAsync(&bad, d_count, 8, cudaMemcpyDeviceToHost, s));
-        CK(cudaMemcpyAsync(got, res2, 64, cudaMemcpyDeviceToHost, s));
+        CK(cudaMemcpyAsync(got.data(), r, got.size() * 8, cudaMemcpyDeviceToHost, s));
         CK(cudaStreamSynchronize(s));
-        char extra[160];
+        unsigned long long fold[8] = {0};
+        for (size_t i = 0; i < got.size(); i++) { if (i % 8 == 4) fold[4] ^= got[i]; else fold[i % 8] += got[i]; }
+        if (tail == 1) fold[0] = n;
+        char extra[200];
         snprintf(extra, sizeof extra, ",\"grid\":%u,\"mismatch_u4\":%llu,\"result_block_ok\":%s", grid, bad,
-                 memcmp(got, ref_res, 64) == 0 ? "true" : "false");
+                 tail == 2 ? "null" : memcmp(fold, ref_res, 64) == 0 ? "true" : "false");
         T.run(name, 52.0 * n, [&] {
-            cudaMemsetAsync(res2, 0, 64, s);
-            kern<<<grid, 256, 0, s>>>(recs, n / 128, bc2, umi2, hi_bc, hi_umi, res2);
+            if (tail != 2) cudaMemsetAsync(r, 0, tail == 1 ? 256 * 64 : 64, s);
+            kern<<<grid, warps * 32, 0, s>>>(recs, n / 128, bc2, umi2, hi_bc, hi_umi, r);
         }, extra);
     };
-    run_np(k_unpack_np<1, 0>, "k_unpack_np<1 tile/warp, plain st>", 1);
-    run_np(k_unpack_np<1, 1>, "k_unpack_np<1 tile/warp, st.cs>", 1);
-    run_np(k_unpack_np<2, 0>, "k_unpack_np<2 tiles/warp, plain st>", 2);
-    run_np(k_unpack_np<2, 1>, "k_unpack_np<2 tiles/warp, st.cs>", 2);
-    run_np(k_unpack_np<4, 1>, "k_unpack_np<4 tiles/warp, st.cs>", 4);
+    run_np(k_unpack_np<1, 0, 8, 0>, "np W=8 tail=CTA-reduce, default carve-out", 1, 8, 0, -1);
+    run_np(k_unpack_np<1, 0, 8, 0>, "np W=8 tail=CTA-reduce, carve-out 64", 1, 8, 0, 64);
+    run_np(k_unpack_np<1, 0, 8, 1>, "np W=8 tail=per-warp RED spread, carve-out 64", 1, 8, 1, 64);
+    run_np(k_unpack_np<1, 0, 8, 2>, "np W=8 no result, carve-out 64", 1, 8, 2, 64);
+    run_np(k_unpack_np<1, 0, 4, 0>, "np W=4 tail=CTA-reduce, carve-out 64", 1, 4, 0, 64);
+    run_np(k_unpack_np<1, 0, 4, 1>, "np W=4 tail=per-warp RED spread, carve-out 64", 1, 4, 1, 64);
+    run_np(k_unpack_np<1, 0, 4, 0>, "np W=4 tail=CTA-reduce, carve-out 50", 1, 4, 0, 50);
+    run_np(k_unpack_np<1, 0, 4, 0>, "np W=4 tail=CTA-reduce, carve-out 75", 1, 4, 0, 75);
+    run_np(k_unpack_np<1, 0, 8, 1>, "np W=8 tail=per-warp RED spread, carve-out 75", 1, 8, 1, 75);
+    run_np(k_unpack_np<2, 0, 8, 0>, "np W=8 TPW=2 tail=CTA-reduce, carve-out 64", 2, 8, 0, 64);
 
     // bulk-async K2 variants
     run_tma<2, 2, 8, 1>(T, sms, recs, n, bc2, umi2, res2, bc, umi, ref_res, d_count);
