@@ -359,7 +359,7 @@ struct PackArgs {
     const uint64_t *index;
     uint64_t index_base, n;
     uint8_t *recs_out, *flags;
-    ibu_reduce_result_t *res;
+    unsigned long long *res_blocks;  // 256 spread result blocks or nullptr
     uint32_t bc_len, umi_len;
     uint32_t warp_smem_bytes, bc_stage_off, umi_stage_off;
 };
@@ -559,20 +559,10 @@ __global__ void __launch_bounds__(kBlockThreads, MINB) k_pack(const PackArgs a) 
         }
     }
 
-    if (a.res) {  // counters: warp -> CTA -> one RED instruction per CTA that saw a bad row
-        __shared__ uint32_t red[kWarpsPerBlock][4];
-        n_bb = __reduce_add_sync(0xffffffffu, n_bb);
-        n_bu = __reduce_add_sync(0xffffffffu, n_bu);
-        n_br = __reduce_add_sync(0xffffffffu, n_br);
-        if (lane == 0) { red[warp][0] = n_bb; red[warp][1] = n_bu; red[warp][2] = n_br; }
-        __syncthreads();
-        unsigned long long *out = reinterpret_cast<unsigned long long *>(a.res);
-        if (threadIdx.x < 3) {
-            uint32_t v = 0;
-            for (int w = 0; w < kWarpsPerBlock; w++) v += red[w][threadIdx.x];
-            if (v) atomicAdd(out + 5 + threadIdx.x, (unsigned long long)v);
-        }
-        if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(out, (unsigned long long)a.n);
+    if (a.res_blocks) {  // counters: one RED per warp that saw a bad row, into a spread result block
+        const uint64_t c_bb = __reduce_add_sync(0xffffffffu, n_bb), c_bu = __reduce_add_sync(0xffffffffu, n_bu),
+                       c_br = __reduce_add_sync(0xffffffffu, n_br);
+        if (c_br) red_spread(a.res_blocks, blockIdx.x * kWarpsPerBlock + warp, lane, 0, 0, 0, 0, c_bb, c_bu, c_br);
     }
 }
 
@@ -827,7 +817,9 @@ int ibu_gpu_pack_async(ibu_gpu_ctx_t *ctx, const uint8_t *d_bc_ascii, const uint
         return set_error(err, IBU_ERR_ARG, 0, 0, 0, "device pointers must be 16-byte aligned");
     DeviceGuard guard(ctx->device);
     cudaStream_t s = pick_stream(ctx, stream);
-    if (d_result) IBU_CUDA(cudaMemsetAsync(d_result, 0, sizeof(*d_result), s));
+    ibu_result_scratch *scratch = nullptr;
+    if (d_result)
+        if (int rc = result_acquire(ctx, s, &scratch, err)) return rc;
     PackArgs a{};
     a.bc_in = d_bc_ascii;
     a.umi_in = d_umi_ascii;
@@ -836,20 +828,23 @@ int ibu_gpu_pack_async(ibu_gpu_ctx_t *ctx, const uint8_t *d_bc_ascii, const uint
     a.n = n;
     a.recs_out = (uint8_t *)d_records;
     a.flags = d_flags;
-    a.res = d_result;
+    a.res_blocks = scratch ? scratch->blocks : nullptr;
     a.bc_len = bc_len;
     a.umi_len = umi_len;
     const int bm = (bc_len == 32 && aligned(d_bc_ascii, 32)) ? 32 : bc_len == 16 ? 16 : 0;
     const int um = (umi_len == 32 && aligned(d_umi_ascii, 32)) ? 32
                    : umi_len == 16 ? 16 : umi_len == 12 ? 12 : umi_len == 10 ? 10 : 0;
+    int rc = -1;
 #define IBU_PACK_CASE(B, U) \
-    if (bm == B && um == U) return launch_pack<B, U>(ctx, a, s, err);
+    if (bm == B && um == U) rc = launch_pack<B, U>(ctx, a, s, err);
     IBU_PACK_CASE(32, 32) IBU_PACK_CASE(32, 16) IBU_PACK_CASE(32, 12) IBU_PACK_CASE(32, 0)
     IBU_PACK_CASE(16, 32) IBU_PACK_CASE(16, 16) IBU_PACK_CASE(16, 12) IBU_PACK_CASE(16, 0)
     IBU_PACK_CASE(0, 12) IBU_PACK_CASE(16, 10) IBU_PACK_CASE(32, 10) IBU_PACK_CASE(0, 10)
     IBU_PACK_CASE(0, 32) IBU_PACK_CASE(0, 16) IBU_PACK_CASE(0, 0)
 #undef IBU_PACK_CASE
-    return set_error(err, IBU_ERR_ARG, 0, 0, 0, "no pack kernel for this shape");
+    if (rc < 0) return set_error(err, IBU_ERR_ARG, 0, 0, 0, "no pack kernel for this shape");
+    if (rc != IBU_OK || !scratch) return rc;
+    return result_fold(scratch, d_result, n, s, err);
 }
 
 int ibu_gpu_generate_records_async(ibu_gpu_ctx_t *ctx, ibu_record_t *d_records, uint64_t first,
