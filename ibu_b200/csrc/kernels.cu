@@ -188,6 +188,37 @@ struct LenOf<0> {
     static __device__ __forceinline__ uint32_t get(uint32_t rt) { return rt; }
 };
 
+// Stage one decoded row of compile-time length L (any 1..32) at byte offset r * L.
+//   L % 4 == 0: word stores;  L even: halfword stores;  L odd: rows start at any byte, so the row is
+//   shifted into place with funnel shifts and OR-ed into the (zeroed) stage word by word with
+//   shared-memory atomics - neighbouring rows share boundary words.
+template <int L>
+__device__ __forceinline__ void stage_row(uint64_t w, uint8_t *stage, uint32_t r) {
+    constexpr int NG = (L + 3) / 4;
+    uint32_t asc[8];
+    decode_word<NG>(w, asc);
+    if constexpr (L % 4 == 0) {
+        uint32_t *s32 = reinterpret_cast<uint32_t *>(stage) + r * (L / 4);
+#pragma unroll
+        for (int g = 0; g < NG; g++) s32[g] = asc[g];
+    } else if constexpr (L % 2 == 0) {
+        uint16_t *s16 = reinterpret_cast<uint16_t *>(stage) + r * (L / 2);
+#pragma unroll
+        for (int h = 0; h < L / 2; h++) s16[h] = (uint16_t)(asc[h / 2] >> (16 * (h & 1)));
+    } else {
+        const uint32_t o = r * L, sh = (o & 3u) * 8u;
+        uint32_t *s32 = reinterpret_cast<uint32_t *>(stage) + (o >> 2);
+        asc[NG - 1] &= (1u << (8 * (L & 3))) - 1u;  // bytes past the row in its last word
+        uint32_t prev = 0;
+#pragma unroll
+        for (int g = 0; g <= NG; g++) {
+            const uint32_t cur = g < NG ? asc[g < NG ? g : 0] : 0u;
+            if (4u * g < (o & 3u) + L) atomicOr(s32 + g, __funnelshift_l(prev, cur, sh));
+            prev = cur;
+        }
+    }
+}
+
 // Emit one decoded row.  L = 32 / 16: straight from registers with a 256 / 128-bit store
 // (a warp covers 1024 / 512 contiguous bytes).  Otherwise the row is staged in shared memory
 // and the whole tile (128 x len bytes, 16-byte aligned in the output) is copied out afterwards.
@@ -202,60 +233,37 @@ __device__ __forceinline__ void emit_row(uint64_t w, uint32_t len, uint8_t *gout
     } else if (L == 16) {
         decode_word<4>(w, asc);
         stg_stream(reinterpret_cast<uint4 *>(gout) + rec, make_uint4(asc[0], asc[1], asc[2], asc[3]));
-    } else if (L > 0 && L % 4 == 0) {  // compile-time length, multiple of 4: word stores into the stage
-        decode_word<L / 4>(w, asc);
-        uint32_t *s32 = reinterpret_cast<uint32_t *>(stage) + r * (L / 4);
-#pragma unroll
-        for (int g = 0; g < L / 4; g++) s32[g] = asc[g];
-    } else if (L > 0) {  // compile-time even length (10-base UMIs): halfword stores
-        static_assert(L % 2 == 0, "compile-time staged lengths are even");
-        decode_word<(L + 3) / 4>(w, asc);
-        uint16_t *s16 = reinterpret_cast<uint16_t *>(stage) + r * (L / 2);
-#pragma unroll
-        for (int h = 0; h < L / 2; h++) s16[h] = (uint16_t)(asc[h / 2] >> (16 * (h & 1)));
-    } else {  // runtime length
-        const uint32_t ng = (len + 3) >> 2;
-        const uint32_t lo = (uint32_t)w, hi = (uint32_t)(w >> 32);
-        decode8<0>(lo, asc[0], asc[1]);
-        if (ng > 2) decode8<1>(lo, asc[2], asc[3]);
-        if (ng > 4) decode8<0>(hi, asc[4], asc[5]);
-        if (ng > 6) decode8<1>(hi, asc[6], asc[7]);
-        if ((len & 3u) == 0) {
-            uint32_t *s32 = reinterpret_cast<uint32_t *>(stage) + r * (len >> 2);
-#pragma unroll
-            for (int g = 0; g < 8; g++)
-                if (g < ng) s32[g] = asc[g];
-        } else {
-            // rows start at any byte: the row is shifted into place with funnel shifts and OR-ed
-            // into the stage (zeroed beforehand, zero_stage) word by word — neighbouring rows
-            // share boundary words, hence the shared-memory atomics.  <= 9 word operations per
-            // row instead of up to 32 byte stores.
-            const uint32_t o = r * len, sh = (o & 3u) * 8u, rem = len & 3u;
-            uint32_t *s32 = reinterpret_cast<uint32_t *>(stage) + (o >> 2);
-            const uint32_t span = (o & 3u) + len;  // bytes from the first touched word's start
-            uint32_t prev = 0;
-#pragma unroll
-            for (int g = 0; g < 9; g++) {
-                uint32_t cur = 0;
-                if (g < 8 && (uint32_t)g < ng) {
-                    cur = asc[g < 8 ? g : 0];
-                    if ((uint32_t)g == ng - 1) cur &= (1u << (8u * rem)) - 1u;  // rem is 1..3 here
-                }
-                if (4u * g < span) atomicOr(s32 + g, __funnelshift_l(prev, cur, sh));
-                prev = cur;
-            }
-        }
+    } else if (L > 0) {  // compile-time length, staged
+        stage_row<L>(w, stage, r);
     }
+    // L == 0 (runtime length): staged per tile by stage_tile_rt, not per row
 }
 
-// zero a runtime-length stage whose rows are OR-ed in (len % 4 != 0); no-op otherwise
+// All four rows of a lane for one runtime-length output.  The length is warp-uniform, so one
+// switch per tile selects a fully specialised body: generic-length shapes then execute about the
+// same instructions as the compile-time shapes instead of ~3x as many predicated ones.
 template <int L>
-__device__ __forceinline__ void zero_stage(uint32_t len, uint8_t *stage, uint32_t lane) {
-    if constexpr (L == 0) {
-        if (len & 3u) {
-            uint4 *s4 = reinterpret_cast<uint4 *>(stage);
-            for (uint32_t i = lane; i < 8 * len; i += 32) s4[i] = make_uint4(0, 0, 0, 0);
-        }
+__device__ __forceinline__ void stage_tile(const uint64_t *in64, uint32_t word, uint8_t *stage, uint32_t lane) {
+    if constexpr (L % 2 == 1) {  // OR-ed rows need a zeroed stage
+        uint4 *s4 = reinterpret_cast<uint4 *>(stage);
+        for (uint32_t i = lane; i < 8 * L; i += 32) s4[i] = make_uint4(0, 0, 0, 0);
+        __syncwarp();
+    }
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+        const uint32_t r = lane + 32 * q;
+        stage_row<L>(in64[3 * r + word], stage, r);
+    }
+}
+__device__ __forceinline__ void stage_tile_rt(uint32_t len, const uint64_t *in64, uint32_t word, uint8_t *stage,
+                                           uint32_t lane) {
+    switch (len) {
+#define IBU_CASE(L) case L: stage_tile<L>(in64, word, stage, lane); break;
+        IBU_CASE(1) IBU_CASE(2) IBU_CASE(3) IBU_CASE(4) IBU_CASE(5) IBU_CASE(6) IBU_CASE(7) IBU_CASE(8)
+        IBU_CASE(9) IBU_CASE(10) IBU_CASE(11) IBU_CASE(12) IBU_CASE(13) IBU_CASE(14) IBU_CASE(15) IBU_CASE(16)
+        IBU_CASE(17) IBU_CASE(18) IBU_CASE(19) IBU_CASE(20) IBU_CASE(21) IBU_CASE(22) IBU_CASE(23) IBU_CASE(24)
+        IBU_CASE(25) IBU_CASE(26) IBU_CASE(27) IBU_CASE(28) IBU_CASE(29) IBU_CASE(30) IBU_CASE(31) IBU_CASE(32)
+#undef IBU_CASE
     }
 }
 
@@ -304,9 +312,9 @@ __global__ void __launch_bounds__(kBlockThreads) k_unpack(const UnpackArgs a) {
         const uint4 *g4 = reinterpret_cast<const uint4 *>(a.recs) + t * kTileU4;
 #pragma unroll
         for (int k = 0; k < 6; k++) in4[lane + 32 * k] = ldg_stream(g4 + lane + 32 * k);
-        zero_stage<BC>(bc_len, bc_stage, lane);
-        zero_stage<UMI>(umi_len, umi_stage, lane);
         __syncwarp();
+        if constexpr (BC == 0) stage_tile_rt(bc_len, in64, 0, bc_stage, lane);
+        if constexpr (UMI == 0) stage_tile_rt(umi_len, in64, 1, umi_stage, lane);
 #pragma unroll
         for (int q = 0; q < 4; q++) {
             const uint32_t r = lane + 32 * q;  // record of the tile handled by this lane
@@ -424,56 +432,42 @@ struct RowRegs<12, Q> : RowRegs<0, Q> {};  // 12- and 10-byte rows are staged to
 template <int Q>
 struct RowRegs<10, Q> : RowRegs<0, Q> {};
 
-// gather one staged row into two 16-byte halves, padded with 'A' (code 0, valid)
+// Gather the staged row r of compile-time length L (any 1..32) into two 16-byte halves, padded
+// with 'A' (code 0, valid).  L % 4 == 0: word loads (odd word strides are conflict-free);
+// L even: halfword loads; L odd: rows start at any byte - aligned words + funnel shift (the stage
+// has 16 spare bytes behind the tile for the one-word over-read).
 template <int L>
-__device__ __forceinline__ void staged_row(const uint8_t *stage, uint32_t r, uint32_t len,
-                                           uint4 &lo, uint4 &hi) {
-    if constexpr (L == 12) {  // word stride 3: conflict-free
-        const uint32_t *r32 = reinterpret_cast<const uint32_t *>(stage) + 3 * r;
-        lo = make_uint4(r32[0], r32[1], r32[2], 0x41414141u);
-        hi = make_uint4(0x41414141u, 0x41414141u, 0x41414141u, 0x41414141u);
-        return;
-    }
-    if constexpr (L == 10) {  // halfword stride 5
-        const uint16_t *r16 = reinterpret_cast<const uint16_t *>(stage) + 5 * r;
-        lo = make_uint4(r16[0] | ((uint32_t)r16[1] << 16), r16[2] | ((uint32_t)r16[3] << 16),
-                        r16[4] | 0x41410000u, 0x41414141u);
-        hi = make_uint4(0x41414141u, 0x41414141u, 0x41414141u, 0x41414141u);
-        return;
-    }
+__device__ __forceinline__ void load_row(const uint8_t *stage, uint32_t r, uint4 &lo, uint4 &hi) {
+    constexpr int NG = (L + 3) / 4;
     uint32_t w[8];
 #pragma unroll
     for (int g = 0; g < 8; g++) w[g] = 0x41414141u;
-    const uint8_t *row = stage + r * len;
-    if ((len & 3u) == 0) {
-        const uint32_t *r32 = reinterpret_cast<const uint32_t *>(row);
+    if constexpr (L % 4 == 0) {
+        const uint32_t *r32 = reinterpret_cast<const uint32_t *>(stage) + r * (L / 4);
 #pragma unroll
-        for (int g = 0; g < 8; g++)
-            if (4u * g < len) w[g] = r32[g];
-    } else if ((len & 1u) == 0) {  // even lengths: 2-byte aligned rows, halfword loads
-        const uint16_t *r16 = reinterpret_cast<const uint16_t *>(row);
+        for (int g = 0; g < NG; g++) w[g] = r32[g];
+    } else if constexpr (L % 2 == 0) {
+        const uint16_t *r16 = reinterpret_cast<const uint16_t *>(stage) + r * (L / 2);
 #pragma unroll
-        for (int g = 0; g < 8; g++) {
-            if (4u * g < len) {
-                const uint32_t lo16 = r16[2 * g];
-                const uint32_t hi16 = (4u * g + 2 < len) ? (uint32_t)r16[2 * g + 1] : 0x4141u;
-                w[g] = lo16 | (hi16 << 16);
-            }
+        for (int g = 0; g < NG; g++) {
+            const uint32_t lo16 = r16[2 * g];
+            const uint32_t hi16 = (4 * g + 2 < L) ? (uint32_t)r16[2 * g + 1] : 0x4141u;
+            w[g] = lo16 | (hi16 << 16);
         }
-    } else {  // odd lengths, rows start at any byte: aligned words + funnel shift, tail padded with 'A'
-        const uint32_t o = r * len, sh = (o & 3u) * 8u;
+    } else {
+        const uint32_t o = r * L, sh = (o & 3u) * 8u;
         const uint32_t *r32 = reinterpret_cast<const uint32_t *>(stage) + (o >> 2);
         uint32_t cur = r32[0];
 #pragma unroll
-        for (int g = 0; g < 8; g++) {
-            if (4u * g < len) {
-                const uint32_t nxt = r32[g + 1];  // (the stage has 16 spare bytes behind the tile)
-                uint32_t v = __funnelshift_r(cur, nxt, sh);
-                const uint32_t rem = len - 4u * g;
-                if (rem < 4u) v = (v & ((1u << (8u * rem)) - 1u)) | (0x41414141u << (8u * rem));
-                w[g] = v;
-                cur = nxt;
+        for (int g = 0; g < NG; g++) {
+            const uint32_t nxt = r32[g + 1];
+            uint32_t v = __funnelshift_r(cur, nxt, sh);
+            if (g == NG - 1) {
+                constexpr uint32_t rem = L & 3;  // 1 or 3 bytes of the row in its last word
+                v = (v & ((1u << (8 * rem)) - 1u)) | (0x41414141u << (8 * rem));
             }
+            w[g] = v;
+            cur = nxt;
         }
     }
     lo = make_uint4(w[0], w[1], w[2], w[3]);
@@ -481,12 +475,38 @@ __device__ __forceinline__ void staged_row(const uint8_t *stage, uint32_t r, uin
 }
 
 template <int L>
-__device__ __forceinline__ uint64_t pack_row(uint4 lo, uint4 hi, uint32_t len, uint32_t &badflag) {
+__device__ __forceinline__ uint64_t pack_row(uint4 lo, uint4 hi, uint32_t &badflag) {
     uint32_t bad = 0;
     uint64_t w = pack16(lo, bad);
-    if (L == 32 || (L == 0 && len > 16)) w |= (uint64_t)pack16(hi, bad) << 32;  // L = 12, 16: one half
+    if constexpr (L > 16) w |= (uint64_t)pack16(hi, bad) << 32;
     badflag = bad != 0;
     return w;
+}
+
+// All Q rows of a lane for one runtime-length input: packed words and a bad-row mask.  The length
+// is warp-uniform: one switch per tile selects a fully specialised body (see stage_tile_rt).
+template <int L, int Q>
+__device__ __forceinline__ void pack_tile(const uint8_t *stage, uint32_t lane, uint64_t (&w)[Q], uint32_t &badmask) {
+#pragma unroll
+    for (int q = 0; q < Q; q++) {
+        uint4 lo, hi;
+        uint32_t bad;
+        load_row<L>(stage, lane + 32 * q, lo, hi);
+        w[q] = pack_row<L>(lo, hi, bad);
+        badmask |= bad << q;
+    }
+}
+template <int Q>
+__device__ __forceinline__ void pack_tile_rt(uint32_t len, const uint8_t *stage, uint32_t lane, uint64_t (&w)[Q],
+                                          uint32_t &badmask) {
+    switch (len) {
+#define IBU_CASE(L) case L: pack_tile<L, Q>(stage, lane, w, badmask); break;
+        IBU_CASE(1) IBU_CASE(2) IBU_CASE(3) IBU_CASE(4) IBU_CASE(5) IBU_CASE(6) IBU_CASE(7) IBU_CASE(8)
+        IBU_CASE(9) IBU_CASE(10) IBU_CASE(11) IBU_CASE(12) IBU_CASE(13) IBU_CASE(14) IBU_CASE(15) IBU_CASE(16)
+        IBU_CASE(17) IBU_CASE(18) IBU_CASE(19) IBU_CASE(20) IBU_CASE(21) IBU_CASE(22) IBU_CASE(23) IBU_CASE(24)
+        IBU_CASE(25) IBU_CASE(26) IBU_CASE(27) IBU_CASE(28) IBU_CASE(29) IBU_CASE(30) IBU_CASE(31) IBU_CASE(32)
+#undef IBU_CASE
+    }
 }
 
 // One tile of 32 Q rows per warp, no grid-stride loop (see k_unpack for the measurement).
@@ -513,18 +533,30 @@ __global__ void __launch_bounds__(kBlockThreads, MINB) k_pack(const PackArgs a) 
         bc_rows.park(bc_stage, lane, bc_len);
         umi_rows.park(umi_stage, lane, umi_len);
         if (kStageBc || kStageUmi) __syncwarp();
+        uint64_t bcw[Q], umw[Q];
+        uint32_t bcbad = 0, umbad = 0;
+        if constexpr (BC == 0) pack_tile_rt<Q>(bc_len, bc_stage, lane, bcw, bcbad);
+        if constexpr (UMI == 0) pack_tile_rt<Q>(umi_len, umi_stage, lane, umw, umbad);
 #pragma unroll
         for (int q = 0; q < Q; q++) {
-            uint4 bl, bh, ul, uh;
-            if constexpr (!kStageBc) bc_rows.get(q, bl, bh);
-            else staged_row<BC>(bc_stage, lane + 32 * q, bc_len, bl, bh);
-            if constexpr (!kStageUmi) umi_rows.get(q, ul, uh);
-            else staged_row<UMI>(umi_stage, lane + 32 * q, umi_len, ul, uh);
             const uint32_t r = lane + 32 * q;
             const uint64_t row = t * kRows + r;
             uint32_t bb, bu;
-            const uint64_t bw = pack_row<BC>(bl, bh, bc_len, bb);
-            const uint64_t uw = pack_row<UMI>(ul, uh, umi_len, bu);
+            uint64_t bw, uw;
+            if constexpr (BC == 0) {
+                bw = bcw[q]; bb = (bcbad >> q) & 1u;
+            } else {
+                uint4 lo, hi;
+                if constexpr (!kStageBc) bc_rows.get(q, lo, hi); else load_row<BC>(bc_stage, r, lo, hi);
+                bw = pack_row<BC>(lo, hi, bb);
+            }
+            if constexpr (UMI == 0) {
+                uw = umw[q]; bu = (umbad >> q) & 1u;
+            } else {
+                uint4 lo, hi;
+                if constexpr (!kStageUmi) umi_rows.get(q, lo, hi); else load_row<UMI>(umi_stage, r, lo, hi);
+                uw = pack_row<UMI>(lo, hi, bu);
+            }
             const uint64_t idx = a.index ? ldg_stream64(a.index + row) : a.index_base + row;
             out64[3 * r] = bw; out64[3 * r + 1] = uw; out64[3 * r + 2] = idx;
             n_bb += bb; n_bu += bu; n_br += (bb | bu);

@@ -179,6 +179,36 @@ def test_kernels_stay_inside_their_buffers(ctx, n, bc, umi):
         d.free()
 
 
+def test_result_blocks_under_concurrent_streams(ctx):
+    """K1/K2/K3 accumulate into a 16-entry ring of spread result blocks folded by a second kernel;
+    48 launches in flight on 8 streams (3 x the ring) must each get exactly their own result."""
+    import torch
+
+    streams = [torch.cuda.Stream() for _ in range(8)]
+    jobs = []
+    for j in range(48):
+        n = 20_000 + 1_777 * j
+        recs = oc.generate_records(1000 * j, n, 16, 12, 1, 50_000 + 1000 * j, 100 + j)
+        d = Dev(ctx, recs.nbytes, recs)
+        jobs.append((recs, d, Dev(ctx, n * 16), Dev(ctx, n * 12), Dev(ctx, 64), Dev(ctx, 64), Dev(ctx, 64), Dev(ctx, n * 24)))
+    ctx.synchronize()
+    for j, (recs, d, b, u, r1, r2, r3, back) in enumerate(jobs):
+        st = streams[j % 8]
+        ctx.validate_reduce_async(d, len(recs), 16, 12, r1, st)
+        ctx.unpack_async(d, len(recs), 16, 12, b, u, None, r2, st)
+        ctx.pack_async(b, u, len(recs), 16, 12, back, d_result=r3, stream=st)
+    for st in streams:
+        st.synchronize()
+    for recs, d, b, u, r1, r2, r3, back in jobs:
+        want = oc.reduce_records(recs, 16, 12)
+        assert ctx.read_result(r1.ptr) == want
+        assert ctx.read_result(r2.ptr) == want
+        got3 = ctx.read_result(r3.ptr)
+        assert got3["n_records"] == len(recs) and got3["n_bad_records"] == 0 and got3["sum_index"] == 0
+        for x in (d, b, u, r1, r2, r3, back):
+            x.free()
+
+
 # ---- K3 -----------------------------------------------------------------------------------
 def gpu_pack(ctx, bc_rows, umi_rows, index=None, index_base=0):
     n, bc = bc_rows.shape
