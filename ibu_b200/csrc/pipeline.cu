@@ -11,7 +11,11 @@
 #include <algorithm>
 #include <atomic>
 #include <cerrno>
+#include <condition_variable>
 #include <cstdlib>
+#include <deque>
+#include <functional>
+#include <memory>
 #include <fcntl.h>
 #if defined(__SSE2__)
 #include <emmintrin.h>
@@ -70,30 +74,125 @@ void stream_copy(void *dst, const void *src, size_t bytes) {
 #endif
 }
 
+// Persistent host workers for the staging copies.  A chunk is staged in ~2 ms; creating and
+// joining 16 threads per chunk cost a tenth of that.  One process-wide pool (hardware threads - 1
+// workers, the caller works too); jobs from several contexts interleave safely.
+class WorkPool {
+public:
+    static WorkPool &instance() {
+        static WorkPool pool;
+        return pool;
+    }
+    // fn(0) .. fn(pieces - 1), each exactly once, on the caller and the workers; returns when all are done
+    template <class F>
+    void run(unsigned pieces, F &&fn) {
+        if (pieces == 0) return;
+        if (pieces == 1 || workers_.empty()) {
+            for (unsigned i = 0; i < pieces; i++) fn(i);
+            return;
+        }
+        auto job = std::make_shared<Job>();
+        job->fn = [&fn](unsigned i) { fn(i); };
+        job->pieces = pieces;
+        {
+            std::lock_guard<std::mutex> lock(m_);
+            jobs_.push_back(job);
+        }
+        cv_work_.notify_all();
+        work_on(*job);
+        std::unique_lock<std::mutex> lock(job->m);
+        job->cv.wait(lock, [&] { return job->done == job->pieces; });
+    }
+
+private:
+    struct Job {
+        std::function<void(unsigned)> fn;
+        unsigned pieces = 0;
+        std::atomic<unsigned> next{0};
+        unsigned done = 0;  // guarded by m
+        std::mutex m;
+        std::condition_variable cv;
+    };
+    static void work_on(Job &job) {
+        unsigned mine = 0;
+        for (unsigned i; (i = job.next.fetch_add(1, std::memory_order_relaxed)) < job.pieces;) {
+            job.fn(i);
+            mine++;
+        }
+        if (mine) {
+            std::lock_guard<std::mutex> lock(job.m);
+            job.done += mine;
+            if (job.done == job.pieces) job.cv.notify_all();
+        }
+    }
+    WorkPool() : owner_(getpid()) {
+        unsigned hc = std::thread::hardware_concurrency();
+        unsigned n = hc > 1 ? std::min(31u, hc - 1) : 0;
+        for (unsigned i = 0; i < n; i++) workers_.emplace_back([this] { loop(); });
+    }
+    ~WorkPool() {
+        {
+            std::lock_guard<std::mutex> lock(m_);
+            stop_ = true;
+        }
+        cv_work_.notify_all();
+        // (in a forked child the workers do not exist: run() then does every piece itself)
+        for (auto &t : workers_) {
+            if (getpid() == owner_) t.join(); else t.detach();
+        }
+    }
+    void loop() {
+        for (;;) {
+            std::shared_ptr<Job> job;
+            {
+                std::unique_lock<std::mutex> lock(m_);
+                cv_work_.wait(lock, [&] {
+                    while (!jobs_.empty() && jobs_.front()->next.load(std::memory_order_relaxed) >= jobs_.front()->pieces)
+                        jobs_.pop_front();  // fully handed out
+                    return stop_ || !jobs_.empty();
+                });
+                if (stop_) return;
+                job = jobs_.front();
+            }
+            work_on(*job);
+        }
+    }
+    std::mutex m_;
+    std::condition_variable cv_work_;
+    std::deque<std::shared_ptr<Job>> jobs_;
+    std::vector<std::thread> workers_;
+    bool stop_ = false;
+    pid_t owner_;
+};
+
+// [0, bytes) cut into `threads` page-aligned pieces, piece i handed to fn(offset, length)
+template <class F>
+void for_pieces(size_t bytes, unsigned threads, size_t granule, F &&fn) {
+    if (threads < 1) threads = 1;
+    const size_t per = align_up((bytes + threads - 1) / threads, granule);
+    const unsigned pieces = (unsigned)((bytes + per - 1) / per);
+    WorkPool::instance().run(pieces, [&](unsigned i) {
+        const size_t off = (size_t)i * per;
+        fn(off, std::min(per, bytes - off));
+    });
+}
+
 void parallel_memcpy(void *dst, const void *src, size_t bytes, unsigned threads) {
-    if (threads <= 1 || bytes < (8u << 20)) {
+    if (threads <= 1 || bytes < (1u << 20)) {
         stream_copy(dst, src, bytes);
         return;
     }
-    size_t per = align_up(bytes / threads, 4096);
-    std::vector<std::thread> pool;
-    for (unsigned i = 0; i < threads; i++) {
-        size_t off = (size_t)i * per;
-        if (off >= bytes) break;
-        size_t len = std::min(per, bytes - off);
-        pool.emplace_back([=] { stream_copy((uint8_t *)dst + off, (const uint8_t *)src + off, len); });
-    }
-    for (auto &t : pool) t.join();
+    for_pieces(bytes, threads, 4096, [&](size_t off, size_t len) {
+        stream_copy((uint8_t *)dst + off, (const uint8_t *)src + off, len);
+    });
 }
 
 // The same fan-out with pread(2): no page tables are populated for the mapping and an I/O error
 // is a return code, not a SIGBUS.  Each thread reads 64 KB pieces into a cache-resident bounce
 // buffer and streams them on (pread straight into the pinned buffer is the 38 GB/s case above).
 bool parallel_pread(void *dst, int fd, uint64_t file_off, size_t bytes, unsigned threads) {
-    if (threads < 1) threads = 1;
-    size_t per = align_up((bytes + threads - 1) / threads, 1 << 20);
     std::atomic<bool> ok{true};
-    auto work = [&](size_t off, size_t len) {
+    for_pieces(bytes, threads, 1 << 20, [&](size_t off, size_t len) {
         constexpr size_t kBounce = 64u << 10;
         alignas(64) uint8_t bounce[kBounce];
         uint8_t *p = (uint8_t *)dst + off;
@@ -110,19 +209,7 @@ bool parallel_pread(void *dst, int fd, uint64_t file_off, size_t bytes, unsigned
             fo += (uint64_t)got;
             len -= (size_t)got;
         }
-    };
-    std::vector<std::thread> pool;
-    for (unsigned i = 0; i < threads; i++) {
-        size_t off = (size_t)i * per;
-        if (off >= bytes) break;
-        size_t len = std::min(per, bytes - off);
-        if (i + 1 == threads || off + per >= bytes) {
-            work(off, len);  // the calling thread takes the last piece
-            break;
-        }
-        pool.emplace_back(work, off, len);
-    }
-    for (auto &t : pool) t.join();
+    });
     return ok;
 }
 
