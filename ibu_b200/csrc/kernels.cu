@@ -243,22 +243,18 @@ __device__ __forceinline__ void emit_row(uint64_t w, uint32_t len, uint8_t *gout
 // switch per tile selects a fully specialised body: generic-length shapes then execute about the
 // same instructions as the compile-time shapes instead of ~3x as many predicated ones.
 template <int L>
-__device__ __forceinline__ void stage_tile(const uint64_t *in64, uint32_t word, uint8_t *stage, uint32_t lane) {
+__device__ __forceinline__ void stage_tile(const uint64_t (&w)[4], uint8_t *stage, uint32_t lane) {
     if constexpr (L % 2 == 1) {  // OR-ed rows need a zeroed stage
         uint4 *s4 = reinterpret_cast<uint4 *>(stage);
         for (uint32_t i = lane; i < 8 * L; i += 32) s4[i] = make_uint4(0, 0, 0, 0);
         __syncwarp();
     }
 #pragma unroll
-    for (int q = 0; q < 4; q++) {
-        const uint32_t r = lane + 32 * q;
-        stage_row<L>(in64[3 * r + word], stage, r);
-    }
+    for (int q = 0; q < 4; q++) stage_row<L>(w[q], stage, lane + 32 * q);
 }
-__device__ __forceinline__ void stage_tile_rt(uint32_t len, const uint64_t *in64, uint32_t word, uint8_t *stage,
-                                           uint32_t lane) {
+__device__ __forceinline__ void stage_tile_rt(uint32_t len, const uint64_t (&w)[4], uint8_t *stage, uint32_t lane) {
     switch (len) {
-#define IBU_CASE(L) case L: stage_tile<L>(in64, word, stage, lane); break;
+#define IBU_CASE(L) case L: stage_tile<L>(w, stage, lane); break;
         IBU_CASE(1) IBU_CASE(2) IBU_CASE(3) IBU_CASE(4) IBU_CASE(5) IBU_CASE(6) IBU_CASE(7) IBU_CASE(8)
         IBU_CASE(9) IBU_CASE(10) IBU_CASE(11) IBU_CASE(12) IBU_CASE(13) IBU_CASE(14) IBU_CASE(15) IBU_CASE(16)
         IBU_CASE(17) IBU_CASE(18) IBU_CASE(19) IBU_CASE(20) IBU_CASE(21) IBU_CASE(22) IBU_CASE(23) IBU_CASE(24)
@@ -313,13 +309,29 @@ __global__ void __launch_bounds__(kBlockThreads) k_unpack(const UnpackArgs a) {
 #pragma unroll
         for (int k = 0; k < 6; k++) in4[lane + 32 * k] = ldg_stream(g4 + lane + 32 * k);
         __syncwarp();
-        if constexpr (BC == 0) stage_tile_rt(bc_len, in64, 0, bc_stage, lane);
-        if constexpr (UMI == 0) stage_tile_rt(umi_len, in64, 1, umi_stage, lane);
+        // Kernels with a runtime-length output take their four records into registers first.  When
+        // BOTH outputs are staged the tile's shared memory then becomes the stage (kReuse: 55 ->
+        // 31 KB per CTA at bc20/umi10), which is what lets them run in the large-L1 configurations.
+        constexpr bool kRegs = (BC == 0 || UMI == 0);
+        constexpr bool kReuse = (BC == 0) && !(UMI == 16 || UMI == 32);
+        uint64_t rb[4], ru[4], ri[4];
+        if constexpr (kRegs) {
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                const uint32_t r = lane + 32 * q;
+                rb[q] = in64[3 * r]; ru[q] = in64[3 * r + 1];
+                if (SUMS) ri[q] = in64[3 * r + 2];
+            }
+            if constexpr (kReuse) __syncwarp();  // every lane holds its records: the tile may be overwritten
+            if constexpr (BC == 0) stage_tile_rt(bc_len, rb, bc_stage, lane);
+            if constexpr (UMI == 0) stage_tile_rt(umi_len, ru, umi_stage, lane);
+        }
 #pragma unroll
         for (int q = 0; q < 4; q++) {
             const uint32_t r = lane + 32 * q;  // record of the tile handled by this lane
             // 64-bit shared loads at a 24-byte stride: conflict-free per half-warp
-            const uint64_t bc = in64[3 * r], umi = in64[3 * r + 1];
+            uint64_t bc, umi;
+            if constexpr (kRegs) { bc = rb[q]; umi = ru[q]; } else { bc = in64[3 * r]; umi = in64[3 * r + 1]; }
             const uint64_t rec = t * kTileRecords + r;
             emit_row<BC>(bc, bc_len, a.bc_out, rec, bc_stage, r);
             emit_row<UMI>(umi, umi_len, a.umi_out, rec, umi_stage, r);
@@ -327,7 +339,8 @@ __global__ void __launch_bounds__(kBlockThreads) k_unpack(const UnpackArgs a) {
             n_bb += bb; n_bu += bu; n_br += (bb | bu);
             if (a.flags) a.flags[rec] = (uint8_t)(bb | (bu << 1));
             if (SUMS) {  // the reference processors' sums / checksum ride along (the tile is on chip)
-                const uint64_t idx = in64[3 * r + 2];
+                uint64_t idx;
+                if constexpr (kRegs) idx = ri[q]; else idx = in64[3 * r + 2];
                 s_bc += bc; s_umi += umi; s_idx += idx; x_all ^= bc ^ umi ^ idx;
             }
         }
@@ -533,6 +546,10 @@ __global__ void __launch_bounds__(kBlockThreads, MINB) k_pack(const PackArgs a) 
         bc_rows.park(bc_stage, lane, bc_len);
         umi_rows.park(umi_stage, lane, umi_len);
         if (kStageBc || kStageUmi) __syncwarp();
+        // Packed words of the lane's Q rows.  When both inputs are staged (kReuse) every row is
+        // packed before the first record is written, so the record tile can overlay the input
+        // stages (55 -> 31 KB of shared memory per CTA at bc20/umi10: the large-L1 configurations).
+        constexpr bool kReuse = kStageBc && kStageUmi;
         uint64_t bcw[Q], umw[Q];
         uint32_t bcbad = 0, umbad = 0;
         if constexpr (BC == 0) pack_tile_rt<Q>(bc_len, bc_stage, lane, bcw, bcbad);
@@ -540,25 +557,28 @@ __global__ void __launch_bounds__(kBlockThreads, MINB) k_pack(const PackArgs a) 
 #pragma unroll
         for (int q = 0; q < Q; q++) {
             const uint32_t r = lane + 32 * q;
-            const uint64_t row = t * kRows + r;
-            uint32_t bb, bu;
-            uint64_t bw, uw;
-            if constexpr (BC == 0) {
-                bw = bcw[q]; bb = (bcbad >> q) & 1u;
-            } else {
+            uint32_t bad;
+            if constexpr (BC != 0) {
                 uint4 lo, hi;
                 if constexpr (!kStageBc) bc_rows.get(q, lo, hi); else load_row<BC>(bc_stage, r, lo, hi);
-                bw = pack_row<BC>(lo, hi, bb);
+                bcw[q] = pack_row<BC>(lo, hi, bad);
+                bcbad |= bad << q;
             }
-            if constexpr (UMI == 0) {
-                uw = umw[q]; bu = (umbad >> q) & 1u;
-            } else {
+            if constexpr (UMI != 0) {
                 uint4 lo, hi;
                 if constexpr (!kStageUmi) umi_rows.get(q, lo, hi); else load_row<UMI>(umi_stage, r, lo, hi);
-                uw = pack_row<UMI>(lo, hi, bu);
+                umw[q] = pack_row<UMI>(lo, hi, bad);
+                umbad |= bad << q;
             }
+        }
+        if constexpr (kReuse) __syncwarp();  // every staged row has been read
+#pragma unroll
+        for (int q = 0; q < Q; q++) {
+            const uint32_t r = lane + 32 * q;
+            const uint64_t row = t * kRows + r;
+            const uint32_t bb = (bcbad >> q) & 1u, bu = (umbad >> q) & 1u;
             const uint64_t idx = a.index ? ldg_stream64(a.index + row) : a.index_base + row;
-            out64[3 * r] = bw; out64[3 * r + 1] = uw; out64[3 * r + 2] = idx;
+            out64[3 * r] = bcw[q]; out64[3 * r + 1] = umw[q]; out64[3 * r + 2] = idx;
             n_bb += bb; n_bu += bu; n_br += (bb | bu);
             if (a.flags) a.flags[row] = (uint8_t)(bb | (bu << 1));
         }
@@ -696,12 +716,15 @@ static bool aligned(const void *p, size_t a) { return ((uintptr_t)p & (a - 1)) =
 
 template <int BC, int UMI>
 static int launch_unpack(ibu_gpu_ctx *ctx, UnpackArgs &a, cudaStream_t s, ibu_error_t *err) {
-    // per-warp shared memory: input tile, then the staged outputs that are not stored directly
-    uint32_t off = kTileBytes;
+    // per-warp shared memory: input tile, then the staged outputs that are not stored directly;
+    // when both outputs are staged (runtime-length barcode) the stage overlays the input tile
+    constexpr bool kReuse = (BC == 0) && !(UMI == 16 || UMI == 32);
+    uint32_t off = kReuse ? 0u : (uint32_t)kTileBytes;
     a.bc_stage_off = off;
     if (!(BC == 32 || BC == 16)) off += (kTileRecords * a.bc_len + 15u) & ~15u;
     a.umi_stage_off = off;
     if (!(UMI == 32 || UMI == 16)) off += (kTileRecords * a.umi_len + 15u) & ~15u;
+    if (off < (uint32_t)kTileBytes) off = kTileBytes;
     a.warp_smem_bytes = off;
     const size_t smem = (size_t)off * kWarpsPerBlock;
     // with a result block the pass also carries K1's sums / checksum
@@ -724,11 +747,15 @@ static int launch_unpack(ibu_gpu_ctx *ctx, UnpackArgs &a, cudaStream_t s, ibu_er
 template <int BC, int UMI, int Q, int MINB>
 static int launch_pack_q(ibu_gpu_ctx *ctx, PackArgs &a, cudaStream_t s, ibu_error_t *err) {
     constexpr uint32_t kRows = 32 * Q;  // rows per warp tile, Q per lane
-    uint32_t off = kRows * 24;
+    // per-warp shared memory: the record tile, then the staged inputs; with both inputs staged
+    // the record tile overlays them (it is written after every row has been read)
+    constexpr bool kReuse = (BC != 16 && BC != 32) && (UMI != 16 && UMI != 32);
+    uint32_t off = kReuse ? 0u : kRows * 24;
     a.bc_stage_off = off;
     if (BC != 16 && BC != 32) off += ((kRows * a.bc_len + 15u) & ~15u) + 16u;  // +16: funnel-shift over-read
     a.umi_stage_off = off;
     if (UMI != 16 && UMI != 32) off += ((kRows * a.umi_len + 15u) & ~15u) + 16u;
+    if (off < kRows * 24) off = kRows * 24;
     a.warp_smem_bytes = off;
     const size_t smem = (size_t)off * kWarpsPerBlock;
     auto kern = k_pack<BC, UMI, Q, MINB>;
