@@ -1,5 +1,6 @@
 // ctx.h — the GPU context behind ibu_gpu_ctx_t (internal).
 #pragma once
+#include <array>
 #include <atomic>
 #include <cuda_runtime.h>
 #include <mutex>
@@ -25,6 +26,7 @@ struct ibu_chunk_slot {
 struct ibu_result_scratch {
     unsigned long long *blocks = nullptr;
     cudaEvent_t folded = nullptr;
+    std::mutex in_use;  // held from the wait on `folded` to its next record (see ResultLease)
 };
 constexpr int kResultBlocks = 256;
 constexpr int kResultRing = 16;
@@ -37,7 +39,7 @@ struct ibu_gpu_ctx {
     std::vector<ibu_chunk_slot> slots;
     // grow-only device scratch of the blocking table builder (K4): cudaMalloc/cudaFree per call
     // would cost more than the streaming pass itself
-    std::vector<ibu_result_scratch> result_ring;
+    std::array<ibu_result_scratch, kResultRing> result_ring;
     std::atomic<uint32_t> result_next{0};
     std::mutex pipe_mutex;  // the chunk slots serve one host-buffer call at a time
     std::mutex arena_mutex;

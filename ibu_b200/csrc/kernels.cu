@@ -694,23 +694,30 @@ static int set_carveout(const void *kern, int carve, ibu_error_t *err) {
     return IBU_OK;
 }
 
-// Take the next entry of the context's result-scratch ring for a launch on stream s (the stream
-// first waits for the fold of the entry's previous user), and, after the kernel, fold it into
-// d_result on the same stream.
-static int result_acquire(ibu_gpu_ctx *ctx, cudaStream_t s, ibu_result_scratch **out, ibu_error_t *err) {
-    ibu_result_scratch &r = ctx->result_ring[ctx->result_next.fetch_add(1, std::memory_order_relaxed) % kResultRing];
-    IBU_CUDA(cudaStreamWaitEvent(s, r.folded, 0));
-    *out = &r;
-    return IBU_OK;
-}
-static int result_fold(ibu_result_scratch *r, ibu_reduce_result_t *d_result, uint64_t n, cudaStream_t s,
-                       ibu_error_t *err) {
-    k_fold_result<<<1, kResultBlocks, 0, s>>>(r->blocks, d_result, n);
-    g_launches.fetch_add(1, std::memory_order_relaxed);
-    IBU_CUDA(cudaGetLastError());
-    IBU_CUDA(cudaEventRecord(r->folded, s));
-    return IBU_OK;
-}
+// One launch's hold on an entry of the context's result-scratch ring.  acquire(): take the next
+// entry and make stream s wait for the fold of its previous user; fold(): fold the blocks into
+// d_result behind the kernel and record the entry's event.  The entry's mutex is held in between,
+// so a second host thread that wraps around the ring cannot read a stale event.
+struct ResultLease {
+    ibu_result_scratch *r = nullptr;
+    ~ResultLease() {
+        if (r) r->in_use.unlock();
+    }
+    int acquire(ibu_gpu_ctx *ctx, cudaStream_t s, ibu_error_t *err) {
+        r = &ctx->result_ring[ctx->result_next.fetch_add(1, std::memory_order_relaxed) % kResultRing];
+        r->in_use.lock();
+        IBU_CUDA(cudaStreamWaitEvent(s, r->folded, 0));
+        return IBU_OK;
+    }
+    unsigned long long *blocks() const { return r ? r->blocks : nullptr; }
+    int fold(ibu_reduce_result_t *d_result, uint64_t n, cudaStream_t s, ibu_error_t *err) {
+        k_fold_result<<<1, kResultBlocks, 0, s>>>(r->blocks, d_result, n);
+        g_launches.fetch_add(1, std::memory_order_relaxed);
+        IBU_CUDA(cudaGetLastError());
+        IBU_CUDA(cudaEventRecord(r->folded, s));
+        return IBU_OK;
+    }
+};
 
 static bool aligned(const void *p, size_t a) { return ((uintptr_t)p & (a - 1)) == 0; }
 
@@ -805,18 +812,18 @@ int ibu_gpu_validate_reduce_async(ibu_gpu_ctx_t *ctx, const ibu_record_t *d_reco
     if (!aligned(d_records, 8)) return set_error(err, IBU_ERR_ARG, 0, 0, 0, "d_records must be 8-byte aligned");
     DeviceGuard guard(ctx->device);
     cudaStream_t s = pick_stream(ctx, stream);
-    ibu_result_scratch *scratch = nullptr;
-    if (int rc = result_acquire(ctx, s, &scratch, err)) return rc;
+    ResultLease lease;
+    if (int rc = lease.acquire(ctx, s, err)) return rc;
     // records until the next 32-byte boundary: 24 h = -p (mod 32)  <=>  h = (p / 8) mod 4
     const uint32_t head = (uint32_t)std::min<uint64_t>(n, ((uintptr_t)d_records >> 3) & 3u);
     const uint64_t n_tiles = (n - head) / kTileRecords;
     constexpr int kTpw = 4;  // tiles per warp: a CTA covers 4096 records
     const unsigned grid = (unsigned)std::max<uint64_t>(1, (n_tiles + kWarpsPerBlock * kTpw - 1) / (kWarpsPerBlock * kTpw));
     k_validate_reduce<kTpw><<<grid, kBlockThreads, 0, s>>>((const uint8_t *)d_records, n, head, high_mask(bc_len),
-                                                           high_mask(umi_len), scratch->blocks);
+                                                           high_mask(umi_len), lease.blocks());
     g_launches.fetch_add(1, std::memory_order_relaxed);
     IBU_CUDA(cudaGetLastError());
-    return result_fold(scratch, d_result, n, s, err);
+    return lease.fold(d_result, n, s, err);
 }
 
 int ibu_gpu_unpack_async(ibu_gpu_ctx_t *ctx, const ibu_record_t *d_records, uint64_t n,
@@ -831,9 +838,9 @@ int ibu_gpu_unpack_async(ibu_gpu_ctx_t *ctx, const ibu_record_t *d_records, uint
         return set_error(err, IBU_ERR_ARG, 0, 0, 0, "device pointers must be 16-byte aligned");
     DeviceGuard guard(ctx->device);
     cudaStream_t s = pick_stream(ctx, stream);
-    ibu_result_scratch *scratch = nullptr;
+    ResultLease lease;
     if (d_result)
-        if (int rc = result_acquire(ctx, s, &scratch, err)) return rc;
+        if (int rc = lease.acquire(ctx, s, err)) return rc;
     UnpackArgs a{};
     a.recs = (const uint8_t *)d_records;
     a.n = n;
@@ -842,7 +849,7 @@ int ibu_gpu_unpack_async(ibu_gpu_ctx_t *ctx, const ibu_record_t *d_records, uint
     a.flags = d_flags;
     a.bc_hi = high_mask(bc_len);
     a.umi_hi = high_mask(umi_len);
-    a.res_blocks = scratch ? scratch->blocks : nullptr;
+    a.res_blocks = lease.blocks();
     a.bc_len = bc_len;
     a.umi_len = umi_len;
     // store mode per output: 32 / 16 = direct vector store (needs that alignment), 12 =
@@ -859,8 +866,8 @@ int ibu_gpu_unpack_async(ibu_gpu_ctx_t *ctx, const ibu_record_t *d_records, uint
     IBU_UNPACK_CASE(0, 12) IBU_UNPACK_CASE(0, 16) IBU_UNPACK_CASE(0, 32) IBU_UNPACK_CASE(0, 0)
 #undef IBU_UNPACK_CASE
     if (rc < 0) return set_error(err, IBU_ERR_ARG, 0, 0, 0, "no unpack kernel for this shape");
-    if (rc != IBU_OK || !scratch) return rc;
-    return result_fold(scratch, d_result, n, s, err);
+    if (rc != IBU_OK || !lease.r) return rc;
+    return lease.fold(d_result, n, s, err);
 }
 
 int ibu_gpu_pack_async(ibu_gpu_ctx_t *ctx, const uint8_t *d_bc_ascii, const uint8_t *d_umi_ascii,
@@ -876,9 +883,9 @@ int ibu_gpu_pack_async(ibu_gpu_ctx_t *ctx, const uint8_t *d_bc_ascii, const uint
         return set_error(err, IBU_ERR_ARG, 0, 0, 0, "device pointers must be 16-byte aligned");
     DeviceGuard guard(ctx->device);
     cudaStream_t s = pick_stream(ctx, stream);
-    ibu_result_scratch *scratch = nullptr;
+    ResultLease lease;
     if (d_result)
-        if (int rc = result_acquire(ctx, s, &scratch, err)) return rc;
+        if (int rc = lease.acquire(ctx, s, err)) return rc;
     PackArgs a{};
     a.bc_in = d_bc_ascii;
     a.umi_in = d_umi_ascii;
@@ -887,7 +894,7 @@ int ibu_gpu_pack_async(ibu_gpu_ctx_t *ctx, const uint8_t *d_bc_ascii, const uint
     a.n = n;
     a.recs_out = (uint8_t *)d_records;
     a.flags = d_flags;
-    a.res_blocks = scratch ? scratch->blocks : nullptr;
+    a.res_blocks = lease.blocks();
     a.bc_len = bc_len;
     a.umi_len = umi_len;
     const int bm = (bc_len == 32 && aligned(d_bc_ascii, 32)) ? 32 : bc_len == 16 ? 16 : 0;
@@ -902,8 +909,8 @@ int ibu_gpu_pack_async(ibu_gpu_ctx_t *ctx, const uint8_t *d_bc_ascii, const uint
     IBU_PACK_CASE(0, 32) IBU_PACK_CASE(0, 16) IBU_PACK_CASE(0, 0)
 #undef IBU_PACK_CASE
     if (rc < 0) return set_error(err, IBU_ERR_ARG, 0, 0, 0, "no pack kernel for this shape");
-    if (rc != IBU_OK || !scratch) return rc;
-    return result_fold(scratch, d_result, n, s, err);
+    if (rc != IBU_OK || !lease.r) return rc;
+    return lease.fold(d_result, n, s, err);
 }
 
 int ibu_gpu_generate_records_async(ibu_gpu_ctx_t *ctx, ibu_record_t *d_records, uint64_t first,

@@ -449,7 +449,6 @@ int ibu_gpu_ctx_create(int device, const ibu_gpu_config_t *cfg, ibu_gpu_ctx_t **
         if (e == cudaSuccess) e = cudaMalloc((void **)&s.d_result, sizeof(ibu_reduce_result_t));
         if (e == cudaSuccess) e = cudaHostAlloc((void **)&s.h_result, sizeof(ibu_reduce_result_t), cudaHostAllocDefault);
     }
-    ctx->result_ring.resize(kResultRing);
     for (auto &r : ctx->result_ring) {
         const size_t bytes = (size_t)kResultBlocks * sizeof(ibu_reduce_result_t);
         if (e == cudaSuccess) e = cudaMalloc((void **)&r.blocks, bytes);
