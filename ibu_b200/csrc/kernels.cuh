@@ -80,7 +80,7 @@ __device__ __forceinline__ void decode_word(uint64_t w, uint32_t (&asc)[8]) {
 // table: bits 1-2 of a byte are its code by construction and bit 5 is the case, so only bits
 // {7,6,4,3,0} remain to be checked; they must read 0x41, or 0x50 for T (c' = 2: bit 2 set, bit 1
 // clear): ((c & 0xD9) ^ (T ? 0x11 : 0)) == 0x41  <=>  (c & 0xDF) in {A, C, G, T}  (exhaustive
-// over all 256 byte values: tests/test_oracle_kat.py).  The four codes of a 32-bit group
+// over all 256 byte values: tests/test_oracle_cross.py).  The four codes of a 32-bit group
 // gather into the top byte of one multiply (no carries); pack16 collects four top bytes with
 // three PRMTs.
 __device__ __forceinline__ uint32_t pack4_top(uint32_t w, uint32_t &bad) {
