@@ -779,6 +779,8 @@ static int segment_pass(ibu_gpu_ctx *ctx, const uint64_t *src, int stride, uint6
     void (*kern)(const SegArgs) =
         stride == 3 ? (pair_mode ? k_segments<3, kSegSubsDefault, true> : k_segments<3, kSegSubsDefault, false>)
                     : (pair_mode ? k_segments<2, kSegSubsDefault, true> : k_segments<2, kSegSubsDefault, false>);
+    static const int carve = getenv("IBU_K4_CARVEOUT") ? atoi(getenv("IBU_K4_CARVEOUT")) : -1;  // tuning hook
+    if (carve >= 0) IBU_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, carve));
     int per_sm = 0;
     IBU_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kBlockThreads, 0));
     // tile ids are claimed in order at run time, so a waiting tile only ever waits on tiles
