@@ -326,7 +326,10 @@ def run_ours(args):
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": ncu_traffic(), "peak_kind": peak_kind,
                          "kernel": "k_unpack<16,12>", "alg_bytes_per_record": ALG_BYTES,
-                         "kernel_ms": kern_mean, "frac_of_nominal_8TBs": achieved / 8000.0},
+                         "kernel_ms": kern_mean, "frac_of_nominal_8TBs": achieved / 8000.0,
+                         "note": "peak is torch's copy_ rate (MEASURED_PEAKS.json); a block-scheduled copy kernel on the "
+                                 "same GPU moves 6.84 TB/s and a decode-free kernel of K2's byte mix 6.8 TB/s "
+                                 "(profiles/r1_k2lab_traffic_vs_kernels.jsonl), so frac can exceed 1"},
             "cpu_baseline": None,
             "e2e": {"value": world * n / e2e_s, "unit": "records/s", "h2d_bytes_per_step": n * 24,
                     "d2h_bytes_per_step": n * (BC_LEN + UMI_LEN) + 64 * ((n + chunk - 1) // chunk),
