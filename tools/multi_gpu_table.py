@@ -58,5 +58,30 @@ if rank == 0:
     print(json.dumps(dict(world=world, records=n_total, per_rank=n, k1_reduce_allreduce_ms=t_red * 1e3,
                           k1_grec_s=n_total / t_red / 1e9, exact_table_ms=t_tab * 1e3,
                           table_grec_s=n_total / t_tab / 1e9, rows=len(table), closed_form_ok=bool(ok))), flush=True)
+# ---- sorted shards: host merge of the per-rank tables (boundary fix-up) vs the pair all-to-all ----
+# GEN_SORTED is sorted by Record's Ord over the whole job, so every rank's contiguous range is a
+# sorted shard and only runs cut by a shard boundary can repeat.
+ctx.generate_records_async(recs, s, n, 16, 12, ibu.GEN_SORTED, (5 << 32) | 1000, 0)
+ctx.synchronize()
+
+
+def host_merge():
+    rows, info = ctx.barcode_count(recs, n)
+    assert info["input_was_sorted"]
+    edge = ibu.records(2)
+    ctx.d2h(edge[:1], recs.data_ptr())
+    ctx.d2h(edge[1:], recs.data_ptr() + (n - 1) * 24)
+    boundary = ((int(edge["barcode"][0]), int(edge["umi"][0])), (int(edge["barcode"][1]), int(edge["umi"][1])))
+    return ibd.gather_tables(rows, boundary)
+
+
+for rep in range(2):
+    merged_rows, t_host = timed(host_merge)
+    exact_rows, t_a2a = timed(lambda: ibd.exact_barcode_table(ctx, recs, n, dev))
+same = bool(len(merged_rows) == len(exact_rows) and np.array_equal(merged_rows, exact_rows))
+if rank == 0:
+    print(json.dumps(dict(world=world, records=n_total, data="sorted (1000 records, 200 distinct UMIs per barcode)",
+                          sorted_stream_tables_plus_host_merge_ms=t_host * 1e3, pair_all_to_all_ms=t_a2a * 1e3,
+                          rows=len(merged_rows), tables_identical=same)), flush=True)
 ctx.close()
 dist.destroy_process_group()
