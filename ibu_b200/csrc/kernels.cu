@@ -288,7 +288,7 @@ __device__ __forceinline__ void copy_out_stage(uint32_t len, uint8_t *gout, uint
 // Measured on B200 (tools/k2lab.cu, 10^8 records): a persistent grid marching through memory
 // in lock step moves this byte mix at 5.95-6.05 TB/s whatever the kernel does (a decode-free
 // traffic kernel of the same shape is no faster), the same tiles handed out by the block
-// scheduler at 6.5 TB/s (traffic-only: 6.8); every extra tile per warp costs bandwidth.
+// scheduler at 6.8 TB/s (traffic-only: 6.8); every extra tile per warp costs bandwidth.
 template <int BC, int UMI, bool SUMS>
 __global__ void __launch_bounds__(kBlockThreads) k_unpack(const UnpackArgs a) {
     extern __shared__ __align__(16) uint8_t smem[];
