@@ -241,8 +241,15 @@ void merge(ibu_reduce_result_t &t, const ibu_reduce_result_t &c) {
 
 unsigned copy_threads(const ibu_gpu_ctx *ctx) {
     if (ctx->cfg.copy_threads) return ctx->cfg.copy_threads;
-    unsigned hc = std::thread::hardware_concurrency();
-    return std::max(1u, std::min(32u, hc));  // staging is a DRAM-bandwidth job: use the cores
+    // staging is a DRAM-bandwidth job: use the cores — this process's share of them when a launcher
+    // says how many ranks run on the node (torchrun sets LOCAL_WORLD_SIZE)
+    static const unsigned ranks = [] {
+        const char *e = getenv("LOCAL_WORLD_SIZE");
+        const int v = e ? atoi(e) : 1;
+        return (unsigned)std::max(1, v);
+    }();
+    const unsigned hc = std::thread::hardware_concurrency();
+    return std::max(2u, std::min(32u, hc / ranks));
 }
 
 // What one chunk moves: inputs (host -> device) and outputs (device -> host) as byte spans
