@@ -37,7 +37,7 @@ def hx(a) -> str:
     return np.ascontiguousarray(a).tobytes().hex()
 
 
-def main():
+def main(out_dir: str = HERE):
     out = {}
     # ---- the reference's KAT file ----------------------------------------------------------
     i = np.arange(10_000, dtype=U64)
@@ -45,7 +45,7 @@ def main():
     recs["barcode"], recs["umi"], recs["index"] = i, 2 * i, 3 * i
     blob = on.file_bytes(16, 12, recs)
     assert len(blob) == 32 + 24 * 10_000
-    with open(os.path.join(HERE, "ref_kat_10000.ibu"), "wb") as f:
+    with open(os.path.join(out_dir, "ref_kat_10000.ibu"), "wb") as f:
         f.write(blob)
     red = on.reduce_records(recs, 16, 12)
     assert red == oc.reduce_records(recs, 16, 12)
@@ -117,11 +117,11 @@ def main():
         assert int(v, 16) == oc.splitmix64(int(x))
     assert out["splitmix64"]["0"] == "0xe220a8397b1dcdaf"  # the published first output of splitmix64 seeded with 0
 
-    with open(os.path.join(HERE, "golden.json"), "w") as f:
+    with open(os.path.join(out_dir, "golden.json"), "w") as f:
         json.dump(out, f, indent=1, sort_keys=True)
         f.write("\n")
-    print("wrote", os.path.join(HERE, "ref_kat_10000.ibu"), "and golden.json")
+    print("wrote", os.path.join(out_dir, "ref_kat_10000.ibu"), "and golden.json")
 
 
 if __name__ == "__main__":
-    main()
+    main(sys.argv[1] if len(sys.argv) > 1 else HERE)

@@ -24,6 +24,18 @@ def recs_from_hex(h: str) -> np.ndarray:
 
 
 # ------------------------------------------------------------------ CPU: oracles and host API
+def test_generator_script_reproduces_the_committed_fixtures(tmp_path):
+    import importlib.util
+
+    spec = importlib.util.spec_from_file_location("make_golden", os.path.join(HERE, "make_golden.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    mod.main(str(tmp_path))
+    for name in ("golden.json", "ref_kat_10000.ibu"):
+        assert open(tmp_path / name, "rb").read() == open(os.path.join(HERE, name), "rb").read(), name
+
+
+
 def test_kat_file_bytes_and_oracles():
     blob = open(KAT, "rb").read()
     assert len(blob) == G["ref_kat_10000"]["bytes"] == 32 + 24 * 10_000  # writer.rs:645,673
