@@ -53,6 +53,15 @@ def test_host_stream_copy_any_alignment_and_size():
         assert (dst[:do] == 0xEE).all() and (dst[do + n:do + n + 64] == 0xEE).all(), (so, do, n, thr)
 
 
+def test_cpp_example_builds_against_the_header():
+    """examples/roundtrip.cpp is a plain C++ caller of include/ibu_b200.h (no Python): it must
+    compile and link against the shared library.  (It needs a B200 to run.)"""
+    import subprocess
+
+    subprocess.run(["make", "-C", os.path.join(ROOT, "examples")], check=True, capture_output=True)
+    assert os.access(os.path.join(ROOT, "examples", "roundtrip"), os.X_OK)
+
+
 def test_struct_layouts():
     assert C.sizeof(_lib.Header) == 32 and C.sizeof(_lib.Record) == 24
     assert C.sizeof(_lib.ReduceResult) == 64 and C.sizeof(_lib.Error) == 256
