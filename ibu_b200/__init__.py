@@ -572,18 +572,31 @@ class MmapReader:
         return ReduceResult(res.as_dict())
 
 
+class _LibOwned:
+    """A block allocated by the library, exposed to numpy without a copy and released with
+    ibu_free when the last array that views it is collected."""
+
+    def __init__(self, ptr: int, nbytes: int):
+        self._ptr = ptr
+        self.__array_interface__ = {"data": (ptr, False), "shape": (nbytes,), "typestr": "|u1", "version": 3}
+
+    def __del__(self):
+        try:
+            lib.ibu_free(C.c_void_p(self._ptr))
+        except Exception:
+            pass
+
+
 def load_to_vec(path):
-    """(Header, records) — src/io/reader.rs:510-535."""
+    """(Header, records) — src/io/reader.rs:510-535.  The records array views the library's
+    allocation (no copy); it is freed with the array."""
     h, recs, n, err = _lib.Header(), C.c_void_p(), C.c_size_t(), _lib.Error()
     _check(lib.ibu_load_to_vec(os.fsencode(path), C.byref(h), C.byref(recs), C.byref(n), C.byref(err)), err)
-    try:
-        if n.value:
-            buf = (C.c_uint8 * (n.value * RECORD_SIZE)).from_address(recs.value)
-            out = np.frombuffer(buf, dtype=RECORD_DTYPE).copy()
-        else:
-            out = np.zeros(0, RECORD_DTYPE)
-    finally:
+    if n.value:
+        out = np.asarray(_LibOwned(recs.value, n.value * RECORD_SIZE)).view(RECORD_DTYPE)
+    else:
         lib.ibu_free(recs)
+        out = np.zeros(0, RECORD_DTYPE)
     return Header._wrap(h), out
 
 

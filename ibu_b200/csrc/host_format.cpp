@@ -8,6 +8,8 @@
 #include <cstdlib>
 #include <fcntl.h>
 #include <new>
+#include <algorithm>
+#include <thread>
 #include <sys/mman.h>
 #include <sys/stat.h>
 #include <unistd.h>
@@ -209,6 +211,41 @@ void ibu_shard_range(uint64_t len, uint32_t rank, uint32_t world, uint64_t *star
 
 // ---- load_to_vec (src/io/reader.rs:510-535) ----------------------------------------------
 
+// The record block of load_to_vec.  The reference issues one read_exact (reader.rs:527-533);
+// large files are read here by several threads with pread, each faulting in and filling its own
+// slice of the fresh allocation (2.4 GB: 2.1 s single-threaded, bound by first-touch page
+// faults).  Same result, same error for a file that ends early.
+static bool read_all(int fd, void *dst, size_t len) {
+    auto pread_exact = [fd](uint8_t *p, size_t n, off_t off) {
+        while (n) {
+            ssize_t got = ::pread(fd, p, n, off);
+            if (got < 0 && errno == EINTR) continue;
+            if (got <= 0) return false;  // error or unexpected EOF
+            p += got;
+            off += got;
+            n -= (size_t)got;
+        }
+        return true;
+    };
+    const size_t kPiece = 32u << 20;
+    unsigned threads = (unsigned)std::min<size_t>(std::min(16u, std::max(1u, std::thread::hardware_concurrency())),
+                                                  len / kPiece);
+    if (threads <= 1) return pread_exact((uint8_t *)dst, len, IBU_HEADER_SIZE);
+    const size_t per = ((len + threads - 1) / threads + 4095) / 4096 * 4096;
+    std::atomic<bool> ok{true};
+    std::vector<std::thread> pool;
+    for (unsigned i = 0; i < threads; i++) {
+        const size_t off = (size_t)i * per;
+        if (off >= len) break;
+        const size_t n = std::min(per, len - off);
+        pool.emplace_back([&, off, n] {
+            if (!pread_exact((uint8_t *)dst + off, n, (off_t)(IBU_HEADER_SIZE + off))) ok = false;
+        });
+    }
+    for (auto &t : pool) t.join();
+    return ok;
+}
+
 int ibu_load_to_vec(const char *path, ibu_header_t *header, ibu_record_t **records, size_t *n,
                     ibu_error_t *err) {
     clear_error(err);
@@ -247,7 +284,7 @@ int ibu_load_to_vec(const char *path, ibu_header_t *header, ibu_record_t **recor
             // an uninitialised 64-byte aligned block is equivalent and skips a pass over memory
             if (posix_memalign((void **)&buf, 64, data ? data : 64) != 0) {
                 rc = set_error(err, IBU_ERR_NOMEM, 0, data, 0, "cannot allocate %zu bytes", data);
-            } else if (!read_exact(buf, data)) {
+            } else if (!read_all(fd, buf, data)) {
                 rc = io_error(err, errno ? errno : EIO, "read records of", path);
             } else {
                 *records = buf;
