@@ -73,6 +73,10 @@ def main():
     ctx = ibu.GpuContext(0)
     t0 = time.perf_counter()
     hd, d = ibu.load_to_device(ctx, path)
+    t_dev_first = time.perf_counter() - t0  # fresh context: allocates the pinned staging slots
+    d.free()
+    t0 = time.perf_counter()
+    hd, d = ibu.load_to_device(ctx, path)
     t_dev = time.perf_counter() - t0
     for rep in range(2):  # configs[3]: per-barcode record / distinct-UMI table of the loaded file
         t0 = time.perf_counter()
@@ -88,7 +92,8 @@ def main():
         t0 = time.perf_counter()
         hv, v = ibu.load_to_vec(path)
         t_vec = time.perf_counter() - t0
-    print(json.dumps(dict(stage="load_to_device vs load_to_vec", dev_sec=t_dev, dev_gb_s=24 * n / t_dev / 1e9,
+    print(json.dumps(dict(stage="load_to_device vs load_to_vec", dev_first_call_sec=t_dev_first, dev_sec=t_dev,
+                          dev_gb_s=24 * n / t_dev / 1e9,
                           vec_sec=t_vec, vec_gb_s=24 * n / t_vec / 1e9)), flush=True)
     ctx.close()
     os.unlink(path)
