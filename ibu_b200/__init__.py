@@ -32,8 +32,15 @@ BATCH_SIZE = 1024 * 1024
 RECORD_DTYPE = np.dtype([("barcode", "<u8"), ("umi", "<u8"), ("index", "<u8")])
 ROW_DTYPE = np.dtype([("barcode", "<u8"), ("n_records", "<u8"), ("n_distinct_umi", "<u8")])
 
-GEN_CLEAN, GEN_DIRTY, GEN_PATTERN, GEN_WHITELIST, GEN_SORTED = 0, 1, 2, 3, 4
+GEN_CLEAN, GEN_DIRTY, GEN_PATTERN, GEN_WHITELIST, GEN_SORTED, GEN_ZIPF = 0, 1, 2, 3, 4, 5
 COUNT_WEIGHTED = 8
+COUNT_PATH_PARTITION, COUNT_PATH_SORT, COUNT_PATH_LEGACY = 0x10, 0x20, 0x30
+PAIRS_WEIGHTED, PAIRS_UNORDERED = 1, 2
+
+
+def count_lens(bc_len: int, umi_len: int) -> int:
+    """IBU_COUNT_LENS: the header's lengths, OR-ed into `mode` of barcode_count / `flags` of pair_table."""
+    return ((bc_len & 0x3F) << 8) | ((umi_len & 0x3F) << 16)
 
 
 # ---- errors (src/error.rs:56-128) ---------------------------------------------------------
@@ -346,12 +353,12 @@ class GpuContext:
             lib.ibu_gpu_table_free(self._h, C.byref(table))
         return rows, info
 
-    def pair_table(self, d_records, n, weighted: bool = False, stream=None):
+    def pair_table(self, d_records, n, weighted: bool = False, stream=None, flags: int = 0):
         """Distinct (barcode, umi) pairs with multiplicities as device records: (ptr, n_pairs).
-        Release with .free(ptr)."""
+        `flags`: PAIRS_UNORDERED, count_lens(...), COUNT_PATH_*.  Release with .free(ptr)."""
         p, cnt, err = C.c_void_p(), C.c_uint64(), _lib.Error()
-        _check(lib.ibu_gpu_pair_table(self._h, _ptr(d_records), n, int(weighted), C.byref(p), C.byref(cnt),
-                                      _stream(stream), C.byref(err)), err)
+        _check(lib.ibu_gpu_pair_table(self._h, _ptr(d_records), n, int(bool(weighted)) | flags, C.byref(p),
+                                      C.byref(cnt), _stream(stream), C.byref(err)), err)
         return int(p.value or 0), int(cnt.value)
 
     def partition_by_owner(self, d_pairs, n, world: int, d_out, stream=None) -> list[int]:

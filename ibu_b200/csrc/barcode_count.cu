@@ -24,6 +24,7 @@
 #include <cstdlib>
 
 #include "ctx.h"
+#include "k4.h"
 #include "kernels.cuh"
 
 namespace ibu {
@@ -803,7 +804,7 @@ static int segment_pass(ibu_gpu_ctx *ctx, const uint64_t *src, int stride, uint6
         }
         kern<<<grid, kBlockThreads, 0, s>>>(a);
         g_launches.fetch_add(1, std::memory_order_relaxed);
-        IBU_CUDA(cudaGetLastError());
+        if (cudaError_t e__ = cudaGetLastError()) return cuda_fail(err, e__, "k_segments");
         if (tr.on) {
             cudaEventRecord(ev1, s);
             cudaEventSynchronize(ev1);
@@ -873,7 +874,7 @@ static int key_masks(ibu_gpu_ctx *ctx, const uint64_t *recs, uint64_t n, uint64_
     k_key_masks<WORDS><<<(int)std::min<uint64_t>(blocks, (uint64_t)ctx->sm_count * 8), kBlockThreads, 0, s>>>(
         recs, n, pairs, masks);
     g_launches.fetch_add(1, std::memory_order_relaxed);
-    IBU_CUDA(cudaGetLastError());
+    if (cudaError_t e__ = cudaGetLastError()) return cuda_fail(err, e__, "k_key_masks");
     unsigned long long m[6];
     IBU_CUDA(cudaMemcpyAsync(m, masks, sizeof(m), cudaMemcpyDeviceToHost, s));
     IBU_CUDA(cudaStreamSynchronize(s));
@@ -917,7 +918,7 @@ static int radix_sort(ibu_gpu_ctx *ctx, const uint64_t *in, uint64_t *first_dst,
             k_radix_scatter<STRIDE><<<(int)n_tiles, kBlockThreads, kSortTile * STRIDE * 8, s>>>(
                 src, dst, n, word, shift, hist, digit_total, n_tiles);
             g_launches.fetch_add(3, std::memory_order_relaxed);
-            IBU_CUDA(cudaGetLastError());
+            if (cudaError_t e__ = cudaGetLastError()) return cuda_fail(err, e__, "radix pass");
             src = dst;
             std::swap(dst, spare);
         }
@@ -997,7 +998,7 @@ static int hash_aggregate(ibu_gpu_ctx *ctx, const uint64_t *recs, uint64_t n, bo
         const uint64_t blocks = (cnt / kSegSub + kWarpsPerBlock) / kWarpsPerBlock;
         k_hash_insert<<<(int)std::min<uint64_t>(blocks, max_grid), kBlockThreads, 0, s>>>(a);
         g_launches.fetch_add(1, std::memory_order_relaxed);
-        IBU_CUDA(cudaGetLastError());
+        if (cudaError_t e__ = cudaGetLastError()) return cuda_fail(err, e__, "k_hash_insert");
         IBU_CUDA(cudaMemcpyAsync(h, ctr, sizeof(h), cudaMemcpyDeviceToHost, s));
         IBU_CUDA(cudaStreamSynchronize(s));
         tr.mark("hash: insert chunk");
@@ -1029,7 +1030,7 @@ static int hash_aggregate(ibu_gpu_ctx *ctx, const uint64_t *recs, uint64_t n, bo
             HashArgs b{nullptr, 0, next, bigger - 1, ctr, 1};
             k_hash_rehash<<<max_grid, kBlockThreads, 0, s>>>(table, slots, b);
             g_launches.fetch_add(1, std::memory_order_relaxed);
-            IBU_CUDA(cudaGetLastError());
+            if (cudaError_t e__ = cudaGetLastError()) return cuda_fail(err, e__, "k_hash_rehash");
             table = next;
             slots = bigger;
         }
@@ -1051,7 +1052,7 @@ static int hash_aggregate(ibu_gpu_ctx *ctx, const uint64_t *recs, uint64_t n, bo
     k_hash_compact<<<(int)std::min<uint64_t>(blocks, (uint64_t)ctx->sm_count * 16), kBlockThreads, 0, s>>>(
         table, slots, out, ctr);
     g_launches.fetch_add(1, std::memory_order_relaxed);
-    IBU_CUDA(cudaGetLastError());
+    if (cudaError_t e__ = cudaGetLastError()) return cuda_fail(err, e__, "k_hash_compact");
     if (h[2]) {
         const unsigned long long special[3] = {kHashEmpty, kHashEmpty, h[2]};
         IBU_CUDA(cudaMemcpyAsync(out + 3 * h[0], special, sizeof(special), cudaMemcpyHostToDevice, s));
@@ -1068,17 +1069,72 @@ static size_t sort_scratch_bytes(uint64_t n, int elem_bytes) {
     return n * 2 * elem_bytes + n_tiles * 1024 + 16 * 256;
 }
 
+// The pre-partition unsorted path: hash-aggregate into a global table (or, when nearly every pair is
+// distinct, radix sort 16-byte pairs), then the segment pass.  Caller holds ctx->arena_mutex.
+int k4_legacy_unsorted(ibu_gpu_ctx *ctx, const uint64_t *src, uint64_t n, cudaStream_t s, bool pair_mode,
+                       bool weighted, uint64_t **rows, uint64_t *n_rows, uint64_t *n_pairs, ibu_error_t *err) {
+    // duplicate-heavy inputs: fold to distinct pairs first, then sort/count only those
+    // room for the first table (256 MiB), the compacted pairs and their sort; a larger
+    // full-size table falls back to a one-off allocation inside Scratch
+    IBU_CUDA(arena_reset(ctx, (768ull << 20) + seg_scratch_bytes(std::min<uint64_t>(n, 8ull << 20))));
+    Trace tr;
+    tr.mark("table: arena");
+    bool use_sort = getenv("IBU_B200_NO_HASH") != nullptr;
+    if (!use_sort) {
+        Scratch sc(ctx);
+        uint64_t *pairs = nullptr, k = 0;
+        if (int rc = hash_aggregate(ctx, src, n, weighted, s, sc, &pairs, &k, &use_sort, err)) return rc;
+        tr.mark("table: hash aggregate total");
+        if (!use_sort) {  // the pairs live in `sc` (arena or fallback allocations) until we return
+            int rc = unsorted_table(ctx, pairs, k, s, pair_mode, true, rows, n_rows, n_pairs, err);
+            tr.mark("table: sort+count of pairs");
+            return rc;
+        }
+    }
+    IBU_CUDA(arena_reset(ctx, sort_scratch_bytes(n, weighted ? 24 : 16) + seg_scratch_bytes(n)));
+    return unsorted_table(ctx, src, n, s, pair_mode, weighted, rows, n_rows, n_pairs, err);
+}
+
+int k4_sort_rows(ibu_gpu_ctx *ctx, const uint64_t *rows, uint64_t n, const uint64_t vary[3], const int *key_order,
+                 int n_keys, cudaStream_t s, uint64_t *dst, ibu_error_t *err) {
+    if (n == 0) return IBU_OK;
+    IBU_CUDA(arena_reset(ctx, sort_scratch_bytes(n, 24)));
+    Scratch sc(ctx);
+    uint64_t *spare;
+    IBU_CUDA(sc.alloc(&spare, n * 24));
+    // an odd number of passes must start into dst to end there
+    const int passes = count_passes(vary, key_order, n_keys);
+    const uint64_t *result = nullptr;
+    if (int rc = radix_sort<3>(ctx, rows, (passes & 1) ? dst : spare, (passes & 1) ? spare : dst, n, vary, key_order,
+                               n_keys, s, sc, &result, err))
+        return rc;
+    if (result != dst) IBU_CUDA(cudaMemcpyAsync(dst, result, n * 24, cudaMemcpyDeviceToDevice, s));
+    return IBU_OK;
+}
+
 // Shared driver of ibu_gpu_barcode_count / ibu_gpu_pair_table.
-static int build_table(ibu_gpu_ctx *ctx, const ibu_record_t *d_records, uint64_t n, int mode, bool pair_mode,
-                       bool weighted, cudaStream_t s, uint64_t **rows, uint64_t *n_rows, uint64_t *n_pairs,
-                       bool *was_sorted, ibu_error_t *err) {
+static int build_table(ibu_gpu_ctx *ctx, const ibu_record_t *d_records, uint64_t n, int mode, const K4Hints &hints,
+                       bool pair_mode, bool pairs_sorted, bool weighted, cudaStream_t s, uint64_t **rows,
+                       uint64_t *n_rows, uint64_t *n_pairs, bool *was_sorted, ibu_error_t *err) {
     *rows = nullptr;
     *n_rows = *n_pairs = 0;
     *was_sorted = false;
     const uint64_t *src = reinterpret_cast<const uint64_t *>(d_records);
     std::lock_guard<std::mutex> lock(ctx->arena_mutex);  // one table build per context at a time
     bool unsorted = mode == 2;
-    if (mode != 2) {
+    // Below 64 Ki records everything is launch latency and the round-1 flow is as good.  Above, a
+    // sample decides first: unsorted input (the common case: the header's flag is advisory) never
+    // pays for the streaming attempt, which cannot stop early enough to be free.
+    K4Sample smp;
+    const bool use_new = hints.force_path == kPathPartition ||
+                         (n >= (1u << 16) && hints.force_path != kPathLegacy && hints.force_path != kPathSort);
+    if (use_new && mode != 1) {
+        Trace tr;
+        if (int rc = k4_sample(ctx, src, n, s, &smp, err)) return rc;
+        tr.mark("table: sample");
+        if (smp.unordered) unsorted = true;
+    }
+    if (!unsorted) {
         Trace tr;
         IBU_CUDA(arena_reset(ctx, seg_scratch_bytes(n)));
         if (int rc = segment_pass(ctx, src, 3, n, s, pair_mode, weighted, rows, n_rows, n_pairs, &unsorted, err))
@@ -1088,26 +1144,16 @@ static int build_table(ibu_gpu_ctx *ctx, const ibu_record_t *d_records, uint64_t
     }
     if (unsorted) {
         if (mode == 1) return IBU_OK;  // caller required sorted input: was_sorted = false, no rows
-        // duplicate-heavy inputs: fold to distinct pairs first, then sort/count only those
-        // room for the first table (256 MiB), the compacted pairs and their sort; a larger
-        // full-size table falls back to a one-off allocation inside Scratch
-        IBU_CUDA(arena_reset(ctx, (768ull << 20) + seg_scratch_bytes(std::min<uint64_t>(n, 8ull << 20))));
-        Trace tr;
-        tr.mark("table: arena");
-        bool use_sort = getenv("IBU_B200_NO_HASH") != nullptr;
-        if (!use_sort) {
-            Scratch sc(ctx);
-            uint64_t *pairs = nullptr, k = 0;
-            if (int rc = hash_aggregate(ctx, src, n, weighted, s, sc, &pairs, &k, &use_sort, err)) return rc;
-            tr.mark("table: hash aggregate total");
-            if (!use_sort) {  // the pairs live in `sc` (arena or fallback allocations) until we return
-                int rc = unsorted_table(ctx, pairs, k, s, pair_mode, true, rows, n_rows, n_pairs, err);
-                tr.mark("table: sort+count of pairs");
+        if (use_new) {
+            Trace tr;
+            bool handled = false;
+            if (int rc = k4_partition_table(ctx, src, n, hints, smp, pair_mode, pairs_sorted, weighted, s, rows, n_rows,
+                                            n_pairs, &handled, err))
                 return rc;
-            }
+            tr.mark("table: partition path total");
+            if (handled) return IBU_OK;
         }
-        IBU_CUDA(arena_reset(ctx, sort_scratch_bytes(n, weighted ? 24 : 16) + seg_scratch_bytes(n)));
-        return unsorted_table(ctx, src, n, s, pair_mode, weighted, rows, n_rows, n_pairs, err);
+        return k4_legacy_unsorted(ctx, src, n, s, pair_mode, weighted, rows, n_rows, n_pairs, err);
     }
     return IBU_OK;
 }
@@ -1116,6 +1162,16 @@ static int build_table(ibu_gpu_ctx *ctx, const ibu_record_t *d_records, uint64_t
 
 using namespace ibu;
 
+// key-layout hints and forced path carried in the upper bits of `mode` / `flags`
+static K4Hints hints_of(int mode) {
+    K4Hints h;
+    h.bc_len = ((unsigned)mode >> 8) & 0x3Fu;
+    h.umi_len = ((unsigned)mode >> 16) & 0x3Fu;
+    if (h.bc_len > 32 || h.umi_len > 32) h.bc_len = h.umi_len = 0;
+    h.force_path = ((unsigned)mode >> 4) & 3u;
+    return h;
+}
+
 extern "C" {
 
 int ibu_gpu_barcode_count(ibu_gpu_ctx_t *ctx, const ibu_record_t *d_records, uint64_t n, int mode,
@@ -1123,7 +1179,8 @@ int ibu_gpu_barcode_count(ibu_gpu_ctx_t *ctx, const ibu_record_t *d_records, uin
     clear_error(err);
     if (!ctx || !table || (!d_records && n)) return set_error(err, IBU_ERR_ARG, 0, 0, 0, "null argument");
     const bool weighted = (mode & IBU_COUNT_WEIGHTED) != 0;
-    mode &= ~IBU_COUNT_WEIGHTED;
+    const K4Hints hints = hints_of(mode);
+    mode &= 7;
     if (mode < 0 || mode > 2) return set_error(err, IBU_ERR_ARG, 0, mode, 0, "mode must be 0, 1 or 2");
     if (((uintptr_t)d_records & 31u) != 0)
         return set_error(err, IBU_ERR_ARG, 0, 0, 0, "d_records must be 32-byte aligned");
@@ -1136,8 +1193,8 @@ int ibu_gpu_barcode_count(ibu_gpu_ctx_t *ctx, const ibu_record_t *d_records, uin
     DeviceGuard guard(ctx->device);
     uint64_t *rows = nullptr, n_rows = 0, n_pairs = 0;
     bool was_sorted = false;
-    if (int rc = build_table(ctx, d_records, n, mode, false, weighted, pick_stream(ctx, stream), &rows, &n_rows,
-                             &n_pairs, &was_sorted, err))
+    if (int rc = build_table(ctx, d_records, n, mode, hints, false, false, weighted, pick_stream(ctx, stream), &rows,
+                             &n_rows, &n_pairs, &was_sorted, err))
         return rc;
     table->d_rows = reinterpret_cast<ibu_barcode_row_t *>(rows);
     table->n_rows = n_rows;
@@ -1168,8 +1225,9 @@ int ibu_gpu_pair_table(ibu_gpu_ctx_t *ctx, const ibu_record_t *d_records, uint64
     DeviceGuard guard(ctx->device);
     uint64_t *rows = nullptr, n_rows = 0, np = 0;
     bool was_sorted = false;
-    if (int rc = build_table(ctx, d_records, n, 0, true, weighted != 0, pick_stream(ctx, stream), &rows, &n_rows,
-                             &np, &was_sorted, err))
+    if (int rc = build_table(ctx, d_records, n, 0, hints_of(weighted), true, (weighted & IBU_PAIRS_UNORDERED) == 0,
+                             (weighted & IBU_PAIRS_WEIGHTED) != 0, pick_stream(ctx, stream), &rows, &n_rows, &np,
+                             &was_sorted, err))
         return rc;
     *d_pairs = reinterpret_cast<ibu_record_t *>(rows);
     *n_pairs = n_rows;

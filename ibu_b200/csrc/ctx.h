@@ -45,7 +45,11 @@ struct ibu_gpu_ctx {
     std::mutex arena_mutex;
     void *arena_base = nullptr;
     size_t arena_cap = 0, arena_off = 0;
+    // pinned mailbox for the small device -> host read-backs of the table builder (guarded by
+    // arena_mutex): a copy into it is a DMA, not a staged pageable copy
+    unsigned long long *h_mail = nullptr;
 };
+constexpr size_t kMailBytes = 4096;
 
 namespace ibu {
 

@@ -1,0 +1,91 @@
+// k4.h — internal interfaces between the K4 (per-barcode table) translation units.
+//   barcode_count.cu  streaming sorted path (k_segments), radix sort, legacy global-hash path, C ABI
+//   barcode_agg.cu    partition-then-aggregate path for unsorted inputs
+#pragma once
+#include <vector>
+
+#include "ctx.h"
+
+namespace ibu {
+
+// Stream-ordered scratch from the device's memory pool (cudaMallocAsync; the context keeps freed
+// blocks cached, so after the first call an allocation costs about a microsecond).  Everything
+// still listed is freed on scope exit, in stream order.
+struct PoolScratch {
+    cudaStream_t s;
+    std::vector<void *> ptrs;
+    explicit PoolScratch(cudaStream_t stream) : s(stream) {}
+    PoolScratch(const PoolScratch &) = delete;
+    PoolScratch &operator=(const PoolScratch &) = delete;
+    ~PoolScratch() {
+        for (void *p : ptrs)
+            if (cudaFreeAsync(p, s) != cudaSuccess) cudaGetLastError();
+    }
+    template <class T>
+    cudaError_t alloc(T **out, size_t bytes) {
+        void *p = nullptr;
+        cudaError_t e = cudaMallocAsync(&p, bytes ? bytes : 256, s);
+        if (e == cudaSuccess) ptrs.push_back(p);
+        *out = (T *)p;
+        return e;
+    }
+    void free_now(void *p) {  // release one block early (stream ordered)
+        for (size_t i = 0; i < ptrs.size(); i++)
+            if (ptrs[i] == p) {
+                ptrs.erase(ptrs.begin() + i);
+                if (cudaFreeAsync(p, s) != cudaSuccess) cudaGetLastError();
+                return;
+            }
+    }
+    void *keep(void *p) {  // ownership passes to the caller
+        for (size_t i = 0; i < ptrs.size(); i++)
+            if (ptrs[i] == p) {
+                ptrs.erase(ptrs.begin() + i);
+                break;
+            }
+        return p;
+    }
+};
+
+// What the caller tells the table builder about the key layout (0 = find out from a sample).
+struct K4Hints {
+    uint32_t bc_len = 0, umi_len = 0;  // header lengths in bases
+    int force_path = 0;                // 0 auto, 1 partition, 2 composite sort, 3 legacy (tests / tuning)
+};
+enum { kPathAuto = 0, kPathPartition = 1, kPathSort = 2, kPathLegacy = 3 };
+
+// ---- barcode_count.cu (all of these expect ctx->arena_mutex to be held by the caller) ----
+
+// Legacy unsorted path: global hash aggregation or 16-byte pair radix sort, then the segment pass.
+// *rows comes from cudaMallocAsync on `s` (3 u64 per row).
+int k4_legacy_unsorted(ibu_gpu_ctx *ctx, const uint64_t *recs, uint64_t n, cudaStream_t s, bool pair_mode,
+                       bool weighted, uint64_t **rows, uint64_t *n_rows, uint64_t *n_pairs, ibu_error_t *err);
+
+// Stable LSD radix sort of n 3-word rows by the key words listed in key_order (least significant
+// first), restricted to the bits set in vary[word]; the sorted rows are written to dst (n * 24 B).
+int k4_sort_rows(ibu_gpu_ctx *ctx, const uint64_t *rows, uint64_t n, const uint64_t vary[3], const int *key_order,
+                 int n_keys, cudaStream_t s, uint64_t *dst, ibu_error_t *err);
+
+// ---- barcode_agg.cu ----
+
+// What a look at ~256 Ki records at hashed positions shows (k_sample): enough to tell sorted
+// from unsorted input, to lay out the (barcode, umi) key and to size the tables.
+struct K4Sample {
+    bool valid = false;
+    uint64_t m = 0;          // records sampled
+    double pairs = 0, barcodes = 0;          // distinct among them
+    uint64_t unordered = 0;                  // sampled records whose successor is smaller: 0 for sorted input
+    double pair_coll = 0;                    // sum over pairs of C(occurrences, 2)
+    double pair_f1 = 0, pair_f2 = 0, bc_f1 = 0, bc_f2 = 0;  // seen exactly once / twice
+    uint32_t hist[130] = {};                 // [2][65] bit widths of the barcode / umi words
+};
+int k4_sample(ibu_gpu_ctx *ctx, const uint64_t *recs, uint64_t n, cudaStream_t s, K4Sample *out, ibu_error_t *err);
+
+// Partition-then-aggregate table of an unsorted input.  *handled = false (and nothing produced)
+// when the input does not suit this path (keys wider than 64 bits, too few distinct keys, too
+// many distinct barcodes, a capacity overflow): the caller then takes the legacy path.
+int k4_partition_table(ibu_gpu_ctx *ctx, const uint64_t *recs, uint64_t n, const K4Hints &hints, const K4Sample &smp,
+                       bool pair_mode, bool pairs_sorted, bool weighted, cudaStream_t s, uint64_t **rows,
+                       uint64_t *n_rows, uint64_t *n_pairs, bool *handled, ibu_error_t *err);
+
+}  // namespace ibu

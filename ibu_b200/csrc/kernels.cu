@@ -647,6 +647,13 @@ k_generate_records(uint64_t *__restrict__ out, uint64_t first, uint64_t n, uint3
             if (nb == 0) nb = 1000;
             b = splitmix64((rb % nb) ^ seed ^ 0xB) & mb;
             u = (us ? ru % us : ru) & mu;
+        } else if (mode == IBU_GEN_ZIPF) {
+            uint64_t nb = param & 0xFFFFFFFFull, us = param >> 32;
+            if (nb == 0) nb = 1000;
+            const uint32_t e = (uint32_t)(rb % (uint64_t)(64 - __clzll((long long)nb)));  // 0 .. floor(log2 nb)
+            const uint64_t r = (((1ull << e) - 1) + (splitmix64(key ^ 7) & ((1ull << e) - 1))) % nb;
+            b = splitmix64(r ^ seed ^ 0xB) & mb;
+            u = (us ? ru % us : ru) & mu;
         } else {
             b = rb & mb;
             u = ru & mu;
@@ -919,7 +926,7 @@ int ibu_gpu_generate_records_async(ibu_gpu_ctx_t *ctx, ibu_record_t *d_records, 
     clear_error(err);
     if (!ctx || (!d_records && n)) return set_error(err, IBU_ERR_ARG, 0, 0, 0, "null argument");
     if (int rc = check_lens(bc_len, umi_len, err)) return rc;
-    if (mode < IBU_GEN_CLEAN || mode > IBU_GEN_SORTED) return set_error(err, IBU_ERR_ARG, 0, 0, 0, "bad mode");
+    if (mode < IBU_GEN_CLEAN || mode > IBU_GEN_ZIPF) return set_error(err, IBU_ERR_ARG, 0, 0, 0, "bad mode");
     if (n == 0) return IBU_OK;
     DeviceGuard guard(ctx->device);
     cudaStream_t s = pick_stream(ctx, stream);

@@ -456,6 +456,7 @@ int ibu_gpu_ctx_create(int device, const ibu_gpu_config_t *cfg, ibu_gpu_ctx_t **
         if (e == cudaSuccess) e = cudaMalloc((void **)&s.d_result, sizeof(ibu_reduce_result_t));
         if (e == cudaSuccess) e = cudaHostAlloc((void **)&s.h_result, sizeof(ibu_reduce_result_t), cudaHostAllocDefault);
     }
+    if (e == cudaSuccess) e = cudaHostAlloc((void **)&ctx->h_mail, kMailBytes, cudaHostAllocDefault);
     for (auto &r : ctx->result_ring) {
         const size_t bytes = (size_t)kResultBlocks * sizeof(ibu_reduce_result_t);
         if (e == cudaSuccess) e = cudaMalloc((void **)&r.blocks, bytes);
@@ -498,6 +499,7 @@ void ibu_gpu_ctx_destroy(ibu_gpu_ctx_t *ctx) {
         if (r.blocks) cudaFree(r.blocks);
     }
     if (ctx->arena_base) cudaFree(ctx->arena_base);
+    if (ctx->h_mail) cudaFreeHost(ctx->h_mail);
     delete ctx;
 }
 

@@ -265,12 +265,14 @@ typedef struct ibu_barcode_table {
 /* Blocking (the table size is data dependent).  d_records must be 32-byte aligned.
  * mode 0 = auto: one streaming pass that also verifies the (barcode, umi) order
  *          (the header's `sorted` flag is advisory: examples/parallel.rs:52-53 sets it on
- *          unsorted data); if the order does not hold, the records are hash-aggregated
- *          into distinct pairs (or radix sorted when nearly all pairs are distinct) and
- *          the pairs are counted;
+ *          unsorted data); if the order does not hold, the records are partitioned by a hash of
+ *          their (barcode, umi) key and de-duplicated bucket by bucket in shared memory (inputs
+ *          that do not suit that — keys wider than 64 bits, a handful of distinct keys, about as
+ *          many barcodes as records — are hash-aggregated in a global table or radix sorted);
  * mode 1 = streaming pass only: unsorted input is not an error, it returns
  *          input_was_sorted = 0 and no rows;
- * mode 2 = skip the streaming attempt. */
+ * mode 2 = skip the streaming attempt.
+ * OR-able into mode: IBU_COUNT_WEIGHTED, IBU_COUNT_LENS(bc_len, umi_len), IBU_COUNT_PATH_*. */
 int ibu_gpu_barcode_count(ibu_gpu_ctx_t *ctx, const ibu_record_t *d_records, uint64_t n,
                           int mode, ibu_barcode_table_t *table, void *stream,
                           ibu_error_t *err);
@@ -280,13 +282,24 @@ void ibu_gpu_table_free(ibu_gpu_ctx_t *ctx, ibu_barcode_table_t *table);
  * table (index = how many records the pair stands for), e.g. the concatenation of several
  * shards' ibu_gpu_pair_table outputs; n_records sums the multiplicities. */
 #define IBU_COUNT_WEIGHTED 8
+/* The header's lengths (Header.bc_len / umi_len, header.rs:48-61), so that the (barcode, umi)
+ * key layout need not be detected from a sample.  Words wider than that (invalid per the
+ * header) are still counted exactly, on a side path. */
+#define IBU_COUNT_LENS(bc_len, umi_len) ((((bc_len) & 0x3F) << 8) | (((umi_len) & 0x3F) << 16))
+/* Tuning / tests: force one implementation of the unsorted path (default: chosen from a sample). */
+#define IBU_COUNT_PATH_PARTITION 0x10 /* hash partition + shared-memory de-duplication */
+#define IBU_COUNT_PATH_SORT 0x20      /* radix sort, then the streaming pass */
+#define IBU_COUNT_PATH_LEGACY 0x30    /* global hash table (round-1 path) */
 
-/* De-duplicated (barcode, umi) pairs of a record range with their multiplicities, sorted by
- * (barcode, umi): rows are ibu_record_t {barcode, umi, index = count}.  This is what shards
- * exchange to merge distinct-UMI counts exactly (they are not additive across shards).
- * weighted != 0: the input's index words are multiplicities already.  *d_pairs is released
- * with ibu_gpu_free.  Blocking. */
-int ibu_gpu_pair_table(ibu_gpu_ctx_t *ctx, const ibu_record_t *d_records, uint64_t n, int weighted,
+/* De-duplicated (barcode, umi) pairs of a record range with their multiplicities: rows are
+ * ibu_record_t {barcode, umi, index = count}.  This is what shards exchange to merge
+ * distinct-UMI counts exactly (they are not additive across shards).  `flags`:
+ * IBU_PAIRS_WEIGHTED = the input's index words are multiplicities already; IBU_PAIRS_UNORDERED =
+ * rows in no particular order (default: sorted by (barcode, umi)); IBU_COUNT_LENS / IBU_COUNT_PATH_*
+ * as above.  *d_pairs is released with ibu_gpu_free.  Blocking. */
+#define IBU_PAIRS_WEIGHTED 1
+#define IBU_PAIRS_UNORDERED 2
+int ibu_gpu_pair_table(ibu_gpu_ctx_t *ctx, const ibu_record_t *d_records, uint64_t n, int flags,
                        ibu_record_t **d_pairs, uint64_t *n_pairs, void *stream, ibu_error_t *err);
 
 /* Send side of the multi-GPU pair exchange: groups the rows of a pair table by
@@ -312,8 +325,10 @@ enum {
     IBU_GEN_DIRTY = 1,     /* as CLEAN, `param` ppm of records carry an unmasked word */
     IBU_GEN_PATTERN = 2,   /* (i % 1e6, 31 i % 1e6, i): examples/parallel.rs:65-69 */
     IBU_GEN_WHITELIST = 3, /* param: low 32 bits = #distinct barcodes, high 32 = umi space; unsorted */
-    IBU_GEN_SORTED = 4     /* param: low 32 bits = records per barcode, high 32 = records per umi;
+    IBU_GEN_SORTED = 4,    /* param: low 32 bits = records per barcode, high 32 = records per umi;
                               sorted by Record's Ord: (i / rpb, (i % rpb) / dup, i) */
+    IBU_GEN_ZIPF = 5       /* as WHITELIST, barcode ranks log-uniform (rank r about as likely as 1/r):
+                              a few cells hold most records, like a real library; unsorted */
 };
 int ibu_gpu_generate_records_async(ibu_gpu_ctx_t *ctx, ibu_record_t *d_records,
                                    uint64_t first, uint64_t n, uint32_t bc_len,

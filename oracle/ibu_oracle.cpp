@@ -697,6 +697,17 @@ static inline orc_record_t gen_record(uint64_t i, uint32_t bc_len, uint32_t umi_
             uint64_t u = (us ? ru % us : ru) & mu;
             return {b, u, i};
         }
+        case 5: {  // ZIPF: as WHITELIST with log-uniform barcode ranks: the exponent e is uniform in
+                   // 0..floor(log2 nb) and the rank uniform in [2^e - 1, 2^(e+1) - 2] (mod nb)
+            uint64_t nb = param & 0xFFFFFFFFull, us = param >> 32;
+            if (nb == 0) nb = 1000;
+            uint32_t levels = 64 - (uint32_t)__builtin_clzll(nb);
+            uint32_t e = (uint32_t)(rb % levels);
+            uint64_t r = (((1ull << e) - 1) + (orc_splitmix64(key ^ 7) & ((1ull << e) - 1))) % nb;
+            uint64_t b = orc_splitmix64(r ^ seed ^ 0xB) & mb;
+            uint64_t u = (us ? ru % us : ru) & mu;
+            return {b, u, i};
+        }
     }
 }
 

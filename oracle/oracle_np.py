@@ -171,6 +171,13 @@ def generate_records(first: int, n: int, bc_len: int, umi_len: int, mode: int, p
         nb = nb or 1000
         out["barcode"] = splitmix64((rb % U64(nb)) ^ U64(seed) ^ U64(0xB)) & mb
         out["umi"] = ((ru % U64(us)) if us else ru) & mu
+    elif mode == 5:
+        nb, us = (param & 0xFFFFFFFF) or 1000, param >> 32
+        e = rb % U64(nb.bit_length())
+        one = U64(1)
+        r = (((one << e) - one) + (splitmix64(key ^ U64(7)) & ((one << e) - one))) % U64(nb)
+        out["barcode"] = splitmix64(r ^ U64(seed) ^ U64(0xB)) & mb
+        out["umi"] = ((ru % U64(us)) if us else ru) & mu
     elif mode == 4:
         rpb, dup = (param & 0xFFFFFFFF) or 1000, (param >> 32) or 1
         out["barcode"], out["umi"] = (i // U64(rpb)) & mb, ((i % U64(rpb)) // U64(dup)) & mu

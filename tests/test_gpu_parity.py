@@ -251,7 +251,8 @@ def test_pack_every_byte_value(ctx):
 
 
 # ---- generators ---------------------------------------------------------------------------
-@pytest.mark.parametrize("mode,param", [(0, 0), (1, 100_000), (2, 0), (3, (4096 << 32) | 10_000), (4, (5 << 32) | 1000)])
+@pytest.mark.parametrize("mode,param", [(0, 0), (1, 100_000), (2, 0), (3, (4096 << 32) | 10_000), (4, (5 << 32) | 1000),
+                                        (5, (20 << 32) | 100_000)])
 @pytest.mark.parametrize("bc,umi", [(16, 12), (32, 32), (3, 9)])
 def test_device_generators_match_oracle(ctx, mode, param, bc, umi):
     n = 100_003
@@ -346,8 +347,14 @@ def test_barcode_table_unsorted(ctx, n, bc, umi, mode, param):
     want = on.barcode_table(recs)
     assert np.array_equal(rows, want)
     assert info["n_distinct_pairs"] == int(want["n_distinct_umi"].sum())
-    rows2, info2 = gpu_table(ctx, recs, mode=2)  # forced sort path gives the same table
+    rows2, info2 = gpu_table(ctx, recs, mode=2)  # without the streaming attempt: the same table
     assert np.array_equal(rows2, want) and not info2["input_was_sorted"]
+    # every implementation of the unsorted path, with and without the header's lengths as a hint
+    for path in (ibu.COUNT_PATH_PARTITION, ibu.COUNT_PATH_LEGACY):
+        for lens in (0, ibu.count_lens(bc, umi)):
+            rows3, info3 = gpu_table(ctx, recs, mode=2 | path | lens)
+            assert np.array_equal(rows3, want), (path, lens)
+            assert info3["n_distinct_pairs"] == int(want["n_distinct_umi"].sum()) and info3["n_records"] == n
 
 
 def test_barcode_table_require_sorted_mode(ctx):
@@ -380,6 +387,70 @@ def test_barcode_table_capacity_retry(ctx):
     want = on.barcode_table(recs)
     assert info["input_was_sorted"] and len(rows) > (8 << 20)
     assert np.array_equal(rows, want)
+
+
+def zipf_records(n, n_barcodes, umi_space, seed, bc=16, umi=12):
+    """10x-like shape: a whitelist of barcodes drawn log-uniformly (Zipf-ish),
+    UMIs uniform in a small space, unsorted."""
+    rng = np.random.default_rng(seed)
+    white = rng.integers(0, 1 << (2 * bc), n_barcodes, dtype=U64)
+    rank = np.minimum((n_barcodes ** rng.random(n)).astype(np.int64), n_barcodes - 1)
+    recs = np.zeros(n, ibu.RECORD_DTYPE)
+    recs["barcode"] = white[rank]
+    recs["umi"] = rng.integers(0, umi_space, n, dtype=U64)
+    recs["index"] = np.arange(n, dtype=U64)
+    return recs
+
+
+@pytest.mark.parametrize("n,n_barcodes,umi_space", [(70_000, 300, 50), (1_000_003, 5000, 40), (3_000_005, 100_000, 1 << 24),
+                                                    (2_000_000, 1, 1 << 24), (2_000_000, 1_000_000, 1)])
+def test_barcode_table_partition_path_skewed(ctx, n, n_barcodes, umi_space):
+    """Heavy barcodes (one holds ~1/ln(B) of the records) and heavy duplication: the partition path's
+    buckets are balanced by the hash of the pair, whatever the barcode distribution."""
+    recs = zipf_records(n, n_barcodes, umi_space, 41)
+    want = on.barcode_table(recs)
+    for mode in (2 | ibu.COUNT_PATH_PARTITION | ibu.count_lens(16, 12), 0):
+        rows, info = gpu_table(ctx, recs, mode=mode)
+        assert np.array_equal(rows, want)
+        assert info["n_distinct_pairs"] == int(want["n_distinct_umi"].sum())
+
+
+def test_barcode_table_partition_path_wide_words(ctx):
+    """Words wider than the header allows (examples/random.rs:46 writes a full random u64 into a 12-base
+    UMI) go through the side list and land in the same table — including the barcode 2^64 - 1."""
+    n = 1_500_000
+    recs = zipf_records(n, 20_000, 64, 42)
+    rng = np.random.default_rng(43)
+    wide = rng.random(n) < 0.01
+    recs["umi"][wide] = rng.integers(0, 1 << 63, int(wide.sum()), dtype=U64) | U64(1 << 40)
+    recs["barcode"][rng.random(n) < 0.002] |= U64(1 << 50)
+    recs["barcode"][:7] = U64(2**64 - 1)
+    recs["umi"][:3] = U64(2**64 - 1)
+    recs["umi"][3:7] = np.arange(1, 5, dtype=U64)
+    want = on.barcode_table(recs)
+    for lens in (0, ibu.count_lens(16, 12)):
+        rows, info = gpu_table(ctx, recs, mode=2 | ibu.COUNT_PATH_PARTITION | lens)
+        assert np.array_equal(rows, want)
+        assert info["n_distinct_pairs"] == int(want["n_distinct_umi"].sum())
+    assert rows["barcode"][-1] == U64(2**64 - 1) and rows["n_records"][-1] == 7 and rows["n_distinct_umi"][-1] == 5
+
+
+def test_barcode_table_random_rs_full_width_umis(ctx):
+    """examples/random.rs:35-47: barcode in [0, 1000), umi a full random u64, index in [0, 10000) —
+    almost every umi word is invalid for umi12 (n (1 - 2^-40) of them) and every pair is distinct."""
+    n = 1_000_000
+    rng = np.random.default_rng(44)
+    recs = np.zeros(n, ibu.RECORD_DTYPE)
+    recs["barcode"] = rng.integers(0, 1000, n, dtype=U64)
+    recs["umi"] = rng.integers(0, 2**64, n, dtype=U64)
+    recs["index"] = rng.integers(0, 10000, n, dtype=U64)
+    red = gpu_reduce(ctx, recs, 16, 12)
+    assert red == oc.reduce_records(recs, 16, 12)
+    assert red["n_bad_umi"] == int((recs["umi"] >> U64(24) != 0).sum()) and red["n_bad_umi"] > n - 10 and red["n_bad_barcode"] == 0
+    want = on.barcode_table(recs)
+    for mode in (0, 2 | ibu.COUNT_PATH_PARTITION | ibu.count_lens(16, 12)):
+        rows, info = gpu_table(ctx, recs, mode=mode)
+        assert np.array_equal(rows, want) and len(rows) == 1000
 
 
 def test_barcode_table_sorted_full_size_closed_form(ctx):
@@ -445,9 +516,18 @@ def test_pair_table(ctx, n, mode, param, pre_sorted):
     ptr, n_pairs = ctx.pair_table(d, n)
     got = np.zeros(n_pairs, ibu.RECORD_DTYPE)
     ctx.d2h(got, ptr)
-    ctx.free(ptr), d.free()
+    ctx.free(ptr)
     want = np_pair_table(recs)
     assert np.array_equal(got, want) and int(got["index"].sum()) == n
+    for flags in (ibu.COUNT_PATH_PARTITION, ibu.COUNT_PATH_PARTITION | ibu.PAIRS_UNORDERED | ibu.count_lens(16, 12)):
+        ptr, n_pairs = ctx.pair_table(d, n, flags=flags)
+        got = np.zeros(n_pairs, ibu.RECORD_DTYPE)
+        ctx.d2h(got, ptr)
+        ctx.free(ptr)
+        if flags & ibu.PAIRS_UNORDERED:
+            got = got[np.lexsort((got["umi"], got["barcode"]))]
+        assert np.array_equal(got, want), flags
+    d.free()
 
 
 @pytest.mark.parametrize("world", [2, 3, 8])
@@ -469,9 +549,11 @@ def test_weighted_merge_of_shard_pair_tables_is_exact(ctx, world):
     assert len(merged) < n
     d = Dev(ctx, merged.nbytes, merged)
     rows, info = ctx.barcode_count(d, len(merged), ibu.COUNT_WEIGHTED)
-    d.free()
     assert np.array_equal(rows, on.barcode_table(recs))
     assert int(rows["n_records"].sum()) == n
+    rows, info = ctx.barcode_count(d, len(merged), ibu.COUNT_WEIGHTED | 2 | ibu.COUNT_PATH_PARTITION)
+    d.free()
+    assert np.array_equal(rows, on.barcode_table(recs)) and info["n_records"] == len(merged)
 
 
 def test_partition_by_owner_and_emulated_all_to_all(ctx):

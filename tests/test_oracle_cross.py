@@ -57,7 +57,8 @@ def test_codec_roundtrip_cross(length):
 
 
 @pytest.mark.parametrize("mode,param", [(0, 0), (1, 10_000), (1, 1_000_000), (2, 0), (3, 1000),
-                                        (3, (4096 << 32) | 50_000), (4, (5 << 32) | 1000), (4, 0)])
+                                        (3, (4096 << 32) | 50_000), (4, (5 << 32) | 1000), (4, 0), (5, (20 << 32) | 100_000),
+                                        (5, 1), (5, 0)])
 @pytest.mark.parametrize("bc,umi", [(16, 12), (32, 32), (1, 1), (7, 31)])
 def test_generators_agree(mode, param, bc, umi):
     a = oc.generate_records(123, 20_000, bc, umi, mode, param, 42)
