@@ -36,6 +36,7 @@ GEN_CLEAN, GEN_DIRTY, GEN_PATTERN, GEN_WHITELIST, GEN_SORTED, GEN_ZIPF = 0, 1, 2
 COUNT_WEIGHTED = 8
 COUNT_PATH_PARTITION, COUNT_PATH_SORT, COUNT_PATH_LEGACY = 0x10, 0x20, 0x30
 PAIRS_WEIGHTED, PAIRS_UNORDERED = 1, 2
+OP_REDUCE, OP_TABLE, OP_KEEP, OP_UNPACK = 1, 2, 4, 8
 
 
 def count_lens(bc_len: int, umi_len: int) -> int:
@@ -387,6 +388,17 @@ class GpuContext:
                                         C.byref(err)), err)
         return ReduceResult(res.as_dict())
 
+    def process_host_ops(self, h_records: np.ndarray, bc_len: int, umi_len: int, table=False, keep=False, unpack=False,
+                         flags=False, table_mode: int = 0, on_chunk=None, **outs):
+        """One pass over host records with an operation mask (ibu_gpu_process_host_ops):
+        (ReduceResult, ProcessOutput)."""
+        recs = _as_records(h_records)
+
+        def call(req, res, cb, err):
+            return lib.ibu_gpu_process_host_ops(self._h, _ptr(recs), len(recs), bc_len, umi_len, req, res, cb, None, err)
+
+        return _run_ops(self, call, len(recs), bc_len, umi_len, table, keep, unpack, flags, table_mode, on_chunk, **outs)
+
     def unpack_host(self, h_records, bc_len, umi_len, bc_out=None, umi_out=None, flags_out=None):
         recs = _as_records(h_records)
         n = len(recs)
@@ -405,6 +417,46 @@ class GpuContext:
         _check(lib.ibu_gpu_pack_host(self._h, _ptr(bc_ascii), _ptr(umi_ascii), _ptr(index), index_base, n, bc_len,
                                      umi_len, _ptr(recs), _ptr(flags_out), C.byref(res), C.byref(err)), err)
         return recs, ReduceResult(res.as_dict())
+
+
+class ProcessOutput:
+    """What an ops pass returns besides the reduction: `rows` / `table_info` (OP_TABLE; rows are a
+    host copy, ROW_DTYPE), `records` (OP_KEEP: DeviceRecords), `bc_ascii` / `umi_ascii` / `flags` (OP_UNPACK)."""
+
+    rows = table_info = records = bc_ascii = umi_ascii = flags = None
+
+
+def _run_ops(ctx: "GpuContext", call, n: int, bc_len: int, umi_len: int, table: bool, keep: bool, unpack: bool,
+             flags: bool, table_mode: int, on_chunk, bc_out=None, umi_out=None, flags_out=None):
+    out = ProcessOutput()
+    req = _lib.ProcessRequest()
+    req.ops = OP_REDUCE | (OP_TABLE if table else 0) | (OP_KEEP if keep else 0) | (OP_UNPACK if unpack else 0)
+    req.table_mode = table_mode
+    tab, dptr = _lib.BarcodeTable(), C.c_void_p()
+    req.table = C.pointer(tab)
+    req.d_records = C.pointer(dptr)
+    if unpack:
+        out.bc_ascii = bc_out if bc_out is not None else np.empty((n, bc_len), np.uint8)
+        out.umi_ascii = umi_out if umi_out is not None else np.empty((n, umi_len), np.uint8)
+        req.h_bc_ascii, req.h_umi_ascii = _ptr(out.bc_ascii), _ptr(out.umi_ascii)
+        if flags or flags_out is not None:
+            out.flags = flags_out if flags_out is not None else np.empty(n, np.uint8)
+            req.h_flags = _ptr(out.flags)
+    res, err = _lib.ReduceResult(), _lib.Error()
+    cb, keep_cb = _wrap_cb(on_chunk)
+    _check(call(C.byref(req), C.byref(res), cb, C.byref(err)), err)
+    if table:
+        out.table_info = dict(n_rows=int(tab.n_rows), n_records=int(tab.n_records),
+                              n_distinct_pairs=int(tab.n_distinct_pairs), input_was_sorted=bool(tab.input_was_sorted))
+        out.rows = np.zeros(int(tab.n_rows), ROW_DTYPE)
+        try:
+            if tab.n_rows:
+                ctx.d2h(out.rows, int(tab.d_rows))
+        finally:
+            lib.ibu_gpu_table_free(ctx._h, C.byref(tab))
+    if keep:
+        out.records = DeviceRecords(ctx, int(dptr.value or 0), n)
+    return ReduceResult(res.as_dict()), out
 
 
 class GpuStream:
@@ -577,6 +629,25 @@ class MmapReader:
         end_v = 2**64 - 1 if end is None else end
         _check(lib.ibu_gpu_process_mmap(ctx._h, self._h, start, end_v, C.byref(res), cb, None, C.byref(err)), err)
         return ReduceResult(res.as_dict())
+
+
+def _process_gpu_ops(self, ctx: GpuContext, start: int = 0, end: int | None = None, table=False, keep=False,
+                     unpack=False, flags=False, table_mode: int = 0, on_chunk=None, **outs):
+    """process_gpu with an operation mask (ibu_gpu_process_mmap_ops): one pass over records
+    [start, end) that validates / reduces, and optionally unpacks to ASCII, builds the per-barcode
+    table (parallel.rs:79-98 + distinct UMIs) and keeps the records on the device.
+    Returns (ReduceResult, ProcessOutput)."""
+    end_v = 2**64 - 1 if end is None else end
+    n = (self.len() if end is None else end) - start
+    h = self.header()
+
+    def call(req, res, cb, err):
+        return lib.ibu_gpu_process_mmap_ops(ctx._h, self._h, start, end_v, req, res, cb, None, err)
+
+    return _run_ops(ctx, call, max(n, 0), h.bc_len, h.umi_len, table, keep, unpack, flags, table_mode, on_chunk, **outs)
+
+
+MmapReader.process_gpu_ops = _process_gpu_ops
 
 
 class _LibOwned:

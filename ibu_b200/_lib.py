@@ -50,6 +50,12 @@ class BarcodeTable(C.Structure):
                 ("reserved", C.c_uint32)]
 
 
+class ProcessRequest(C.Structure):
+    _fields_ = [("ops", C.c_uint32), ("table_mode", C.c_int32), ("table", C.POINTER(BarcodeTable)),
+                ("d_records", C.POINTER(C.c_void_p)), ("h_bc_ascii", C.c_void_p), ("h_umi_ascii", C.c_void_p),
+                ("h_flags", C.c_void_p)]
+
+
 CHUNK_CB = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_uint64, C.c_uint64, C.POINTER(ReduceResult))
 
 _P = C.POINTER
@@ -112,6 +118,9 @@ SIGNATURES = {
     "ibu_mmap_unpin": (None, [_vp]),
     "ibu_gpu_process_mmap": (_int, [_vp, _vp, _u64, _u64, _P(ReduceResult), CHUNK_CB, _vp, _err]),
     "ibu_gpu_process_host": (_int, [_vp, _vp, _u64, _u32, _u32, _P(ReduceResult), CHUNK_CB, _vp, _err]),
+    "ibu_gpu_process_mmap_ops": (_int, [_vp, _vp, _u64, _u64, _P(ProcessRequest), _P(ReduceResult), CHUNK_CB, _vp, _err]),
+    "ibu_gpu_process_host_ops": (_int, [_vp, _vp, _u64, _u32, _u32, _P(ProcessRequest), _P(ReduceResult), CHUNK_CB, _vp,
+                                  _err]),
     "ibu_gpu_stream_open": (_int, [_vp, _P(_vp), _err]),
     "ibu_gpu_stream_push": (_int, [_vp, _vp, _sz, _err]),
     "ibu_gpu_stream_header": (_int, [_vp, _P(Header), _err]),

@@ -31,6 +31,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdlib>
+#include <memory>
 #include <mutex>
 #include <set>
 #include <utility>
@@ -250,6 +251,17 @@ struct TableRef {
 };
 constexpr uint32_t kPackShift = 36;
 
+// the counters of a slot that is known to hold the barcode
+__device__ __forceinline__ void table_hit(const TableRef &t, uint64_t slot, uint64_t n_rec, uint64_t n_dist) {
+    uint64_t *s = t.slots + (t.packed ? 2 : 4) * slot;
+    if (t.packed) {
+        atomicAdd(reinterpret_cast<unsigned long long *>(s + 1), (unsigned long long)(n_rec + (n_dist << kPackShift)));
+    } else {
+        atomicAdd(reinterpret_cast<unsigned long long *>(s + 1), (unsigned long long)n_rec);
+        atomicAdd(reinterpret_cast<unsigned long long *>(s + 2), (unsigned long long)n_dist);
+    }
+}
+
 __device__ __forceinline__ void table_add(const TableRef &t, uint64_t bc, uint64_t n_rec, uint64_t n_dist) {
     if (bc == kEmpty) {  // only a wide record can carry it
         atomicAdd(t.ctr + kCtrOnesRec, (unsigned long long)n_rec);
@@ -295,7 +307,7 @@ struct DedupArgs {
 // (load <= ~0.5 by construction); its slot index comes from the key bits just below the bucket
 // bits, which are as uniform as the bucket bits.
 template <bool WEIGHTED, bool PAIRS>
-__global__ void __launch_bounds__(kBlockThreads) k_bucket_dedup(const DedupArgs a) {
+__global__ void __launch_bounds__(kBlockThreads, 5) k_bucket_dedup(const DedupArgs a) {
     using Cnt = typename std::conditional<WEIGHTED, unsigned long long, uint32_t>::type;
     extern __shared__ __align__(16) unsigned long long smem[];
     const uint32_t S = 1u << a.s_bits, smask = S - 1u;
@@ -334,8 +346,16 @@ __global__ void __launch_bounds__(kBlockThreads) k_bucket_dedup(const DedupArgs 
             if (cur != k) {
                 if (cur != kEmpty) continue;  // a slot never changes once claimed
                 cur = atomicCAS(tkey + slot, kEmpty, (unsigned long long)k);
-                if (cur == kEmpty) fresh++;
-                else if (cur != k) continue;
+                if (cur == kEmpty) {
+                    fresh++;
+                    // unweighted: the counter holds the occurrences AFTER the first, so claiming a
+                    // slot is the only atomic of a new key and a repeat costs one add: one shared-
+                    // memory atomic per record (the unit's rate, ~0.5 per clock per SM, is what
+                    // bounds this kernel)
+                    if (!WEIGHTED) return;
+                } else if (cur != k) {
+                    continue;
+                }
             }
             atomicAdd(tcnt + slot, (Cnt)w);
             return;
@@ -381,34 +401,54 @@ __global__ void __launch_bounds__(kBlockThreads) k_bucket_dedup(const DedupArgs 
             if (s_full) atomicOr(a.table.ctr + kCtrFlags, (unsigned long long)kFlagSmem);
         }
         // every distinct pair of the bucket: one row (pair tables) or one add to its barcode's row
-        for (uint32_t base = 0; base < S; base += blockDim.x) {  // warp-uniform trip count
-            const uint32_t i = base + threadIdx.x;
-            const unsigned long long key = tkey[i];
-            const bool live = key != kEmpty;
-            uint64_t bc = 0, um = 0;
-            if (live) {
-                const uint64_t comp = unmix64(key);
-                bc = comp >> a.ub;
-                um = comp & umask;
-            }
-            if (PAIRS) {
+        if (PAIRS) {
+            for (uint32_t base = 0; base < S; base += blockDim.x) {  // warp-uniform trip count
+                const uint32_t i = base + threadIdx.x;
+                const unsigned long long key = tkey[i];
+                const bool live = key != kEmpty;
                 const uint32_t m = __ballot_sync(0xffffffffu, live);
-                if (m) {
-                    unsigned long long pos = 0;
-                    if (lane == 0) pos = atomicAdd(a.table.ctr + kCtrCursor, (unsigned long long)__popc(m));
-                    pos = __shfl_sync(0xffffffffu, pos, 0) + __popc(m & ((1u << lane) - 1u));
-                    if (live) {
-                        if (pos < a.pairs_cap) {
-                            a.pairs_out[3 * pos] = bc;
-                            a.pairs_out[3 * pos + 1] = um;
-                            a.pairs_out[3 * pos + 2] = (uint64_t)tcnt[i];
-                        } else {
-                            atomicOr(a.table.ctr + kCtrFlags, (unsigned long long)kFlagPairsOut);
-                        }
+                if (!m) continue;
+                unsigned long long pos = 0;
+                if (lane == 0) pos = atomicAdd(a.table.ctr + kCtrCursor, (unsigned long long)__popc(m));
+                pos = __shfl_sync(0xffffffffu, pos, 0) + __popc(m & ((1u << lane) - 1u));
+                if (live) {
+                    const uint64_t comp = unmix64(key);
+                    if (pos < a.pairs_cap) {
+                        a.pairs_out[3 * pos] = comp >> a.ub;
+                        a.pairs_out[3 * pos + 1] = comp & umask;
+                        a.pairs_out[3 * pos + 2] = (uint64_t)tcnt[i] + (WEIGHTED ? 0ull : 1ull);
+                    } else {
+                        atomicOr(a.table.ctr + kCtrFlags, (unsigned long long)kFlagPairsOut);
                     }
                 }
-            } else if (live) {
-                table_add(a.table, bc, (uint64_t)tcnt[i], 1ull);
+            }
+        } else {
+            // Four slots per thread at a time: the home slots of their barcodes are read from the
+            // global table together (independent loads in flight), then resolved — a dependent
+            // load per pair would expose its latency once per pair.
+            const uint32_t words = a.table.packed ? 2 : 4;
+            for (uint32_t base = 0; base < S; base += 4 * blockDim.x) {
+                uint64_t bc[4], seen[4];
+#pragma unroll
+                for (int q = 0; q < 4; q++) {
+                    const uint32_t i = base + q * blockDim.x + threadIdx.x;
+                    const unsigned long long key = i < S ? tkey[i] : kEmpty;
+                    bc[q] = kEmpty;
+                    if (key != kEmpty) bc[q] = unmix64(key) >> a.ub;  // (a narrow barcode is never all ones)
+                }
+#pragma unroll
+                for (int q = 0; q < 4; q++)
+                    seen[q] = bc[q] != kEmpty
+                                  ? *reinterpret_cast<volatile uint64_t *>(a.table.slots + words * (mix64(bc[q]) & a.table.mask))
+                                  : 0ull;
+#pragma unroll
+                for (int q = 0; q < 4; q++) {
+                    if (bc[q] == kEmpty) continue;
+                    const uint32_t i = base + q * blockDim.x + threadIdx.x;
+                    const uint64_t c = (uint64_t)tcnt[i] + (WEIGHTED ? 0ull : 1ull);
+                    if (seen[q] == bc[q]) table_hit(a.table, mix64(bc[q]) & a.table.mask, c, 1ull);  // the common case
+                    else table_add(a.table, bc[q], c, 1ull);
+                }
             }
         }
         __syncthreads();
@@ -587,7 +627,7 @@ template <bool W, bool P>
 int launch_dedup(ibu_gpu_ctx *ctx, const DedupArgs &a, cudaStream_t s, ibu_error_t *err) {
     const size_t smem = ((size_t)1 << a.s_bits) * (8 + (W ? 8 : 4));
     if (int rc = set_max_smem(k_bucket_dedup<W, P>, ctx->device, kDedupMaxSmem, err)) return rc;
-    const int per_sm = std::max<int>(1, std::min<size_t>(8, (200u << 10) / (smem + 1024)));
+    const int per_sm = std::max<int>(1, std::min<size_t>(5, (200u << 10) / (smem + 1024)));  // 48 registers: 5 CTAs by registers
     const uint32_t grid = (uint32_t)std::min<uint64_t>(a.n_buckets, (uint64_t)ctx->sm_count * per_sm);
     k_bucket_dedup<W, P><<<grid, kBlockThreads, smem, s>>>(a);
     IBU_LAUNCHED("k_bucket_dedup");
@@ -642,20 +682,42 @@ int k4_sample(ibu_gpu_ctx *ctx, const uint64_t *recs, uint64_t n, cudaStream_t s
     return IBU_OK;
 }
 
-int k4_partition_table(ibu_gpu_ctx *ctx, const uint64_t *recs, uint64_t n, const K4Hints &hints, const K4Sample &smp,
-                       bool pair_mode, bool pairs_sorted, bool weighted, cudaStream_t s, uint64_t **rows_out,
-                       uint64_t *n_rows, uint64_t *n_pairs, bool *handled, ibu_error_t *err) {
-    *handled = false;
-    *rows_out = nullptr;
-    *n_rows = *n_pairs = 0;
+// One table build of the partition path, in three steps so that an ingest pipeline can feed it chunk by
+// chunk: begin (sizes from the sample, scratch), add (scatter a chunk's keys, stream ordered, any
+// stream that waited for ready()), finish (de-duplicate, rows).
+struct K4Job {
+    ibu_gpu_ctx *ctx;
+    cudaStream_t s0;
+    PoolScratch sc;
+    StageTimer timer;
+    bool trace;
+    uint64_t n = 0;       // records the job was sized for
+    uint64_t added = 0;
+    uint32_t bb = 0, ub = 0, pb = 0, s_bits = 11;
+    uint64_t P = 0, cap = 0, wide_cap = 0, t_slots = 0;
+    double r_est = 0;
+    bool exact = false, weighted = false, packed = false;
+    uint32_t *cursors = nullptr;
+    uint64_t *keys = nullptr, *wts = nullptr, *wide = nullptr, *bases = nullptr;
+    unsigned long long *ctr = nullptr;
+    cudaEvent_t ready_ev = nullptr;
+    K4Job(ibu_gpu_ctx *c, cudaStream_t s, bool tr) : ctx(c), s0(s), sc(s), timer(tr, s), trace(tr) {}
+    ~K4Job() {
+        if (ready_ev) cudaEventDestroy(ready_ev);
+    }
+};
+
+void k4_job_destroy(K4Job *job) { delete job; }
+cudaEvent_t k4_job_ready(K4Job *job) { return job->ready_ev; }
+
+int k4_job_begin(ibu_gpu_ctx *ctx, uint64_t n, const K4Hints &hints, const K4Sample &smp, bool pair_mode,
+                 bool weighted, cudaStream_t s, K4Job **out, ibu_error_t *err) {
+    *out = nullptr;
     const bool forced = hints.force_path == kPathPartition;
     if (!smp.valid || n == 0 || n >= (1ull << 40)) return IBU_OK;
     static const bool trace = getenv("IBU_B200_TRACE") != nullptr;
-    PoolScratch sc(s);
-    StageTimer timer(trace, s);
-    unsigned long long *mail = ctx->h_mail;  // pinned: device -> host read-backs without a staged copy
 
-    // ---- 1. what the sample says ----
+    // ---- what the sample says ----
     const double m = (double)smp.m;
     uint32_t bb, ub;
     if (hints.bc_len && hints.umi_len) {
@@ -683,73 +745,118 @@ int k4_partition_table(ibu_gpu_ctx *ctx, const uint64_t *recs, uint64_t n, const
         if (!pair_mode && r_est > 8.0e6 && r_est > 0.05 * (double)n) return IBU_OK;
     }
 
-    // ---- 2. sizes ----
+    // ---- sizes ----
     // ~512-1024 records per bucket, whatever the data: a bucket's distinct keys then always fit the
-    // 4096-slot shared-memory table (load <= 0.25 on average; duplicates only lengthen a bucket)
-    uint64_t P = std::min<uint64_t>(std::max<uint64_t>(pow2_ceil((n + 1023) / 1024), 2), 1u << 21);
-    const uint32_t pb = log2_of(P);
-    const double mean = (double)n / (double)P;
-    const double sigma = std::sqrt(sum_sq / (double)P);
+    // shared-memory table (duplicates only lengthen a bucket)
+    std::unique_ptr<K4Job> job(new K4Job(ctx, s, trace));
+    job->n = n;
+    job->bb = bb;
+    job->ub = ub;
+    job->r_est = r_est;
+    job->weighted = weighted;
+    job->P = std::min<uint64_t>(std::max<uint64_t>(pow2_ceil((n + 1023) / 1024), 2), 1u << 21);
+    job->pb = log2_of(job->P);
+    const double mean = (double)n / (double)job->P;
+    const double sigma = std::sqrt(sum_sq / (double)job->P);
     // uniform layout with mean + 6 sigma room per bucket; when duplicates make the loads too uneven
     // for that (or the first attempt overflows) the buckets are laid out exactly from a histogram
-    uint64_t cap = ((uint64_t)(mean + 6.0 * sigma) + 64 + 15) & ~15ull;
-    bool exact = (double)cap > 3.0 * mean + 256.0;
+    job->cap = ((uint64_t)(mean + 6.0 * sigma) + 64 + 15) & ~15ull;
+    job->exact = (double)job->cap > 3.0 * mean + 256.0;
     // shared-memory table: 1.6 slots per key of the fullest bucket the uniform layout admits (all of
     // them distinct at worst); duplicate-heavy data (exact layout) has far fewer distinct keys than
     // records per bucket.  Smaller tables = more resident CTAs = more buckets in flight per SM.
-    uint32_t s_bits = 11;
-    while (s_bits < 13 && (double)(1u << s_bits) < 1.6 * (exact ? mean + 6.0 * std::sqrt(mean) : (double)cap)) s_bits++;
-    const uint64_t wide_cap = n / 8 + 4096;
-    const bool packed = !weighted && n < (1ull << 28);
-    // barcode table: generous (skewed barcode frequencies make the estimate a lower bound); only the
-    // slots that are hit occupy L2
-    uint64_t t_slots = pair_mode ? 0 : std::max<uint64_t>(1u << 14, pow2_ceil((uint64_t)(8.0 * std::min(r_est, (double)n))));
-    const uint64_t pairs_cap = pair_mode ? n : 0;
-    const uint32_t slot_words = packed ? 2 : 4;
+    while (job->s_bits < 13 &&
+           (double)(1u << job->s_bits) < 1.6 * (job->exact ? mean + 6.0 * std::sqrt(mean) : (double)job->cap))
+        job->s_bits++;
+    if (job->pb + job->s_bits > 60) return IBU_OK;
+    job->wide_cap = n / 8 + 4096;
+    job->packed = !weighted && n < (1ull << 28);
+    if (!job->exact && job->P * job->cap * (weighted ? 16 : 8) > (64ull << 30)) return IBU_OK;
 
-    uint32_t *cursors;
-    uint64_t *keys = nullptr, *wts = nullptr, *wide, *pairs = nullptr, *bases = nullptr;
-    unsigned long long *ctr;
-    IBU_CUDA(sc.alloc(&cursors, P * 4));
-    IBU_CUDA(sc.alloc(&wide, wide_cap * 24));
-    IBU_CUDA(sc.alloc(&ctr, kCtrWords * 8));
-    if (pair_mode) IBU_CUDA(sc.alloc(&pairs, pairs_cap * 24));
-    IBU_CUDA(cudaMemsetAsync(cursors, 0, P * 4, s));
-    IBU_CUDA(cudaMemsetAsync(ctr, 0, kCtrWords * 8, s));
+    IBU_CUDA(job->sc.alloc(&job->cursors, job->P * 4));
+    IBU_CUDA(job->sc.alloc(&job->wide, job->wide_cap * 24));
+    IBU_CUDA(job->sc.alloc(&job->ctr, kCtrWords * 8));
+    IBU_CUDA(cudaMemsetAsync(job->cursors, 0, job->P * 4, s));
+    IBU_CUDA(cudaMemsetAsync(job->ctr, 0, kCtrWords * 8, s));
+    if (!job->exact) {
+        IBU_CUDA(job->sc.alloc(&job->keys, job->P * job->cap * 8));
+        if (weighted) IBU_CUDA(job->sc.alloc(&job->wts, job->P * job->cap * 8));
+    }
+    IBU_CUDA(cudaEventCreateWithFlags(&job->ready_ev, cudaEventDisableTiming));
+    IBU_CUDA(cudaEventRecord(job->ready_ev, s));
+    *out = job.release();
+    return IBU_OK;
+}
 
-    // ---- 3. scatter ----
-    for (int attempt = 0;; attempt++) {
-        if (exact) {
-            if (attempt == 0) {  // histogram pass; after an overflow the cursors already hold the counts
-                ScatterArgs h{recs, n, bb, ub, pb, 0, nullptr, cursors, nullptr, nullptr, nullptr, 0, ctr};
-                if (int rc = launch_scatter<true>(h, weighted, s, err)) return rc;
-                timer.lap("histogram");
-            }
-            IBU_CUDA(sc.alloc(&bases, (P + 1) * 8));
-            k_bucket_bases<<<1, 1024, 0, s>>>(cursors, (uint32_t)P, bases);
-            IBU_LAUNCHED("k_bucket_bases");
-            IBU_CUDA(cudaMemsetAsync(cursors, 0, P * 4, s));
-            IBU_CUDA(cudaMemsetAsync(ctr, 0, kCtrWords * 8, s));
-        }
-        const uint64_t n_keys = exact ? n : P * cap;
-        if (n_keys * (weighted ? 16 : 8) > (64ull << 30)) return IBU_OK;
-        IBU_CUDA(sc.alloc(&keys, n_keys * 8));
-        if (weighted) IBU_CUDA(sc.alloc(&wts, n_keys * 8));
-        ScatterArgs a{recs, n, bb, ub, pb, (uint32_t)cap, bases, cursors, keys, wts, wide, wide_cap, ctr};
-        if (int rc = launch_scatter<false>(a, weighted, s, err)) return rc;
-        timer.lap("k_scatter_keys");
-        if (exact) break;  // cannot overflow
+// Scatter (uniform layout) or count (exact layout) the keys of `cnt` records on stream s, which
+// must be the job's stream or have waited for k4_job_ready().  recs must be 32-byte aligned.
+int k4_job_add(K4Job *job, const uint64_t *recs, uint64_t cnt, cudaStream_t s, ibu_error_t *err) {
+    if (cnt == 0) return IBU_OK;
+    job->added += cnt;
+    ScatterArgs a{recs, cnt, job->bb, job->ub, job->pb, (uint32_t)job->cap, nullptr, job->cursors, job->keys, job->wts,
+                  job->wide, job->wide_cap, job->ctr};
+    return job->exact ? launch_scatter<true>(a, job->weighted, s, err) : launch_scatter<false>(a, job->weighted, s, err);
+}
+
+// Everything after the scatter, on the job's stream (which must have waited for every stream that
+// added).  all_recs (nullable): the records the job saw, contiguous — needed when the buckets have
+// to be laid out exactly (duplicate-heavy data, or an overflow of the uniform layout); without
+// them such a job ends unhandled.  *handled = false: nothing produced, take another path.
+int k4_job_finish(K4Job *job, const uint64_t *all_recs, bool pair_mode, bool pairs_sorted, uint64_t **rows_out,
+                  uint64_t *n_rows, uint64_t *n_pairs, bool *handled, ibu_error_t *err) {
+    *handled = false;
+    *rows_out = nullptr;
+    *n_rows = *n_pairs = 0;
+    ibu_gpu_ctx *ctx = job->ctx;
+    cudaStream_t s = job->s0;
+    PoolScratch &sc = job->sc;
+    StageTimer &timer = job->timer;
+    const bool trace = job->trace, weighted = job->weighted, packed = job->packed;
+    unsigned long long *mail = ctx->h_mail;  // pinned: device -> host read-backs without a staged copy
+    const uint64_t n = job->added, P = job->P, cap = job->cap;
+    const uint32_t pb = job->pb, bb = job->bb, ub = job->ub, s_bits = job->s_bits;
+    uint32_t *cursors = job->cursors;
+    unsigned long long *ctr = job->ctr;
+    uint64_t *wide = job->wide, *pairs = nullptr;
+    if (n > job->n) return IBU_OK;  // more records than the job was sized for
+    timer.lap(job->exact ? "histogram" : "k_scatter_keys");
+
+    // ---- exact layout: the cursors hold the histogram; lay the buckets out and scatter everything ----
+    if (!job->exact) {
         IBU_CUDA(cudaMemcpyAsync(mail, ctr, kCtrWords * 8, cudaMemcpyDeviceToHost, s));
         IBU_CUDA(cudaStreamSynchronize(s));
         if (mail[kCtrFlags] & kFlagWide) return IBU_OK;
-        if (!(mail[kCtrFlags] & kFlagBucket)) break;
-        if (trace) fprintf(stderr, "[ibu trace] a bucket overflowed (cap %llu): exact layout\n", (unsigned long long)cap);
-        sc.free_now(keys);
-        if (wts) sc.free_now(wts);
-        exact = true;  // the cursors counted every key, stored or not: they are the histogram
+        if (mail[kCtrFlags] & kFlagBucket) {
+            if (trace) fprintf(stderr, "[ibu trace] a bucket overflowed (cap %llu): exact layout\n", (unsigned long long)cap);
+            sc.free_now(job->keys);
+            if (job->wts) sc.free_now(job->wts);
+            job->keys = job->wts = nullptr;
+            job->exact = true;  // the cursors counted every key, stored or not
+        }
     }
+    if (job->exact && !job->bases) {
+        if (!all_recs) return IBU_OK;
+        if (n * (weighted ? 16 : 8) > (64ull << 30)) return IBU_OK;
+        IBU_CUDA(sc.alloc(&job->bases, (P + 1) * 8));
+        k_bucket_bases<<<1, 1024, 0, s>>>(cursors, (uint32_t)P, job->bases);
+        IBU_LAUNCHED("k_bucket_bases");
+        IBU_CUDA(cudaMemsetAsync(cursors, 0, P * 4, s));
+        IBU_CUDA(cudaMemsetAsync(ctr, 0, kCtrWords * 8, s));
+        IBU_CUDA(sc.alloc(&job->keys, n * 8));
+        if (weighted) IBU_CUDA(sc.alloc(&job->wts, n * 8));
+        ScatterArgs a{all_recs, n, bb, ub, pb, (uint32_t)cap, job->bases, cursors, job->keys, job->wts, wide, job->wide_cap, ctr};
+        if (int rc = launch_scatter<false>(a, weighted, s, err)) return rc;
+        timer.lap("k_scatter_keys (exact)");
+    }
+    uint64_t *keys = job->keys, *wts = job->wts, *bases = job->bases;
 
-    // ---- 4. per-bucket de-duplication into the barcode table (grown if the estimate was short) ----
+    // ---- per-bucket de-duplication into the barcode table (grown if the estimate was short) ----
+    // barcode table: generous (skewed barcode frequencies make the estimate a lower bound); only the
+    // slots that are hit occupy L2
+    uint64_t t_slots = pair_mode ? 0 : std::max<uint64_t>(1u << 14, pow2_ceil((uint64_t)(8.0 * std::min(job->r_est, (double)n))));
+    const uint64_t pairs_cap = pair_mode ? n : 0;
+    const uint32_t slot_words = packed ? 2 : 4;
+    if (pair_mode) IBU_CUDA(sc.alloc(&pairs, pairs_cap * 24));
     uint64_t *slots = nullptr;
     for (int attempt = 0;; attempt++) {
         if (!pair_mode) {
@@ -767,7 +874,7 @@ int k4_partition_table(ibu_gpu_ctx *ctx, const uint64_t *recs, uint64_t n, const
         const uint64_t flags = mail[kCtrFlags];
         if (trace)
             fprintf(stderr, "[ibu trace] partition: P=2^%u %s cap=%llu S=2^%u table=%llu x %u B -> wide %llu pairs %llu rows %llu flags %llx\n",
-                    pb, exact ? "exact" : "uniform", (unsigned long long)cap, s_bits, (unsigned long long)t_slots,
+                    pb, job->exact ? "exact" : "uniform", (unsigned long long)cap, s_bits, (unsigned long long)t_slots,
                     slot_words * 8, mail[kCtrWide], mail[kCtrPairs], mail[kCtrClaimed], (unsigned long long)flags);
         if (flags & (kFlagBucket | kFlagWide | kFlagSmem | kFlagPairsOut)) return IBU_OK;  // legacy path
         const bool crowded = !pair_mode && mail[kCtrClaimed] > t_slots / 10 * 6;
@@ -783,6 +890,7 @@ int k4_partition_table(ibu_gpu_ctx *ctx, const uint64_t *recs, uint64_t n, const
     const uint64_t n_wide = mail[kCtrWide];
     sc.free_now(keys);
     if (wts) sc.free_now(wts);
+    job->keys = job->wts = nullptr;
 
     // ---- 5. wide records and the special key ----
     uint64_t wide_pairs = 0;
@@ -869,6 +977,21 @@ int k4_partition_table(ibu_gpu_ctx *ctx, const uint64_t *recs, uint64_t n, const
     *n_pairs = total_pairs;
     *handled = true;
     return IBU_OK;
+}
+
+int k4_partition_table(ibu_gpu_ctx *ctx, const uint64_t *recs, uint64_t n, const K4Hints &hints, const K4Sample &smp,
+                       bool pair_mode, bool pairs_sorted, bool weighted, cudaStream_t s, uint64_t **rows_out,
+                       uint64_t *n_rows, uint64_t *n_pairs, bool *handled, ibu_error_t *err) {
+    *handled = false;
+    *rows_out = nullptr;
+    *n_rows = *n_pairs = 0;
+    K4Job *job = nullptr;
+    if (int rc = k4_job_begin(ctx, n, hints, smp, pair_mode, weighted, s, &job, err)) return rc;
+    if (!job) return IBU_OK;
+    int rc = k4_job_add(job, recs, n, s, err);
+    if (rc == IBU_OK) rc = k4_job_finish(job, recs, pair_mode, pairs_sorted, rows_out, n_rows, n_pairs, handled, err);
+    k4_job_destroy(job);
+    return rc;
 }
 
 }  // namespace ibu

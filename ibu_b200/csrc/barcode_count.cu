@@ -1113,9 +1113,9 @@ int k4_sort_rows(ibu_gpu_ctx *ctx, const uint64_t *rows, uint64_t n, const uint6
 }
 
 // Shared driver of ibu_gpu_barcode_count / ibu_gpu_pair_table.
-static int build_table(ibu_gpu_ctx *ctx, const ibu_record_t *d_records, uint64_t n, int mode, const K4Hints &hints,
-                       bool pair_mode, bool pairs_sorted, bool weighted, cudaStream_t s, uint64_t **rows,
-                       uint64_t *n_rows, uint64_t *n_pairs, bool *was_sorted, ibu_error_t *err) {
+int k4_build_table(ibu_gpu_ctx *ctx, const ibu_record_t *d_records, uint64_t n, int mode, const K4Hints &hints,
+                   bool pair_mode, bool pairs_sorted, bool weighted, cudaStream_t s, uint64_t **rows,
+                   uint64_t *n_rows, uint64_t *n_pairs, bool *was_sorted, ibu_error_t *err) {
     *rows = nullptr;
     *n_rows = *n_pairs = 0;
     *was_sorted = false;
@@ -1163,7 +1163,7 @@ static int build_table(ibu_gpu_ctx *ctx, const ibu_record_t *d_records, uint64_t
 using namespace ibu;
 
 // key-layout hints and forced path carried in the upper bits of `mode` / `flags`
-static K4Hints hints_of(int mode) {
+K4Hints ibu::k4_hints_of(int mode) {
     K4Hints h;
     h.bc_len = ((unsigned)mode >> 8) & 0x3Fu;
     h.umi_len = ((unsigned)mode >> 16) & 0x3Fu;
@@ -1179,7 +1179,7 @@ int ibu_gpu_barcode_count(ibu_gpu_ctx_t *ctx, const ibu_record_t *d_records, uin
     clear_error(err);
     if (!ctx || !table || (!d_records && n)) return set_error(err, IBU_ERR_ARG, 0, 0, 0, "null argument");
     const bool weighted = (mode & IBU_COUNT_WEIGHTED) != 0;
-    const K4Hints hints = hints_of(mode);
+    const K4Hints hints = k4_hints_of(mode);
     mode &= 7;
     if (mode < 0 || mode > 2) return set_error(err, IBU_ERR_ARG, 0, mode, 0, "mode must be 0, 1 or 2");
     if (((uintptr_t)d_records & 31u) != 0)
@@ -1193,7 +1193,7 @@ int ibu_gpu_barcode_count(ibu_gpu_ctx_t *ctx, const ibu_record_t *d_records, uin
     DeviceGuard guard(ctx->device);
     uint64_t *rows = nullptr, n_rows = 0, n_pairs = 0;
     bool was_sorted = false;
-    if (int rc = build_table(ctx, d_records, n, mode, hints, false, false, weighted, pick_stream(ctx, stream), &rows,
+    if (int rc = k4_build_table(ctx, d_records, n, mode, hints, false, false, weighted, pick_stream(ctx, stream), &rows,
                              &n_rows, &n_pairs, &was_sorted, err))
         return rc;
     table->d_rows = reinterpret_cast<ibu_barcode_row_t *>(rows);
@@ -1225,7 +1225,7 @@ int ibu_gpu_pair_table(ibu_gpu_ctx_t *ctx, const ibu_record_t *d_records, uint64
     DeviceGuard guard(ctx->device);
     uint64_t *rows = nullptr, n_rows = 0, np = 0;
     bool was_sorted = false;
-    if (int rc = build_table(ctx, d_records, n, 0, hints_of(weighted), true, (weighted & IBU_PAIRS_UNORDERED) == 0,
+    if (int rc = k4_build_table(ctx, d_records, n, 0, k4_hints_of(weighted), true, (weighted & IBU_PAIRS_UNORDERED) == 0,
                              (weighted & IBU_PAIRS_WEIGHTED) != 0, pick_stream(ctx, stream), &rows, &n_rows, &np,
                              &was_sorted, err))
         return rc;

@@ -43,7 +43,24 @@ inline uint64_t high_mask(uint32_t len) { return len >= 32 ? 0ull : ~((1ull << (
 }  // namespace ibu
 
 // the mmap reader is shared between host_format.cpp and the staging pipeline
-struct ibu_mmap_shared;
+#include <atomic>
+#include <mutex>
+#include <vector>
+struct ibu_mmap_shared {  // Arc<Mmap> (src/io/mmap.rs:99-107)
+    const uint8_t *base;
+    size_t bytes;
+    int fd;  // kept open: the staging pipeline may pread() instead of touching the mapping
+    std::atomic<long> refs;
+    // page-locked parts of the mapping (ibu_mmap_pin / ibu_mmap_pin_range): registered once however
+    // many clones ask, released by the matching unpin or, at the latest, before the mapping goes away
+    struct PinnedRange {
+        uint8_t *p;
+        size_t bytes;
+        long count;
+    };
+    std::mutex pin_mutex;
+    std::vector<PinnedRange> pinned;
+};
 struct ibu_mmap_reader {
     ibu_mmap_shared *shared;  // Arc<Mmap>
     ibu_header_t header;

@@ -15,17 +15,12 @@
 #include <unistd.h>
 #include <vector>
 
+#include <cuda_runtime.h>
+
 #include "common.h"
 
 using ibu::clear_error;
 using ibu::set_error;
-
-struct ibu_mmap_shared {
-    const uint8_t *base;
-    size_t bytes;
-    int fd;  // kept open: the staging pipeline may pread() instead of touching the mapping
-    std::atomic<long> refs;
-};
 
 const uint8_t *ibu_mmap_base(const ibu_mmap_reader *r) { return r->shared->base; }
 size_t ibu_mmap_bytes(const ibu_mmap_reader *r) { return r->shared->bytes; }
@@ -149,7 +144,13 @@ int ibu_mmap_open(const char *path, ibu_mmap_reader_t **out, ibu_error_t *err) {
         ::close(fd);
         return rc;
     }
-    auto *shared = new (std::nothrow) ibu_mmap_shared{(const uint8_t *)p, bytes, fd, {1}};
+    auto *shared = new (std::nothrow) ibu_mmap_shared;
+    if (shared) {
+        shared->base = (const uint8_t *)p;
+        shared->bytes = bytes;
+        shared->fd = fd;
+        shared->refs.store(1);
+    }
     auto *r = new (std::nothrow) ibu_mmap_reader{shared, header, (bytes - IBU_HEADER_SIZE) / IBU_RECORD_SIZE};
     if (!shared || !r) {
         munmap(p, bytes);
@@ -172,6 +173,10 @@ ibu_mmap_reader_t *ibu_mmap_clone(ibu_mmap_reader_t *r) {
 void ibu_mmap_close(ibu_mmap_reader_t *r) {
     if (!r) return;
     if (r->shared->refs.fetch_sub(1, std::memory_order_acq_rel) == 1) {
+        // a registration must not outlive the mapping: the driver would keep treating the address
+        // range as page-locked after something else is mapped there
+        for (auto &pr : r->shared->pinned)
+            if (cudaHostUnregister(pr.p) != cudaSuccess) cudaGetLastError();
         munmap((void *)r->shared->base, r->shared->bytes);
         ::close(r->shared->fd);
         delete r->shared;

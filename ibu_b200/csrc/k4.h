@@ -53,6 +53,7 @@ struct K4Hints {
     int force_path = 0;                // 0 auto, 1 partition, 2 composite sort, 3 legacy (tests / tuning)
 };
 enum { kPathAuto = 0, kPathPartition = 1, kPathSort = 2, kPathLegacy = 3 };
+K4Hints k4_hints_of(int mode);  // from the upper bits of `mode` / `flags` (IBU_COUNT_LENS, IBU_COUNT_PATH_*)
 
 // ---- barcode_count.cu (all of these expect ctx->arena_mutex to be held by the caller) ----
 
@@ -87,5 +88,24 @@ int k4_sample(ibu_gpu_ctx *ctx, const uint64_t *recs, uint64_t n, cudaStream_t s
 int k4_partition_table(ibu_gpu_ctx *ctx, const uint64_t *recs, uint64_t n, const K4Hints &hints, const K4Sample &smp,
                        bool pair_mode, bool pairs_sorted, bool weighted, cudaStream_t s, uint64_t **rows,
                        uint64_t *n_rows, uint64_t *n_pairs, bool *handled, ibu_error_t *err);
+
+
+// The same in three steps, for an ingest pipeline that feeds the table chunk by chunk while the
+// next chunk is still on the link (pipeline.cu).  begin leaves *job NULL when the input does not
+// suit the path.  Caller holds ctx->arena_mutex from begin to destroy.
+struct K4Job;
+int k4_job_begin(ibu_gpu_ctx *ctx, uint64_t n, const K4Hints &hints, const K4Sample &smp, bool pair_mode,
+                 bool weighted, cudaStream_t s, K4Job **job, ibu_error_t *err);
+cudaEvent_t k4_job_ready(K4Job *job);  // recorded on the job's stream once its scratch is initialised
+int k4_job_add(K4Job *job, const uint64_t *recs, uint64_t cnt, cudaStream_t s, ibu_error_t *err);
+int k4_job_finish(K4Job *job, const uint64_t *all_recs, bool pair_mode, bool pairs_sorted, uint64_t **rows,
+                  uint64_t *n_rows, uint64_t *n_pairs, bool *handled, ibu_error_t *err);
+void k4_job_destroy(K4Job *job);
+
+// barcode_count.cu: the whole decision tree (sorted streaming pass, partition path, legacy) over
+// device-resident records; locks ctx->arena_mutex itself.
+int k4_build_table(ibu_gpu_ctx *ctx, const ibu_record_t *d_records, uint64_t n, int mode, const K4Hints &hints,
+                   bool pair_mode, bool pairs_sorted, bool weighted, cudaStream_t s, uint64_t **rows, uint64_t *n_rows,
+                   uint64_t *n_pairs, bool *was_sorted, ibu_error_t *err);
 
 }  // namespace ibu

@@ -11,6 +11,7 @@
 #include <algorithm>
 #include <atomic>
 #include <cerrno>
+#include <chrono>
 #include <condition_variable>
 #include <cstdlib>
 #include <deque>
@@ -26,6 +27,7 @@
 #include <unistd.h>
 
 #include "ctx.h"
+#include "k4.h"
 
 using namespace ibu;
 
@@ -262,6 +264,7 @@ struct Span {
     bool pinned = false;          // host side is pinned: DMA straight from / to it
     int fd = -1;                  // inputs only: stage with pread(fd, file_off) instead of memcpy
     uint64_t file_off = 0;
+    void *d_dst = nullptr;        // inputs only: device destination outside the slot (records that stay resident)
 };
 
 struct ChunkPlan {
@@ -269,6 +272,7 @@ struct ChunkPlan {
     Span out[3];
     int n_in = 0, n_out = 0;
     size_t d_in_bytes = 0, d_out_bytes = 0;
+    size_t h_in_bytes = 0;        // pinned staging for pageable inputs (0 = d_in_bytes)
 };
 
 // Drives chunks through the slots.  `enqueue(slot, chunk_idx)` launches the kernel(s) for a
@@ -307,7 +311,7 @@ int run_chunks_impl(ibu_gpu_ctx *ctx, uint64_t n_chunks, PlanFn plan_of, Enqueue
         for (int k = 0; k < p.n_in; k++) need_h_in |= !p.in[k].pinned;
         for (int k = 0; k < p.n_out; k++) need_h_out |= !p.out[k].pinned;
         if (need_h_in)
-            if (int rc = ensure(&slot.h_in, &slot.h_in_bytes, p.d_in_bytes, true, err)) return rc;
+            if (int rc = ensure(&slot.h_in, &slot.h_in_bytes, p.h_in_bytes ? p.h_in_bytes : p.d_in_bytes, true, err)) return rc;
         if (need_h_out)
             if (int rc = ensure(&slot.h_out, &slot.h_out_bytes, p.d_out_bytes, true, err)) return rc;
         for (int k = 0; k < p.n_in; k++) {
@@ -323,7 +327,7 @@ int run_chunks_impl(ibu_gpu_ctx *ctx, uint64_t n_chunks, PlanFn plan_of, Enqueue
                 }
                 src = (uint8_t *)slot.h_in + sp.d_off;
             }
-            IBU_CUDA(cudaMemcpyAsync((uint8_t *)slot.d_in + sp.d_off, src, sp.bytes,
+            IBU_CUDA(cudaMemcpyAsync(sp.d_dst ? sp.d_dst : (void *)((uint8_t *)slot.d_in + sp.d_off), src, sp.bytes,
                                      cudaMemcpyHostToDevice, slot.stream));
         }
         if (int rc = enqueue(slot, c)) return rc;
@@ -404,6 +408,169 @@ int process_host_records(ibu_gpu_ctx *ctx, const ibu_record_t *h_records, uint64
             return on_chunk ? on_chunk(user, first_record + start, cnt, &r) : 0;
         },
         err);
+}
+
+// Ingest with more than the reduction: the records land in ONE device allocation (chunk by chunk,
+// same slots and streams), every chunk is validated / reduced (K1) or unpacked (K2, which carries
+// K1's reductions) as it lands, and for IBU_OP_TABLE its (barcode, umi) keys are scattered into the
+// table's buckets on the same stream — while the next chunk is still on the link.  After the last
+// chunk only the bucket de-duplication and the rows remain.  This is process_parallel
+// (mmap.rs:286-332) running the HashMap<barcode, count> processor of parallel.rs:79-98 (+ distinct
+// UMIs) next to the count / sum processors, in one pass over the file.
+int process_records_ops(ibu_gpu_ctx *ctx, const ibu_record_t *h_records, uint64_t n, uint32_t bc_len, uint32_t umi_len,
+                        uint64_t first_record, const ibu_process_request_t *req, ibu_reduce_result_t *h_result,
+                        ibu_chunk_cb on_chunk, void *user, ibu_error_t *err, int fd = -1, uint64_t file_off = 0) {
+    const uint32_t ops = req->ops;
+    const bool want_table = (ops & IBU_OP_TABLE) != 0, keep = (ops & IBU_OP_KEEP) != 0, unpack = (ops & IBU_OP_UNPACK) != 0;
+    if (want_table && !req->table) return set_error(err, IBU_ERR_ARG, 0, 0, 0, "IBU_OP_TABLE needs request.table");
+    if (keep && !req->d_records) return set_error(err, IBU_ERR_ARG, 0, 0, 0, "IBU_OP_KEEP needs request.d_records");
+    if (unpack && n && (!req->h_bc_ascii || !req->h_umi_ascii))
+        return set_error(err, IBU_ERR_ARG, 0, 0, 0, "IBU_OP_UNPACK needs request.h_bc_ascii and h_umi_ascii");
+    if (want_table) memset(req->table, 0, sizeof(*req->table));
+    if (keep) *req->d_records = nullptr;
+    if (!want_table && !keep && !unpack)
+        return process_host_records(ctx, h_records, n, bc_len, umi_len, first_record, h_result, on_chunk, user, err, fd, file_off);
+    DeviceGuard guard(ctx->device);
+    std::lock_guard<std::mutex> lock(ctx->pipe_mutex);
+    memset(h_result, 0, sizeof(*h_result));
+    if (want_table) {
+        req->table->n_records = n;
+        req->table->input_was_sorted = n == 0;
+    }
+    if (n == 0) return IBU_OK;
+    const uint64_t chunk = chunk_records(ctx);
+    const uint64_t n_chunks = (n + chunk - 1) / chunk;
+    const bool pinned = is_pinned(h_records);
+    const bool resident = want_table || keep;
+    // IBU_B200_TRACE=1: host-side phase times on stderr (tuning only)
+    static const bool trace = getenv("IBU_B200_TRACE") != nullptr;
+    auto t_last = std::chrono::steady_clock::now();
+    auto mark = [&](const char *what) {
+        if (!trace) return;
+        const auto now = std::chrono::steady_clock::now();
+        fprintf(stderr, "[ibu trace] ops: %-24s %8.3f ms\n", what, std::chrono::duration<double, std::milli>(now - t_last).count());
+        t_last = now;
+    };
+    // the resident copy comes from the stream-ordered pool: after the first call of a size it is
+    // a cached block, not a fresh cudaMalloc (and cudaFree of GBs is a device-wide synchronisation)
+    ibu_record_t *d_all = nullptr;
+    if (resident) {
+        IBU_CUDA(cudaMallocAsync((void **)&d_all, n * IBU_RECORD_SIZE, ctx->stream));
+        IBU_CUDA(cudaStreamSynchronize(ctx->stream));
+    }
+    mark("resident allocation");
+    uint8_t *h_bc = req->h_bc_ascii, *h_umi = req->h_umi_ascii, *h_fl = req->h_flags;
+    const bool pin_bc = unpack && is_pinned(h_bc), pin_umi = unpack && is_pinned(h_umi), pin_fl = unpack && h_fl && is_pinned(h_fl);
+    const size_t off_umi = align_up(chunk * bc_len), off_fl = off_umi + align_up(chunk * umi_len);
+    const size_t out_bytes = unpack ? off_fl + (h_fl ? align_up(chunk) : 0) : kAlign;
+
+    K4Hints hints = k4_hints_of(req->table_mode);
+    if (!hints.bc_len || !hints.umi_len) {
+        hints.bc_len = bc_len;
+        hints.umi_len = umi_len;
+    }
+    K4Job *job = nullptr;
+    bool job_tried = false, saw_unordered = false;
+    std::unique_lock<std::mutex> arena_lock(ctx->arena_mutex, std::defer_lock);
+    auto span = [&](uint64_t c, uint64_t &start, uint64_t &cnt) {
+        start = c * chunk;
+        cnt = std::min(chunk, n - start);
+    };
+    int rc = run_chunks(
+        ctx, n_chunks,
+        [&](uint64_t c) {
+            uint64_t start, cnt;
+            span(c, start, cnt);
+            ChunkPlan p;
+            p.n_in = 1;
+            p.in[0].h_src = h_records + start;
+            p.in[0].bytes = cnt * IBU_RECORD_SIZE;
+            p.in[0].pinned = pinned;
+            p.in[0].fd = fd;
+            p.in[0].file_off = file_off + start * IBU_RECORD_SIZE;
+            p.in[0].d_dst = resident ? (void *)(d_all + start) : nullptr;
+            p.h_in_bytes = align_up(chunk * IBU_RECORD_SIZE);
+            p.d_in_bytes = resident ? kAlign : p.h_in_bytes;
+            if (unpack) {
+                p.out[0] = {nullptr, h_bc + start * bc_len, cnt * bc_len, 0, pin_bc};
+                p.out[1] = {nullptr, h_umi + start * umi_len, cnt * umi_len, off_umi, pin_umi};
+                p.n_out = 2;
+                if (h_fl) p.out[p.n_out++] = {nullptr, h_fl + start, cnt, off_fl, pin_fl};
+            }
+            p.d_out_bytes = out_bytes;
+            return p;
+        },
+        [&](ibu_chunk_slot &slot, uint64_t c) -> int {
+            uint64_t start, cnt;
+            span(c, start, cnt);
+            const ibu_record_t *d_chunk = resident ? d_all + start : (const ibu_record_t *)slot.d_in;
+            if (unpack) {
+                uint8_t *d_out = (uint8_t *)slot.d_out;
+                if (int r = ibu_gpu_unpack_async(ctx, d_chunk, cnt, bc_len, umi_len, d_out, d_out + off_umi,
+                                                 h_fl ? d_out + off_fl : nullptr, slot.d_result, slot.stream, err))
+                    return r;
+            } else if (int r = ibu_gpu_validate_reduce_async(ctx, d_chunk, cnt, bc_len, umi_len, slot.d_result, slot.stream, err)) {
+                return r;
+            }
+            if (!want_table) return IBU_OK;
+            if (!job_tried) {  // the first chunk decides: what it looks like sizes the table's buckets
+                job_tried = true;
+                arena_lock.lock();
+                K4Sample smp;
+                if (int r = k4_sample(ctx, reinterpret_cast<const uint64_t *>(d_chunk), cnt, slot.stream, &smp, err)) return r;
+                saw_unordered = smp.unordered != 0;
+                const int mode = req->table_mode & 7;
+                // (sorted-looking input: the streaming pass over the resident records at the end is the fast path)
+                if ((saw_unordered || mode == 2) && mode != 1 && hints.force_path != kPathLegacy && hints.force_path != kPathSort &&
+                    (n >= (1u << 16) || hints.force_path == kPathPartition))
+                    if (int r = k4_job_begin(ctx, n, hints, smp, false, false, ctx->stream, &job, err)) return r;
+            }
+            if (job) {
+                IBU_CUDA(cudaStreamWaitEvent(slot.stream, k4_job_ready(job), 0));
+                return k4_job_add(job, reinterpret_cast<const uint64_t *>(d_chunk), cnt, slot.stream, err);
+            }
+            return IBU_OK;
+        },
+        [&](uint64_t c, const ibu_reduce_result_t &r) {
+            uint64_t start, cnt;
+            span(c, start, cnt);
+            merge(*h_result, r);
+            return on_chunk ? on_chunk(user, first_record + start, cnt, &r) : 0;
+        },
+        err);
+    mark("chunks (ingest + per-chunk kernels)");
+    if (rc == IBU_OK && want_table) {
+        // every slot has drained (run_chunks waited for each chunk's event), so the context's stream
+        // may read what the slot streams wrote
+        uint64_t *rows = nullptr, n_rows = 0, n_pairs = 0;
+        bool handled = false, was_sorted = false;
+        if (job) rc = k4_job_finish(job, reinterpret_cast<const uint64_t *>(d_all), false, false, &rows, &n_rows, &n_pairs, &handled, err);
+        if (job) k4_job_destroy(job);
+        job = nullptr;
+        if (arena_lock.owns_lock()) arena_lock.unlock();
+        if (rc == IBU_OK && !handled) {
+            int mode = req->table_mode & 7;
+            if (mode == 0 && saw_unordered) mode = 2;  // already known not to be sorted
+            rc = k4_build_table(ctx, d_all, n, mode, hints, false, false, false, ctx->stream, &rows, &n_rows, &n_pairs,
+                                &was_sorted, err);
+        }
+        if (rc == IBU_OK) {
+            req->table->d_rows = reinterpret_cast<ibu_barcode_row_t *>(rows);
+            req->table->n_rows = n_rows;
+            req->table->n_distinct_pairs = n_pairs;
+            req->table->input_was_sorted = was_sorted ? 1 : 0;
+        }
+    }
+    if (job) k4_job_destroy(job);
+    if (arena_lock.owns_lock()) arena_lock.unlock();
+    mark("table finish");
+    if (rc == IBU_OK && keep) {
+        *req->d_records = d_all;
+    } else if (d_all) {
+        if (cudaFreeAsync(d_all, ctx->stream) != cudaSuccess) cudaGetLastError();
+    }
+    mark("release");
+    return rc;
 }
 
 }  // namespace
@@ -593,26 +760,99 @@ void ibu_host_stream_copy(void *dst, const void *src, size_t bytes, unsigned thr
     parallel_memcpy(dst, src, bytes, threads);
 }
 
-int ibu_mmap_pin(ibu_mmap_reader_t *reader, ibu_error_t *err) {
-    clear_error(err);
-    if (!reader) return set_error(err, IBU_ERR_ARG, 0, 0, 0, "null reader");
-    // The driver refuses to page-lock a mapping without write permission (cudaErrorInvalidValue,
-    // read-only flag or not) but takes a private file mapping that has it, and with the read-only
-    // flag it pins the page-cache pages themselves, no copy-on-write (tools/probe_pin.cu).  The
-    // mapping is MAP_PRIVATE, so the permission never reaches the file; it is dropped again once
-    // the pages are locked.
-    void *base = (void *)ibu_mmap_base(reader);
-    const size_t bytes = ibu_mmap_bytes(reader);
-    if (mprotect(base, bytes, PROT_READ | PROT_WRITE) != 0)
+// Page-locks [p, p + bytes) of the mapping (page aligned), once per distinct range however many
+// clones ask.  The driver refuses to page-lock a mapping without write permission
+// (cudaErrorInvalidValue, read-only flag or not) but takes a private file mapping that has it, and
+// with the read-only flag it pins the page-cache pages themselves, no copy-on-write
+// (tools/probe_pin.cu).  The mapping is MAP_PRIVATE, so the permission never reaches the file; it
+// is dropped again once the pages are locked.
+static int pin_bytes(ibu_mmap_reader_t *reader, uint8_t *p, size_t bytes, ibu_error_t *err) {
+    ibu_mmap_shared *sh = reader->shared;
+    std::lock_guard<std::mutex> lock(sh->pin_mutex);
+    for (auto &pr : sh->pinned) {
+        if (pr.p == p && pr.bytes == bytes) {
+            pr.count++;
+            return IBU_OK;
+        }
+        if (p < pr.p + pr.bytes && pr.p < p + bytes)
+            return set_error(err, IBU_ERR_ARG, 0, 0, 0, "range overlaps a differently pinned part of the mapping");
+    }
+    if (mprotect(p, bytes, PROT_READ | PROT_WRITE) != 0)
         return set_error(err, IBU_ERR_IO, errno, 0, 0, "I/O error: mprotect of the mapping failed");
-    cudaError_t e = cudaHostRegister(base, bytes, cudaHostRegisterPortable | cudaHostRegisterReadOnly);
-    mprotect(base, bytes, PROT_READ);
+    // fault the pages in on all cores first: registration itself walks them on one thread
+    static const bool populate = getenv("IBU_B200_NO_POPULATE") == nullptr;
+    if (populate && bytes >= (64u << 20)) {
+        for_pieces(bytes, std::max(2u, std::thread::hardware_concurrency()), 2u << 20, [&](size_t off, size_t len) {
+#ifdef MADV_POPULATE_READ
+            if (madvise(p + off, len, MADV_POPULATE_READ) == 0) return;
+#endif
+            volatile uint8_t sink = 0;
+            for (size_t i = 0; i < len; i += 4096) sink += p[off + i];
+            (void)sink;
+        });
+    }
+    cudaError_t e = cudaHostRegister(p, bytes, cudaHostRegisterPortable | cudaHostRegisterReadOnly);
+    mprotect(p, bytes, PROT_READ);
     if (e != cudaSuccess) return cuda_fail(err, e, "cudaHostRegister(mmap)");
+    sh->pinned.push_back({p, bytes, 1});
     return IBU_OK;
 }
 
+static void unpin_bytes(ibu_mmap_reader_t *reader, uint8_t *p, size_t bytes) {
+    ibu_mmap_shared *sh = reader->shared;
+    std::lock_guard<std::mutex> lock(sh->pin_mutex);
+    for (size_t i = 0; i < sh->pinned.size(); i++) {
+        auto &pr = sh->pinned[i];
+        if (pr.p == p && (bytes == 0 || pr.bytes == bytes)) {
+            if (--pr.count == 0) {
+                if (cudaHostUnregister(pr.p) != cudaSuccess) cudaGetLastError();
+                sh->pinned.erase(sh->pinned.begin() + i);
+            }
+            return;
+        }
+    }
+}
+
+// byte range of records [start, end) widened to whole pages
+static void page_range(const ibu_mmap_reader_t *reader, uint64_t start, uint64_t end, uint8_t **p, size_t *bytes) {
+    const size_t page = (size_t)sysconf(_SC_PAGESIZE);
+    const uint8_t *base = ibu_mmap_base(reader);
+    size_t lo = IBU_HEADER_SIZE + start * IBU_RECORD_SIZE, hi = IBU_HEADER_SIZE + end * IBU_RECORD_SIZE;
+    lo = lo / page * page;
+    hi = std::min(ibu_mmap_bytes(reader), (hi + page - 1) / page * page);
+    *p = const_cast<uint8_t *>(base) + lo;
+    *bytes = hi - lo;
+}
+
+int ibu_mmap_pin(ibu_mmap_reader_t *reader, ibu_error_t *err) {
+    clear_error(err);
+    if (!reader) return set_error(err, IBU_ERR_ARG, 0, 0, 0, "null reader");
+    return pin_bytes(reader, (uint8_t *)ibu_mmap_base(reader), ibu_mmap_bytes(reader), err);
+}
+
 void ibu_mmap_unpin(ibu_mmap_reader_t *reader) {
-    if (reader && cudaHostUnregister((void *)ibu_mmap_base(reader)) != cudaSuccess) cudaGetLastError();
+    if (reader) unpin_bytes(reader, (uint8_t *)ibu_mmap_base(reader), ibu_mmap_bytes(reader));
+}
+
+int ibu_mmap_pin_range(ibu_mmap_reader_t *reader, uint64_t start, uint64_t end, ibu_error_t *err) {
+    clear_error(err);
+    if (!reader) return set_error(err, IBU_ERR_ARG, 0, 0, 0, "null reader");
+    if (start > end || end > reader->len)
+        return set_error(err, IBU_ERR_INVALID_INDEX, 0, end, reader->len,
+                         "Invalid index (%llu) - Must be less than %zu", (unsigned long long)end, reader->len);
+    if (start == end) return IBU_OK;
+    uint8_t *p;
+    size_t bytes;
+    page_range(reader, start, end, &p, &bytes);
+    return pin_bytes(reader, p, bytes, err);
+}
+
+void ibu_mmap_unpin_range(ibu_mmap_reader_t *reader, uint64_t start, uint64_t end) {
+    if (!reader || start >= end || end > reader->len) return;
+    uint8_t *p;
+    size_t bytes;
+    page_range(reader, start, end, &p, &bytes);
+    unpin_bytes(reader, p, bytes);
 }
 
 // ---- GPU counterpart of process_parallel -------------------------------------------------
@@ -643,6 +883,32 @@ int ibu_gpu_process_mmap(ibu_gpu_ctx_t *ctx, const ibu_mmap_reader_t *reader, ui
     return process_host_records(ctx, recs, end - start, reader->header.bc_len, reader->header.umi_len,
                                 start, h_result, on_chunk, user, err, fd,
                                 IBU_HEADER_SIZE + start * IBU_RECORD_SIZE);
+}
+
+int ibu_gpu_process_host_ops(ibu_gpu_ctx_t *ctx, const ibu_record_t *h_records, uint64_t n, uint32_t bc_len,
+                             uint32_t umi_len, const ibu_process_request_t *req, ibu_reduce_result_t *h_result,
+                             ibu_chunk_cb on_chunk, void *user, ibu_error_t *err) {
+    clear_error(err);
+    if (!ctx || !req || !h_result || (!h_records && n)) return set_error(err, IBU_ERR_ARG, 0, 0, 0, "null argument");
+    if (bc_len < 1 || bc_len > 32 || umi_len < 1 || umi_len > 32)
+        return set_error(err, IBU_ERR_ARG, 0, bc_len, umi_len, "bc_len and umi_len must be in 1..32");
+    return process_records_ops(ctx, h_records, n, bc_len, umi_len, 0, req, h_result, on_chunk, user, err);
+}
+
+int ibu_gpu_process_mmap_ops(ibu_gpu_ctx_t *ctx, const ibu_mmap_reader_t *reader, uint64_t start, uint64_t end,
+                             const ibu_process_request_t *req, ibu_reduce_result_t *h_result, ibu_chunk_cb on_chunk,
+                             void *user, ibu_error_t *err) {
+    clear_error(err);
+    if (!ctx || !reader || !req || !h_result) return set_error(err, IBU_ERR_ARG, 0, 0, 0, "null argument");
+    if (end == UINT64_MAX) end = reader->len;
+    if (start > end || end > reader->len)
+        return set_error(err, IBU_ERR_INVALID_INDEX, 0, end, reader->len,
+                         "Invalid index (%llu) - Must be less than %zu", (unsigned long long)end, reader->len);
+    const ibu_record_t *recs = (const ibu_record_t *)(ibu_mmap_base(reader) + IBU_HEADER_SIZE) + start;
+    const char *mode = getenv("IBU_B200_STAGE");
+    const int fd = (mode && !strcmp(mode, "mmap")) ? -1 : ibu_mmap_fd(reader);
+    return process_records_ops(ctx, recs, end - start, reader->header.bc_len, reader->header.umi_len, start, req,
+                               h_result, on_chunk, user, err, fd, IBU_HEADER_SIZE + start * IBU_RECORD_SIZE);
 }
 
 // ---- streaming ingest ----------------------------------------------------------------------

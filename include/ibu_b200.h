@@ -362,10 +362,47 @@ int ibu_gpu_process_mmap(ibu_gpu_ctx_t *ctx, const ibu_mmap_reader_t *reader, ui
  * staged path then still applies. */
 int ibu_mmap_pin(ibu_mmap_reader_t *reader, ibu_error_t *err);
 void ibu_mmap_unpin(ibu_mmap_reader_t *reader);
+/* The same for the pages that hold records [start, end) only — what one rank of a range-sharded
+ * job locks (mmap.rs:297-307).  Pins are counted per range and shared by the clones of a reader;
+ * whatever is still pinned is released when the last clone closes. */
+int ibu_mmap_pin_range(ibu_mmap_reader_t *reader, uint64_t start, uint64_t end, ibu_error_t *err);
+void ibu_mmap_unpin_range(ibu_mmap_reader_t *reader, uint64_t start, uint64_t end);
 /* Same over a host array (pinned: copied directly; pageable: staged). */
 int ibu_gpu_process_host(ibu_gpu_ctx_t *ctx, const ibu_record_t *h_records, uint64_t n,
                          uint32_t bc_len, uint32_t umi_len, ibu_reduce_result_t *h_result,
                          ibu_chunk_cb on_chunk, void *user, ibu_error_t *err);
+
+/* The same with an operation mask — ONE pass over the file for everything the north star lists:
+ *   IBU_OP_REDUCE  validate + the built-in reductions (always on; the result of every call)
+ *   IBU_OP_UNPACK  2-bit unpack of every record to ASCII in host memory (K2 instead of K1 per chunk)
+ *   IBU_OP_TABLE   the per-barcode record / distinct-UMI table of the whole range: the
+ *                  HashMap<barcode, count> processor of src/parallel.rs:79-98 driven by
+ *                  process_parallel (mmap.rs:312-320), + distinct UMIs.  Each chunk's keys are
+ *                  inserted on the chunk's stream while the next chunk is on the link; only the
+ *                  de-duplication and the rows remain after the last chunk.
+ *   IBU_OP_KEEP    the records stay on the device (*d_records, release with ibu_gpu_free)
+ * table_mode: OR-able bits of ibu_gpu_barcode_count's mode (the header's lengths are filled in). */
+#define IBU_OP_REDUCE 1u
+#define IBU_OP_TABLE 2u
+#define IBU_OP_KEEP 4u
+#define IBU_OP_UNPACK 8u
+typedef struct ibu_process_request {
+    uint32_t ops;
+    int32_t table_mode;
+    ibu_barcode_table_t *table;  /* out: IBU_OP_TABLE (rows on the device: ibu_gpu_table_free) */
+    ibu_record_t **d_records;    /* out: IBU_OP_KEEP */
+    uint8_t *h_bc_ascii;         /* out: IBU_OP_UNPACK, [n][bc_len] host bytes */
+    uint8_t *h_umi_ascii;        /* out: IBU_OP_UNPACK, [n][umi_len] */
+    uint8_t *h_flags;            /* out: IBU_OP_UNPACK, nullable, [n] */
+} ibu_process_request_t;
+int ibu_gpu_process_mmap_ops(ibu_gpu_ctx_t *ctx, const ibu_mmap_reader_t *reader, uint64_t start,
+                             uint64_t end, const ibu_process_request_t *req,
+                             ibu_reduce_result_t *h_result, ibu_chunk_cb on_chunk, void *user,
+                             ibu_error_t *err);
+int ibu_gpu_process_host_ops(ibu_gpu_ctx_t *ctx, const ibu_record_t *h_records, uint64_t n,
+                             uint32_t bc_len, uint32_t umi_len, const ibu_process_request_t *req,
+                             ibu_reduce_result_t *h_result, ibu_chunk_cb on_chunk, void *user,
+                             ibu_error_t *err);
 
 /* Streaming ingest — the Reader<R> of src/io/reader.rs feeding the GPU.
  * The bytes of an .ibu stream (header first) are pushed in pieces of any size, from any source

@@ -245,3 +245,91 @@ def test_stream_ingest_errors(ctx):
         st.push(good)
         assert st.finish()["n_records"] == 10
     assert ctx.process_host(np.frombuffer(good[32:], ibu.RECORD_DTYPE), 16, 12)["n_records"] == 10  # lock released
+
+
+# ---- one pass with an operation mask: ingest -> validate/reduce (+ unpack) (+ per-barcode table) ----
+def zipf_file_records(n, seed, dirty=True):
+    recs = oc.generate_records(0, n, 16, 12, 5, (64 << 32) | 20_000, seed)  # Zipf-ish barcodes, heavy duplication
+    if dirty:  # a few words wider than the header allows (examples/random.rs:46)
+        rng = np.random.default_rng(seed)
+        hit = rng.random(n) < 0.003
+        recs["umi"][hit] |= np.uint64(1 << 45)
+    return recs
+
+
+@pytest.mark.parametrize("n", [0, 1, 70_000, (1 << 18) * 3 + 17, 1_500_003])
+@pytest.mark.parametrize("pre_sorted", [False, True])
+def test_process_ops_table_matches_oracle(ctx, tmp_ibu, n, pre_sorted):
+    """mmap.rs:312-320 driving the HashMap<barcode, count> processor of parallel.rs:79-98 (+ distinct
+    UMIs): the table of the whole file out of the same pass that validates and reduces it."""
+    recs = zipf_file_records(n, 61)
+    if pre_sorted:
+        recs = recs[np.lexsort((recs["index"], recs["umi"], recs["barcode"]))]
+    write(tmp_ibu, recs)
+    want_red, _ = oc.MmapReader(tmp_ibu).process_parallel_reduce(0)
+    want = on.barcode_table(recs)
+    reader = ibu.MmapReader(tmp_ibu)
+    chunks = []
+    red, out = reader.process_gpu_ops(ctx, table=True, on_chunk=lambda s, c, r: chunks.append((s, c)))
+    assert red == want_red
+    assert np.array_equal(out.rows, want)
+    assert out.table_info["n_records"] == n and out.table_info["n_distinct_pairs"] == int(want["n_distinct_umi"].sum())
+    if n > 1000:
+        assert out.table_info["input_was_sorted"] == pre_sorted
+    csz = 1 << 18
+    assert chunks == [(s, min(csz, n - s)) for s in range(0, n, csz)]
+    # a sub-range of the file, forced through the partition path (small inputs default to the legacy one)
+    if n > 1000:
+        a, b = n // 7, n - n // 5
+        red, out = reader.process_gpu_ops(ctx, a, b, table=True, table_mode=2 | ibu.COUNT_PATH_PARTITION)
+        assert red == oc.reduce_records(recs[a:b], 16, 12)
+        assert np.array_equal(out.rows, on.barcode_table(recs[a:b]))
+
+
+def test_process_ops_unpack_table_keep_in_one_pass(ctx, tmp_ibu):
+    """decode + validate + count: ASCII, counters, the table and the resident records from ONE pass."""
+    n = 900_001
+    recs = zipf_file_records(n, 62)
+    write(tmp_ibu, recs)
+    reader = ibu.MmapReader(tmp_ibu)
+    red, out = reader.process_gpu_ops(ctx, table=True, keep=True, unpack=True, flags=True)
+    ob, ou, ofl, ores = oc.unpack_records(recs, 16, 12, 0)
+    assert np.array_equal(out.bc_ascii, ob) and np.array_equal(out.umi_ascii, ou) and np.array_equal(out.flags, ofl)
+    assert red == oc.reduce_records(recs, 16, 12)
+    assert np.array_equal(out.rows, on.barcode_table(recs))
+    assert np.array_equal(out.records.to_host(), recs)
+    out.records.free()
+    # host-array form, pinned source
+    pin = ibu.PinnedBuffer(recs.nbytes)
+    h = pin.array(ibu.RECORD_DTYPE, (n,))
+    h[:] = recs
+    red2, out2 = ctx.process_host_ops(h, 16, 12, table=True)
+    assert red2 == red and np.array_equal(out2.rows, out.rows)
+    del h
+    pin.free()
+
+
+def test_process_ops_table_exact_layout_when_duplicates_dominate(ctx, tmp_ibu):
+    """The reference's example pattern (examples/parallel.rs:65-69): 10^6 distinct pairs however long the
+    file is — the bucket loads are too uneven for a uniform layout and the exact one takes over."""
+    n = 3_000_000
+    recs = oc.generate_records(0, n, 16, 12, 2, 0, 0)
+    write(tmp_ibu, recs)
+    red, out = ibu.MmapReader(tmp_ibu).process_gpu_ops(ctx, table=True)
+    assert red["n_records"] == n and len(out.rows) == 1_000_000
+    assert np.array_equal(out.rows["barcode"], np.arange(1_000_000, dtype=np.uint64))
+    assert np.all(out.rows["n_records"] == 3) and np.all(out.rows["n_distinct_umi"] == 1)
+
+
+def test_process_ops_argument_errors(ctx, tmp_ibu):
+    write(tmp_ibu, oc.generate_records(0, 10, 16, 12, 0, 0, 1))
+    reader = ibu.MmapReader(tmp_ibu)
+    from ibu_b200 import _lib
+    import ctypes as C
+    req, res, err = _lib.ProcessRequest(), _lib.ReduceResult(), _lib.Error()
+    req.ops = ibu.OP_TABLE  # no table pointer
+    rc = _lib.lib.ibu_gpu_process_mmap_ops(ctx._h, reader._h, 0, 2**64 - 1, C.byref(req), C.byref(res), _lib.CHUNK_CB(0), None,
+                                           C.byref(err))
+    assert rc == 13 and err.code == 13
+    with pytest.raises(ibu.InvalidIndex):
+        reader.process_gpu_ops(ctx, 5, 11, table=True)
