@@ -37,6 +37,7 @@ COUNT_WEIGHTED = 8
 COUNT_PATH_PARTITION, COUNT_PATH_SORT, COUNT_PATH_LEGACY = 0x10, 0x20, 0x30
 PAIRS_WEIGHTED, PAIRS_UNORDERED = 1, 2
 OP_REDUCE, OP_TABLE, OP_KEEP, OP_UNPACK = 1, 2, 4, 8
+EXCHANGE_AUTO, EXCHANGE_P2P, EXCHANGE_HOST, EXCHANGE_NCCL = 0, 1, 2, 3
 
 
 def count_lens(bc_len: int, umi_len: int) -> int:
@@ -423,11 +424,11 @@ class ProcessOutput:
     """What an ops pass returns besides the reduction: `rows` / `table_info` (OP_TABLE; rows are a
     host copy, ROW_DTYPE), `records` (OP_KEEP: DeviceRecords), `bc_ascii` / `umi_ascii` / `flags` (OP_UNPACK)."""
 
-    rows = table_info = records = bc_ascii = umi_ascii = flags = None
+    rows = table = table_info = records = bc_ascii = umi_ascii = flags = timing = shard_records = None
 
 
 def _run_ops(ctx: "GpuContext", call, n: int, bc_len: int, umi_len: int, table: bool, keep: bool, unpack: bool,
-             flags: bool, table_mode: int, on_chunk, bc_out=None, umi_out=None, flags_out=None):
+             flags: bool, table_mode: int, on_chunk, bc_out=None, umi_out=None, flags_out=None, rows_on_device=False):
     out = ProcessOutput()
     req = _lib.ProcessRequest()
     req.ops = OP_REDUCE | (OP_TABLE if table else 0) | (OP_KEEP if keep else 0) | (OP_UNPACK if unpack else 0)
@@ -448,15 +449,114 @@ def _run_ops(ctx: "GpuContext", call, n: int, bc_len: int, umi_len: int, table: 
     if table:
         out.table_info = dict(n_rows=int(tab.n_rows), n_records=int(tab.n_records),
                               n_distinct_pairs=int(tab.n_distinct_pairs), input_was_sorted=bool(tab.input_was_sorted))
-        out.rows = np.zeros(int(tab.n_rows), ROW_DTYPE)
-        try:
-            if tab.n_rows:
-                ctx.d2h(out.rows, int(tab.d_rows))
-        finally:
-            lib.ibu_gpu_table_free(ctx._h, C.byref(tab))
+        if rows_on_device:  # (benchmarks: the caller releases out.table with ctx.table_free)
+            out.table = tab
+        else:
+            out.rows = np.zeros(int(tab.n_rows), ROW_DTYPE)
+            try:
+                if tab.n_rows:
+                    ctx.d2h(out.rows, int(tab.d_rows))
+            finally:
+                lib.ibu_gpu_table_free(ctx._h, C.byref(tab))
     if keep:
         out.records = DeviceRecords(ctx, int(dptr.value or 0), n)
     return ReduceResult(res.as_dict()), out
+
+
+class GpuGroup:
+    """Several GPUs of one box behind one handle (ibu_gpu_group_*): records shard by contiguous range
+    (mmap.rs:297-307), one host thread per GPU, results and tables merged inside the library."""
+
+    def __init__(self, devices, chunk_records: int = 0, n_slots: int = 0, copy_threads: int = 0):
+        self.devices = list(devices)
+        self._h = C.c_void_p()
+        cfg = _lib.GpuConfig(chunk_records, n_slots, copy_threads, 0)
+        arr = (C.c_int * len(self.devices))(*self.devices)
+        err = _lib.Error()
+        _check(lib.ibu_gpu_group_create(arr, len(self.devices), C.byref(cfg), C.byref(self._h), C.byref(err)), err)
+
+    def __len__(self):
+        return len(self.devices)
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib.ibu_gpu_group_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def ctx(self, rank: int) -> "GpuContext":
+        """Borrowed view of rank's context (owned by the group: do not close)."""
+        c = GpuContext.__new__(GpuContext)
+        c._h = C.c_void_p(lib.ibu_gpu_group_ctx(self._h, rank))
+        c.device = int(lib.ibu_gpu_ctx_device(c._h))
+        c.sm_count = int(lib.ibu_gpu_ctx_sm_count(c._h))
+        c.close = lambda: None
+        return c
+
+    @staticmethod
+    def _take_table(tab: "_lib.HostTable"):
+        rows = np.zeros(int(tab.n_rows), ROW_DTYPE)
+        if tab.n_rows:
+            C.memmove(rows.ctypes.data, tab.h_rows, rows.nbytes)
+        lib.ibu_free(tab.h_rows)
+        info = dict(n_rows=int(tab.n_rows), n_records=int(tab.n_records), n_distinct_pairs=int(tab.n_distinct_pairs))
+        return rows, info
+
+    def _process(self, call, table, keep, table_mode, exchange):
+        n = len(self.devices)
+        req, tab, tim = _lib.GroupRequest(), _lib.HostTable(), _lib.GroupTiming()
+        shards, lens = (C.c_void_p * n)(), (C.c_uint64 * n)()
+        req.ops = OP_REDUCE | (OP_TABLE if table else 0) | (OP_KEEP if keep else 0)
+        req.table_mode, req.exchange = table_mode, exchange
+        req.table, req.timing = C.pointer(tab), C.pointer(tim)
+        req.d_records = C.cast(shards, C.POINTER(C.c_void_p))
+        req.shard_records = C.cast(lens, C.POINTER(C.c_uint64))
+        res, err = _lib.ReduceResult(), _lib.Error()
+        _check(call(C.byref(req), C.byref(res), C.byref(err)), err)
+        out = ProcessOutput()
+        out.timing = tim.as_dict()
+        out.shard_records = [int(x) for x in lens]
+        if table:
+            out.rows, out.table_info = self._take_table(tab)
+        if keep:
+            out.records = [DeviceRecords(self.ctx(r), int(shards[r] or 0), int(lens[r])) for r in range(n)]
+        return ReduceResult(res.as_dict()), out
+
+    def process_mmap(self, reader: "MmapReader", start: int = 0, end: int | None = None, table=False, keep=False,
+                     table_mode: int = 0, exchange: int = 0):
+        """process_parallel across the group: (merged ReduceResult, ProcessOutput with .rows/.table_info,
+        .records (per-rank DeviceRecords), .timing, .shard_records)."""
+        end_v = 2**64 - 1 if end is None else end
+        return self._process(lambda req, res, err: lib.ibu_gpu_group_process_mmap(self._h, reader._h, start, end_v, req, res, err),
+                             table, keep, table_mode, exchange)
+
+    def process_host(self, h_records, bc_len: int, umi_len: int, table=False, keep=False, table_mode: int = 0,
+                     exchange: int = 0):
+        recs = _as_records(h_records)
+        return self._process(lambda req, res, err: lib.ibu_gpu_group_process_host(self._h, _ptr(recs), len(recs), bc_len,
+                                                                                   umi_len, req, res, err),
+                             table, keep, table_mode, exchange)
+
+    def barcode_count(self, d_shards, shard_records, mode: int = 0, exchange: int = 0):
+        """Exact table of device-resident shards (one per rank): (rows, info, timing dict)."""
+        n = len(self.devices)
+        ptrs = (C.c_void_p * n)(*[_ptr(p).value for p in d_shards])
+        lens = (C.c_uint64 * n)(*shard_records)
+        tab, tim, err = _lib.HostTable(), _lib.GroupTiming(), _lib.Error()
+        _check(lib.ibu_gpu_group_barcode_count(self._h, ptrs, lens, mode, exchange, C.byref(tab), C.byref(tim), C.byref(err)), err)
+        rows, info = self._take_table(tab)
+        return rows, info, tim.as_dict()
 
 
 class GpuStream:
@@ -619,6 +719,14 @@ class MmapReader:
 
     def unpin(self):
         lib.ibu_mmap_unpin(self._h)
+
+    def pin_range(self, start: int, end: int):
+        """Page-lock only the pages of records [start, end) (one rank's shard)."""
+        err = _lib.Error()
+        _check(lib.ibu_mmap_pin_range(self._h, start, end, C.byref(err)), err)
+
+    def unpin_range(self, start: int, end: int):
+        lib.ibu_mmap_unpin_range(self._h, start, end)
 
     def process_gpu(self, ctx: GpuContext, start: int = 0, end: int | None = None, on_chunk=None) -> ReduceResult:
         """GPU counterpart of process_parallel for the built-in reductions (mmap.rs:286-332):

@@ -56,6 +56,27 @@ class ProcessRequest(C.Structure):
                 ("h_flags", C.c_void_p)]
 
 
+class HostTable(C.Structure):
+    _fields_ = [("h_rows", C.c_void_p), ("n_rows", C.c_uint64), ("n_records", C.c_uint64),
+                ("n_distinct_pairs", C.c_uint64)]
+
+
+class GroupTiming(C.Structure):
+    _fields_ = [("ingest_ms", C.c_double), ("local_ms", C.c_double), ("exchange_ms", C.c_double),
+                ("owner_ms", C.c_double), ("gather_ms", C.c_double), ("table_ms", C.c_double),
+                ("total_ms", C.c_double), ("pairs_local", C.c_uint64), ("bytes_sent", C.c_uint64),
+                ("exchange", C.c_uint32), ("reserved", C.c_uint32)]
+
+    def as_dict(self) -> dict:
+        return {k: getattr(self, k) for k, _ in self._fields_ if k != "reserved"}
+
+
+class GroupRequest(C.Structure):
+    _fields_ = [("ops", C.c_uint32), ("table_mode", C.c_int32), ("exchange", C.c_uint32), ("reserved", C.c_uint32),
+                ("table", C.POINTER(HostTable)), ("d_records", C.POINTER(C.c_void_p)),
+                ("shard_records", C.POINTER(C.c_uint64)), ("timing", C.POINTER(GroupTiming))]
+
+
 CHUNK_CB = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_uint64, C.c_uint64, C.POINTER(ReduceResult))
 
 _P = C.POINTER
@@ -121,6 +142,15 @@ SIGNATURES = {
     "ibu_gpu_process_mmap_ops": (_int, [_vp, _vp, _u64, _u64, _P(ProcessRequest), _P(ReduceResult), CHUNK_CB, _vp, _err]),
     "ibu_gpu_process_host_ops": (_int, [_vp, _vp, _u64, _u32, _u32, _P(ProcessRequest), _P(ReduceResult), CHUNK_CB, _vp,
                                   _err]),
+    "ibu_mmap_pin_range": (_int, [_vp, _u64, _u64, _err]),
+    "ibu_mmap_unpin_range": (None, [_vp, _u64, _u64]),
+    "ibu_gpu_group_create": (_int, [_P(_int), _u32, _P(GpuConfig), _P(_vp), _err]),
+    "ibu_gpu_group_destroy": (None, [_vp]),
+    "ibu_gpu_group_size": (_u32, [_vp]),
+    "ibu_gpu_group_ctx": (_vp, [_vp, _u32]),
+    "ibu_gpu_group_process_mmap": (_int, [_vp, _vp, _u64, _u64, _P(GroupRequest), _P(ReduceResult), _err]),
+    "ibu_gpu_group_process_host": (_int, [_vp, _vp, _u64, _u32, _u32, _P(GroupRequest), _P(ReduceResult), _err]),
+    "ibu_gpu_group_barcode_count": (_int, [_vp, _P(_vp), _P(_u64), _int, _u32, _P(HostTable), _P(GroupTiming), _err]),
     "ibu_gpu_stream_open": (_int, [_vp, _P(_vp), _err]),
     "ibu_gpu_stream_push": (_int, [_vp, _vp, _sz, _err]),
     "ibu_gpu_stream_header": (_int, [_vp, _P(Header), _err]),

@@ -108,4 +108,19 @@ int k4_build_table(ibu_gpu_ctx *ctx, const ibu_record_t *d_records, uint64_t n, 
                    bool pair_mode, bool pairs_sorted, bool weighted, cudaStream_t s, uint64_t **rows, uint64_t *n_rows,
                    uint64_t *n_pairs, bool *was_sorted, ibu_error_t *err);
 
+
+// pipeline.cu: one pass over host records (or a file range, fd >= 0) with an operation mask; the
+// engine behind ibu_gpu_process_{mmap,host}_ops.  `extra` (group mode): IBU_OP_TABLE produces the
+// range's de-duplicated (barcode, umi, multiplicity) rows (unordered, cudaMallocAsync on the
+// context's stream) instead of its table — what the ranks of a multi-GPU job exchange.
+struct OpsExtra {
+    bool pairs = false;
+    uint64_t **pair_rows = nullptr;
+    uint64_t *n_pair_rows = nullptr;
+};
+int process_records_ops(ibu_gpu_ctx *ctx, const ibu_record_t *h_records, uint64_t n, uint32_t bc_len, uint32_t umi_len,
+                        uint64_t first_record, const ibu_process_request_t *req, ibu_reduce_result_t *h_result,
+                        ibu_chunk_cb on_chunk, void *user, ibu_error_t *err, int fd, uint64_t file_off,
+                        const OpsExtra *extra);
+
 }  // namespace ibu

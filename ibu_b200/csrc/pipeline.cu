@@ -410,6 +410,8 @@ int process_host_records(ibu_gpu_ctx *ctx, const ibu_record_t *h_records, uint64
         err);
 }
 
+}  // namespace
+
 // Ingest with more than the reduction: the records land in ONE device allocation (chunk by chunk,
 // same slots and streams), every chunk is validated / reduced (K1) or unpacked (K2, which carries
 // K1's reductions) as it lands, and for IBU_OP_TABLE its (barcode, umi) keys are scattered into the
@@ -417,23 +419,29 @@ int process_host_records(ibu_gpu_ctx *ctx, const ibu_record_t *h_records, uint64
 // chunk only the bucket de-duplication and the rows remain.  This is process_parallel
 // (mmap.rs:286-332) running the HashMap<barcode, count> processor of parallel.rs:79-98 (+ distinct
 // UMIs) next to the count / sum processors, in one pass over the file.
-int process_records_ops(ibu_gpu_ctx *ctx, const ibu_record_t *h_records, uint64_t n, uint32_t bc_len, uint32_t umi_len,
-                        uint64_t first_record, const ibu_process_request_t *req, ibu_reduce_result_t *h_result,
-                        ibu_chunk_cb on_chunk, void *user, ibu_error_t *err, int fd = -1, uint64_t file_off = 0) {
+int ibu::process_records_ops(ibu_gpu_ctx *ctx, const ibu_record_t *h_records, uint64_t n, uint32_t bc_len, uint32_t umi_len,
+                             uint64_t first_record, const ibu_process_request_t *req, ibu_reduce_result_t *h_result,
+                             ibu_chunk_cb on_chunk, void *user, ibu_error_t *err, int fd, uint64_t file_off,
+                             const OpsExtra *extra) {
+    const bool pair_rows = extra && extra->pairs;  // group mode: the shard's de-duplicated pairs instead of its table
     const uint32_t ops = req->ops;
     const bool want_table = (ops & IBU_OP_TABLE) != 0, keep = (ops & IBU_OP_KEEP) != 0, unpack = (ops & IBU_OP_UNPACK) != 0;
-    if (want_table && !req->table) return set_error(err, IBU_ERR_ARG, 0, 0, 0, "IBU_OP_TABLE needs request.table");
+    if (want_table && !req->table && !pair_rows) return set_error(err, IBU_ERR_ARG, 0, 0, 0, "IBU_OP_TABLE needs request.table");
+    if (pair_rows) {
+        *extra->pair_rows = nullptr;
+        *extra->n_pair_rows = 0;
+    }
     if (keep && !req->d_records) return set_error(err, IBU_ERR_ARG, 0, 0, 0, "IBU_OP_KEEP needs request.d_records");
     if (unpack && n && (!req->h_bc_ascii || !req->h_umi_ascii))
         return set_error(err, IBU_ERR_ARG, 0, 0, 0, "IBU_OP_UNPACK needs request.h_bc_ascii and h_umi_ascii");
-    if (want_table) memset(req->table, 0, sizeof(*req->table));
+    if (want_table && req->table) memset(req->table, 0, sizeof(*req->table));
     if (keep) *req->d_records = nullptr;
     if (!want_table && !keep && !unpack)
         return process_host_records(ctx, h_records, n, bc_len, umi_len, first_record, h_result, on_chunk, user, err, fd, file_off);
     DeviceGuard guard(ctx->device);
     std::lock_guard<std::mutex> lock(ctx->pipe_mutex);
     memset(h_result, 0, sizeof(*h_result));
-    if (want_table) {
+    if (want_table && req->table) {
         req->table->n_records = n;
         req->table->input_was_sorted = n == 0;
     }
@@ -523,7 +531,7 @@ int process_records_ops(ibu_gpu_ctx *ctx, const ibu_record_t *h_records, uint64_
                 // (sorted-looking input: the streaming pass over the resident records at the end is the fast path)
                 if ((saw_unordered || mode == 2) && mode != 1 && hints.force_path != kPathLegacy && hints.force_path != kPathSort &&
                     (n >= (1u << 16) || hints.force_path == kPathPartition))
-                    if (int r = k4_job_begin(ctx, n, hints, smp, false, false, ctx->stream, &job, err)) return r;
+                    if (int r = k4_job_begin(ctx, n, hints, smp, pair_rows, false, ctx->stream, &job, err)) return r;
             }
             if (job) {
                 IBU_CUDA(cudaStreamWaitEvent(slot.stream, k4_job_ready(job), 0));
@@ -544,17 +552,20 @@ int process_records_ops(ibu_gpu_ctx *ctx, const ibu_record_t *h_records, uint64_
         // may read what the slot streams wrote
         uint64_t *rows = nullptr, n_rows = 0, n_pairs = 0;
         bool handled = false, was_sorted = false;
-        if (job) rc = k4_job_finish(job, reinterpret_cast<const uint64_t *>(d_all), false, false, &rows, &n_rows, &n_pairs, &handled, err);
+        if (job) rc = k4_job_finish(job, reinterpret_cast<const uint64_t *>(d_all), pair_rows, false, &rows, &n_rows, &n_pairs, &handled, err);
         if (job) k4_job_destroy(job);
         job = nullptr;
         if (arena_lock.owns_lock()) arena_lock.unlock();
         if (rc == IBU_OK && !handled) {
             int mode = req->table_mode & 7;
             if (mode == 0 && saw_unordered) mode = 2;  // already known not to be sorted
-            rc = k4_build_table(ctx, d_all, n, mode, hints, false, false, false, ctx->stream, &rows, &n_rows, &n_pairs,
+            rc = k4_build_table(ctx, d_all, n, mode, hints, pair_rows, false, false, ctx->stream, &rows, &n_rows, &n_pairs,
                                 &was_sorted, err);
         }
-        if (rc == IBU_OK) {
+        if (rc == IBU_OK && pair_rows) {
+            *extra->pair_rows = rows;
+            *extra->n_pair_rows = n_rows;
+        } else if (rc == IBU_OK) {
             req->table->d_rows = reinterpret_cast<ibu_barcode_row_t *>(rows);
             req->table->n_rows = n_rows;
             req->table->n_distinct_pairs = n_pairs;
@@ -572,8 +583,6 @@ int process_records_ops(ibu_gpu_ctx *ctx, const ibu_record_t *h_records, uint64_
     mark("release");
     return rc;
 }
-
-}  // namespace
 
 extern "C" {
 
@@ -892,7 +901,7 @@ int ibu_gpu_process_host_ops(ibu_gpu_ctx_t *ctx, const ibu_record_t *h_records, 
     if (!ctx || !req || !h_result || (!h_records && n)) return set_error(err, IBU_ERR_ARG, 0, 0, 0, "null argument");
     if (bc_len < 1 || bc_len > 32 || umi_len < 1 || umi_len > 32)
         return set_error(err, IBU_ERR_ARG, 0, bc_len, umi_len, "bc_len and umi_len must be in 1..32");
-    return process_records_ops(ctx, h_records, n, bc_len, umi_len, 0, req, h_result, on_chunk, user, err);
+    return process_records_ops(ctx, h_records, n, bc_len, umi_len, 0, req, h_result, on_chunk, user, err, -1, 0, nullptr);
 }
 
 int ibu_gpu_process_mmap_ops(ibu_gpu_ctx_t *ctx, const ibu_mmap_reader_t *reader, uint64_t start, uint64_t end,
@@ -908,7 +917,7 @@ int ibu_gpu_process_mmap_ops(ibu_gpu_ctx_t *ctx, const ibu_mmap_reader_t *reader
     const char *mode = getenv("IBU_B200_STAGE");
     const int fd = (mode && !strcmp(mode, "mmap")) ? -1 : ibu_mmap_fd(reader);
     return process_records_ops(ctx, recs, end - start, reader->header.bc_len, reader->header.umi_len, start, req,
-                               h_result, on_chunk, user, err, fd, IBU_HEADER_SIZE + start * IBU_RECORD_SIZE);
+                               h_result, on_chunk, user, err, fd, IBU_HEADER_SIZE + start * IBU_RECORD_SIZE, nullptr);
 }
 
 // ---- streaming ingest ----------------------------------------------------------------------

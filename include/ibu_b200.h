@@ -71,7 +71,7 @@ typedef enum ibu_status {
     IBU_ERR_INVALID_INDEX = 9,          /* a = idx, b = max */
     IBU_ERR_PROCESS = 10,               /* Process(Box<dyn Error>): callback failure */
     IBU_ERR_CUDA = 11,                  /* sys = cudaError_t */
-    IBU_ERR_NCCL = 12,
+    IBU_ERR_NCCL = 12,                  /* sys = ncclResult_t (IBU_EXCHANGE_NCCL only) */
     IBU_ERR_ARG = 13,                   /* NULL / misaligned / out-of-range argument */
     IBU_ERR_NOMEM = 14
 } ibu_status;
@@ -403,6 +403,79 @@ int ibu_gpu_process_host_ops(ibu_gpu_ctx_t *ctx, const ibu_record_t *h_records, 
                              uint32_t bc_len, uint32_t umi_len, const ibu_process_request_t *req,
                              ibu_reduce_result_t *h_result, ibu_chunk_cb on_chunk, void *user,
                              ibu_error_t *err);
+
+/* ------------------------------------------------------------- several GPUs */
+
+/* The GPUs of one box behind one handle (SURVEY §8b `ibu_gpu_ctx_create(devices[], n, cfg)`, §8e).
+ * Records shard across them by contiguous range with the partition rule of process_parallel
+ * (src/io/mmap.rs:297-307: len / n each, the last rank takes the remainder — ibu_shard_range);
+ * one host thread per GPU drives its context, all staging copies share the process-wide worker
+ * pool and the one mapping.  The 8-word results are merged on the host exactly like the reference
+ * processors' on_batch_complete merge (mmap.rs:365-372); the per-barcode tables are merged
+ * exactly by exchanging the shards' de-duplicated (barcode, umi) pairs by owner(barcode) — the
+ * path's one exchange step — see `exchange`.  The same device may be listed more than once
+ * (ranks then share it; useful for tests on a single GPU; not with IBU_EXCHANGE_NCCL). */
+typedef struct ibu_gpu_group ibu_gpu_group_t;
+int ibu_gpu_group_create(const int *devices, uint32_t n_devices, const ibu_gpu_config_t *cfg,
+                         ibu_gpu_group_t **out, ibu_error_t *err);
+void ibu_gpu_group_destroy(ibu_gpu_group_t *g);
+uint32_t ibu_gpu_group_size(const ibu_gpu_group_t *g);
+/* the context of rank `rank` (owned by the group), e.g. for ibu_gpu_free of kept shards */
+ibu_gpu_ctx_t *ibu_gpu_group_ctx(ibu_gpu_group_t *g, uint32_t rank);
+
+#define IBU_EXCHANGE_AUTO 0u /* the fastest measured on NVLink boxes: P2P */
+#define IBU_EXCHANGE_P2P 1u  /* owners pull with cudaMemcpyPeerAsync (NVLink / NVSwitch) */
+#define IBU_EXCHANGE_HOST 2u /* through pinned host memory (D2H, then H2D by the owner) */
+#define IBU_EXCHANGE_NCCL 3u /* ncclSend / ncclRecv; libnccl.so.2 is loaded at run time, IBU_ERR_NCCL if absent */
+
+/* merged table in host memory: h_rows is released with ibu_free */
+typedef struct ibu_host_table {
+    ibu_barcode_row_t *h_rows; /* sorted by barcode */
+    uint64_t n_rows;
+    uint64_t n_records;
+    uint64_t n_distinct_pairs;
+} ibu_host_table_t;
+
+/* where the time of a group call went (milliseconds, the slowest rank of each phase) */
+typedef struct ibu_group_timing {
+    double ingest_ms;   /* staging + H2D + per-chunk kernels (+ the shard's pair de-duplication) */
+    double local_ms;    /* pair table of a resident shard (ibu_gpu_group_barcode_count only) */
+    double exchange_ms; /* grouping by owner + the pair exchange */
+    double owner_ms;    /* weighted count on the owners */
+    double gather_ms;   /* rows to rank 0, barcode order, device -> host */
+    double table_ms;    /* local + exchange + owner + gather as one span */
+    double total_ms;
+    uint64_t pairs_local; /* de-duplicated pairs before the exchange, all ranks */
+    uint64_t bytes_sent;  /* most bytes one rank sent to other ranks */
+    uint32_t exchange;    /* the exchange that ran */
+    uint32_t reserved;
+} ibu_group_timing_t;
+
+typedef struct ibu_group_request {
+    uint32_t ops;               /* IBU_OP_REDUCE | IBU_OP_TABLE | IBU_OP_KEEP */
+    int32_t table_mode;         /* as ibu_process_request_t */
+    uint32_t exchange;          /* IBU_EXCHANGE_* */
+    uint32_t reserved;
+    ibu_host_table_t *table;    /* out: IBU_OP_TABLE */
+    ibu_record_t **d_records;   /* out[size]: IBU_OP_KEEP, shard r on the device of rank r */
+    uint64_t *shard_records;    /* out[size], nullable: records of each shard */
+    ibu_group_timing_t *timing; /* out, nullable */
+} ibu_group_request_t;
+
+/* GPU counterpart of process_parallel across the group: rank r processes
+ * ibu_shard_range(end - start, r, size) of the range. */
+int ibu_gpu_group_process_mmap(ibu_gpu_group_t *g, const ibu_mmap_reader_t *reader, uint64_t start,
+                               uint64_t end, const ibu_group_request_t *req,
+                               ibu_reduce_result_t *h_result, ibu_error_t *err);
+int ibu_gpu_group_process_host(ibu_gpu_group_t *g, const ibu_record_t *h_records, uint64_t n,
+                               uint32_t bc_len, uint32_t umi_len, const ibu_group_request_t *req,
+                               ibu_reduce_result_t *h_result, ibu_error_t *err);
+/* The exact table of device-resident shards (d_shards[r] on the device of rank r, 32-byte aligned;
+ * mode as ibu_gpu_barcode_count without IBU_COUNT_WEIGHTED). */
+int ibu_gpu_group_barcode_count(ibu_gpu_group_t *g, const ibu_record_t *const *d_shards,
+                                const uint64_t *shard_records, int mode, uint32_t exchange,
+                                ibu_host_table_t *table, ibu_group_timing_t *timing,
+                                ibu_error_t *err);
 
 /* Streaming ingest — the Reader<R> of src/io/reader.rs feeding the GPU.
  * The bytes of an .ibu stream (header first) are pushed in pieces of any size, from any source

@@ -60,6 +60,13 @@ def main():
 
     t_red, red = best_of(lambda: reader.process_gpu(ctx), args.reps)
     line("staged: ingest + validate/reduce (K1)", t_red, {})
+    def table_call():  # the C call alone: the rows stay on the device
+        red, out = reader.process_gpu_ops(ctx, table=True, rows_on_device=True)
+        ctx.table_free(out.table)
+        return red, out
+
+    t_call, _ = best_of(table_call, args.reps)
+    line("staged: ingest + validate/reduce + per-barcode table (rows left on the device)", t_call, dict(table_overhead_ms=(t_call - t_red) * 1e3))
     t_tab, (red2, out) = best_of(lambda: reader.process_gpu_ops(ctx, table=True), args.reps)
     line("staged: ingest + validate/reduce + per-barcode table", t_tab,
          dict(rows=len(out.rows), pairs=out.table_info["n_distinct_pairs"], table_overhead_ms=(t_tab - t_red) * 1e3,
@@ -69,6 +76,9 @@ def main():
         reader.pin()
         t_red_p, _ = best_of(lambda: reader.process_gpu(ctx), args.reps)
         line("pinned mapping: ingest + validate/reduce (K1)", t_red_p, {})
+        t_call_p, _ = best_of(table_call, args.reps)
+        line("pinned mapping: ingest + validate/reduce + per-barcode table (rows left on the device)", t_call_p,
+             dict(table_overhead_ms=(t_call_p - t_red_p) * 1e3))
         t_tab_p, (_, out) = best_of(lambda: reader.process_gpu_ops(ctx, table=True), args.reps)
         line("pinned mapping: ingest + validate/reduce + per-barcode table", t_tab_p,
              dict(rows=len(out.rows), table_overhead_ms=(t_tab_p - t_red_p) * 1e3, same_rows=bool(np.array_equal(out.rows, rows))))
