@@ -463,11 +463,31 @@ def _run_ops(ctx: "GpuContext", call, n: int, bc_len: int, umi_len: int, table: 
     return ReduceResult(res.as_dict()), out
 
 
+def _prefer_bundled_nccl():
+    """IBU_EXCHANGE_NCCL loads libnccl.so.2 at run time.  In a Python process the NCCL bundled with
+    torch (site-packages/nvidia/nccl/lib) must be the one: a system copy loaded first would shadow
+    it for a later `import torch` (same soname)."""
+    if "IBU_B200_NCCL_LIB" in os.environ:
+        return
+    try:
+        import importlib.util
+
+        spec = importlib.util.find_spec("nvidia.nccl")
+        for base in (spec.submodule_search_locations if spec else []):
+            cand = os.path.join(base, "lib", "libnccl.so.2")
+            if os.path.exists(cand):
+                os.environ["IBU_B200_NCCL_LIB"] = cand
+                return
+    except Exception:
+        pass
+
+
 class GpuGroup:
     """Several GPUs of one box behind one handle (ibu_gpu_group_*): records shard by contiguous range
     (mmap.rs:297-307), one host thread per GPU, results and tables merged inside the library."""
 
     def __init__(self, devices, chunk_records: int = 0, n_slots: int = 0, copy_threads: int = 0):
+        _prefer_bundled_nccl()
         self.devices = list(devices)
         self._h = C.c_void_p()
         cfg = _lib.GpuConfig(chunk_records, n_slots, copy_threads, 0)

@@ -761,7 +761,7 @@ int k4_job_begin(ibu_gpu_ctx *ctx, uint64_t n, const K4Hints &hints, const K4Sam
     // uniform layout with mean + 6 sigma room per bucket; when duplicates make the loads too uneven
     // for that (or the first attempt overflows) the buckets are laid out exactly from a histogram
     job->cap = ((uint64_t)(mean + 6.0 * sigma) + 64 + 15) & ~15ull;
-    job->exact = (double)job->cap > 4.0 * mean + 256.0;
+    job->exact = (double)job->cap > 3.0 * mean + 256.0;
     // shared-memory table: 1.6 slots per key of the fullest bucket the uniform layout admits (all of
     // them distinct at worst); duplicate-heavy data (exact layout) has far fewer distinct keys than
     // records per bucket.  Smaller tables = more resident CTAs = more buckets in flight per SM.

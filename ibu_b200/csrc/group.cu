@@ -47,12 +47,14 @@ constexpr int kNcclUint64 = 5;  // ncclDataType_t: ncclUint64
 
 NcclApi load_nccl() {
     NcclApi a;
+    // An NCCL that the process already holds (e.g. the one bundled with torch) is reused: loading a
+    // second libnccl.so.2 next to it would make later loads resolve against the wrong one.
     const char *env = getenv("IBU_B200_NCCL_LIB");
+    a.lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD);
     const char *names[] = {env, "libnccl.so.2", "libnccl.so", "/usr/local/cuda/lib64/libnccl.so.2"};
     for (const char *name : names) {
-        if (!name) continue;
-        a.lib = dlopen(name, RTLD_NOW | RTLD_GLOBAL);
         if (a.lib) break;
+        if (name) a.lib = dlopen(name, RTLD_NOW | RTLD_LOCAL);
     }
     if (!a.lib) return a;
     a.CommInitAll = (int (*)(ncclComm_t *, int, const int *))dlsym(a.lib, "ncclCommInitAll");
