@@ -163,11 +163,32 @@ SIGNATURES = {
 }
 
 
+def _prefer_bundled_nccl() -> None:
+    """IBU_EXCHANGE_NCCL loads libnccl.so.2 at run time.  In a Python process that may import torch
+    LATER, the library must pick the NCCL torch ships (nvidia/nccl/lib): the loader keeps one object
+    per soname, so a system libnccl loaded first would later be handed to torch, which then fails to
+    import on the newer symbols it needs.  Only sets IBU_B200_NCCL_LIB when the caller has not."""
+    if os.environ.get("IBU_B200_NCCL_LIB"):
+        return
+    try:
+        import importlib.util
+
+        spec = importlib.util.find_spec("nvidia.nccl")
+        for base in (spec.submodule_search_locations if spec else ()):
+            path = os.path.join(base, "lib", "libnccl.so.2")
+            if os.path.exists(path):
+                os.environ["IBU_B200_NCCL_LIB"] = path
+                return
+    except (ImportError, ValueError, AttributeError):
+        pass
+
+
 def _load() -> C.CDLL:
     if not os.path.exists(LIB_PATH):
         raise ImportError(
             f"{LIB_PATH} is missing: build it with `make -C ibu_b200/csrc` (or "
             "`python -c 'import __graft_entry__ as g; g.build()'`). ibu_b200 has no CPU fallback.")
+    _prefer_bundled_nccl()
     lib = C.CDLL(LIB_PATH)
     for name, (res, args) in SIGNATURES.items():
         fn = getattr(lib, name)  # AttributeError if the library does not export it
