@@ -37,507 +37,14 @@
 #include <utility>
 
 #include "k4.h"
+#include "k4_partition.cuh"
 #include "kernels.cuh"
 
 namespace ibu {
 
+using namespace k4p;
+
 namespace {
-
-constexpr uint64_t kEmpty = ~0ull;
-
-// murmur3's 64-bit finaliser: a bijection on u64 (xor-shifts by >= 32 bits are involutions, the
-// multipliers are odd), so unmix64(mix64(x)) == x.
-__host__ __device__ __forceinline__ uint64_t mix64(uint64_t h) {
-    h ^= h >> 33;
-    h *= 0xff51afd7ed558ccdull;
-    h ^= h >> 33;
-    h *= 0xc4ceb9fe1a85ec53ull;
-    h ^= h >> 33;
-    return h;
-}
-__host__ __device__ __forceinline__ uint64_t unmix64(uint64_t h) {
-    h ^= h >> 33;
-    h *= 0x9cb4b2f8129337dbull;  // inverse of 0xc4ceb9fe1a85ec53 mod 2^64
-    h ^= h >> 33;
-    h *= 0x4f74430c22a54005ull;  // inverse of 0xff51afd7ed558ccd mod 2^64
-    h ^= h >> 33;
-    return h;
-}
-
-// counters shared by the kernels of one call
-enum {
-    kCtrWide = 0,      // records on the wide list
-    kCtrFlags = 1,     // overflow flags, below
-    kCtrSpecial = 2,   // weight of the one key whose mixed value equals the empty marker
-    kCtrClaimed = 3,   // slots claimed in the barcode table = rows
-    kCtrPairs = 4,     // distinct pairs seen so far
-    kCtrCursor = 5,    // append cursor (pair output / row output)
-    kCtrOnesRec = 6,   // n_records of barcode 0xFFFF'FFFF'FFFF'FFFF (collides with the table's empty marker)
-    kCtrOnesDist = 7,  // n_distinct_umi of that barcode
-    kCtrWords = 16
-};
-enum { kFlagBucket = 1, kFlagWide = 2, kFlagTable = 4, kFlagSmem = 8, kFlagPairsOut = 16 };
-
-// ------------------------------------------------------------------------------------ sample
-struct SampleArgs {
-    const uint64_t *recs;
-    uint64_t n, m;
-    uint64_t *ptab;  // fingerprints of sampled pairs, memset to 0xFF
-    uint64_t *btab;  // fingerprints of sampled barcodes
-    uint32_t *pcnt, *bcnt;  // occurrences per slot, zeroed
-    uint64_t mask;   // slots - 1 of both
-    unsigned long long *out;  // kSmp* words
-    uint32_t *hist;           // [2][65]: bit width of barcode / umi words
-};
-enum { kSmpPairs = 0, kSmpBarcodes = 1, kSmpUnordered = 2, kSmpPairColl = 3, kSmpPairF1 = 4, kSmpPairF2 = 5,
-       kSmpBcF1 = 6, kSmpBcF2 = 7, kSmpWords = 8 };
-
-// Inserts a fingerprint and returns how often it had been seen before (0 = new).
-__device__ __forceinline__ uint32_t fp_insert(uint64_t *tab, uint32_t *cnt, uint64_t mask, uint64_t fp) {
-    if (fp == kEmpty) fp = 0;
-    uint64_t slot = fp & mask;
-    for (uint32_t probe = 0; probe < 4096; probe++, slot = (slot + 1) & mask) {
-        const uint64_t old = atomicCAS(reinterpret_cast<unsigned long long *>(tab + slot), kEmpty, fp);
-        if (old == kEmpty || old == fp) return atomicAdd(cnt + slot, 1u);
-    }
-    return 0;
-}
-
-// Seen-once / seen-twice bookkeeping for the Chao1 estimate: `before` occurrences existed.
-__device__ __forceinline__ void tally(uint32_t before, uint32_t &distinct, int32_t &f1, int32_t &f2) {
-    if (before == 0) { distinct++; f1++; }
-    else if (before == 1) { f1--; f2++; }
-    else if (before == 2) { f2--; }
-}
-
-__global__ void __launch_bounds__(kBlockThreads) k_sample(const SampleArgs a) {
-    __shared__ uint32_t h[2][65];
-    for (uint32_t i = threadIdx.x; i < 130; i += blockDim.x) (&h[0][0])[i] = 0;
-    __syncthreads();
-    uint32_t np = 0, nb = 0, bad = 0, coll = 0;
-    int32_t pf1 = 0, pf2 = 0, bf1 = 0, bf2 = 0;
-    for (uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; j < a.m; j += (uint64_t)gridDim.x * blockDim.x) {
-        const uint64_t i = a.m >= a.n ? j : mix64(j ^ 0x5bd1e995u) % a.n;  // hashed positions: no aliasing with periodic data
-        const uint64_t bc = a.recs[3 * i], um = a.recs[3 * i + 1];
-        atomicAdd(&h[0][bc ? 64 - __clzll((long long)bc) : 0], 1u);
-        atomicAdd(&h[1][um ? 64 - __clzll((long long)um) : 0], 1u);
-        if (i + 1 < a.n) {
-            const uint64_t b2 = a.recs[3 * i + 3], u2 = a.recs[3 * i + 4];
-            bad += (b2 < bc) | ((b2 == bc) & (u2 < um));
-        }
-        const uint32_t before = fp_insert(a.ptab, a.pcnt, a.mask, mix64(bc ^ mix64(um + 0x9E3779B97F4A7C15ull)));
-        coll += before;
-        tally(before, np, pf1, pf2);
-        tally(fp_insert(a.btab, a.bcnt, a.mask, mix64(bc)), nb, bf1, bf2);
-    }
-    const uint32_t vals[8] = {np, nb, bad, coll, (uint32_t)pf1, (uint32_t)pf2, (uint32_t)bf1, (uint32_t)bf2};
-#pragma unroll
-    for (int k = 0; k < 8; k++) {  // (f1 / f2 deltas may be negative: two's-complement sums are exact)
-        const uint32_t v = __reduce_add_sync(0xffffffffu, vals[k]);
-        if ((threadIdx.x & 31u) == 0 && v) atomicAdd(a.out + k, (unsigned long long)(long long)(int32_t)v);
-    }
-    __syncthreads();
-    for (uint32_t i = threadIdx.x; i < 130; i += blockDim.x)
-        if ((&h[0][0])[i]) atomicAdd(a.hist + i, (&h[0][0])[i]);
-}
-
-// ------------------------------------------------------------------------------------ scatter
-struct ScatterArgs {
-    const uint64_t *recs;
-    uint64_t n;
-    uint32_t bb, ub, pb;  // barcode bits, umi bits (bb + ub <= 64, both in 1..63), log2(#buckets)
-    uint32_t cap;         // keys per bucket (uniform layout)
-    const uint64_t *bases;  // nullable: exact layout, bucket b owns keys[bases[b] .. bases[b + 1])
-    uint32_t *cursors;    // [2^pb], zeroed
-    uint64_t *keys;
-    uint64_t *wts;        // same shape (WEIGHTED only)
-    uint64_t *wide;       // records that do not fit the key layout
-    uint64_t wide_cap;
-    unsigned long long *ctr;
-};
-
-// COUNT_ONLY: the histogram pass of the exact layout (cursors[b] = keys of bucket b, nothing stored).
-template <bool WEIGHTED, bool COUNT_ONLY>
-__device__ __forceinline__ void scatter_one(const ScatterArgs &a, uint64_t bc, uint64_t um, uint64_t w) {
-    if (((bc >> a.bb) | (um >> a.ub)) == 0ull) {
-        const uint64_t k = mix64((bc << a.ub) | um);
-        if (k == kEmpty) {  // the one key that looks like an empty slot
-            if (!COUNT_ONLY) atomicAdd(a.ctr + kCtrSpecial, (unsigned long long)(WEIGHTED ? w : 1ull));
-            return;
-        }
-        const uint32_t b = (uint32_t)(k >> (64 - a.pb));
-        const uint32_t pos = atomicAdd(a.cursors + b, 1u);
-        if (COUNT_ONLY) return;
-        uint64_t base = (uint64_t)b * a.cap, room = a.cap;
-        if (a.bases) {
-            base = a.bases[b];
-            room = a.bases[b + 1] - base;
-        }
-        if (pos < room) {
-            a.keys[base + pos] = k;
-            if (WEIGHTED) a.wts[base + pos] = w;
-        } else {
-            atomicOr(a.ctr + kCtrFlags, (unsigned long long)kFlagBucket);
-        }
-    } else if (!COUNT_ONLY) {
-        const uint64_t pos = atomicAdd(a.ctr + kCtrWide, 1ull);
-        if (pos < a.wide_cap) {
-            a.wide[3 * pos] = bc;
-            a.wide[3 * pos + 1] = um;
-            a.wide[3 * pos + 2] = WEIGHTED ? w : 1ull;
-        } else {
-            atomicOr(a.ctr + kCtrFlags, (unsigned long long)kFlagWide);
-        }
-    }
-}
-
-// One 128-record tile per warp (lane l owns records 4l..4l+3: three LDG.E.256), block-scheduled
-// like K1-K3.  Four independent atomics + stores per lane are in flight at a time.  The kernel is
-// bound by its 8-byte scattered stores (one L2 write transaction each: 10^8 of them take 2.0 ms on
-// B200 whatever the bucket count, tools/k4lab.cu), not by the atomics (1.1 ms at 2^17 cursors).
-template <bool WEIGHTED, bool COUNT_ONLY>
-__global__ void __launch_bounds__(kBlockThreads) k_scatter_keys(const ScatterArgs a) {
-    const uint32_t lane = threadIdx.x & 31u;
-    const uint64_t t = (uint64_t)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
-    const uint64_t n_tiles = a.n / 128;
-    if (t < n_tiles) {
-        const uint8_t *p = reinterpret_cast<const uint8_t *>(a.recs) + t * (128 * 24) + lane * 96;
-        const u64x4 v0 = ldg_stream256(p), v1 = ldg_stream256(p + 32), v2 = ldg_stream256(p + 64);
-        scatter_one<WEIGHTED, COUNT_ONLY>(a, v0.x, v0.y, v0.z);
-        scatter_one<WEIGHTED, COUNT_ONLY>(a, v0.w, v1.x, v1.y);
-        scatter_one<WEIGHTED, COUNT_ONLY>(a, v1.z, v1.w, v2.x);
-        scatter_one<WEIGHTED, COUNT_ONLY>(a, v2.y, v2.z, v2.w);
-    } else if (t == n_tiles) {  // ragged tail (< 128 records)
-        for (uint64_t i = n_tiles * 128 + lane; i < a.n; i += 32)
-            scatter_one<WEIGHTED, COUNT_ONLY>(a, a.recs[3 * i], a.recs[3 * i + 1], a.recs[3 * i + 2]);
-    }
-}
-
-// bases[b] = sum of counts[0..b) for b in 0..n (one CTA; n <= 2^21 buckets)
-__global__ void __launch_bounds__(1024) k_bucket_bases(const uint32_t *__restrict__ counts, uint32_t n,
-                                                       uint64_t *__restrict__ bases) {
-    __shared__ uint64_t part[1024];
-    const uint32_t tid = threadIdx.x, per = (n + 1023) / 1024;
-    const uint32_t lo = min(n, tid * per), hi = min(n, lo + per);
-    uint64_t sum = 0;
-    for (uint32_t i = lo; i < hi; i++) sum += counts[i];
-    part[tid] = sum;
-    __syncthreads();
-    for (uint32_t o = 1; o < 1024; o <<= 1) {
-        const uint64_t v = tid >= o ? part[tid - o] : 0;
-        __syncthreads();
-        part[tid] += v;
-        __syncthreads();
-    }
-    uint64_t run = part[tid] - sum;
-    for (uint32_t i = lo; i < hi; i++) {
-        bases[i] = run;
-        run += counts[i];
-    }
-    if (tid == 1023) bases[n] = part[1023];
-}
-
-// ------------------------------------------------------------------------------ barcode table
-// Global open-addressing table keyed by barcode, memset to 0xFF; a slot is claimed with a 64-bit
-// CAS on the barcode and the counters take REDs.
-//   packed (fewer than 2^28 unweighted records): 16-byte slots {barcode, n_distinct << 36 | n_records},
-//     ONE RED per distinct pair (the word starts at -1: low 36 bits end at n_records - 1);
-//   wide: 32-byte slots {barcode, n_records - 1, n_distinct - 1, unused}, two REDs.
-struct TableRef {
-    uint64_t *slots;
-    uint64_t mask;
-    unsigned long long *ctr;
-    uint32_t packed;
-};
-constexpr uint32_t kPackShift = 36;
-
-// the counters of a slot that is known to hold the barcode
-__device__ __forceinline__ void table_hit(const TableRef &t, uint64_t slot, uint64_t n_rec, uint64_t n_dist) {
-    uint64_t *s = t.slots + (t.packed ? 2 : 4) * slot;
-    if (t.packed) {
-        atomicAdd(reinterpret_cast<unsigned long long *>(s + 1), (unsigned long long)(n_rec + (n_dist << kPackShift)));
-    } else {
-        atomicAdd(reinterpret_cast<unsigned long long *>(s + 1), (unsigned long long)n_rec);
-        atomicAdd(reinterpret_cast<unsigned long long *>(s + 2), (unsigned long long)n_dist);
-    }
-}
-
-__device__ __forceinline__ void table_add(const TableRef &t, uint64_t bc, uint64_t n_rec, uint64_t n_dist) {
-    if (bc == kEmpty) {  // only a wide record can carry it
-        atomicAdd(t.ctr + kCtrOnesRec, (unsigned long long)n_rec);
-        atomicAdd(t.ctr + kCtrOnesDist, (unsigned long long)n_dist);
-        return;
-    }
-    const uint32_t words = t.packed ? 2 : 4;
-    uint64_t slot = mix64(bc) & t.mask;
-    for (uint32_t probe = 0; probe < 96; probe++, slot = (slot + 1) & t.mask) {  // a crowded table fails fast
-        uint64_t *s = t.slots + words * slot;
-        uint64_t cur = *reinterpret_cast<volatile uint64_t *>(s);
-        if (cur != bc) {
-            if (cur != kEmpty) continue;  // another barcode lives here (a slot never changes once claimed)
-            cur = atomicCAS(reinterpret_cast<unsigned long long *>(s), kEmpty, bc);
-            if (cur == kEmpty) atomicAdd(t.ctr + kCtrClaimed, 1ull);
-            else if (cur != bc) continue;
-        }
-        if (t.packed) {
-            atomicAdd(reinterpret_cast<unsigned long long *>(s + 1), (unsigned long long)(n_rec + (n_dist << kPackShift)));
-        } else {
-            atomicAdd(reinterpret_cast<unsigned long long *>(s + 1), (unsigned long long)n_rec);
-            atomicAdd(reinterpret_cast<unsigned long long *>(s + 2), (unsigned long long)n_dist);
-        }
-        return;
-    }
-    atomicOr(t.ctr + kCtrFlags, (unsigned long long)kFlagTable);
-}
-
-// ------------------------------------------------------------------------------------- dedup
-struct DedupArgs {
-    const uint32_t *cursors;
-    const uint64_t *bases;  // nullable (uniform layout: bucket b starts at b * cap)
-    const uint64_t *keys;
-    const uint64_t *wts;
-    uint32_t n_buckets, cap, pb, ub;
-    uint32_t s_bits;  // log2(slots of the shared-memory table)
-    TableRef table;   // table mode
-    uint64_t *pairs_out;  // pair mode: rows {barcode, umi, multiplicity}
-    uint64_t pairs_cap;
-};
-
-// One CTA per bucket (block-strided over the buckets).  The table holds the bucket's DISTINCT keys
-// (load <= ~0.5 by construction); its slot index comes from the key bits just below the bucket
-// bits, which are as uniform as the bucket bits.
-template <bool WEIGHTED, bool PAIRS>
-__global__ void __launch_bounds__(kBlockThreads, 5) k_bucket_dedup(const DedupArgs a) {
-    using Cnt = typename std::conditional<WEIGHTED, unsigned long long, uint32_t>::type;
-    extern __shared__ __align__(16) unsigned long long smem[];
-    const uint32_t S = 1u << a.s_bits, smask = S - 1u;
-    unsigned long long *tkey = smem;
-    Cnt *tcnt = reinterpret_cast<Cnt *>(smem + S);
-    __shared__ uint32_t s_distinct, s_full;
-    const uint32_t lane = threadIdx.x & 31u;
-    const uint64_t umask = (1ull << a.ub) - 1ull;
-    const uint32_t hshift = 64 - a.pb - a.s_bits;
-    constexpr uint32_t kMaxProbe = 128;  // at the design load (<= 0.6) a probe sequence this long does not occur
-    constexpr uint32_t kBatch = 4 * kBlockThreads;
-
-    // the first kBatch keys of a bucket, one batch of loads per thread; issued one bucket ahead so
-    // that their latency (and the cursor's) hides behind the bucket being folded
-    auto fetch = [&](uint32_t b, uint32_t &cnt, uint64_t &first, uint64_t (&k)[4], uint64_t (&w)[4]) {
-        cnt = 0;
-        first = 0;
-        if (b < a.n_buckets) {
-            first = a.bases ? a.bases[b] : (uint64_t)b * a.cap;
-            cnt = min(a.cursors[b], a.bases ? (uint32_t)(a.bases[b + 1] - first) : a.cap);
-        }
-#pragma unroll
-        for (int q = 0; q < 4; q++) {
-            const uint32_t i = q * kBlockThreads + threadIdx.x;
-            k[q] = i < cnt ? ldg_stream64(a.keys + first + i) : kEmpty;
-            w[q] = (WEIGHTED && i < cnt) ? ldg_stream64(a.wts + first + i) : 1ull;
-        }
-    };
-    uint32_t fresh = 0;
-    auto insert = [&](uint64_t k, uint64_t w) {
-        if (k == kEmpty) return;
-        uint32_t slot = (uint32_t)(k >> hshift) & smask;
-        uint32_t probe = 0;
-        for (; probe < kMaxProbe; probe++, slot = (slot + 1) & smask) {
-            unsigned long long cur = *reinterpret_cast<volatile unsigned long long *>(tkey + slot);
-            if (cur != k) {
-                if (cur != kEmpty) continue;  // a slot never changes once claimed
-                cur = atomicCAS(tkey + slot, kEmpty, (unsigned long long)k);
-                if (cur == kEmpty) {
-                    fresh++;
-                    // unweighted: the counter holds the occurrences AFTER the first, so claiming a
-                    // slot is the only atomic of a new key and a repeat costs one add: one shared-
-                    // memory atomic per record (the unit's rate, ~0.5 per clock per SM, is what
-                    // bounds this kernel)
-                    if (!WEIGHTED) return;
-                } else if (cur != k) {
-                    continue;
-                }
-            }
-            atomicAdd(tcnt + slot, (Cnt)w);
-            return;
-        }
-        s_full = 1;  // (many) more distinct keys than the table was sized for
-    };
-
-    uint32_t cnt_n;
-    uint64_t first_n, kn[4], wn[4];
-    fetch(blockIdx.x, cnt_n, first_n, kn, wn);
-    for (uint32_t b = blockIdx.x; b < a.n_buckets; b += gridDim.x) {
-        const uint32_t cnt = cnt_n;
-        const uint64_t first = first_n;
-        uint64_t k[4], w[4];
-#pragma unroll
-        for (int q = 0; q < 4; q++) { k[q] = kn[q]; w[q] = wn[q]; }
-        fetch(b + gridDim.x, cnt_n, first_n, kn, wn);
-        for (uint32_t i = threadIdx.x; i < S; i += blockDim.x) {
-            tkey[i] = kEmpty;
-            tcnt[i] = 0;
-        }
-        if (threadIdx.x == 0) s_distinct = 0, s_full = 0;
-        __syncthreads();
-        fresh = 0;
-#pragma unroll
-        for (int q = 0; q < 4; q++) insert(k[q], w[q]);
-        for (uint32_t base = kBatch; base < cnt; base += kBatch) {  // long buckets (duplicate-heavy data)
-            if (*reinterpret_cast<volatile uint32_t *>(&s_full)) break;  // the call is void anyway: do not crawl a full table
-#pragma unroll
-            for (int q = 0; q < 4; q++) {
-                const uint32_t i = base + q * kBlockThreads + threadIdx.x;
-                k[q] = i < cnt ? ldg_stream64(a.keys + first + i) : kEmpty;
-                w[q] = (WEIGHTED && i < cnt) ? ldg_stream64(a.wts + first + i) : 1ull;
-            }
-#pragma unroll
-            for (int q = 0; q < 4; q++) insert(k[q], w[q]);
-        }
-        fresh = __reduce_add_sync(0xffffffffu, fresh);
-        if (lane == 0 && fresh) atomicAdd(&s_distinct, fresh);
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            if (s_distinct) atomicAdd(a.table.ctr + kCtrPairs, (unsigned long long)s_distinct);
-            if (s_full) atomicOr(a.table.ctr + kCtrFlags, (unsigned long long)kFlagSmem);
-        }
-        // every distinct pair of the bucket: one row (pair tables) or one add to its barcode's row
-        if (PAIRS) {
-            for (uint32_t base = 0; base < S; base += blockDim.x) {  // warp-uniform trip count
-                const uint32_t i = base + threadIdx.x;
-                const unsigned long long key = tkey[i];
-                const bool live = key != kEmpty;
-                const uint32_t m = __ballot_sync(0xffffffffu, live);
-                if (!m) continue;
-                unsigned long long pos = 0;
-                if (lane == 0) pos = atomicAdd(a.table.ctr + kCtrCursor, (unsigned long long)__popc(m));
-                pos = __shfl_sync(0xffffffffu, pos, 0) + __popc(m & ((1u << lane) - 1u));
-                if (live) {
-                    const uint64_t comp = unmix64(key);
-                    if (pos < a.pairs_cap) {
-                        a.pairs_out[3 * pos] = comp >> a.ub;
-                        a.pairs_out[3 * pos + 1] = comp & umask;
-                        a.pairs_out[3 * pos + 2] = (uint64_t)tcnt[i] + (WEIGHTED ? 0ull : 1ull);
-                    } else {
-                        atomicOr(a.table.ctr + kCtrFlags, (unsigned long long)kFlagPairsOut);
-                    }
-                }
-            }
-        } else {
-            // Four slots per thread at a time: the home slots of their barcodes are read from the
-            // global table together (independent loads in flight), then resolved — a dependent
-            // load per pair would expose its latency once per pair.
-            const uint32_t words = a.table.packed ? 2 : 4;
-            for (uint32_t base = 0; base < S; base += 4 * blockDim.x) {
-                uint64_t bc[4], seen[4];
-#pragma unroll
-                for (int q = 0; q < 4; q++) {
-                    const uint32_t i = base + q * blockDim.x + threadIdx.x;
-                    const unsigned long long key = i < S ? tkey[i] : kEmpty;
-                    bc[q] = kEmpty;
-                    if (key != kEmpty) bc[q] = unmix64(key) >> a.ub;  // (a narrow barcode is never all ones)
-                }
-#pragma unroll
-                for (int q = 0; q < 4; q++)
-                    seen[q] = bc[q] != kEmpty
-                                  ? *reinterpret_cast<volatile uint64_t *>(a.table.slots + words * (mix64(bc[q]) & a.table.mask))
-                                  : 0ull;
-#pragma unroll
-                for (int q = 0; q < 4; q++) {
-                    if (bc[q] == kEmpty) continue;
-                    const uint32_t i = base + q * blockDim.x + threadIdx.x;
-                    const uint64_t c = (uint64_t)tcnt[i] + (WEIGHTED ? 0ull : 1ull);
-                    if (seen[q] == bc[q]) table_hit(a.table, mix64(bc[q]) & a.table.mask, c, 1ull);  // the common case
-                    else table_add(a.table, bc[q], c, 1ull);
-                }
-            }
-        }
-        __syncthreads();
-    }
-}
-
-// (barcode, umi, multiplicity) rows from outside the buckets — the de-duplicated wide list and the
-// one special key — folded into the same table / pair output.
-struct ExtraArgs {
-    const uint64_t *rows;  // nullable
-    uint64_t n;
-    uint32_t ub;
-    TableRef table;
-    uint64_t *pairs_out;  // nullable: table mode
-    uint64_t pairs_cap;
-};
-
-__global__ void __launch_bounds__(kBlockThreads) k_extra_pairs(const ExtraArgs a) {
-    const uint64_t gid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    for (uint64_t i = gid; i < a.n; i += (uint64_t)gridDim.x * blockDim.x) {
-        const uint64_t bc = a.rows[3 * i], um = a.rows[3 * i + 1], c = a.rows[3 * i + 2];
-        if (a.pairs_out) {
-            const uint64_t pos = atomicAdd(a.table.ctr + kCtrCursor, 1ull);
-            if (pos < a.pairs_cap) {
-                a.pairs_out[3 * pos] = bc;
-                a.pairs_out[3 * pos + 1] = um;
-                a.pairs_out[3 * pos + 2] = c;
-            } else {
-                atomicOr(a.table.ctr + kCtrFlags, (unsigned long long)kFlagPairsOut);
-            }
-        } else {
-            table_add(a.table, bc, c, 1ull);
-        }
-    }
-    if (gid == 0) {
-        const uint64_t w = a.table.ctr[kCtrSpecial];
-        if (w) {  // the key whose mixed value is the empty marker
-            const uint64_t comp = unmix64(kEmpty);
-            const uint64_t bc = comp >> a.ub, um = comp & ((1ull << a.ub) - 1ull);
-            atomicAdd(a.table.ctr + kCtrPairs, 1ull);
-            if (a.pairs_out) {
-                const uint64_t pos = atomicAdd(a.table.ctr + kCtrCursor, 1ull);
-                if (pos < a.pairs_cap) {
-                    a.pairs_out[3 * pos] = bc;
-                    a.pairs_out[3 * pos + 1] = um;
-                    a.pairs_out[3 * pos + 2] = w;
-                } else {
-                    atomicOr(a.table.ctr + kCtrFlags, (unsigned long long)kFlagPairsOut);
-                }
-            } else {
-                table_add(a.table, bc, w, 1ull);
-            }
-        }
-    }
-}
-
-// occupied slots -> rows {barcode, n_records, n_distinct_umi}, order unspecified
-__global__ void __launch_bounds__(kBlockThreads)
-k_table_rows(const uint64_t *__restrict__ slots, uint64_t n_slots, uint32_t packed, uint64_t *__restrict__ rows,
-             unsigned long long *__restrict__ ctr) {
-    const uint32_t lane = threadIdx.x & 31u;
-    const uint64_t step = (uint64_t)gridDim.x * blockDim.x;
-    for (uint64_t base = (uint64_t)blockIdx.x * blockDim.x; base < n_slots; base += step) {  // warp-uniform trips
-        const uint64_t i = base + threadIdx.x;
-        uint64_t bc = kEmpty, nr = 0, nd = 0;
-        if (i < n_slots) {
-            if (packed) {
-                const ulonglong2 v = reinterpret_cast<const ulonglong2 *>(slots)[i];
-                bc = v.x;
-                nr = (v.y & ((1ull << kPackShift) - 1)) + 1ull;
-                nd = v.y >> kPackShift;
-            } else {
-                const u64x4 v = ldg_stream256(slots + 4 * i);
-                bc = v.x; nr = v.y + 1ull; nd = v.z + 1ull;
-            }
-        }
-        const bool live = bc != kEmpty;
-        const uint32_t m = __ballot_sync(0xffffffffu, live);
-        if (!m) continue;
-        unsigned long long pos = 0;
-        if (lane == 0) pos = atomicAdd(ctr + kCtrCursor, (unsigned long long)__popc(m));
-        pos = __shfl_sync(0xffffffffu, pos, 0) + __popc(m & ((1u << lane) - 1u));
-        if (live) {
-            rows[3 * pos] = bc;
-            rows[3 * pos + 1] = nr;
-            rows[3 * pos + 2] = nd;
-        }
-    }
-}
 
 // ---------------------------------------------------------------------------------------- host
 
@@ -621,16 +128,16 @@ struct StageTimer {
     }
 };
 
-constexpr size_t kDedupMaxSmem = 8192 * 16;  // 8 Ki slots x (key + 64-bit count)
+constexpr size_t kDedupMaxSmem = 8192 * 18;  // 8 Ki slots x (key + 64-bit count + list entry)
 
 template <bool W, bool P>
 int launch_dedup(ibu_gpu_ctx *ctx, const DedupArgs &a, cudaStream_t s, ibu_error_t *err) {
-    const size_t smem = ((size_t)1 << a.s_bits) * (8 + (W ? 8 : 4));
-    if (int rc = set_max_smem(k_bucket_dedup<W, P>, ctx->device, kDedupMaxSmem, err)) return rc;
+    const size_t smem = ((size_t)1 << a.s_bits) * (8 + (W ? 8 : 4) + 2);  // keys, counts, claimed-slot list
+    if (int rc = set_max_smem(k_bucket_dedup2<W, P>, ctx->device, kDedupMaxSmem, err)) return rc;
     const int per_sm = std::max<int>(1, std::min<size_t>(5, (200u << 10) / (smem + 1024)));  // 48 registers: 5 CTAs by registers
     const uint32_t grid = (uint32_t)std::min<uint64_t>(a.n_buckets, (uint64_t)ctx->sm_count * per_sm);
-    k_bucket_dedup<W, P><<<grid, kBlockThreads, smem, s>>>(a);
-    IBU_LAUNCHED("k_bucket_dedup");
+    k_bucket_dedup2<W, P><<<grid, kBlockThreads, smem, s>>>(a);
+    IBU_LAUNCHED("k_bucket_dedup2");
     return IBU_OK;
 }
 
@@ -683,8 +190,14 @@ int k4_sample(ibu_gpu_ctx *ctx, const uint64_t *recs, uint64_t n, cudaStream_t s
 }
 
 // One table build of the partition path, in three steps so that an ingest pipeline can feed it chunk by
-// chunk: begin (sizes from the sample, scratch), add (scatter a chunk's keys, stream ordered, any
-// stream that waited for ready()), finish (de-duplicate, rows).
+// chunk: begin (sizes from the sample, scratch), add (level-1 partition of a chunk's keys, stream
+// ordered, any stream that waited for ready()), finish (further levels, de-duplicate, rows).
+struct K4Level {
+    uint32_t bits_in = 0, bits = 0;  // key bits consumed before this level / by it
+    uint64_t cap = 0;                // keys per output bucket (uniform layout)
+    uint32_t *cursors = nullptr;     // [2^(bits_in + bits)]
+    uint64_t *keys = nullptr, *wts = nullptr;
+};
 struct K4Job {
     ibu_gpu_ctx *ctx;
     cudaStream_t s0;
@@ -694,11 +207,11 @@ struct K4Job {
     uint64_t n = 0;       // records the job was sized for
     uint64_t added = 0;
     uint32_t bb = 0, ub = 0, pb = 0, s_bits = 11;
-    uint64_t P = 0, cap = 0, wide_cap = 0, t_slots = 0;
+    uint64_t P = 0, wide_cap = 0;
     double r_est = 0;
     bool exact = false, weighted = false, packed = false;
-    uint32_t *cursors = nullptr;
-    uint64_t *keys = nullptr, *wts = nullptr, *wide = nullptr, *bases = nullptr;
+    std::vector<K4Level> levels;  // levels[0] is filled by add(); the last one feeds the de-duplication
+    uint64_t *wide = nullptr, *bases = nullptr;
     unsigned long long *ctr = nullptr;
     cudaEvent_t ready_ev = nullptr;
     K4Job(ibu_gpu_ctx *c, cudaStream_t s, bool tr) : ctx(c), s0(s), sc(s), timer(tr, s), trace(tr) {}
@@ -710,11 +223,31 @@ struct K4Job {
 void k4_job_destroy(K4Job *job) { delete job; }
 cudaEvent_t k4_job_ready(K4Job *job) { return job->ready_ev; }
 
+namespace {
+
+template <bool COUNT_ONLY>
+int launch_part2(ibu_gpu_ctx *ctx, const Part2Args &a, uint64_t n_in_buckets, bool weighted, cudaStream_t s, ibu_error_t *err) {
+    const size_t smem = (size_t)kPartTile * 8 * (weighted ? 2 : 1);
+    const uint64_t grid = n_in_buckets * a.tiles_per_bucket;
+    if (grid == 0 || grid > 0x7fffffffull) return set_error(err, IBU_ERR_ARG, 0, grid, 0, "partition grid out of range");
+    if (weighted) {
+        if (int rc = set_max_smem(k_part2<true, COUNT_ONLY>, ctx->device, (size_t)kPartTile * 16, err)) return rc;
+        k_part2<true, COUNT_ONLY><<<(uint32_t)grid, kBlockThreads, smem, s>>>(a);
+    } else {
+        if (int rc = set_max_smem(k_part2<false, COUNT_ONLY>, ctx->device, (size_t)kPartTile * 16, err)) return rc;
+        k_part2<false, COUNT_ONLY><<<(uint32_t)grid, kBlockThreads, smem, s>>>(a);
+    }
+    IBU_LAUNCHED("k_part2");
+    return IBU_OK;
+}
+
+}  // namespace
+
 int k4_job_begin(ibu_gpu_ctx *ctx, uint64_t n, const K4Hints &hints, const K4Sample &smp, bool pair_mode,
                  bool weighted, cudaStream_t s, K4Job **out, ibu_error_t *err) {
     *out = nullptr;
     const bool forced = hints.force_path == kPathPartition;
-    if (!smp.valid || n == 0 || n >= (1ull << 40)) return IBU_OK;
+    if (!smp.valid || n == 0 || n >= (1ull << 36)) return IBU_OK;
     static const bool trace = getenv("IBU_B200_TRACE") != nullptr;
 
     // ---- what the sample says ----
@@ -756,54 +289,84 @@ int k4_job_begin(ibu_gpu_ctx *ctx, uint64_t n, const K4Hints &hints, const K4Sam
     job->weighted = weighted;
     job->P = std::min<uint64_t>(std::max<uint64_t>(pow2_ceil((n + 1023) / 1024), 2), 1u << 21);
     job->pb = log2_of(job->P);
+    // fan-out per level: at most 2^8 from the records, 2^9 from keys (a 4096-key tile then leaves
+    // runs of 16 / 8 keys per bucket); up to 2^9 buckets the records are only turned into keys first
+    const uint32_t pb = job->pb;
+    std::vector<uint32_t> bits;
+    if (pb <= 9) bits = {0, pb};
+    else if (pb <= 17) bits = {pb / 2, pb - pb / 2};
+    else bits = {pb / 3, (pb - pb / 3) / 2, pb - pb / 3 - (pb - pb / 3) / 2};
+    uint64_t bytes = 0;
+    uint32_t used = 0;
+    for (size_t l = 0; l < bits.size(); l++) {
+        K4Level lv;
+        lv.bits_in = used;
+        lv.bits = bits[l];
+        used += bits[l];
+        // uniform layout with mean + 6 sigma room per bucket
+        const double buckets = (double)(1ull << used);
+        const double mean = (double)n / buckets, sigma = std::sqrt(sum_sq / buckets);
+        lv.cap = ((uint64_t)(mean + 6.0 * sigma) + 64 + 15) & ~15ull;
+        if (l + 1 < bits.size()) {
+            // a level whose loads are this uneven (a few keys hold most of the records) is not worth
+            // laying out: the global hash of the legacy path keeps such keys in L2
+            if ((double)lv.cap > 2.0 * mean + 65536.0) return IBU_OK;
+            bytes += (uint64_t)buckets * lv.cap * (weighted ? 16 : 8);
+        }
+        job->levels.push_back(lv);
+    }
+    const K4Level &last = job->levels.back();
     const double mean = (double)n / (double)job->P;
-    const double sigma = std::sqrt(sum_sq / (double)job->P);
-    // uniform layout with mean + 6 sigma room per bucket; when duplicates make the loads too uneven
-    // for that (or the first attempt overflows) the buckets are laid out exactly from a histogram
-    job->cap = ((uint64_t)(mean + 6.0 * sigma) + 64 + 15) & ~15ull;
-    job->exact = (double)job->cap > 3.0 * mean + 256.0;
+    // when duplicates make the final loads too uneven for the uniform layout (or the first attempt
+    // overflows) the final buckets are laid out exactly from a histogram of the level before
+    job->exact = (double)last.cap > 3.0 * mean + 256.0;
+    bytes += job->exact ? n * (weighted ? 16 : 8) : job->P * last.cap * (weighted ? 16 : 8);
+    if (bytes > (64ull << 30)) return IBU_OK;
     // shared-memory table: 1.6 slots per key of the fullest bucket the uniform layout admits (all of
     // them distinct at worst); duplicate-heavy data (exact layout) has far fewer distinct keys than
     // records per bucket.  Smaller tables = more resident CTAs = more buckets in flight per SM.
     while (job->s_bits < 13 &&
-           (double)(1u << job->s_bits) < 1.6 * (job->exact ? mean + 6.0 * std::sqrt(mean) : (double)job->cap))
+           (double)(1u << job->s_bits) < 1.6 * (job->exact ? mean + 6.0 * std::sqrt(mean) : (double)last.cap))
         job->s_bits++;
     if (job->pb + job->s_bits > 60) return IBU_OK;
     job->wide_cap = n / 8 + 4096;
     job->packed = !weighted && n < (1ull << 28);
-    if (!job->exact && job->P * job->cap * (weighted ? 16 : 8) > (64ull << 30)) return IBU_OK;
 
-    IBU_CUDA(job->sc.alloc(&job->cursors, job->P * 4));
+    K4Level &l0 = job->levels[0];
+    IBU_CUDA(job->sc.alloc(&l0.cursors, ((size_t)4 << l0.bits) + 256));
+    IBU_CUDA(job->sc.alloc(&l0.keys, ((size_t)l0.cap << l0.bits) * 8));
+    if (weighted) IBU_CUDA(job->sc.alloc(&l0.wts, ((size_t)l0.cap << l0.bits) * 8));
     IBU_CUDA(job->sc.alloc(&job->wide, job->wide_cap * 24));
     IBU_CUDA(job->sc.alloc(&job->ctr, kCtrWords * 8));
-    IBU_CUDA(cudaMemsetAsync(job->cursors, 0, job->P * 4, s));
+    IBU_CUDA(cudaMemsetAsync(l0.cursors, 0, (size_t)4 << l0.bits, s));
     IBU_CUDA(cudaMemsetAsync(job->ctr, 0, kCtrWords * 8, s));
-    if (!job->exact) {
-        IBU_CUDA(job->sc.alloc(&job->keys, job->P * job->cap * 8));
-        if (weighted) IBU_CUDA(job->sc.alloc(&job->wts, job->P * job->cap * 8));
-    }
+    if (int rc = set_max_smem(k_part1<false>, ctx->device, (size_t)kPartTile * 8, err)) return rc;
+    if (int rc = set_max_smem(k_part1<true>, ctx->device, (size_t)kPartTile * 16, err)) return rc;
     IBU_CUDA(cudaEventCreateWithFlags(&job->ready_ev, cudaEventDisableTiming));
     IBU_CUDA(cudaEventRecord(job->ready_ev, s));
     *out = job.release();
     return IBU_OK;
 }
 
-// Scatter (uniform layout) or count (exact layout) the keys of `cnt` records on stream s, which
-// must be the job's stream or have waited for k4_job_ready().  recs must be 32-byte aligned.
+// Level-1 partition of the keys of `cnt` records on stream s, which must be the job's stream or
+// have waited for k4_job_ready().  recs must be 32-byte aligned.
 int k4_job_add(K4Job *job, const uint64_t *recs, uint64_t cnt, cudaStream_t s, ibu_error_t *err) {
     if (cnt == 0) return IBU_OK;
     job->added += cnt;
-    ScatterArgs a{recs, cnt, job->bb, job->ub, job->pb, (uint32_t)job->cap, nullptr, job->cursors, job->keys, job->wts,
-                  job->wide, job->wide_cap, job->ctr};
-    return job->exact ? launch_scatter<true>(a, job->weighted, s, err) : launch_scatter<false>(a, job->weighted, s, err);
+    const K4Level &l0 = job->levels[0];
+    Part1Args a{recs, cnt, job->bb, job->ub, l0.bits, l0.cap, l0.cursors, l0.keys, l0.wts, job->wide, job->wide_cap, job->ctr};
+    const uint32_t grid = (uint32_t)((cnt + kPartTile - 1) / kPartTile);
+    if (job->weighted) k_part1<true><<<grid, kBlockThreads, (size_t)kPartTile * 16, s>>>(a);
+    else k_part1<false><<<grid, kBlockThreads, (size_t)kPartTile * 8, s>>>(a);
+    IBU_LAUNCHED("k_part1");
+    return IBU_OK;
 }
 
-// Everything after the scatter, on the job's stream (which must have waited for every stream that
-// added).  all_recs (nullable): the records the job saw, contiguous — needed when the buckets have
-// to be laid out exactly (duplicate-heavy data, or an overflow of the uniform layout); without
-// them such a job ends unhandled.  *handled = false: nothing produced, take another path.
+// Everything after the first level, on the job's stream (which must have waited for every stream
+// that added).  *handled = false: nothing produced, take another path.
 int k4_job_finish(K4Job *job, const uint64_t *all_recs, bool pair_mode, bool pairs_sorted, uint64_t **rows_out,
                   uint64_t *n_rows, uint64_t *n_pairs, bool *handled, ibu_error_t *err) {
+    (void)all_recs;
     *handled = false;
     *rows_out = nullptr;
     *n_rows = *n_pairs = 0;
@@ -813,42 +376,60 @@ int k4_job_finish(K4Job *job, const uint64_t *all_recs, bool pair_mode, bool pai
     StageTimer &timer = job->timer;
     const bool trace = job->trace, weighted = job->weighted, packed = job->packed;
     unsigned long long *mail = ctx->h_mail;  // pinned: device -> host read-backs without a staged copy
-    const uint64_t n = job->added, P = job->P, cap = job->cap;
+    const uint64_t n = job->added, P = job->P;
     const uint32_t pb = job->pb, bb = job->bb, ub = job->ub, s_bits = job->s_bits;
-    uint32_t *cursors = job->cursors;
     unsigned long long *ctr = job->ctr;
     uint64_t *wide = job->wide, *pairs = nullptr;
     if (n > job->n) return IBU_OK;  // more records than the job was sized for
-    timer.lap(job->exact ? "histogram" : "k_scatter_keys");
+    timer.lap("k_part1");
 
-    // ---- exact layout: the cursors hold the histogram; lay the buckets out and scatter everything ----
-    if (!job->exact) {
-        IBU_CUDA(cudaMemcpyAsync(mail, ctr, kCtrWords * 8, cudaMemcpyDeviceToHost, s));
-        IBU_CUDA(cudaStreamSynchronize(s));
-        if (mail[kCtrFlags] & kFlagWide) return IBU_OK;
-        if (mail[kCtrFlags] & kFlagBucket) {
-            if (trace) fprintf(stderr, "[ibu trace] a bucket overflowed (cap %llu): exact layout\n", (unsigned long long)cap);
-            sc.free_now(job->keys);
-            if (job->wts) sc.free_now(job->wts);
-            job->keys = job->wts = nullptr;
-            job->exact = true;  // the cursors counted every key, stored or not
+    // ---- the further levels; the last one uniform first, exact if told so or after an overflow ----
+    const size_t L = job->levels.size();
+    auto run_level = [&](size_t l, bool count_only, const uint64_t *bases) -> int {
+        const K4Level &in = job->levels[l - 1];
+        K4Level &lv = job->levels[l];
+        Part2Args a{in.cursors, in.keys, in.wts, in.cap, (uint32_t)((in.cap + kPartTile - 1) / kPartTile), lv.bits_in, lv.bits,
+                    lv.cap, bases, lv.cursors, lv.keys, lv.wts, ctr, l + 1 == L ? (uint32_t)kFlagBucket : (uint32_t)kFlagLevel};
+        const uint64_t n_in = 1ull << lv.bits_in;
+        return count_only ? launch_part2<true>(ctx, a, n_in, weighted, s, err) : launch_part2<false>(ctx, a, n_in, weighted, s, err);
+    };
+    for (size_t l = 1; l < L; l++) {
+        K4Level &lv = job->levels[l];
+        const size_t n_out = (size_t)1 << (lv.bits_in + lv.bits);
+        IBU_CUDA(sc.alloc(&lv.cursors, n_out * 4 + 256));
+        IBU_CUDA(cudaMemsetAsync(lv.cursors, 0, n_out * 4, s));
+        if (l + 1 == L && job->exact) break;  // laid out below
+        IBU_CUDA(sc.alloc(&lv.keys, n_out * lv.cap * 8));
+        if (weighted) IBU_CUDA(sc.alloc(&lv.wts, n_out * lv.cap * 8));
+        if (int rc = run_level(l, false, nullptr)) return rc;
+        if (l >= 2) {  // the level before the previous one is no longer needed
+            sc.free_now(job->levels[l - 2].keys);
+            if (job->levels[l - 2].wts) sc.free_now(job->levels[l - 2].wts);
+            job->levels[l - 2].keys = job->levels[l - 2].wts = nullptr;
         }
+        timer.lap("k_part2");
     }
-    if (job->exact && !job->bases) {
-        if (!all_recs) return IBU_OK;
-        if (n * (weighted ? 16 : 8) > (64ull << 30)) return IBU_OK;
-        IBU_CUDA(sc.alloc(&job->bases, (P + 1) * 8));
-        k_bucket_bases<<<1, 1024, 0, s>>>(cursors, (uint32_t)P, job->bases);
+    K4Level &last = job->levels[L - 1];
+    auto layout_exact = [&]() -> int {
+        // cursors of the last level: histogram -> bases -> the real pass
+        if (n * (weighted ? 16 : 8) > (64ull << 30)) return -1;
+        IBU_CUDA(cudaMemsetAsync(last.cursors, 0, (size_t)P * 4, s));
+        if (int rc = run_level(L - 1, true, nullptr)) return rc;
+        if (!job->bases) IBU_CUDA(sc.alloc(&job->bases, (P + 1) * 8));
+        k_bucket_bases<<<1, 1024, 0, s>>>(last.cursors, (uint32_t)P, job->bases);
         IBU_LAUNCHED("k_bucket_bases");
-        IBU_CUDA(cudaMemsetAsync(cursors, 0, P * 4, s));
-        IBU_CUDA(cudaMemsetAsync(ctr, 0, kCtrWords * 8, s));
-        IBU_CUDA(sc.alloc(&job->keys, n * 8));
-        if (weighted) IBU_CUDA(sc.alloc(&job->wts, n * 8));
-        ScatterArgs a{all_recs, n, bb, ub, pb, (uint32_t)cap, job->bases, cursors, job->keys, job->wts, wide, job->wide_cap, ctr};
-        if (int rc = launch_scatter<false>(a, weighted, s, err)) return rc;
-        timer.lap("k_scatter_keys (exact)");
+        IBU_CUDA(cudaMemsetAsync(last.cursors, 0, (size_t)P * 4, s));
+        IBU_CUDA(sc.alloc(&last.keys, n * 8));
+        if (weighted) IBU_CUDA(sc.alloc(&last.wts, n * 8));
+        if (int rc = run_level(L - 1, false, job->bases)) return rc;
+        timer.lap("k_part2 (histogram + exact)");
+        return IBU_OK;
+    };
+    if (job->exact) {
+        const int rc = layout_exact();
+        if (rc < 0) return IBU_OK;
+        if (rc) return rc;
     }
-    uint64_t *keys = job->keys, *wts = job->wts, *bases = job->bases;
 
     // ---- per-bucket de-duplication into the barcode table (grown if the estimate was short) ----
     // barcode table: generous (skewed barcode frequencies make the estimate a lower bound); only the
@@ -860,37 +441,53 @@ int k4_job_finish(K4Job *job, const uint64_t *all_recs, bool pair_mode, bool pai
     uint64_t *slots = nullptr;
     for (int attempt = 0;; attempt++) {
         if (!pair_mode) {
+            if (slots) sc.free_now(slots);
             IBU_CUDA(sc.alloc(&slots, t_slots * slot_words * 8));
             IBU_CUDA(cudaMemsetAsync(slots, 0xFF, t_slots * slot_words * 8, s));
         }
-        DedupArgs a{cursors, bases, keys, wts, (uint32_t)P, (uint32_t)cap, pb, ub, s_bits,
-                    TableRef{slots, t_slots - 1, ctr, packed ? 1u : 0u}, pairs, pairs_cap};
+        DedupArgs a{last.cursors, job->exact ? job->bases : nullptr, last.keys, last.wts, (uint32_t)P, (uint32_t)last.cap, pb, ub,
+                    s_bits, TableRef{slots, t_slots - 1, ctr, packed ? 1u : 0u}, pairs, pairs_cap};
         int rc = weighted ? (pair_mode ? launch_dedup<true, true>(ctx, a, s, err) : launch_dedup<true, false>(ctx, a, s, err))
                           : (pair_mode ? launch_dedup<false, true>(ctx, a, s, err) : launch_dedup<false, false>(ctx, a, s, err));
         if (rc) return rc;
-        timer.lap("k_bucket_dedup");
+        timer.lap("k_bucket_dedup2");
         IBU_CUDA(cudaMemcpyAsync(mail, ctr, kCtrWords * 8, cudaMemcpyDeviceToHost, s));
         IBU_CUDA(cudaStreamSynchronize(s));
         const uint64_t flags = mail[kCtrFlags];
         if (trace)
-            fprintf(stderr, "[ibu trace] partition: P=2^%u %s cap=%llu S=2^%u table=%llu x %u B -> wide %llu pairs %llu rows %llu flags %llx\n",
-                    pb, job->exact ? "exact" : "uniform", (unsigned long long)cap, s_bits, (unsigned long long)t_slots,
+            fprintf(stderr, "[ibu trace] partition: %zu levels to P=2^%u %s cap=%llu S=2^%u table=%llu x %u B -> wide %llu pairs %llu rows %llu flags %llx\n",
+                    L, pb, job->exact ? "exact" : "uniform", (unsigned long long)last.cap, s_bits, (unsigned long long)t_slots,
                     slot_words * 8, mail[kCtrWide], mail[kCtrPairs], mail[kCtrClaimed], (unsigned long long)flags);
-        if (flags & (kFlagBucket | kFlagWide | kFlagSmem | kFlagPairsOut)) return IBU_OK;  // legacy path
+        if (flags & (kFlagLevel | kFlagWide | kFlagSmem | kFlagPairsOut)) return IBU_OK;  // legacy path
         const bool crowded = !pair_mode && mail[kCtrClaimed] > t_slots / 10 * 6;
-        if (!(flags & kFlagTable) && !crowded) break;
+        if (!(flags & (kFlagTable | kFlagBucket)) && !crowded) break;
         if (attempt == 3 || t_slots >= (1ull << 31)) return IBU_OK;
-        // more barcodes than estimated: the buckets are intact, only this stage is repeated
-        sc.free_now(slots);
-        t_slots *= 8;
         const unsigned long long keep[3] = {mail[kCtrWide], 0ull, mail[kCtrSpecial]};
         IBU_CUDA(cudaMemsetAsync(ctr, 0, kCtrWords * 8, s));
         IBU_CUDA(cudaMemcpyAsync(ctr, keep, sizeof(keep), cudaMemcpyHostToDevice, s));
+        if (flags & kFlagBucket) {
+            // a final bucket overflowed the uniform layout: the level before is intact, lay the
+            // buckets out exactly and repeat from there
+            if (job->exact) return IBU_OK;
+            if (trace) fprintf(stderr, "[ibu trace] a bucket overflowed (cap %llu): exact layout\n", (unsigned long long)last.cap);
+            sc.free_now(last.keys);
+            if (last.wts) sc.free_now(last.wts);
+            last.keys = last.wts = nullptr;
+            job->exact = true;
+            const int rc2 = layout_exact();
+            if (rc2 < 0) return IBU_OK;
+            if (rc2) return rc2;
+        } else {
+            // more barcodes than estimated: the buckets are intact, only this stage is repeated
+            t_slots *= 8;
+        }
     }
     const uint64_t n_wide = mail[kCtrWide];
-    sc.free_now(keys);
-    if (wts) sc.free_now(wts);
-    job->keys = job->wts = nullptr;
+    for (K4Level &lv : job->levels) {
+        if (lv.keys) sc.free_now(lv.keys);
+        if (lv.wts) sc.free_now(lv.wts);
+        lv.keys = lv.wts = nullptr;
+    }
 
     // ---- 5. wide records and the special key ----
     uint64_t wide_pairs = 0;
