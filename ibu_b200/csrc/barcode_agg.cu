@@ -3,20 +3,26 @@
 // The per-barcode table (src/parallel.rs:79-98 HashMap<barcode, count>, extended with the number
 // of distinct UMI words) needs every (barcode, umi) pair de-duplicated.  A global hash table is
 // one random DRAM access per record once it outgrows L2, and a full sort moves every record
-// once per digit.  This path touches a record twice:
+// once per digit.  This path reads a record once and its 8-byte key two or three times:
 //
-//   k_sample        ~1 M records at hashed positions: bit widths of the two words, distinct pairs
+//   k_sample        ~256 K records at hashed positions: bit widths of the two words, distinct pairs
 //                   and distinct barcodes among them (sizes every table below; tiny)
-//   k_scatter_keys  24 B read + 8 B written per record.  A record whose words fit the key layout
+//   k_part1         24 B read + 8 B written per record.  A record whose words fit the key layout
 //                   (barcode < 2^bb, umi < 2^ub, bb + ub <= 64) becomes ONE u64:
 //                   key = mix64(barcode << ub | umi), mix64 a bijection, so the key's top bits
-//                   are a uniform hash and the pair can be recovered from it.  The key is
-//                   appended to bucket (key >> (64 - pb)) with one atomicAdd on the bucket's
-//                   cursor; the 8-byte stores of a bucket fill whole lines in the write-back L2
-//                   (2^pb open lines: a few MB) before they reach HBM.  Records that do not fit
-//                   (`wide`: the reference's own generator writes them, examples/random.rs:46)
-//                   are copied to a side list.
-//   k_bucket_dedup  8 B read per record.  One CTA per bucket folds the bucket's keys into a
+//                   are a uniform hash and the pair can be recovered from it.  A CTA groups the
+//                   keys of its 4096-record tile by their top pb1 (<= 8) bits in shared memory
+//                   (rank = shared-memory atomicAdd(+1) on the tile's histogram) and appends each
+//                   group to its level-1 bucket as one run (one global atomicAdd per tile and
+//                   bucket) — 16 keys = a full 128-byte line at fan-out 256.  Records that do
+//                   not fit (`wide`: the reference's own generator writes them,
+//                   examples/random.rs:46) are copied to a side list.
+//   k_part2         8 B read + 8 B written per key: the same on the keys of each level-1 bucket
+//                   with the next pb2 (<= 9) bits, down to 2^17 buckets of ~763 keys per 10^8
+//                   records (three levels above 2^17 buckets).  One level straight to 2^17 buckets
+//                   was the first form of this path: one L2 write transaction per 8-byte key,
+//                   2.1 ms per 10^8 records against 0.63 + 0.46 ms for the two staged levels.
+//   k_bucket_dedup2 8 B read per key.  One CTA per bucket folds the bucket's keys into a
 //                   shared-memory hash table (distinct keys per bucket are balanced by the hash,
 //                   however skewed the barcodes are; duplicates only make a bucket longer) and
 //                   adds every distinct pair to the per-barcode table — a global open-addressing
@@ -141,16 +147,6 @@ int launch_dedup(ibu_gpu_ctx *ctx, const DedupArgs &a, cudaStream_t s, ibu_error
     return IBU_OK;
 }
 
-template <bool COUNT_ONLY>
-int launch_scatter(const ScatterArgs &a, bool weighted, cudaStream_t s, ibu_error_t *err) {
-    const uint64_t tiles = a.n / 128 + 1;
-    const uint32_t grid = (uint32_t)((tiles + kWarpsPerBlock - 1) / kWarpsPerBlock);
-    if (weighted) k_scatter_keys<true, COUNT_ONLY><<<grid, kBlockThreads, 0, s>>>(a);
-    else k_scatter_keys<false, COUNT_ONLY><<<grid, kBlockThreads, 0, s>>>(a);
-    IBU_LAUNCHED("k_scatter_keys");
-    return IBU_OK;
-}
-
 }  // namespace
 
 int k4_sample(ibu_gpu_ctx *ctx, const uint64_t *recs, uint64_t n, cudaStream_t s, K4Sample *out, ibu_error_t *err) {
@@ -211,6 +207,18 @@ struct K4Job {
     double r_est = 0;
     bool exact = false, weighted = false, packed = false;
     std::vector<K4Level> levels;  // levels[0] is filled by add(); the last one feeds the de-duplication
+    // chunked mode: add() takes the records in pieces of `chunk` records, partitions a piece into a
+    // small level-0 area of its stream (written and read back while still in L2) and straight on
+    // into the global level 1; finish() then starts at level 2 (or at the de-duplication)
+    bool chunked = false, overflowed = false;
+    uint64_t chunk = 0;
+    struct Tmp {
+        cudaStream_t s = nullptr;
+        bool taken = false;
+        uint32_t *cursors = nullptr;
+        uint64_t *keys = nullptr, *wts = nullptr;
+    };
+    std::vector<Tmp> tmps;
     uint64_t *wide = nullptr, *bases = nullptr;
     unsigned long long *ctr = nullptr;
     cudaEvent_t ready_ev = nullptr;
@@ -221,6 +229,7 @@ struct K4Job {
 };
 
 void k4_job_destroy(K4Job *job) { delete job; }
+bool k4_job_overflowed(const K4Job *job) { return job->overflowed; }
 cudaEvent_t k4_job_ready(K4Job *job) { return job->ready_ev; }
 
 namespace {
@@ -244,7 +253,7 @@ int launch_part2(ibu_gpu_ctx *ctx, const Part2Args &a, uint64_t n_in_buckets, bo
 }  // namespace
 
 int k4_job_begin(ibu_gpu_ctx *ctx, uint64_t n, const K4Hints &hints, const K4Sample &smp, bool pair_mode,
-                 bool weighted, cudaStream_t s, K4Job **out, ibu_error_t *err) {
+                 bool weighted, const K4Chunking &chunking, cudaStream_t s, K4Job **out, ibu_error_t *err) {
     *out = nullptr;
     const bool forced = hints.force_path == kPathPartition;
     if (!smp.valid || n == 0 || n >= (1ull << 36)) return IBU_OK;
@@ -319,7 +328,7 @@ int k4_job_begin(ibu_gpu_ctx *ctx, uint64_t n, const K4Hints &hints, const K4Sam
     const double mean = (double)n / (double)job->P;
     // when duplicates make the final loads too uneven for the uniform layout (or the first attempt
     // overflows) the final buckets are laid out exactly from a histogram of the level before
-    job->exact = (double)last.cap > 3.0 * mean + 256.0;
+    job->exact = chunking.force_exact || (double)last.cap > 3.0 * mean + 256.0;
     bytes += job->exact ? n * (weighted ? 16 : 8) : job->P * last.cap * (weighted ? 16 : 8);
     if (bytes > (64ull << 30)) return IBU_OK;
     // shared-memory table: 1.6 slots per key of the fullest bucket the uniform layout admits (all of
@@ -332,13 +341,41 @@ int k4_job_begin(ibu_gpu_ctx *ctx, uint64_t n, const K4Hints &hints, const K4Sam
     job->wide_cap = n / 8 + 4096;
     job->packed = !weighted && n < (1ull << 28);
 
+    // chunked unless the final level must be laid out exactly and there are only two levels (the
+    // exact layout needs the whole level before it)
+    // (device-resident input in one piece: pieces of 1 - 8 Mi records measured 2.8 - 4.0 ms against 2.33 ms
+    // per 10^8 records, profiles/r2_k4bench_chunk_sweep.txt — the level-0 area does not stay in L2 long
+    // enough to pay for the extra launches; the ingest pipeline chunks because its pieces arrive that way)
+    static const char *env_chunk = getenv("IBU_B200_K4_CHUNK");  // records per piece for resident input (tuning)
+    uint64_t chunk = chunking.chunk_records ? chunking.chunk_records : (env_chunk ? strtoull(env_chunk, nullptr, 10) : 0);
+    job->chunked = chunk != 0 && !chunking.force_exact && !(job->levels.size() == 2 && job->exact) && n > chunk;
     K4Level &l0 = job->levels[0];
-    IBU_CUDA(job->sc.alloc(&l0.cursors, ((size_t)4 << l0.bits) + 256));
-    IBU_CUDA(job->sc.alloc(&l0.keys, ((size_t)l0.cap << l0.bits) * 8));
-    if (weighted) IBU_CUDA(job->sc.alloc(&l0.wts, ((size_t)l0.cap << l0.bits) * 8));
+    if (job->chunked) {
+        chunk = (chunk + kPartTile - 1) / kPartTile * kPartTile;
+        job->chunk = chunk;
+        const double buckets0 = (double)(1ull << l0.bits), cscale = (double)chunk / m;
+        const double csum_sq = (double)chunk + cscale * cscale * 2.0 * smp.pair_coll;
+        l0.cap = ((uint64_t)((double)chunk / buckets0 + 6.0 * std::sqrt(csum_sq / buckets0)) + 64 + 15) & ~15ull;
+        job->tmps.resize(std::max<uint32_t>(1, chunking.n_streams));
+        for (K4Job::Tmp &t : job->tmps) {
+            IBU_CUDA(job->sc.alloc(&t.cursors, ((size_t)4 << l0.bits) + 256));
+            IBU_CUDA(job->sc.alloc(&t.keys, ((size_t)l0.cap << l0.bits) * 8));
+            if (weighted) IBU_CUDA(job->sc.alloc(&t.wts, ((size_t)l0.cap << l0.bits) * 8));
+        }
+        K4Level &l1 = job->levels[1];
+        const size_t n1 = (size_t)1 << (l1.bits_in + l1.bits);
+        IBU_CUDA(job->sc.alloc(&l1.cursors, n1 * 4 + 256));
+        IBU_CUDA(cudaMemsetAsync(l1.cursors, 0, n1 * 4, s));
+        IBU_CUDA(job->sc.alloc(&l1.keys, n1 * l1.cap * 8));
+        if (weighted) IBU_CUDA(job->sc.alloc(&l1.wts, n1 * l1.cap * 8));
+    } else {
+        IBU_CUDA(job->sc.alloc(&l0.cursors, ((size_t)4 << l0.bits) + 256));
+        IBU_CUDA(job->sc.alloc(&l0.keys, ((size_t)l0.cap << l0.bits) * 8));
+        if (weighted) IBU_CUDA(job->sc.alloc(&l0.wts, ((size_t)l0.cap << l0.bits) * 8));
+        IBU_CUDA(cudaMemsetAsync(l0.cursors, 0, (size_t)4 << l0.bits, s));
+    }
     IBU_CUDA(job->sc.alloc(&job->wide, job->wide_cap * 24));
     IBU_CUDA(job->sc.alloc(&job->ctr, kCtrWords * 8));
-    IBU_CUDA(cudaMemsetAsync(l0.cursors, 0, (size_t)4 << l0.bits, s));
     IBU_CUDA(cudaMemsetAsync(job->ctr, 0, kCtrWords * 8, s));
     if (int rc = set_max_smem(k_part1<false>, ctx->device, (size_t)kPartTile * 8, err)) return rc;
     if (int rc = set_max_smem(k_part1<true>, ctx->device, (size_t)kPartTile * 16, err)) return rc;
@@ -348,17 +385,44 @@ int k4_job_begin(ibu_gpu_ctx *ctx, uint64_t n, const K4Hints &hints, const K4Sam
     return IBU_OK;
 }
 
-// Level-1 partition of the keys of `cnt` records on stream s, which must be the job's stream or
-// have waited for k4_job_ready().  recs must be 32-byte aligned.
+// Partition the keys of `cnt` records on stream s, which must be the job's stream or have waited
+// for k4_job_ready().  recs must be 32-byte aligned.
 int k4_job_add(K4Job *job, const uint64_t *recs, uint64_t cnt, cudaStream_t s, ibu_error_t *err) {
     if (cnt == 0) return IBU_OK;
     job->added += cnt;
     const K4Level &l0 = job->levels[0];
-    Part1Args a{recs, cnt, job->bb, job->ub, l0.bits, l0.cap, l0.cursors, l0.keys, l0.wts, job->wide, job->wide_cap, job->ctr};
-    const uint32_t grid = (uint32_t)((cnt + kPartTile - 1) / kPartTile);
-    if (job->weighted) k_part1<true><<<grid, kBlockThreads, (size_t)kPartTile * 16, s>>>(a);
-    else k_part1<false><<<grid, kBlockThreads, (size_t)kPartTile * 8, s>>>(a);
-    IBU_LAUNCHED("k_part1");
+    auto part1 = [&](const uint64_t *r, uint64_t c, uint32_t *cursors, uint64_t *keys, uint64_t *wts) -> int {
+        Part1Args a{r, c, job->bb, job->ub, l0.bits, l0.cap, cursors, keys, wts, job->wide, job->wide_cap, job->ctr};
+        const uint32_t grid = (uint32_t)((c + kPartTile - 1) / kPartTile);
+        if (job->weighted) k_part1<true><<<grid, kBlockThreads, (size_t)kPartTile * 16, s>>>(a);
+        else k_part1<false><<<grid, kBlockThreads, (size_t)kPartTile * 8, s>>>(a);
+        IBU_LAUNCHED("k_part1");
+        return IBU_OK;
+    };
+    if (!job->chunked) return part1(recs, cnt, l0.cursors, l0.keys, l0.wts);
+    // the level-0 area of this stream (pieces on one stream follow each other; streams do not share)
+    K4Job::Tmp *tmp = nullptr;
+    for (K4Job::Tmp &t : job->tmps)
+        if (t.taken && t.s == s) tmp = &t;
+    if (!tmp)
+        for (K4Job::Tmp &t : job->tmps)
+            if (!t.taken) {
+                t.taken = true;
+                t.s = s;
+                tmp = &t;
+                break;
+            }
+    if (!tmp) return set_error(err, IBU_ERR_ARG, 0, 0, 0, "k4_job_add: more streams than the job was set up for");
+    const K4Level &l1 = job->levels[1];
+    const size_t L = job->levels.size();
+    for (uint64_t off = 0; off < cnt; off += job->chunk) {
+        const uint64_t c = std::min<uint64_t>(job->chunk, cnt - off);
+        IBU_CUDA(cudaMemsetAsync(tmp->cursors, 0, (size_t)4 << l0.bits, s));
+        if (int rc = part1(recs + 3 * off, c, tmp->cursors, tmp->keys, tmp->wts)) return rc;
+        Part2Args a{tmp->cursors, tmp->keys, tmp->wts, l0.cap, (uint32_t)((l0.cap + kPartTile - 1) / kPartTile), l1.bits_in, l1.bits,
+                    l1.cap, nullptr, l1.cursors, l1.keys, l1.wts, job->ctr, L == 2 ? (uint32_t)kFlagBucket : (uint32_t)kFlagLevel};
+        if (int rc = launch_part2<false>(job->ctx, a, 1ull << l1.bits_in, job->weighted, s, err)) return rc;
+    }
     return IBU_OK;
 }
 
@@ -381,7 +445,7 @@ int k4_job_finish(K4Job *job, const uint64_t *all_recs, bool pair_mode, bool pai
     unsigned long long *ctr = job->ctr;
     uint64_t *wide = job->wide, *pairs = nullptr;
     if (n > job->n) return IBU_OK;  // more records than the job was sized for
-    timer.lap("k_part1");
+    timer.lap(job->chunked ? "k_part1 + k_part2 (chunked)" : "k_part1");
 
     // ---- the further levels; the last one uniform first, exact if told so or after an overflow ----
     const size_t L = job->levels.size();
@@ -393,7 +457,7 @@ int k4_job_finish(K4Job *job, const uint64_t *all_recs, bool pair_mode, bool pai
         const uint64_t n_in = 1ull << lv.bits_in;
         return count_only ? launch_part2<true>(ctx, a, n_in, weighted, s, err) : launch_part2<false>(ctx, a, n_in, weighted, s, err);
     };
-    for (size_t l = 1; l < L; l++) {
+    for (size_t l = job->chunked ? 2 : 1; l < L; l++) {
         K4Level &lv = job->levels[l];
         const size_t n_out = (size_t)1 << (lv.bits_in + lv.bits);
         IBU_CUDA(sc.alloc(&lv.cursors, n_out * 4 + 256));
@@ -402,7 +466,7 @@ int k4_job_finish(K4Job *job, const uint64_t *all_recs, bool pair_mode, bool pai
         IBU_CUDA(sc.alloc(&lv.keys, n_out * lv.cap * 8));
         if (weighted) IBU_CUDA(sc.alloc(&lv.wts, n_out * lv.cap * 8));
         if (int rc = run_level(l, false, nullptr)) return rc;
-        if (l >= 2) {  // the level before the previous one is no longer needed
+        if (l >= 2 && job->levels[l - 2].keys) {  // the level before the previous one is no longer needed
             sc.free_now(job->levels[l - 2].keys);
             if (job->levels[l - 2].wts) sc.free_now(job->levels[l - 2].wts);
             job->levels[l - 2].keys = job->levels[l - 2].wts = nullptr;
@@ -468,7 +532,8 @@ int k4_job_finish(K4Job *job, const uint64_t *all_recs, bool pair_mode, bool pai
         if (flags & kFlagBucket) {
             // a final bucket overflowed the uniform layout: the level before is intact, lay the
             // buckets out exactly and repeat from there
-            if (job->exact) return IBU_OK;
+            job->overflowed = true;
+            if (job->exact || (job->chunked && L == 2)) return IBU_OK;  // (chunked: the level before is gone)
             if (trace) fprintf(stderr, "[ibu trace] a bucket overflowed (cap %llu): exact layout\n", (unsigned long long)last.cap);
             sc.free_now(last.keys);
             if (last.wts) sc.free_now(last.wts);
@@ -542,7 +607,7 @@ int k4_job_finish(K4Job *job, const uint64_t *all_recs, bool pair_mode, bool pai
     IBU_CUDA(sc.alloc(&unsorted, R ? R * 24 : 256));
     IBU_CUDA(cudaMemsetAsync(ctr + kCtrCursor, 0, 8, s));
     {
-        const uint64_t blocks = (t_slots + kBlockThreads - 1) / kBlockThreads;
+        const uint64_t blocks = (t_slots + 1023) / 1024;
         k_table_rows<<<(uint32_t)std::min<uint64_t>(blocks, (uint64_t)ctx->sm_count * 16), kBlockThreads, 0, s>>>(
             slots, t_slots, packed ? 1u : 0u, unsorted, ctr);
         IBU_LAUNCHED("k_table_rows");
@@ -582,13 +647,19 @@ int k4_partition_table(ibu_gpu_ctx *ctx, const uint64_t *recs, uint64_t n, const
     *handled = false;
     *rows_out = nullptr;
     *n_rows = *n_pairs = 0;
-    K4Job *job = nullptr;
-    if (int rc = k4_job_begin(ctx, n, hints, smp, pair_mode, weighted, s, &job, err)) return rc;
-    if (!job) return IBU_OK;
-    int rc = k4_job_add(job, recs, n, s, err);
-    if (rc == IBU_OK) rc = k4_job_finish(job, recs, pair_mode, pairs_sorted, rows_out, n_rows, n_pairs, handled, err);
-    k4_job_destroy(job);
-    return rc;
+    for (int attempt = 0; attempt < 2; attempt++) {
+        K4Job *job = nullptr;
+        K4Chunking ch;
+        ch.force_exact = attempt == 1;  // the chunked uniform layout overflowed: whole levels, exact final layout
+        if (int rc = k4_job_begin(ctx, n, hints, smp, pair_mode, weighted, ch, s, &job, err)) return rc;
+        if (!job) return IBU_OK;
+        int rc = k4_job_add(job, recs, n, s, err);
+        if (rc == IBU_OK) rc = k4_job_finish(job, recs, pair_mode, pairs_sorted, rows_out, n_rows, n_pairs, handled, err);
+        const bool again = rc == IBU_OK && !*handled && k4_job_overflowed(job) && attempt == 0;
+        k4_job_destroy(job);
+        if (!again) return rc;
+    }
+    return IBU_OK;
 }
 
 }  // namespace ibu

@@ -94,8 +94,14 @@ int k4_partition_table(ibu_gpu_ctx *ctx, const uint64_t *recs, uint64_t n, const
 // next chunk is still on the link (pipeline.cu).  begin leaves *job NULL when the input does not
 // suit the path.  Caller holds ctx->arena_mutex from begin to destroy.
 struct K4Job;
+struct K4Chunking {
+    uint64_t chunk_records = 0;  // records per piece of add() (0 = default); an ingest pipeline passes its chunk size
+    uint32_t n_streams = 1;      // streams that will call add() concurrently
+    bool force_exact = false;    // whole levels and an exact final layout (after an overflow of the uniform one)
+};
 int k4_job_begin(ibu_gpu_ctx *ctx, uint64_t n, const K4Hints &hints, const K4Sample &smp, bool pair_mode,
-                 bool weighted, cudaStream_t s, K4Job **job, ibu_error_t *err);
+                 bool weighted, const K4Chunking &chunking, cudaStream_t s, K4Job **job, ibu_error_t *err);
+bool k4_job_overflowed(const K4Job *job);  // a final bucket overflowed its uniform layout
 cudaEvent_t k4_job_ready(K4Job *job);  // recorded on the job's stream once its scratch is initialised
 int k4_job_add(K4Job *job, const uint64_t *recs, uint64_t cnt, cudaStream_t s, ibu_error_t *err);
 int k4_job_finish(K4Job *job, const uint64_t *all_recs, bool pair_mode, bool pairs_sorted, uint64_t **rows,

@@ -106,78 +106,7 @@ __global__ void __launch_bounds__(kBlockThreads) k_sample(const SampleArgs a) {
         if ((&h[0][0])[i]) atomicAdd(a.hist + i, (&h[0][0])[i]);
 }
 
-// ------------------------------------------------------------------------------------ scatter
-struct ScatterArgs {
-    const uint64_t *recs;
-    uint64_t n;
-    uint32_t bb, ub, pb;  // barcode bits, umi bits (bb + ub <= 64, both in 1..63), log2(#buckets)
-    uint32_t cap;         // keys per bucket (uniform layout)
-    const uint64_t *bases;  // nullable: exact layout, bucket b owns keys[bases[b] .. bases[b + 1])
-    uint32_t *cursors;    // [2^pb], zeroed
-    uint64_t *keys;
-    uint64_t *wts;        // same shape (WEIGHTED only)
-    uint64_t *wide;       // records that do not fit the key layout
-    uint64_t wide_cap;
-    unsigned long long *ctr;
-};
-
-// COUNT_ONLY: the histogram pass of the exact layout (cursors[b] = keys of bucket b, nothing stored).
-template <bool WEIGHTED, bool COUNT_ONLY>
-__device__ __forceinline__ void scatter_one(const ScatterArgs &a, uint64_t bc, uint64_t um, uint64_t w) {
-    if (((bc >> a.bb) | (um >> a.ub)) == 0ull) {
-        const uint64_t k = mix64((bc << a.ub) | um);
-        if (k == kEmpty) {  // the one key that looks like an empty slot
-            if (!COUNT_ONLY) atomicAdd(a.ctr + kCtrSpecial, (unsigned long long)(WEIGHTED ? w : 1ull));
-            return;
-        }
-        const uint32_t b = (uint32_t)(k >> (64 - a.pb));
-        const uint32_t pos = atomicAdd(a.cursors + b, 1u);
-        if (COUNT_ONLY) return;
-        uint64_t base = (uint64_t)b * a.cap, room = a.cap;
-        if (a.bases) {
-            base = a.bases[b];
-            room = a.bases[b + 1] - base;
-        }
-        if (pos < room) {
-            a.keys[base + pos] = k;
-            if (WEIGHTED) a.wts[base + pos] = w;
-        } else {
-            atomicOr(a.ctr + kCtrFlags, (unsigned long long)kFlagBucket);
-        }
-    } else if (!COUNT_ONLY) {
-        const uint64_t pos = atomicAdd(a.ctr + kCtrWide, 1ull);
-        if (pos < a.wide_cap) {
-            a.wide[3 * pos] = bc;
-            a.wide[3 * pos + 1] = um;
-            a.wide[3 * pos + 2] = WEIGHTED ? w : 1ull;
-        } else {
-            atomicOr(a.ctr + kCtrFlags, (unsigned long long)kFlagWide);
-        }
-    }
-}
-
-// One 128-record tile per warp (lane l owns records 4l..4l+3: three LDG.E.256), block-scheduled
-// like K1-K3.  Four independent atomics + stores per lane are in flight at a time.  The kernel is
-// bound by its 8-byte scattered stores (one L2 write transaction each: 10^8 of them take 2.0 ms on
-// B200 whatever the bucket count, tools/k4lab.cu), not by the atomics (1.1 ms at 2^17 cursors).
-template <bool WEIGHTED, bool COUNT_ONLY>
-__global__ void __launch_bounds__(kBlockThreads) k_scatter_keys(const ScatterArgs a) {
-    const uint32_t lane = threadIdx.x & 31u;
-    const uint64_t t = (uint64_t)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
-    const uint64_t n_tiles = a.n / 128;
-    if (t < n_tiles) {
-        const uint8_t *p = reinterpret_cast<const uint8_t *>(a.recs) + t * (128 * 24) + lane * 96;
-        const u64x4 v0 = ldg_stream256(p), v1 = ldg_stream256(p + 32), v2 = ldg_stream256(p + 64);
-        scatter_one<WEIGHTED, COUNT_ONLY>(a, v0.x, v0.y, v0.z);
-        scatter_one<WEIGHTED, COUNT_ONLY>(a, v0.w, v1.x, v1.y);
-        scatter_one<WEIGHTED, COUNT_ONLY>(a, v1.z, v1.w, v2.x);
-        scatter_one<WEIGHTED, COUNT_ONLY>(a, v2.y, v2.z, v2.w);
-    } else if (t == n_tiles) {  // ragged tail (< 128 records)
-        for (uint64_t i = n_tiles * 128 + lane; i < a.n; i += 32)
-            scatter_one<WEIGHTED, COUNT_ONLY>(a, a.recs[3 * i], a.recs[3 * i + 1], a.recs[3 * i + 2]);
-    }
-}
-
+// ------------------------------------------------------------------------------------ layout
 // bases[b] = sum of counts[0..b) for b in 0..n (one CTA; n <= 2^21 buckets)
 __global__ void __launch_bounds__(1024) k_bucket_bases(const uint32_t *__restrict__ counts, uint32_t n,
                                                        uint64_t *__restrict__ bases) {
@@ -268,164 +197,6 @@ struct DedupArgs {
     uint64_t pairs_cap;
 };
 
-// One CTA per bucket (block-strided over the buckets).  The table holds the bucket's DISTINCT keys
-// (load <= ~0.5 by construction); its slot index comes from the key bits just below the bucket
-// bits, which are as uniform as the bucket bits.
-template <bool WEIGHTED, bool PAIRS>
-__global__ void __launch_bounds__(kBlockThreads, 5) k_bucket_dedup(const DedupArgs a) {
-    using Cnt = typename std::conditional<WEIGHTED, unsigned long long, uint32_t>::type;
-    extern __shared__ __align__(16) unsigned long long smem[];
-    const uint32_t S = 1u << a.s_bits, smask = S - 1u;
-    unsigned long long *tkey = smem;
-    Cnt *tcnt = reinterpret_cast<Cnt *>(smem + S);
-    __shared__ uint32_t s_distinct, s_full;
-    const uint32_t lane = threadIdx.x & 31u;
-    const uint64_t umask = (1ull << a.ub) - 1ull;
-    const uint32_t hshift = 64 - a.pb - a.s_bits;
-    constexpr uint32_t kMaxProbe = 128;  // at the design load (<= 0.6) a probe sequence this long does not occur
-    constexpr uint32_t kBatch = 4 * kBlockThreads;
-
-    // the first kBatch keys of a bucket, one batch of loads per thread; issued one bucket ahead so
-    // that their latency (and the cursor's) hides behind the bucket being folded
-    auto fetch = [&](uint32_t b, uint32_t &cnt, uint64_t &first, uint64_t (&k)[4], uint64_t (&w)[4]) {
-        cnt = 0;
-        first = 0;
-        if (b < a.n_buckets) {
-            first = a.bases ? a.bases[b] : (uint64_t)b * a.cap;
-            cnt = min(a.cursors[b], a.bases ? (uint32_t)(a.bases[b + 1] - first) : a.cap);
-        }
-#pragma unroll
-        for (int q = 0; q < 4; q++) {
-            const uint32_t i = q * kBlockThreads + threadIdx.x;
-            k[q] = i < cnt ? ldg_stream64(a.keys + first + i) : kEmpty;
-            w[q] = (WEIGHTED && i < cnt) ? ldg_stream64(a.wts + first + i) : 1ull;
-        }
-    };
-    uint32_t fresh = 0;
-    auto insert = [&](uint64_t k, uint64_t w) {
-        if (k == kEmpty) return;
-        uint32_t slot = (uint32_t)(k >> hshift) & smask;
-        uint32_t probe = 0;
-        for (; probe < kMaxProbe; probe++, slot = (slot + 1) & smask) {
-            unsigned long long cur = *reinterpret_cast<volatile unsigned long long *>(tkey + slot);
-            if (cur != k) {
-                if (cur != kEmpty) continue;  // a slot never changes once claimed
-                cur = atomicCAS(tkey + slot, kEmpty, (unsigned long long)k);
-                if (cur == kEmpty) {
-                    fresh++;
-                    // unweighted: the counter holds the occurrences AFTER the first, so claiming a
-                    // slot is the only atomic of a new key and a repeat costs one add: one shared-
-                    // memory atomic per record (the unit's rate, ~0.5 per clock per SM, is what
-                    // bounds this kernel)
-                    if (!WEIGHTED) return;
-                } else if (cur != k) {
-                    continue;
-                }
-            }
-            atomicAdd(tcnt + slot, (Cnt)w);
-            return;
-        }
-        s_full = 1;  // (many) more distinct keys than the table was sized for
-    };
-
-    uint32_t cnt_n;
-    uint64_t first_n, kn[4], wn[4];
-    fetch(blockIdx.x, cnt_n, first_n, kn, wn);
-    for (uint32_t b = blockIdx.x; b < a.n_buckets; b += gridDim.x) {
-        const uint32_t cnt = cnt_n;
-        const uint64_t first = first_n;
-        uint64_t k[4], w[4];
-#pragma unroll
-        for (int q = 0; q < 4; q++) { k[q] = kn[q]; w[q] = wn[q]; }
-        fetch(b + gridDim.x, cnt_n, first_n, kn, wn);
-        for (uint32_t i = threadIdx.x; i < S; i += blockDim.x) {
-            tkey[i] = kEmpty;
-            tcnt[i] = 0;
-        }
-        if (threadIdx.x == 0) s_distinct = 0, s_full = 0;
-        __syncthreads();
-        fresh = 0;
-#pragma unroll
-        for (int q = 0; q < 4; q++) insert(k[q], w[q]);
-        for (uint32_t base = kBatch; base < cnt; base += kBatch) {  // long buckets (duplicate-heavy data)
-            if (*reinterpret_cast<volatile uint32_t *>(&s_full)) break;  // the call is void anyway: do not crawl a full table
-#pragma unroll
-            for (int q = 0; q < 4; q++) {
-                const uint32_t i = base + q * kBlockThreads + threadIdx.x;
-                k[q] = i < cnt ? ldg_stream64(a.keys + first + i) : kEmpty;
-                w[q] = (WEIGHTED && i < cnt) ? ldg_stream64(a.wts + first + i) : 1ull;
-            }
-#pragma unroll
-            for (int q = 0; q < 4; q++) insert(k[q], w[q]);
-        }
-        fresh = __reduce_add_sync(0xffffffffu, fresh);
-        if (lane == 0 && fresh) atomicAdd(&s_distinct, fresh);
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            if (s_distinct) atomicAdd(a.table.ctr + kCtrPairs, (unsigned long long)s_distinct);
-            if (s_full) atomicOr(a.table.ctr + kCtrFlags, (unsigned long long)kFlagSmem);
-        }
-        // every distinct pair of the bucket: one row (pair tables) or one add to its barcode's row
-        if (PAIRS) {
-            for (uint32_t base = 0; base < S; base += blockDim.x) {  // warp-uniform trip count
-                const uint32_t i = base + threadIdx.x;
-                const unsigned long long key = tkey[i];
-                const bool live = key != kEmpty;
-                const uint32_t m = __ballot_sync(0xffffffffu, live);
-                if (!m) continue;
-                unsigned long long pos = 0;
-                if (lane == 0) pos = atomicAdd(a.table.ctr + kCtrCursor, (unsigned long long)__popc(m));
-                pos = __shfl_sync(0xffffffffu, pos, 0) + __popc(m & ((1u << lane) - 1u));
-                if (live) {
-                    const uint64_t comp = unmix64(key);
-                    if (pos < a.pairs_cap) {
-                        a.pairs_out[3 * pos] = comp >> a.ub;
-                        a.pairs_out[3 * pos + 1] = comp & umask;
-                        a.pairs_out[3 * pos + 2] = (uint64_t)tcnt[i] + (WEIGHTED ? 0ull : 1ull);
-                    } else {
-                        atomicOr(a.table.ctr + kCtrFlags, (unsigned long long)kFlagPairsOut);
-                    }
-                }
-            }
-        } else {
-            // Four slots per thread at a time: the home slots of their barcodes are read from the
-            // global table together (independent loads in flight), then resolved — a dependent
-            // load per pair would expose its latency once per pair.
-            const uint32_t words = a.table.packed ? 2 : 4;
-#ifdef K4LAB_SKIP_TABLE  // tools/k4lab3.cu: the kernel without its global-table traffic
-            if (a.table.mask == 0)
-                for (uint32_t i = threadIdx.x; i < S; i += blockDim.x)
-                    if (tkey[i] != kEmpty && tcnt[i] == 0x7fffffff) atomicAdd(a.table.ctr + kCtrOnesRec, 1ull);
-            if (a.table.mask != 0)
-#endif
-            for (uint32_t base = 0; base < S; base += 4 * blockDim.x) {
-                uint64_t bc[4], seen[4];
-#pragma unroll
-                for (int q = 0; q < 4; q++) {
-                    const uint32_t i = base + q * blockDim.x + threadIdx.x;
-                    const unsigned long long key = i < S ? tkey[i] : kEmpty;
-                    bc[q] = kEmpty;
-                    if (key != kEmpty) bc[q] = unmix64(key) >> a.ub;  // (a narrow barcode is never all ones)
-                }
-#pragma unroll
-                for (int q = 0; q < 4; q++)
-                    seen[q] = bc[q] != kEmpty
-                                  ? *reinterpret_cast<volatile uint64_t *>(a.table.slots + words * (mix64(bc[q]) & a.table.mask))
-                                  : 0ull;
-#pragma unroll
-                for (int q = 0; q < 4; q++) {
-                    if (bc[q] == kEmpty) continue;
-                    const uint32_t i = base + q * blockDim.x + threadIdx.x;
-                    const uint64_t c = (uint64_t)tcnt[i] + (WEIGHTED ? 0ull : 1ull);
-                    if (seen[q] == bc[q]) table_hit(a.table, mix64(bc[q]) & a.table.mask, c, 1ull);  // the common case
-                    else table_add(a.table, bc[q], c, 1ull);
-                }
-            }
-        }
-        __syncthreads();
-    }
-}
-
 // (barcode, umi, multiplicity) rows from outside the buckets — the de-duplicated wide list and the
 // one special key — folded into the same table / pair output.
 struct ExtraArgs {
@@ -472,40 +243,6 @@ __global__ void __launch_bounds__(kBlockThreads) k_extra_pairs(const ExtraArgs a
             } else {
                 table_add(a.table, bc, w, 1ull);
             }
-        }
-    }
-}
-
-// occupied slots -> rows {barcode, n_records, n_distinct_umi}, order unspecified
-__global__ void __launch_bounds__(kBlockThreads)
-k_table_rows(const uint64_t *__restrict__ slots, uint64_t n_slots, uint32_t packed, uint64_t *__restrict__ rows,
-             unsigned long long *__restrict__ ctr) {
-    const uint32_t lane = threadIdx.x & 31u;
-    const uint64_t step = (uint64_t)gridDim.x * blockDim.x;
-    for (uint64_t base = (uint64_t)blockIdx.x * blockDim.x; base < n_slots; base += step) {  // warp-uniform trips
-        const uint64_t i = base + threadIdx.x;
-        uint64_t bc = kEmpty, nr = 0, nd = 0;
-        if (i < n_slots) {
-            if (packed) {
-                const ulonglong2 v = reinterpret_cast<const ulonglong2 *>(slots)[i];
-                bc = v.x;
-                nr = (v.y & ((1ull << kPackShift) - 1)) + 1ull;
-                nd = v.y >> kPackShift;
-            } else {
-                const u64x4 v = ldg_stream256(slots + 4 * i);
-                bc = v.x; nr = v.y + 1ull; nd = v.z + 1ull;
-            }
-        }
-        const bool live = bc != kEmpty;
-        const uint32_t m = __ballot_sync(0xffffffffu, live);
-        if (!m) continue;
-        unsigned long long pos = 0;
-        if (lane == 0) pos = atomicAdd(ctr + kCtrCursor, (unsigned long long)__popc(m));
-        pos = __shfl_sync(0xffffffffu, pos, 0) + __popc(m & ((1u << lane) - 1u));
-        if (live) {
-            rows[3 * pos] = bc;
-            rows[3 * pos + 1] = nr;
-            rows[3 * pos + 2] = nd;
         }
     }
 }

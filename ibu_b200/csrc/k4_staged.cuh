@@ -16,6 +16,9 @@ namespace k4p {
 constexpr int kPartTile = 4096;                      // keys per CTA tile
 constexpr int kPartKpt = kPartTile / kBlockThreads;  // 16 keys per thread
 constexpr int kPartMaxFan = 512;
+#ifndef K4_PART_MINB
+#define K4_PART_MINB 3  // resident CTAs per SM the partition kernels are compiled for (tools/k4lab3.cu sweeps it)
+#endif
 
 struct Part1Args {
     const uint64_t *recs;
@@ -54,7 +57,7 @@ __device__ __forceinline__ uint32_t block_excl_scan(uint32_t v, uint32_t *tmp, u
 
 // Level 1: records -> keys grouped by the top pb1 bits of the mixed key.
 template <bool WEIGHTED>
-__global__ void __launch_bounds__(kBlockThreads, WEIGHTED ? 2 : 3) k_part1(const Part1Args a) {
+__global__ void __launch_bounds__(kBlockThreads, WEIGHTED ? 2 : K4_PART_MINB) k_part1(const Part1Args a) {
     extern __shared__ __align__(16) unsigned long long stage[];  // [kPartTile] keys (+ [kPartTile] weights)
     __shared__ uint32_t hist[256], start[256], delta[256], tmp[8];
     const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
@@ -158,7 +161,7 @@ struct Part2Args {
 // A further level: the keys of one input bucket -> 2^pb output buckets each.  COUNT_ONLY: the
 // histogram of the exact layout (cursors_out[b] = keys of bucket b; nothing stored).
 template <bool WEIGHTED, bool COUNT_ONLY>
-__global__ void __launch_bounds__(kBlockThreads, WEIGHTED ? 2 : 3) k_part2(const Part2Args a) {
+__global__ void __launch_bounds__(kBlockThreads, WEIGHTED ? 2 : K4_PART_MINB) k_part2(const Part2Args a) {
     extern __shared__ __align__(16) unsigned long long stage[];
     __shared__ uint32_t hist[kPartMaxFan], start[kPartMaxFan], delta[kPartMaxFan], tmp[8];
     const uint32_t b1 = blockIdx.x / a.tiles_per_bucket;
@@ -262,7 +265,7 @@ __device__ __forceinline__ void table_add_from(const TableRef &t, uint64_t bc, u
     atomicOr(t.ctr + kCtrFlags, (unsigned long long)kFlagTable);
 }
 
-// k_bucket_dedup, second form.  ncu on the first form (profiles/r2_k4_dedup_v1_ncu.txt): 13.5 warp
+// k_bucket_dedup, second form.  ncu on the first form (profiles/r2_k4_dedup_v1_ncu_summary.json): 13.5 warp
 // instructions per key, almost half of them in the scan of the bucket's table for live slots — at
 // 5x duplication 7 % of the slots are live, so every warp instruction of the scan (two 64-bit
 // multiplies to unmix a key, two more to hash its barcode) ran for one or two lanes.  Here a thread
@@ -410,6 +413,53 @@ __global__ void __launch_bounds__(kBlockThreads, 5) k_bucket_dedup2(const DedupA
     if (threadIdx.x == 0) {
         if (my_pairs) atomicAdd(a.table.ctr + kCtrPairs, (unsigned long long)my_pairs);
         if (s_full) atomicOr(a.table.ctr + kCtrFlags, (unsigned long long)kFlagSmem);
+    }
+}
+
+// occupied slots -> rows {barcode, n_records, n_distinct_umi}, order unspecified.  A CTA takes 1024
+// slots at a time and reserves its rows with ONE atomicAdd (a warp-level reservation is 262 144
+// same-address atomics for an 8 Mi-slot table: 0.2 ms of serialised atomics around 0.03 ms of reads).
+__global__ void __launch_bounds__(kBlockThreads)
+k_table_rows(const uint64_t *__restrict__ slots, uint64_t n_slots, uint32_t packed, uint64_t *__restrict__ rows,
+             unsigned long long *__restrict__ ctr) {
+    __shared__ uint32_t tmp[2][8];
+    __shared__ unsigned long long s_pos[2];
+    uint32_t par = 0;
+    for (uint64_t base = (uint64_t)blockIdx.x * 1024; base < n_slots; base += (uint64_t)gridDim.x * 1024, par ^= 1u) {
+        uint64_t bc[4], nr[4], nd[4];
+        uint32_t live = 0;
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            const uint64_t i = base + q * kBlockThreads + threadIdx.x;
+            bc[q] = kEmpty;
+            if (i < n_slots) {
+                if (packed) {
+                    ulonglong2 v;
+                    asm("ld.global.nc.L1::no_allocate.v2.u64 {%0,%1}, [%2];" : "=l"(v.x), "=l"(v.y) : "l"(slots + 2 * i));
+                    bc[q] = v.x;
+                    nr[q] = (v.y & ((1ull << kPackShift) - 1)) + 1ull;
+                    nd[q] = v.y >> kPackShift;
+                } else {
+                    const u64x4 v = ldg_stream256(slots + 4 * i);
+                    bc[q] = v.x; nr[q] = v.y + 1ull; nd[q] = v.z + 1ull;
+                }
+            }
+            live += bc[q] != kEmpty;
+        }
+        uint32_t total;
+        uint32_t at = block_excl_scan(live, tmp[par], total);  // (alternating scratch: one barrier per round suffices)
+        if (threadIdx.x == 0 && total) s_pos[par] = atomicAdd(ctr + kCtrCursor, (unsigned long long)total);
+        if (total == 0) continue;
+        __syncthreads();
+        uint64_t pos = s_pos[par] + at;
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            if (bc[q] == kEmpty) continue;
+            rows[3 * pos] = bc[q];
+            rows[3 * pos + 1] = nr[q];
+            rows[3 * pos + 2] = nd[q];
+            pos++;
+        }
     }
 }
 

@@ -531,7 +531,12 @@ int ibu::process_records_ops(ibu_gpu_ctx *ctx, const ibu_record_t *h_records, ui
                 // (sorted-looking input: the streaming pass over the resident records at the end is the fast path)
                 if ((saw_unordered || mode == 2) && mode != 1 && hints.force_path != kPathLegacy && hints.force_path != kPathSort &&
                     (n >= (1u << 16) || hints.force_path == kPathPartition))
-                    if (int r = k4_job_begin(ctx, n, hints, smp, pair_rows, false, ctx->stream, &job, err)) return r;
+                {
+                    K4Chunking ch;
+                    ch.chunk_records = chunk;  // a staged chunk is one piece
+                    ch.n_streams = (uint32_t)ctx->slots.size();
+                    if (int r = k4_job_begin(ctx, n, hints, smp, pair_rows, false, ch, ctx->stream, &job, err)) return r;
+                }
             }
             if (job) {
                 IBU_CUDA(cudaStreamWaitEvent(slot.stream, k4_job_ready(job), 0));

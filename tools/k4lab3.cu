@@ -1,6 +1,8 @@
 // k4lab3.cu — the K4 partition path stage by stage, on the shipped kernels (k4_partition.cuh):
-// one-level scatter (k_scatter_keys) against the staged two-level partition (k_part1 + k_part2),
-// then k_bucket_dedup on either layout.  Checks that both layouts hold the same keys per bucket.
+// the staged two-level partition (k_part1 + k_part2) checked against a naive one-level scatter
+// (same keys in every bucket), then k_bucket_dedup2.  K4_PART_MINB / K4LAB_CARVEOUT sweep occupancy.
+// (The first forms of the path — one-level k_scatter_keys, table-scanning k_bucket_dedup — were
+// measured with this tool before they were removed: profiles/r2_k4lab3_*.jsonl.)
 //   nvcc -O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -lineinfo -I ibu_b200/csrc -o tools/k4lab3 tools/k4lab3.cu
 #include <algorithm>
 #include <cstdint>
@@ -35,6 +37,16 @@ __global__ void k_gen(uint64_t *recs, uint64_t n, uint64_t nb, uint64_t us, int 
             recs[3 * i + 1] = mix64((r >> 32) ^ 77) % us;
         }
         recs[3 * i + 2] = i;
+    }
+}
+
+// naive one-level scatter: the reference layout for the check (and the cost of 8-byte scattered stores)
+__global__ void k_naive_scatter(const uint64_t *recs, uint64_t n, uint32_t ub, uint32_t pb, uint32_t cap, uint32_t *cursors, uint64_t *keys) {
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+        const uint64_t k = mix64((recs[3 * i] << ub) | recs[3 * i + 1]);
+        const uint32_t b = (uint32_t)(k >> (64 - pb));
+        const uint32_t pos = atomicAdd(cursors + b, 1u);
+        if (pos < cap) keys[(uint64_t)b * cap + pos] = k;
     }
 }
 
@@ -96,15 +108,17 @@ int main(int argc, char **argv) {
     Timer tm;
     CK(cudaFuncSetAttribute(k_part1<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kPartTile * 8));
     CK(cudaFuncSetAttribute(k_part2<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kPartTile * 8));
-    CK(cudaFuncSetAttribute(k_bucket_dedup<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8192 * 16));
     CK(cudaFuncSetAttribute(k_bucket_dedup2<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8192 * 18));
+    if (getenv("K4LAB_CARVEOUT")) {
+        CK(cudaFuncSetAttribute(k_part1<false>, cudaFuncAttributePreferredSharedMemoryCarveout, atoi(getenv("K4LAB_CARVEOUT"))));
+        CK(cudaFuncSetAttribute(k_part2<false, false>, cudaFuncAttributePreferredSharedMemoryCarveout, atoi(getenv("K4LAB_CARVEOUT"))));
+    }
     float t_old = 1e9, t_p1 = 1e9, t_p2 = 1e9;
     for (int it = 0; it < 4; it++) {
         CK(cudaMemset(curA, 0, P * 4));
         CK(cudaMemset(ctr, 0, kCtrWords * 8));
-        ScatterArgs sa{recs, n, bb, ub, pb, cap, nullptr, curA, keysA, nullptr, wide, 1000, ctr};
         tm.start();
-        k_scatter_keys<false, false><<<(unsigned)((n / 128 + 1 + 7) / 8), 256>>>(sa);
+        k_naive_scatter<<<148 * 16, 256>>>(recs, n, ub, pb, cap, curA, keysA);
         t_old = std::min(t_old, tm.stop());
         CK(cudaMemset(curB, 0, P * 4));
         CK(cudaMemset(cur1, 0, 4 << pb1));
@@ -112,9 +126,9 @@ int main(int argc, char **argv) {
         tm.start();
         k_part1<false><<<(unsigned)((n + kPartTile - 1) / kPartTile), 256, kPartTile * 8>>>(a1);
         t_p1 = std::min(t_p1, tm.stop());
-        Part2Args a2{cur1, keys1, nullptr, cap1, pb1, pb2, cap, nullptr, curB, keysB, nullptr, ctr};
+        Part2Args a2{cur1, keys1, nullptr, cap1, (uint32_t)((cap1 + kPartTile - 1) / kPartTile), pb1, pb2, cap, nullptr, curB, keysB, nullptr, ctr, (uint32_t)kFlagBucket};
         tm.start();
-        k_part2<false, false><<<dim3((unsigned)((cap1 + kPartTile - 1) / kPartTile), 1u << pb1), 256, kPartTile * 8>>>(a2);
+        k_part2<false, false><<<a2.tiles_per_bucket << pb1, 256, kPartTile * 8>>>(a2);
         t_p2 = std::min(t_p2, tm.stop());
     }
     CK(cudaGetLastError());
@@ -137,17 +151,16 @@ int main(int argc, char **argv) {
             CK(cudaMemset(ctr, 0, kCtrWords * 8));
             DedupArgs d{curB, nullptr, keysB, nullptr, (uint32_t)P, cap, pb, ub, pattern ? 12u : 11u,
                         TableRef{slots, skip_table ? 0 : t_slots - 1, ctr, 1u}, nullptr, 0};
-            const size_t smem = ((size_t)1 << d.s_bits) * (which ? 14 : 12);
+            const size_t smem = ((size_t)1 << d.s_bits) * 14;
             tm.start();
-            if (which) k_bucket_dedup2<false, false><<<148 * dd_ctas, 256, smem>>>(d);
-            else k_bucket_dedup<false, false><<<148 * dd_ctas, 256, smem>>>(d);
+            k_bucket_dedup2<false, false><<<148 * dd_ctas, 256, smem>>>(d);
             t_dd[which] = std::min(t_dd[which], tm.stop());
             CK(cudaMemcpy(h_ctr, ctr, sizeof(h_ctr), cudaMemcpyDeviceToHost));
             pairs[which] = h_ctr[kCtrPairs];
             rows[which] = h_ctr[kCtrClaimed];
         }
-    printf("{\"records\": %llu, \"pattern\": %d, \"umi_space\": %llu, \"scatter_one_level_ms\": %.3f, \"part1_ms\": %.3f, \"part2_ms\": %.3f, "
-           "\"keys\": %llu, \"max_bucket\": %llu, \"same_buckets\": %s, \"flags\": %llu, \"dedup_v1_v2_ms\": [%.3f, %.3f], "
+    printf("{\"records\": %llu, \"pattern\": %d, \"umi_space\": %llu, \"naive_scatter_ms\": %.3f, \"part1_ms\": %.3f, \"part2_ms\": %.3f, "
+           "\"keys\": %llu, \"max_bucket\": %llu, \"same_buckets\": %s, \"flags\": %llu, \"dedup2_ms\": [%.3f, %.3f], "
            "\"pairs\": [%llu, %llu], \"rows\": [%llu, %llu], \"table_slots\": %llu, \"skip_table\": %d, \"dedup_ctas\": %d}\n",
            (unsigned long long)n, pattern, (unsigned long long)umi_space, t_old, t_p1, t_p2, (unsigned long long)total,
            (unsigned long long)maxc, same ? "true" : "false", h_ctr[kCtrFlags], t_dd[0], t_dd[1], pairs[0], pairs[1], rows[0], rows[1], (unsigned long long)t_slots, skip_table, dd_ctas);
