@@ -618,6 +618,108 @@ __global__ void __launch_bounds__(kBlockThreads, MINB) k_pack(const PackArgs a) 
     }
 }
 
+// Runtime lengths on both inputs (no compile-time shape): the packing itself is ~1000 warp
+// instructions per 128-row tile, as long as the tile's loads take to arrive, and with ONE tile per
+// warp nothing is in flight while a warp packs (ncu: issue slots 47 % busy, 7.5 warps per issue
+// waiting on the long scoreboard).  Here a warp walks kTpw consecutive tiles and keeps the next
+// tile's rows arriving in a second stage (cp.async: global -> shared without registers) while it
+// packs the current one; the record tile overlays the stage it was packed from.
+constexpr int kPackRtTpw = 4;
+__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gsrc) {
+    const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gsrc) : "memory");
+}
+template <int Q, int MINB>
+__global__ void __launch_bounds__(kBlockThreads, MINB) k_pack_rt(const PackArgs a) {
+    constexpr int kRows = 32 * Q;
+    extern __shared__ __align__(16) uint8_t smem[];
+    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    uint8_t *wsm = smem + warp * (2 * a.warp_smem_bytes);  // two stages per warp
+    const uint32_t bc_len = a.bc_len, umi_len = a.umi_len;
+    const uint32_t n16_bc = 2 * Q * bc_len, n16_umi = 2 * Q * umi_len;  // 16-byte pieces per tile
+    uint32_t n_bb = 0, n_bu = 0, n_br = 0;
+    const uint64_t n_tiles = a.n / kRows;
+    const uint64_t t0 = ((uint64_t)blockIdx.x * kWarpsPerBlock + warp) * kPackRtTpw;
+    auto prefetch = [&](uint64_t t, uint32_t buf) {
+        if (t < n_tiles) {
+            uint8_t *st = wsm + buf * a.warp_smem_bytes;
+            const uint4 *sb = reinterpret_cast<const uint4 *>(a.bc_in) + t * n16_bc;
+            const uint4 *su = reinterpret_cast<const uint4 *>(a.umi_in) + t * n16_umi;
+#pragma unroll
+            for (int k = 0; k < 2 * Q; k++) {
+                const uint32_t i = lane + 32 * k;
+                if (i < n16_bc) cp_async16(st + a.bc_stage_off + 16 * i, sb + i);
+                if (i < n16_umi) cp_async16(st + a.umi_stage_off + 16 * i, su + i);
+            }
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    prefetch(t0, 0);
+#pragma unroll 1
+    for (int it = 0; it < kPackRtTpw; it++) {
+        const uint64_t t = t0 + it;
+        const uint32_t buf = it & 1;
+        prefetch(t + 1 < t0 + kPackRtTpw ? t + 1 : n_tiles, buf ^ 1u);  // (an empty group past the last tile)
+        asm volatile("cp.async.wait_group 1;" ::: "memory");
+        __syncwarp();
+        if (t >= n_tiles) break;
+        uint8_t *st = wsm + buf * a.warp_smem_bytes;
+        uint64_t bcw[Q], umw[Q];
+        uint32_t bcbad = 0, umbad = 0;
+        pack_tile_rt<Q>(bc_len, st + a.bc_stage_off, lane, bcw, bcbad);
+        pack_tile_rt<Q>(umi_len, st + a.umi_stage_off, lane, umw, umbad);
+        __syncwarp();  // every staged row has been read: the record tile may overlay the stage
+        uint64_t *out64 = reinterpret_cast<uint64_t *>(st);
+#pragma unroll
+        for (int q = 0; q < Q; q++) {
+            const uint32_t r = lane + 32 * q;
+            const uint64_t row = t * kRows + r;
+            const uint32_t bb = (bcbad >> q) & 1u, bu = (umbad >> q) & 1u;
+            const uint64_t idx = a.index ? ldg_stream64(a.index + row) : a.index_base + row;
+            out64[3 * r] = bcw[q]; out64[3 * r + 1] = umw[q]; out64[3 * r + 2] = idx;
+            n_bb += bb; n_bu += bu; n_br += (bb | bu);
+            if (a.flags) a.flags[row] = (uint8_t)(bb | (bu << 1));
+        }
+        __syncwarp();
+        const uint4 *out4 = reinterpret_cast<const uint4 *>(st);
+        uint4 *dst = reinterpret_cast<uint4 *>(a.recs_out) + t * (kRows * 24 / 16);
+#pragma unroll
+        for (int k = 0; k < 3 * Q / 2; k++) stg_stream(dst + lane + 32 * k, out4[lane + 32 * k]);
+        __syncwarp();  // the stores have read the stage before the next prefetch lands in it
+    }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    // ragged tail (< kRows rows): the warp that would own tile n_tiles
+    if (t0 <= n_tiles && n_tiles < t0 + kPackRtTpw) {
+        uint64_t *o64 = reinterpret_cast<uint64_t *>(a.recs_out);
+        for (uint64_t row = n_tiles * kRows + lane; row < a.n; row += 32) {
+            uint64_t w[2];
+            uint32_t bad[2];
+            for (int s = 0; s < 2; s++) {
+                const uint8_t *p = s ? a.umi_in + row * umi_len : a.bc_in + row * bc_len;
+                const uint32_t len = s ? umi_len : bc_len;
+                uint64_t acc = 0;
+                uint32_t b = 0;
+                for (uint32_t i = 0; i < len; i++) {
+                    const uint32_t ch = p[i], c1 = (ch >> 1) & 3u, up = ch & 0xDFu;
+                    acc |= (uint64_t)(c1 ^ (c1 >> 1)) << (2 * i);
+                    b |= !(up == 0x41u || up == 0x43u || up == 0x47u || up == 0x54u);
+                }
+                w[s] = acc;
+                bad[s] = b;
+            }
+            o64[3 * row] = w[0]; o64[3 * row + 1] = w[1];
+            o64[3 * row + 2] = a.index ? a.index[row] : a.index_base + row;
+            n_bb += bad[0]; n_bu += bad[1]; n_br += (bad[0] | bad[1]);
+            if (a.flags) a.flags[row] = (uint8_t)(bad[0] | (bad[1] << 1));
+        }
+    }
+    if (a.res_blocks) {
+        const uint64_t c_bb = __reduce_add_sync(0xffffffffu, n_bb), c_bu = __reduce_add_sync(0xffffffffu, n_bu),
+                       c_br = __reduce_add_sync(0xffffffffu, n_br);
+        if (c_br) red_spread(a.res_blocks, blockIdx.x * kWarpsPerBlock + warp, lane, 0, 0, 0, 0, c_bb, c_bu, c_br);
+    }
+}
+
 // ============================================================================ generators
 __device__ __forceinline__ uint64_t low_mask_dev(uint32_t len) {
     return len >= 32 ? ~0ull : ((1ull << (2 * len)) - 1);
@@ -786,8 +888,43 @@ static int launch_pack_q(ibu_gpu_ctx *ctx, PackArgs &a, cudaStream_t s, ibu_erro
 // or equal for every shape on 10^8 rows — bc32/umi32 7.07 TB/s, bc16/umi12 6.93, bc16/umi16 6.91,
 // bc16/umi10 6.92 (2 rows per lane with the compiler's default allocation: 6.91 / 6.39 / 6.75 /
 // 6.19; profiles/r1_k3_variants.txt).
+// both lengths at run time: the prefetching kernel when two stages per warp still leave room for 4 CTAs
+static int launch_pack_rt(ibu_gpu_ctx *ctx, PackArgs &a, cudaStream_t s, bool *done, ibu_error_t *err) {
+    constexpr int Q = 4;
+    constexpr uint32_t kRows = 32 * Q;
+    *done = false;
+    static const char *env = getenv("IBU_B200_K3_RT");  // 0 = the one-tile-per-warp kernel (tuning)
+    if (env && env[0] == '0') return IBU_OK;
+    uint32_t off = 0;
+    a.bc_stage_off = off;
+    off += ((kRows * a.bc_len + 15u) & ~15u) + 16u;  // +16: funnel-shift over-read
+    a.umi_stage_off = off;
+    off += ((kRows * a.umi_len + 15u) & ~15u) + 16u;
+    if (off < kRows * 24) off = kRows * 24;
+    const size_t smem = (size_t)2 * off * kWarpsPerBlock;
+    if (smem > (56u << 10)) return IBU_OK;
+    a.warp_smem_bytes = off;
+    auto kern = k_pack_rt<Q, 4>;
+    if (int rc = set_carveout((const void *)kern, -1, err)) return rc;
+    static std::once_flag once;  // (the attribute is per function: set to the largest request once)
+    std::call_once(once, [&] { cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 56 << 10); });
+    const uint64_t tiles = a.n / kRows + 1;  // (+1: the warp that owns the ragged tail)
+    const uint64_t warps = (tiles + kPackRtTpw - 1) / kPackRtTpw;
+    const unsigned grid = (unsigned)std::max<uint64_t>(1, (warps + kWarpsPerBlock - 1) / kWarpsPerBlock);
+    kern<<<grid, kBlockThreads, smem, s>>>(a);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    IBU_CUDA(cudaGetLastError());
+    *done = true;
+    return IBU_OK;
+}
+
 template <int BC, int UMI>
 static int launch_pack(ibu_gpu_ctx *ctx, PackArgs &a, cudaStream_t s, ibu_error_t *err) {
+    if constexpr (BC == 0 && UMI == 0) {
+        bool done = false;
+        if (int rc = launch_pack_rt(ctx, a, s, &done, err)) return rc;
+        if (done) return IBU_OK;
+    }
     // (a 32-byte row next to a runtime-length one needs a few more registers: 3 resident CTAs)
     constexpr int kMinB = ((BC == 0 && UMI == 32) || (BC == 32 && UMI == 0)) ? 3 : 4;
     return launch_pack_q<BC, UMI, 4, kMinB>(ctx, a, s, err);

@@ -484,6 +484,38 @@ int ibu::process_records_ops(ibu_gpu_ctx *ctx, const ibu_record_t *h_records, ui
         start = c * chunk;
         cnt = std::min(chunk, n - start);
     };
+    // What the records look like decides how the table is built (and sizes its buckets); `d` holds
+    // `cnt` records on the device once stream `s` gets there.
+    auto decide = [&](const uint64_t *d, uint64_t cnt, cudaStream_t s) -> int {
+        job_tried = true;
+        arena_lock.lock();
+        K4Sample smp;
+        if (int r = k4_sample(ctx, d, cnt, s, &smp, err)) return r;
+        saw_unordered = smp.unordered != 0;
+        const int mode = req->table_mode & 7;
+        // (sorted-looking input: the streaming pass over the resident records at the end is the fast path)
+        if ((saw_unordered || mode == 2) && mode != 1 && hints.force_path != kPathLegacy && hints.force_path != kPathSort &&
+            (n >= (1u << 16) || hints.force_path == kPathPartition)) {
+            K4Chunking ch;
+            ch.chunk_records = chunk;  // a staged chunk is one piece
+            ch.n_streams = (uint32_t)ctx->slots.size();
+            if (int r = k4_job_begin(ctx, n, hints, smp, pair_rows, false, ch, ctx->stream, &job, err)) return r;
+        }
+        return IBU_OK;
+    };
+    if (want_table && n_chunks > 1) {
+        // The head of the range goes ahead of the pipeline (6 MB) and is sampled, so that no chunk has
+        // to wait on the host for the decision (sampling the first chunk blocked the staging thread
+        // for that chunk's whole H2D, ~2 ms).  Chunk 0 writes the same bytes again.
+        const uint64_t head = std::min<uint64_t>(n, 1u << 18);
+        IBU_CUDA(cudaMemcpyAsync(d_all, h_records, head * IBU_RECORD_SIZE, cudaMemcpyHostToDevice, ctx->stream));
+        if (int r = decide(reinterpret_cast<const uint64_t *>(d_all), head, ctx->stream)) {
+            if (arena_lock.owns_lock()) arena_lock.unlock();
+            if (cudaFreeAsync(d_all, ctx->stream) != cudaSuccess) cudaGetLastError();
+            return r;
+        }
+        mark("head sample");
+    }
     int rc = run_chunks(
         ctx, n_chunks,
         [&](uint64_t c) {
@@ -521,23 +553,8 @@ int ibu::process_records_ops(ibu_gpu_ctx *ctx, const ibu_record_t *h_records, ui
                 return r;
             }
             if (!want_table) return IBU_OK;
-            if (!job_tried) {  // the first chunk decides: what it looks like sizes the table's buckets
-                job_tried = true;
-                arena_lock.lock();
-                K4Sample smp;
-                if (int r = k4_sample(ctx, reinterpret_cast<const uint64_t *>(d_chunk), cnt, slot.stream, &smp, err)) return r;
-                saw_unordered = smp.unordered != 0;
-                const int mode = req->table_mode & 7;
-                // (sorted-looking input: the streaming pass over the resident records at the end is the fast path)
-                if ((saw_unordered || mode == 2) && mode != 1 && hints.force_path != kPathLegacy && hints.force_path != kPathSort &&
-                    (n >= (1u << 16) || hints.force_path == kPathPartition))
-                {
-                    K4Chunking ch;
-                    ch.chunk_records = chunk;  // a staged chunk is one piece
-                    ch.n_streams = (uint32_t)ctx->slots.size();
-                    if (int r = k4_job_begin(ctx, n, hints, smp, pair_rows, false, ch, ctx->stream, &job, err)) return r;
-                }
-            }
+            if (!job_tried)  // a single chunk: it is the sample
+                if (int r = decide(reinterpret_cast<const uint64_t *>(d_chunk), cnt, slot.stream)) return r;
             if (job) {
                 IBU_CUDA(cudaStreamWaitEvent(slot.stream, k4_job_ready(job), 0));
                 return k4_job_add(job, reinterpret_cast<const uint64_t *>(d_chunk), cnt, slot.stream, err);

@@ -312,6 +312,63 @@ def test_full_size_roundtrip(ctx, bc, umi, n):
         x.free()
 
 
+def _d2h_slab(ctx, dptr, first, count, width, dtype=np.uint8):
+    out = np.empty((count, width) if width else count, dtype)
+    ctx.d2h(out, dptr + first * out.dtype.itemsize * (width or 1))
+    return out
+
+
+def test_full_size_unpack_every_byte_against_the_oracle(ctx):
+    """configs[1], whole arrays: the 10^8 x 16 barcode bytes, 10^8 x 12 umi bytes, 10^8 flag bytes and the
+    8-word result of ONE K2 launch over 10^8 dirty records equal the oracle's, slab by slab (the
+    oracle regenerates the same records from the shared counter-based generator)."""
+    n, bc, umi, slab = 100_000_000, 16, 12, 20_000_000
+    recs, b, u, f, res = (Dev(ctx, s) for s in (24 * n, bc * n, umi * n, n, 64))
+    ctx.generate_records_async(recs, 0, n, bc, umi, ibu.GEN_DIRTY, 10_000, 2024)
+    ctx.unpack_async(recs, n, bc, umi, b, u, f, res)
+    ctx.synchronize()
+    got = ctx.read_result(res.ptr)
+    total = dict.fromkeys(got, 0)
+    for first in range(0, n, slab):
+        want = oc.generate_records(first, slab, bc, umi, 1, 10_000, 2024)
+        assert np.array_equal(_d2h_slab(ctx, recs.ptr, first, slab, 0, ibu.RECORD_DTYPE), want), first
+        ob, ou, of, ucnt = oc.unpack_records(want, bc, umi, 0)
+        ored = oc.reduce_records(want, bc, umi)  # (the oracle's unpack carries the counters only)
+        assert all(ucnt[k] == ored[k] for k in ("n_records", "n_bad_barcode", "n_bad_umi", "n_bad_records"))
+        assert np.array_equal(_d2h_slab(ctx, b.ptr, first, slab, bc), ob), first
+        assert np.array_equal(_d2h_slab(ctx, u.ptr, first, slab, umi), ou), first
+        assert np.array_equal(_d2h_slab(ctx, f.ptr, first, slab, 0), of), first
+        for k in total:
+            total[k] = (total[k] ^ ored[k]) if k == "xor_all" else (total[k] + ored[k]) % (1 << 64)
+    assert got == total
+    for x in (recs, b, u, f, res):
+        x.free()
+
+
+def test_full_size_pack_every_record_against_the_oracle(ctx):
+    """configs[2], whole array: 10^8 ASCII pairs bc32/umi32 (1 % of the rows carry an 'N', some lower
+    case) -> Records; every record, every flag byte and the result equal the oracle's."""
+    n, bc, umi, slab = 100_000_000, 32, 32, 20_000_000
+    b, u, out, f, res = (Dev(ctx, s) for s in (bc * n, umi * n, 24 * n, n, 64))
+    ctx.generate_ascii_async(b, 0, n, bc, 300, 50_000, 5)
+    ctx.generate_ascii_async(u, 0, n, umi, 300, 50_000, 6)
+    ctx.pack_async(b, u, n, bc, umi, out, d_flags=f, d_result=res, index_base=7)
+    ctx.synchronize()
+    got = ctx.read_result(res.ptr)
+    total = dict.fromkeys(got, 0)
+    for first in range(0, n, slab):
+        hb, hu = oc.generate_ascii(first, slab, bc, 300, 50_000, 5), oc.generate_ascii(first, slab, umi, 300, 50_000, 6)
+        want, wflags, wred = oc.pack_records(hb, hu, None, 7 + first)
+        assert np.array_equal(_d2h_slab(ctx, out.ptr, first, slab, 0, ibu.RECORD_DTYPE), want), first
+        assert np.array_equal(_d2h_slab(ctx, f.ptr, first, slab, 0), wflags), first
+        for k in ("n_records", "n_bad_barcode", "n_bad_umi", "n_bad_records"):
+            total[k] += wred[k]
+    assert all(got[k] == total[k] for k in ("n_records", "n_bad_barcode", "n_bad_umi", "n_bad_records"))
+    assert 0.005 * n < got["n_bad_records"] < 0.03 * n
+    for x in (b, u, out, f, res):
+        x.free()
+
+
 # ---- K4: per-barcode table --------------------------------------------------------------------
 def gpu_table(ctx, recs, mode=0):
     d = Dev(ctx, recs.nbytes, recs)
