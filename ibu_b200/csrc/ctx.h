@@ -42,6 +42,9 @@ struct ibu_gpu_ctx {
     std::array<ibu_result_scratch, kResultRing> result_ring;
     std::atomic<uint32_t> result_next{0};
     std::mutex pipe_mutex;  // the chunk slots serve one host-buffer call at a time
+    // the streaming ingest that owns the slots between its open and close (guarded by pipe_mutex, which
+    // is NOT held across calls: a stream may be closed from another thread, or after the context)
+    struct ibu_gpu_stream *open_stream = nullptr;
     std::mutex arena_mutex;
     void *arena_base = nullptr;
     size_t arena_cap = 0, arena_off = 0;

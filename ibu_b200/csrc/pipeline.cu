@@ -370,6 +370,7 @@ int process_host_records(ibu_gpu_ctx *ctx, const ibu_record_t *h_records, uint64
                          uint64_t file_off = 0) {
     DeviceGuard guard(ctx->device);
     std::lock_guard<std::mutex> lock(ctx->pipe_mutex);
+    if (ctx->open_stream) return set_error(err, IBU_ERR_ARG, 0, 0, 0, "context busy: a streaming ingest is open on it");
     memset(h_result, 0, sizeof(*h_result));
     if (n == 0) return IBU_OK;  // an empty range never calls on_batch_complete (mmap.rs:502-519)
     const uint64_t chunk = chunk_records(ctx);
@@ -440,6 +441,7 @@ int ibu::process_records_ops(ibu_gpu_ctx *ctx, const ibu_record_t *h_records, ui
         return process_host_records(ctx, h_records, n, bc_len, umi_len, first_record, h_result, on_chunk, user, err, fd, file_off);
     DeviceGuard guard(ctx->device);
     std::lock_guard<std::mutex> lock(ctx->pipe_mutex);
+    if (ctx->open_stream) return set_error(err, IBU_ERR_ARG, 0, 0, 0, "context busy: a streaming ingest is open on it");
     memset(h_result, 0, sizeof(*h_result));
     if (want_table && req->table) {
         req->table->n_records = n;
@@ -669,9 +671,16 @@ int ibu_gpu_ctx_create(int device, const ibu_gpu_config_t *cfg, ibu_gpu_ctx_t **
     return IBU_OK;
 }
 
+__attribute__((visibility("hidden"))) void ibu_stream_detach(struct ibu_gpu_stream *st);  // (defined with the stream, below)
+
 void ibu_gpu_ctx_destroy(ibu_gpu_ctx_t *ctx) {
     if (!ctx) return;
     DeviceGuard guard(ctx->device);
+    {   // a stream that is still open is detached: its later calls fail, its close only frees it
+        std::lock_guard<std::mutex> lock(ctx->pipe_mutex);
+        if (ctx->open_stream) ibu_stream_detach(ctx->open_stream);
+        ctx->open_stream = nullptr;
+    }
     for (auto &s : ctx->slots) {
         if (s.stream) {
             cudaStreamSynchronize(s.stream);
@@ -946,7 +955,6 @@ int ibu_gpu_process_mmap_ops(ibu_gpu_ctx_t *ctx, const ibu_mmap_reader_t *reader
 
 struct ibu_gpu_stream {
     ibu_gpu_ctx *ctx = nullptr;
-    std::unique_lock<std::mutex> lock;  // the context's slots are ours until close
     uint8_t header_bytes[IBU_HEADER_SIZE];
     size_t header_have = 0;
     ibu_header_t header{};
@@ -957,6 +965,8 @@ struct ibu_gpu_stream {
     ibu_reduce_result_t total{};
     bool failed = false;
 };
+
+void ibu_stream_detach(ibu_gpu_stream *st) { st->ctx = nullptr; }
 
 namespace {
 
@@ -1005,12 +1015,11 @@ int ibu_gpu_stream_open(ibu_gpu_ctx_t *ctx, ibu_gpu_stream_t **out, ibu_error_t 
     if (!ctx || !out) return set_error(err, IBU_ERR_ARG, 0, 0, 0, "null argument");
     *out = nullptr;
     std::unique_lock<std::mutex> lock(ctx->pipe_mutex, std::try_to_lock);
-    if (!lock.owns_lock())
+    if (!lock.owns_lock() || ctx->open_stream)
         return set_error(err, IBU_ERR_ARG, 0, 0, 0, "context busy: another stream or host-buffer call is active");
     auto *st = new (std::nothrow) ibu_gpu_stream;
     if (!st) return set_error(err, IBU_ERR_NOMEM, 0, 0, 0, "out of memory");
     st->ctx = ctx;
-    st->lock = std::move(lock);
     st->chunk_bytes = chunk_records(ctx) * IBU_RECORD_SIZE;
     st->busy.assign(ctx->slots.size(), 0);
     DeviceGuard guard(ctx->device);
@@ -1019,6 +1028,7 @@ int ibu_gpu_stream_open(ibu_gpu_ctx_t *ctx, ibu_gpu_stream_t **out, ibu_error_t 
         delete st;
         return rc;
     }
+    ctx->open_stream = st;  // the slots are this stream's until close (or until the context goes)
     *out = st;
     return IBU_OK;
 }
@@ -1026,6 +1036,7 @@ int ibu_gpu_stream_open(ibu_gpu_ctx_t *ctx, ibu_gpu_stream_t **out, ibu_error_t 
 int ibu_gpu_stream_push(ibu_gpu_stream_t *st, const void *bytes, size_t len, ibu_error_t *err) {
     clear_error(err);
     if (!st || (!bytes && len)) return set_error(err, IBU_ERR_ARG, 0, 0, 0, "null argument");
+    if (!st->ctx) return set_error(err, IBU_ERR_ARG, 0, 0, 0, "the stream's context has been destroyed");
     if (st->failed) return set_error(err, IBU_ERR_ARG, 0, 0, 0, "stream already failed");
     DeviceGuard guard(st->ctx->device);
     const uint8_t *p = (const uint8_t *)bytes;
@@ -1073,6 +1084,7 @@ int ibu_gpu_stream_finish(ibu_gpu_stream_t *st, ibu_reduce_result_t *h_result, i
     clear_error(err);
     if (!st || !h_result) return set_error(err, IBU_ERR_ARG, 0, 0, 0, "null argument");
     memset(h_result, 0, sizeof(*h_result));
+    if (!st->ctx) return set_error(err, IBU_ERR_ARG, 0, 0, 0, "the stream's context has been destroyed");
     if (st->failed) return set_error(err, IBU_ERR_ARG, 0, 0, 0, "stream already failed");
     if (st->header_have < IBU_HEADER_SIZE)  // read_exact on a short stream: UnexpectedEof
         return set_error(err, IBU_ERR_IO, EIO, st->header_have, 0, "I/O error: stream ended inside the 32-byte header");
@@ -1093,12 +1105,14 @@ int ibu_gpu_stream_finish(ibu_gpu_stream_t *st, ibu_reduce_result_t *h_result, i
 
 void ibu_gpu_stream_close(ibu_gpu_stream_t *st) {
     if (!st) return;
-    {
-        DeviceGuard guard(st->ctx->device);
-        for (auto &slot : st->ctx->slots)
+    if (ibu_gpu_ctx *ctx = st->ctx) {  // (null: the context went first and detached us)
+        DeviceGuard guard(ctx->device);
+        for (auto &slot : ctx->slots)
             if (cudaStreamSynchronize(slot.stream) != cudaSuccess) cudaGetLastError();
+        std::lock_guard<std::mutex> lock(ctx->pipe_mutex);
+        if (ctx->open_stream == st) ctx->open_stream = nullptr;
     }
-    delete st;  // releases the context's pipeline lock
+    delete st;
 }
 
 // ---- device path of load_to_vec -----------------------------------------------------------
@@ -1122,6 +1136,7 @@ int ibu_gpu_load_to_device(ibu_gpu_ctx_t *ctx, const char *path, uint64_t start,
     }
     DeviceGuard guard(ctx->device);
     std::lock_guard<std::mutex> lock(ctx->pipe_mutex);
+    if (ctx->open_stream) return set_error(err, IBU_ERR_ARG, 0, 0, 0, "context busy: a streaming ingest is open on it");
     const uint64_t count = end - start;
     void *dev = nullptr;
     cudaError_t e = cudaMalloc(&dev, count ? count * IBU_RECORD_SIZE : kAlign);
@@ -1178,6 +1193,7 @@ int ibu_gpu_write_records(ibu_gpu_ctx_t *ctx, ibu_writer_t *writer, const ibu_re
     if (n == 0) return IBU_OK;
     DeviceGuard guard(ctx->device);
     std::lock_guard<std::mutex> lock(ctx->pipe_mutex);
+    if (ctx->open_stream) return set_error(err, IBU_ERR_ARG, 0, 0, 0, "context busy: a streaming ingest is open on it");
     const uint64_t chunk = chunk_records(ctx);
     const uint64_t n_chunks = (n + chunk - 1) / chunk;
     const size_t n_slots = ctx->slots.size();
@@ -1219,6 +1235,7 @@ int ibu_gpu_unpack_host(ibu_gpu_ctx_t *ctx, const ibu_record_t *h_records, uint6
     if (n == 0) return IBU_OK;
     DeviceGuard guard(ctx->device);
     std::lock_guard<std::mutex> lock(ctx->pipe_mutex);
+    if (ctx->open_stream) return set_error(err, IBU_ERR_ARG, 0, 0, 0, "context busy: a streaming ingest is open on it");
     const uint64_t chunk = chunk_records(ctx);
     const uint64_t n_chunks = (n + chunk - 1) / chunk;
     const bool pin_in = is_pinned(h_records), pin_bc = is_pinned(h_bc_ascii), pin_umi = is_pinned(h_umi_ascii),
@@ -1268,6 +1285,7 @@ int ibu_gpu_pack_host(ibu_gpu_ctx_t *ctx, const uint8_t *h_bc_ascii, const uint8
     if (n == 0) return IBU_OK;
     DeviceGuard guard(ctx->device);
     std::lock_guard<std::mutex> lock(ctx->pipe_mutex);
+    if (ctx->open_stream) return set_error(err, IBU_ERR_ARG, 0, 0, 0, "context busy: a streaming ingest is open on it");
     const uint64_t chunk = chunk_records(ctx);
     const uint64_t n_chunks = (n + chunk - 1) / chunk;
     const bool pin_bc = is_pinned(h_bc_ascii), pin_umi = is_pinned(h_umi_ascii),

@@ -247,6 +247,36 @@ def test_stream_ingest_errors(ctx):
     assert ctx.process_host(np.frombuffer(good[32:], ibu.RECORD_DTYPE), 16, 12)["n_records"] == 10  # lock released
 
 
+def test_stream_outlives_its_context_and_blocks_host_calls():
+    """A stream owns its context's chunk slots between open and close without holding a lock across
+    calls: host-buffer calls on the context are refused meanwhile, another thread may close it, and a
+    stream that outlives its context fails cleanly instead of touching freed memory."""
+    import threading
+
+    good = on.file_bytes(16, 12, oc.generate_records(0, 1000, 16, 12, 0, 0, 53))
+    recs = np.frombuffer(good[32:], ibu.RECORD_DTYPE)
+    c = ibu.GpuContext(0, chunk_records=1 << 16)
+    st = ibu.GpuStream(c)
+    st.push(good[:5000])
+    with pytest.raises(ibu.ArgError):
+        c.process_host(recs, 16, 12)
+    c.close()  # the context goes first
+    with pytest.raises(ibu.ArgError):
+        st.push(good[5000:])
+    with pytest.raises(ibu.ArgError):
+        st.finish()
+    st.close()
+    c = ibu.GpuContext(0, chunk_records=1 << 16)
+    st = ibu.GpuStream(c)
+    st.push(good)
+    assert st.finish()["n_records"] == 1000
+    t = threading.Thread(target=st.close)  # closed by a thread that did not open it
+    t.start()
+    t.join()
+    assert c.process_host(recs, 16, 12)["n_records"] == 1000
+    c.close()
+
+
 # ---- one pass with an operation mask: ingest -> validate/reduce (+ unpack) (+ per-barcode table) ----
 def zipf_file_records(n, seed, dirty=True):
     recs = oc.generate_records(0, n, 16, 12, 5, (64 << 32) | 20_000, seed)  # Zipf-ish barcodes, heavy duplication
