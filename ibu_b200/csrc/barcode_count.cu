@@ -378,6 +378,7 @@ k_key_masks(const uint64_t *__restrict__ recs, uint64_t n, uint64_t *__restrict_
     uint64_t o[WORDS], a[WORDS];
 #pragma unroll
     for (int k = 0; k < WORDS; k++) { o[k] = 0; a[k] = ~0ull; }
+    uint32_t descents = 0;  // WORDS == 3: records whose third word is smaller than their predecessor's
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
          i += (uint64_t)gridDim.x * blockDim.x) {
         uint64_t w[WORDS];
@@ -387,7 +388,12 @@ k_key_masks(const uint64_t *__restrict__ recs, uint64_t n, uint64_t *__restrict_
             o[k] |= w[k];
             a[k] &= w[k];
         }
+        if (WORDS == 3 && i) descents += w[WORDS - 1] < recs[3 * (i - 1) + 2];
         if (pairs) reinterpret_cast<ulonglong2 *>(pairs)[i] = make_ulonglong2(w[0], w[1]);
+    }
+    if (WORDS == 3) {
+        descents = __reduce_add_sync(0xffffffffu, descents);
+        if ((threadIdx.x & 31u) == 0 && descents) atomicAdd(masks + 6, (unsigned long long)descents);
     }
 #pragma unroll
     for (int k = 0; k < WORDS; k++) {
@@ -451,6 +457,26 @@ k_radix_scan(uint32_t *__restrict__ hist, uint64_t n_tiles, uint64_t *__restrict
     if (tid == kBlockThreads - 1) digit_total[blockIdx.x] = part[tid];
 }
 
+// exclusive scan of one u64 per thread over the 256 threads of a CTA: warp shuffles + one barrier
+// (the Hillis-Steele form in shared memory cost 16 barriers; a 488-tile pass over 10^6 table rows ran
+// 36 us, all of it this latency)
+__device__ __forceinline__ uint64_t block_excl_scan64(uint64_t v, uint64_t *tmp) {
+    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    uint64_t inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint64_t t = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= (uint32_t)o) inc += t;
+    }
+    if (lane == 31) tmp[warp] = inc;
+    __syncthreads();
+    uint64_t before = 0;
+#pragma unroll
+    for (int w = 0; w < kWarpsPerBlock; w++)
+        if ((uint32_t)w < warp) before += tmp[w];
+    return before + inc - v;
+}
+
 // stable scatter of one tile by one 8-bit digit.  The tile is first reordered in shared memory
 // (its elements sorted by the digit), then written out in that order: neighbouring threads
 // store neighbouring elements of the same digit run, i.e. to consecutive global addresses,
@@ -464,21 +490,13 @@ k_radix_scatter(const uint64_t *__restrict__ in, uint64_t *__restrict__ out, uin
     __shared__ uint32_t warp_cnt[kWarpsPerBlock][256];
     __shared__ uint32_t tile_off[256];                 // first tile-local position of each digit
     __shared__ uint64_t base[256];                     // global position of this tile's first element of each digit
+    __shared__ uint64_t scan_tmp[kWarpsPerBlock];
     const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
     const uint64_t tile_id = blockIdx.x;
     for (int w = 0; w < kWarpsPerBlock; w++) warp_cnt[w][tid] = 0;
     {   // exclusive scan of the 256 digit totals -> global base of each digit (+ this tile's offset)
-        uint64_t v = digit_total[tid];
-        base[tid] = v;
-        __syncthreads();
-        for (int o = 1; o < 256; o <<= 1) {
-            uint64_t x = tid >= (uint32_t)o ? base[tid - o] : 0;
-            __syncthreads();
-            base[tid] += x;
-            __syncthreads();
-        }
-        const uint64_t excl = base[tid] - v;
-        __syncthreads();
+        const uint64_t v = digit_total[tid];
+        const uint64_t excl = block_excl_scan64(v, scan_tmp);
         base[tid] = excl + hist[(uint64_t)tid * n_tiles + tile_id];
     }
     __syncthreads();
@@ -496,7 +514,14 @@ k_radix_scatter(const uint64_t *__restrict__ in, uint64_t *__restrict__ out, uin
         if (live) el[k] = load_elem<STRIDE>(in, first + i);
         const uint32_t d = live ? (uint32_t)((el[k].w[word] >> shift) & 0xFFu) : 0x100u;  // 0x100: no element
         dig[k] = d;
-        const uint32_t peers = __match_any_sync(0xffffffffu, d);
+        // lanes with the same digit: nine ballots (0.93 clocks per key and SM against 1.84 for
+        // match.any, tools/k4lab2.cu)
+        uint32_t peers = 0xffffffffu;
+#pragma unroll
+        for (int bit = 0; bit < 9; bit++) {
+            const uint32_t m = __ballot_sync(0xffffffffu, (d >> bit) & 1u);
+            peers &= ((d >> bit) & 1u) ? m : ~m;
+        }
         const uint32_t leader = __ffs(peers) - 1;
         uint32_t old = 0;
         if (live && lane == leader) {
@@ -515,17 +540,7 @@ k_radix_scatter(const uint64_t *__restrict__ in, uint64_t *__restrict__ out, uin
             warp_cnt[w][tid] = run;
             run += c;
         }
-        tile_off[tid] = run;  // the tile's count of digit `tid`
-        __syncthreads();
-        for (int o = 1; o < 256; o <<= 1) {
-            const uint32_t x = tid >= (uint32_t)o ? tile_off[tid - o] : 0;
-            __syncthreads();
-            tile_off[tid] += x;
-            __syncthreads();
-        }
-        const uint32_t excl = tile_off[tid] - run;
-        __syncthreads();
-        tile_off[tid] = excl;
+        tile_off[tid] = (uint32_t)block_excl_scan64(run, scan_tmp);  // first tile-local position of digit `tid`
     }
     __syncthreads();
 #pragma unroll
@@ -536,10 +551,21 @@ k_radix_scatter(const uint64_t *__restrict__ in, uint64_t *__restrict__ out, uin
         }
     }
     __syncthreads();
-    for (uint32_t j = tid; j < count; j += kBlockThreads) {
-        const Elem<STRIDE> e = load_elem<STRIDE>(stage, j);
-        const uint32_t d = (uint32_t)((e.w[word] >> shift) & 0xFFu);
-        store_elem<STRIDE>(out, base[d] + (j - tile_off[d]), e);
+    if constexpr (STRIDE == 3) {
+        // 24-byte elements leave word by word: neighbouring threads store neighbouring 8-byte words of a
+        // digit run (256 contiguous bytes per warp instruction) instead of three 8-byte stores per
+        // thread at a 24-byte stride
+        for (uint32_t x = tid; x < 3 * count; x += kBlockThreads) {
+            const uint32_t j = x / 3u, k = x - 3u * j;
+            const uint32_t d = (uint32_t)((stage[3 * j + word] >> shift) & 0xFFu);
+            out[3 * (base[d] + (j - tile_off[d])) + k] = stage[x];
+        }
+    } else {
+        for (uint32_t j = tid; j < count; j += kBlockThreads) {
+            const Elem<STRIDE> e = load_elem<STRIDE>(stage, j);
+            const uint32_t d = (uint32_t)((e.w[word] >> shift) & 0xFFu);
+            store_elem<STRIDE>(out, base[d] + (j - tile_off[d]), e);
+        }
     }
 }
 
@@ -865,20 +891,21 @@ static int segment_pass(ibu_gpu_ctx *ctx, const uint64_t *src, int stride, uint6
 // pairs extracted to `pairs`): vary[k] = bits of word k on which the records disagree.
 template <int WORDS>
 static int key_masks(ibu_gpu_ctx *ctx, const uint64_t *recs, uint64_t n, uint64_t *pairs, cudaStream_t s,
-                     Scratch &sc, uint64_t vary[3], ibu_error_t *err) {
+                     Scratch &sc, uint64_t vary[3], ibu_error_t *err, uint64_t *third_word_descents = nullptr) {
     unsigned long long *masks;
-    IBU_CUDA(sc.alloc(&masks, 6 * 8));
-    const unsigned long long init[6] = {0ull, ~0ull, 0ull, ~0ull, 0ull, ~0ull};
+    IBU_CUDA(sc.alloc(&masks, 7 * 8));
+    const unsigned long long init[7] = {0ull, ~0ull, 0ull, ~0ull, 0ull, ~0ull, 0ull};
     IBU_CUDA(cudaMemcpyAsync(masks, init, sizeof(init), cudaMemcpyHostToDevice, s));
     const uint64_t blocks = (n + kBlockThreads - 1) / kBlockThreads;
     k_key_masks<WORDS><<<(int)std::min<uint64_t>(blocks, (uint64_t)ctx->sm_count * 8), kBlockThreads, 0, s>>>(
         recs, n, pairs, masks);
     g_launches.fetch_add(1, std::memory_order_relaxed);
     if (cudaError_t e__ = cudaGetLastError()) return cuda_fail(err, e__, "k_key_masks");
-    unsigned long long m[6];
+    unsigned long long m[7];
     IBU_CUDA(cudaMemcpyAsync(m, masks, sizeof(m), cudaMemcpyDeviceToHost, s));
     IBU_CUDA(cudaStreamSynchronize(s));
     for (int k = 0; k < 3; k++) vary[k] = k < WORDS ? (m[2 * k] ^ m[2 * k + 1]) : 0;
+    if (third_word_descents) *third_word_descents = m[6];
     return IBU_OK;
 }
 
@@ -1250,12 +1277,17 @@ int ibu_gpu_sort_records(ibu_gpu_ctx_t *ctx, const ibu_record_t *d_records, uint
     const uint64_t *src = reinterpret_cast<const uint64_t *>(d_records);
     uint64_t *dst = reinterpret_cast<uint64_t *>(d_sorted);
     uint64_t vary[3];
-    if (int rc = key_masks<3>(ctx, src, n, nullptr, s, sc, vary, err)) return rc;
+    uint64_t descents = 0;
+    if (int rc = key_masks<3>(ctx, src, n, nullptr, s, sc, vary, err, &descents)) return rc;
     static const int order[3] = {2, 1, 0};  // Record's Ord: barcode, then umi, then index (record.rs:58)
-    const int passes = count_passes(vary, order, 3);
+    // Records that already come in index order (what a writer that numbers reads as it goes produces)
+    // need no index passes: the sort is stable, so ties on (barcode, umi) keep their input order.
+    const int *keys = descents ? order : order + 1;
+    const int n_keys = descents ? 3 : 2;
+    const int passes = count_passes(vary, keys, n_keys);
     const uint64_t *result = nullptr;
     // an odd number of passes must start into d_sorted to end there
-    if (int rc = radix_sort<3>(ctx, src, (passes & 1) ? dst : spare, (passes & 1) ? spare : dst, n, vary, order, 3,
+    if (int rc = radix_sort<3>(ctx, src, (passes & 1) ? dst : spare, (passes & 1) ? spare : dst, n, vary, keys, n_keys,
                                s, sc, &result, err))
         return rc;
     if (result != dst) IBU_CUDA(cudaMemcpyAsync(dst, result, n * 24, cudaMemcpyDeviceToDevice, s));

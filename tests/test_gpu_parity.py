@@ -537,11 +537,16 @@ def gpu_sort(ctx, recs):
 @pytest.mark.parametrize("n", [0, 1, 2, 2047, 2048, 2049, 100_003, 3_000_005])
 @pytest.mark.parametrize("bc,umi,mode,param", [(16, 12, 3, (64 << 32) | 1000), (16, 12, 1, 500_000), (32, 32, 0, 0),
                                                (16, 12, 2, 0), (16, 12, 4, (5 << 32) | 1000), (3, 2, 0, 0)])
-def test_sort_records_matches_record_ord(ctx, n, bc, umi, mode, param):
-    """record.rs:29-32,58: lexicographic (barcode, umi, index)."""
+@pytest.mark.parametrize("index_order", ["descending", "ascending", "one swap"])
+def test_sort_records_matches_record_ord(ctx, n, bc, umi, mode, param, index_order):
+    """record.rs:29-32,58: lexicographic (barcode, umi, index).  Input that already comes in index order
+    skips the index passes (the sort is stable); a single out-of-order pair must bring them back."""
     recs = oc.generate_records(0, n, bc, umi, mode, param, 31)
-    if n > 10:
+    if n > 10 and index_order == "descending":
         recs["index"] = recs["index"][::-1].copy()  # index must be sorted as the third key, not kept
+    if n > 10 and index_order == "one swap":
+        recs["barcode"][n - 2], recs["umi"][n - 2] = recs["barcode"][n - 1], recs["umi"][n - 1]
+        recs["index"][n - 2], recs["index"][n - 1] = recs["index"][n - 1], recs["index"][n - 2]
     got = gpu_sort(ctx, recs)
     assert np.array_equal(got, sort_records(recs))
     if n:

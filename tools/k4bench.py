@@ -46,6 +46,7 @@ def main():
     ap.add_argument("--only", default="")
     ap.add_argument("--lens", type=int, default=1, help="pass the header's lengths as a hint")
     ap.add_argument("--path", default="", help="partition | legacy | sort: force one unsorted path")
+    ap.add_argument("--sort", type=int, default=0, help="also time ibu_gpu_sort_records on this many random bc16/umi12 records")
     args = ap.parse_args()
     n, pk = args.records, peak()
     dev = torch.device("cuda", 0)
@@ -73,6 +74,25 @@ def main():
                                   sorted_input=info["input_was_sorted"], lens_hint=bool(args.lens), path=args.path or "auto",
                                   timing="wall clock of the blocking ibu_gpu_barcode_count, rows left on the device")),
                   flush=True)
+    if args.sort:
+        m = args.sort
+        with torch.cuda.stream(stream):
+            src = torch.empty(24 * m, dtype=torch.uint8, device=dev)
+            dst = torch.empty(24 * m, dtype=torch.uint8, device=dev)
+            ctx.generate_records_async(src, 0, m, 16, 12, ibu.GEN_CLEAN, 0, 3, stream)
+            stream.synchronize()
+            ts = []
+            for _ in range(args.iters + 1):
+                t0 = time.perf_counter()
+                ctx.sort_records(src, m, dst, stream)
+                ts.append((time.perf_counter() - t0) * 1e3)
+            first, ts = ts[0], sorted(ts[1:])
+            # barcode 32 bits + umi 24 bits + index log2(m) bits, 8 bits per pass
+            passes = 4 + 3 + (max(m - 1, 1).bit_length() + 7) // 8
+            print(json.dumps(dict(case="ibu_gpu_sort_records (random bc16/umi12, index = i)", records=m, ms_best=ts[0],
+                                  ms_mean=sum(ts) / len(ts), ms_first_call=first, digit_passes=passes,
+                                  gbs_of_72B_per_pass=72 * m * passes / ts[0] / 1e6,
+                                  timing="wall clock of the blocking call")), flush=True)
     ctx.close()
 
 
