@@ -258,7 +258,26 @@ def kernel_block(ibu, ctx, torch, dev, stream, n, peak):
             add(name, "bc16/umi12, ibu_gpu_barcode_count (blocking call, rows left on the device)", 24,
                 sum(ts) / len(ts), ts[0], rows=info["n_rows"], distinct_pairs=info["n_distinct_pairs"],
                 sorted_input=info["input_was_sorted"], timing="wall clock")
-        del recs
+        # device sort by Record's Ord: general input (11 digit passes: 32 + 24 + 27 bits) and
+        # input that already comes in index order (the index passes are skipped: 7)
+        back = u8(24 * n)
+        for name, descending in (("ibu_gpu_sort_records, index in input order", False), ("ibu_gpu_sort_records, index descending", True)):
+            ctx.generate_records_async(recs, 0, n, 16, 12, ibu.GEN_CLEAN, 0, 5, stream)
+            if descending:
+                words = recs.view(torch.int64).view(-1, 3)
+                words[:, 2] = (n - 1) - words[:, 2]
+            stream.synchronize()
+            ts = []
+            for _ in range(4):
+                t0 = time.perf_counter()
+                ctx.sort_records(recs, n, back, stream)
+                ts.append((time.perf_counter() - t0) * 1e3)
+            ts = sorted(ts[1:])
+            passes = 7 + (4 if descending else 0)
+            add(name, f"bc16/umi12 random, blocking call, {passes} 8-bit digit passes of 72 B/record + 24 B key scan",
+                72 * passes + 24, sum(ts) / len(ts), ts[0], timing="wall clock", roofline_note="alg_bytes is what the "
+                "three-kernel LSD pass moves; a one-sweep radix would need 48 B per pass")
+        del recs, back
     return out
 
 

@@ -409,6 +409,22 @@ k_key_masks(const uint64_t *__restrict__ recs, uint64_t n, uint64_t *__restrict_
     }
 }
 
+// (barcode, umi) as ONE word, barcode above umi: sorting it is sorting the pair, at 8 bytes per
+// element and pass instead of 16
+__global__ void __launch_bounds__(kBlockThreads)
+k_make_keys(const uint64_t *__restrict__ recs, uint64_t n, uint32_t ub, uint64_t *__restrict__ keys) {
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x)
+        keys[i] = (ldg_stream64(recs + 3 * i) << ub) | ldg_stream64(recs + 3 * i + 1);
+}
+__global__ void __launch_bounds__(kBlockThreads)
+k_keys_to_pairs(const uint64_t *__restrict__ keys, uint64_t n, uint32_t ub, uint64_t *__restrict__ pairs) {
+    const uint64_t umask = (1ull << ub) - 1ull;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+        const uint64_t k = ldg_stream64(keys + i);
+        reinterpret_cast<ulonglong2 *>(pairs)[i] = make_ulonglong2(k >> ub, k & umask);
+    }
+}
+
 // per-tile digit histogram, stored digit-major: hist[d * n_tiles + tile]
 template <int STRIDE>
 __global__ void __launch_bounds__(kBlockThreads)
@@ -891,7 +907,8 @@ static int segment_pass(ibu_gpu_ctx *ctx, const uint64_t *src, int stride, uint6
 // pairs extracted to `pairs`): vary[k] = bits of word k on which the records disagree.
 template <int WORDS>
 static int key_masks(ibu_gpu_ctx *ctx, const uint64_t *recs, uint64_t n, uint64_t *pairs, cudaStream_t s,
-                     Scratch &sc, uint64_t vary[3], ibu_error_t *err, uint64_t *third_word_descents = nullptr) {
+                     Scratch &sc, uint64_t vary[3], ibu_error_t *err, uint64_t *third_word_descents = nullptr,
+                     uint64_t *or_masks = nullptr) {
     unsigned long long *masks;
     IBU_CUDA(sc.alloc(&masks, 7 * 8));
     const unsigned long long init[7] = {0ull, ~0ull, 0ull, ~0ull, 0ull, ~0ull, 0ull};
@@ -906,6 +923,8 @@ static int key_masks(ibu_gpu_ctx *ctx, const uint64_t *recs, uint64_t n, uint64_
     IBU_CUDA(cudaStreamSynchronize(s));
     for (int k = 0; k < 3; k++) vary[k] = k < WORDS ? (m[2 * k] ^ m[2 * k + 1]) : 0;
     if (third_word_descents) *third_word_descents = m[6];
+    if (or_masks)
+        for (int k = 0; k < 3; k++) or_masks[k] = k < WORDS ? m[2 * k] : 0;
     return IBU_OK;
 }
 
@@ -962,12 +981,32 @@ static int unsorted_table(ibu_gpu_ctx *ctx, const uint64_t *recs, uint64_t n, cu
     uint64_t vary[3];
     const uint64_t *sorted = nullptr;
     int stride;
-    if (!weighted) {  // only the keys are needed: sort 16-byte (barcode, umi) pairs
-        uint64_t *a, *b;
+    if (!weighted) {  // only the keys are needed
+        uint64_t *a, *b, ors[3];
         IBU_CUDA(sc.alloc(&a, n * 16));
         IBU_CUDA(sc.alloc(&b, n * 16));
-        if (int rc = key_masks<2>(ctx, recs, n, a, s, sc, vary, err)) return rc;
-        if (int rc = radix_sort<2>(ctx, a, b, a, n, vary, order, 2, s, sc, &sorted, err)) return rc;
+        if (int rc = key_masks<2>(ctx, recs, n, nullptr, s, sc, vary, err, nullptr, ors)) return rc;
+        const uint32_t bb = ors[0] ? 64 - (uint32_t)__builtin_clzll(ors[0]) : 1, ub = ors[1] ? 64 - (uint32_t)__builtin_clzll(ors[1]) : 1;
+        const int grid = (int)std::min<uint64_t>((n + kBlockThreads - 1) / kBlockThreads, (uint64_t)ctx->sm_count * 16);
+        if (bb + ub <= 64 && ub < 64) {
+            // the pair fits one word (bc16/umi12: 56 bits): 8-byte keys through the digit passes
+            // (24 instead of 48 bytes per element and pass), pairs again for the segment pass
+            uint64_t *k0 = a, *k1 = a + n;  // the two halves of `a` ping-pong; `b` receives the pairs
+            k_make_keys<<<grid, kBlockThreads, 0, s>>>(recs, n, ub, k0);
+            g_launches.fetch_add(1, std::memory_order_relaxed);
+            if (cudaError_t e__ = cudaGetLastError()) return cuda_fail(err, e__, "k_make_keys");
+            const uint64_t vary1[3] = {(vary[0] << ub) | vary[1], 0, 0};
+            static const int order1[1] = {0};
+            const uint64_t *skeys = nullptr;
+            if (int rc = radix_sort<1>(ctx, k0, k1, k0, n, vary1, order1, 1, s, sc, &skeys, err)) return rc;
+            k_keys_to_pairs<<<grid, kBlockThreads, 0, s>>>(skeys, n, ub, b);
+            g_launches.fetch_add(1, std::memory_order_relaxed);
+            if (cudaError_t e__ = cudaGetLastError()) return cuda_fail(err, e__, "k_keys_to_pairs");
+            sorted = b;
+        } else {  // 16-byte (barcode, umi) pairs
+            if (int rc = key_masks<2>(ctx, recs, n, a, s, sc, vary, err)) return rc;
+            if (int rc = radix_sort<2>(ctx, a, b, a, n, vary, order, 2, s, sc, &sorted, err)) return rc;
+        }
         stride = 2;
     } else {  // the multiplicity (index word) travels with its key: sort whole records
         uint64_t *a, *b;
