@@ -1344,7 +1344,7 @@ int ibu_gpu_partition_by_owner(ibu_gpu_ctx_t *ctx, const ibu_record_t *d_pairs, 
     DeviceGuard guard(ctx->device);
     cudaStream_t s = pick_stream(ctx, stream);
     unsigned long long *d_counts = nullptr;
-    IBU_CUDA(cudaMalloc((void **)&d_counts, 256 * 8));
+    IBU_CUDA(cudaMallocAsync((void **)&d_counts, 256 * 8, s));  // (cudaMalloc / cudaFree would synchronise the device)
     int rc = IBU_OK;
     do {
         cudaError_t e = cudaMemsetAsync(d_counts, 0, 256 * 8, s);
@@ -1366,7 +1366,7 @@ int ibu_gpu_partition_by_owner(ibu_gpu_ctx_t *ctx, const ibu_record_t *d_pairs, 
         if (e == cudaSuccess) e = cudaStreamSynchronize(s);
         if (e != cudaSuccess) rc = cuda_fail(err, e, "k_owner_scatter");
     } while (0);
-    cudaFree(d_counts);
+    if (cudaFreeAsync(d_counts, s) != cudaSuccess) cudaGetLastError();
     return rc;
 }
 

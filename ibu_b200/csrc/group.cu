@@ -554,6 +554,17 @@ int ibu_gpu_group_create(const int *devices, uint32_t n_devices, const ibu_gpu_c
             if (cudaDeviceCanAccessPeer(&can, devices[i], devices[j]) == cudaSuccess && can) {
                 cudaError_t e = cudaDeviceEnablePeerAccess(devices[j], 0);
                 if (e != cudaSuccess) cudaGetLastError();  // (already enabled is fine)
+                // The exchange buffers come from the stream-ordered pool (cudaMallocAsync), which peer
+                // access enabled above does NOT cover: without this grant a peer copy out of pool memory
+                // is staged through the host (240 MB per rank took 9.5 ms = PCIe rate, not NVLink).
+                cudaMemPool_t pool = nullptr;
+                if (cudaDeviceGetDefaultMemPool(&pool, devices[j]) == cudaSuccess && pool) {
+                    cudaMemAccessDesc desc{};
+                    desc.location.type = cudaMemLocationTypeDevice;
+                    desc.location.id = devices[i];
+                    desc.flags = cudaMemAccessFlagsProtReadWrite;
+                    if (cudaMemPoolSetAccess(pool, &desc, 1) != cudaSuccess) cudaGetLastError();
+                }
             }
         }
     }

@@ -58,7 +58,7 @@ def main():
                 sec, rows, info, tm = best
                 if ref is None:
                     ref = rows
-                print(json.dumps(dict(shape=name, n_gpus=world, records=n, exchange=ex_name, sec=sec, grec_s=n / sec / 1e9,
+                print(json.dumps(dict(shape=name, n_gpus=world, records=n, exchange_name=ex_name, sec=sec, grec_s=n / sec / 1e9,
                                       rows=len(rows), distinct_pairs=info["n_distinct_pairs"],
                                       same_table_as_first_exchange=bool(np.array_equal(rows, ref)),
                                       records_sum_ok=bool(int(rows["n_records"].sum()) == n), **tm)), flush=True)
