@@ -128,7 +128,11 @@ private:
         }
     }
     WorkPool() : owner_(getpid()) {
-        unsigned hc = std::thread::hardware_concurrency();
+        // this process's share of the cores when a launcher runs one process per GPU (torchrun sets
+        // LOCAL_WORLD_SIZE): eight ranks on a 32-thread host get 3 workers each, not 31 idle ones
+        const char *e = getenv("LOCAL_WORLD_SIZE");
+        const unsigned ranks = (unsigned)std::max(1, e ? atoi(e) : 1);
+        unsigned hc = std::max(1u, std::thread::hardware_concurrency() / ranks);
         unsigned n = hc > 1 ? std::min(31u, hc - 1) : 0;
         for (unsigned i = 0; i < n; i++) workers_.emplace_back([this] { loop(); });
     }
