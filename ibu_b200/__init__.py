@@ -349,11 +349,15 @@ class GpuContext:
         info = dict(n_rows=int(table.n_rows), n_records=int(table.n_records),
                     n_distinct_pairs=int(table.n_distinct_pairs), input_was_sorted=bool(table.input_was_sorted))
         try:
-            if table.n_rows:
-                self.d2h(rows, int(table.d_rows))
+            self.table_rows(table, rows)
         finally:
             lib.ibu_gpu_table_free(self._h, C.byref(table))
         return rows, info
+
+    def table_rows(self, table, rows: np.ndarray):
+        """The rows of a device table into `rows` (ROW_DTYPE, table.n_rows long)."""
+        err = _lib.Error()
+        _check(lib.ibu_gpu_table_to_host(self._h, C.byref(table), _ptr(rows), C.byref(err)), err)
 
     def pair_table(self, d_records, n, weighted: bool = False, stream=None, flags: int = 0):
         """Distinct (barcode, umi) pairs with multiplicities as device records: (ptr, n_pairs).
@@ -454,8 +458,7 @@ def _run_ops(ctx: "GpuContext", call, n: int, bc_len: int, umi_len: int, table: 
         else:
             out.rows = np.zeros(int(tab.n_rows), ROW_DTYPE)
             try:
-                if tab.n_rows:
-                    ctx.d2h(out.rows, int(tab.d_rows))
+                ctx.table_rows(tab, out.rows)
             finally:
                 lib.ibu_gpu_table_free(ctx._h, C.byref(tab))
     if keep:

@@ -129,6 +129,7 @@ SIGNATURES = {
     "ibu_gpu_pack_async": (_int, [_vp, _vp, _vp, _vp, _u64, _u64, _u32, _u32, _vp, _vp, _vp, _vp, _err]),
     "ibu_gpu_barcode_count": (_int, [_vp, _vp, _u64, _int, _P(BarcodeTable), _vp, _err]),
     "ibu_gpu_table_free": (None, [_vp, _P(BarcodeTable)]),
+    "ibu_gpu_table_to_host": (_int, [_vp, _P(BarcodeTable), _vp, _err]),
     "ibu_gpu_pair_table": (_int, [_vp, _vp, _u64, _int, _P(_vp), _P(_u64), _vp, _err]),
     "ibu_gpu_partition_by_owner": (_int, [_vp, _vp, _u64, _u32, _vp, _P(_u64), _vp, _err]),
     "ibu_gpu_memcpy": (_int, [_vp, _vp, _vp, _sz, _err]),

@@ -1119,6 +1119,33 @@ void ibu_gpu_stream_close(ibu_gpu_stream_t *st) {
     delete st;
 }
 
+int ibu_gpu_table_to_host(ibu_gpu_ctx_t *ctx, const ibu_barcode_table_t *table, ibu_barcode_row_t *h_rows,
+                          ibu_error_t *err) {
+    clear_error(err);
+    if (!ctx || !table || (table->n_rows && (!table->d_rows || !h_rows))) return set_error(err, IBU_ERR_ARG, 0, 0, 0, "null argument");
+    if (!table->n_rows) return IBU_OK;
+    DeviceGuard guard(ctx->device);
+    const size_t bytes = (size_t)table->n_rows * sizeof(ibu_barcode_row_t);
+    if (is_pinned(h_rows)) {
+        IBU_CUDA(cudaMemcpyAsync(h_rows, table->d_rows, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+        IBU_CUDA(cudaStreamSynchronize(ctx->stream));
+        return IBU_OK;
+    }
+    std::lock_guard<std::mutex> lock(ctx->pipe_mutex);  // the landing area is slot 0's pinned output buffer
+    if (ctx->open_stream) return set_error(err, IBU_ERR_ARG, 0, 0, 0, "context busy: a streaming ingest is open on it");
+    ibu_chunk_slot &slot = ctx->slots[0];
+    const size_t piece_max = std::max<size_t>(slot.h_out_bytes, 32u << 20);
+    if (int rc = ensure(&slot.h_out, &slot.h_out_bytes, std::min(align_up(bytes), piece_max), true, err)) return rc;
+    const unsigned threads = copy_threads(ctx);
+    for (size_t off = 0; off < bytes; off += slot.h_out_bytes) {
+        const size_t len = std::min(slot.h_out_bytes, bytes - off);
+        IBU_CUDA(cudaMemcpyAsync(slot.h_out, (const uint8_t *)table->d_rows + off, len, cudaMemcpyDeviceToHost, ctx->stream));
+        IBU_CUDA(cudaStreamSynchronize(ctx->stream));
+        parallel_memcpy((uint8_t *)h_rows + off, slot.h_out, len, threads);
+    }
+    return IBU_OK;
+}
+
 // ---- device path of load_to_vec -----------------------------------------------------------
 
 int ibu_gpu_load_to_device(ibu_gpu_ctx_t *ctx, const char *path, uint64_t start, uint64_t end,

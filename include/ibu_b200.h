@@ -277,6 +277,13 @@ int ibu_gpu_barcode_count(ibu_gpu_ctx_t *ctx, const ibu_record_t *d_records, uin
                           int mode, ibu_barcode_table_t *table, void *stream,
                           ibu_error_t *err);
 void ibu_gpu_table_free(ibu_gpu_ctx_t *ctx, ibu_barcode_table_t *table);
+/* The rows of a device table into caller memory (h_rows: table->n_rows rows; the HashMap the
+ * reference's processor ends with, parallel.rs:79-98, as a sorted array).  Pageable destinations are
+ * filled through the context's pinned landing area with the multi-threaded copy: a plain D2H into
+ * freshly allocated pageable memory is a staged copy through page faults (5-11 ms per 10^6 rows
+ * against 1-2 ms).  Blocking; waits for the table's stream work first. */
+int ibu_gpu_table_to_host(ibu_gpu_ctx_t *ctx, const ibu_barcode_table_t *table, ibu_barcode_row_t *h_rows,
+                          ibu_error_t *err);
 
 /* OR into `mode` of ibu_gpu_barcode_count: the records are a (barcode, umi, multiplicity) pair
  * table (index = how many records the pair stands for), e.g. the concatenation of several

@@ -247,7 +247,8 @@ impl BarcodeTable<'_> {
     pub fn to_vec(&self) -> Result<Vec<BarcodeRow>> {
         let mut v = vec![BarcodeRow { barcode: 0, n_records: 0, n_distinct_umi: 0 }; self.n_rows()];
         let mut e = new_err();
-        check(unsafe { ffi::ibu_gpu_memcpy_d2h(self.ctx.raw, v.as_mut_ptr() as *mut c_void, self.raw.d_rows as *const c_void, v.len() * 24, &mut e) }, &e)?;
+        // (through the context's pinned landing area: a plain D2H into a fresh Vec is a staged copy)
+        check(unsafe { ffi::ibu_gpu_table_to_host(self.ctx.raw, &self.raw, v.as_mut_ptr(), &mut e) }, &e)?;
         Ok(v)
     }
 }
