@@ -183,34 +183,53 @@ void for_pieces(size_t bytes, unsigned threads, size_t granule, F &&fn) {
     });
 }
 
-void parallel_memcpy(void *dst, const void *src, size_t bytes, unsigned threads) {
+// How a pageable source is written into a pinned chunk slot.  Non-temporal stores (stream_copy) leave
+// the chunk in DRAM for the DMA engine: 3 DRAM transfers per byte (source read, chunk write, DMA read).
+// When the whole ring of slots is small enough to stay in the last-level cache, ordinary stores are
+// better: the DMA engine reads the staged bytes from the cache and the next chunk overwrites them
+// there (tools/stage_sweep.py on the 16-vCPU box, 60 MB L3, 10^8 records: 3 x 24 MB slots 51.7 GB/s
+// plain against 49.4 non-temporal; 3 x 96 MB slots 45.6 against 48.8).  So: plain stores when this is
+// the only context staging on the host and the ring is at most 96 MB.  IBU_B200_STAGE_PLAIN=0/1 forces.
+std::atomic<int> g_live_contexts{0};
+bool stage_plain(const ibu_gpu_ctx *ctx, size_t chunk_bytes) {
+    if (const char *e = getenv("IBU_B200_STAGE_PLAIN")) return e[0] == '1';
+    static const int ranks = [] {
+        const char *e = getenv("LOCAL_WORLD_SIZE");
+        return std::max(1, e ? atoi(e) : 1);
+    }();
+    return ranks == 1 && g_live_contexts.load(std::memory_order_relaxed) <= 1 &&
+           chunk_bytes * ctx->slots.size() <= (96u << 20);
+}
+
+void parallel_memcpy(void *dst, const void *src, size_t bytes, unsigned threads, bool plain = false) {
     if (threads <= 1 || bytes < (1u << 20)) {
-        stream_copy(dst, src, bytes);
+        if (plain) memcpy(dst, src, bytes); else stream_copy(dst, src, bytes);
         return;
     }
     for_pieces(bytes, threads, 4096, [&](size_t off, size_t len) {
-        stream_copy((uint8_t *)dst + off, (const uint8_t *)src + off, len);
+        if (plain) memcpy((uint8_t *)dst + off, (const uint8_t *)src + off, len);
+        else stream_copy((uint8_t *)dst + off, (const uint8_t *)src + off, len);
     });
 }
 
 // The same fan-out with pread(2): no page tables are populated for the mapping and an I/O error
 // is a return code, not a SIGBUS.  Each thread reads 64 KB pieces into a cache-resident bounce
 // buffer and streams them on (pread straight into the pinned buffer is the 38 GB/s case above).
-bool parallel_pread(void *dst, int fd, uint64_t file_off, size_t bytes, unsigned threads) {
+bool parallel_pread(void *dst, int fd, uint64_t file_off, size_t bytes, unsigned threads, bool plain = false) {
     std::atomic<bool> ok{true};
-    for_pieces(bytes, threads, 1 << 20, [&](size_t off, size_t len) {
+    for_pieces(bytes, threads, bytes >= (32u << 20) ? (1u << 20) : (64u << 10), [&](size_t off, size_t len) {
         constexpr size_t kBounce = 64u << 10;
         alignas(64) uint8_t bounce[kBounce];
         uint8_t *p = (uint8_t *)dst + off;
         uint64_t fo = file_off + off;
         while (len) {
-            ssize_t got = ::pread(fd, bounce, std::min(len, kBounce), (off_t)fo);
+            ssize_t got = ::pread(fd, plain ? p : bounce, std::min(len, plain ? len : kBounce), (off_t)fo);
             if (got < 0 && errno == EINTR) continue;
             if (got <= 0) {
                 ok = false;
                 return;
             }
-            stream_copy(p, bounce, (size_t)got);
+            if (!plain) stream_copy(p, bounce, (size_t)got);
             p += got;
             fo += (uint64_t)got;
             len -= (size_t)got;
@@ -323,11 +342,12 @@ int run_chunks_impl(ibu_gpu_ctx *ctx, uint64_t n_chunks, PlanFn plan_of, Enqueue
             if (!sp.bytes) continue;
             const void *src = sp.h_src;
             if (!sp.pinned) {
+                const bool plain = stage_plain(ctx, p.h_in_bytes ? p.h_in_bytes : p.d_in_bytes);
                 if (sp.fd >= 0) {
-                    if (!parallel_pread((uint8_t *)slot.h_in + sp.d_off, sp.fd, sp.file_off, sp.bytes, threads))
+                    if (!parallel_pread((uint8_t *)slot.h_in + sp.d_off, sp.fd, sp.file_off, sp.bytes, threads, plain))
                         return set_error(err, IBU_ERR_IO, errno, 0, 0, "I/O error: pread failed while staging");
                 } else {
-                    parallel_memcpy((uint8_t *)slot.h_in + sp.d_off, sp.h_src, sp.bytes, threads);
+                    parallel_memcpy((uint8_t *)slot.h_in + sp.d_off, sp.h_src, sp.bytes, threads, plain);
                 }
                 src = (uint8_t *)slot.h_in + sp.d_off;
             }
@@ -365,7 +385,9 @@ int run_chunks(ibu_gpu_ctx *ctx, uint64_t n_chunks, PlanFn plan_of, EnqueueFn en
 }
 
 uint64_t chunk_records(const ibu_gpu_ctx *ctx) {
-    return ctx->cfg.chunk_records ? ctx->cfg.chunk_records : 4ull * IBU_BATCH_SIZE;
+    // default: BATCH_SIZE, the granularity at which the reference calls on_batch_complete (mmap.rs:284,
+    // 322-326) — and three 24 MB slots are a ring the last-level cache can hold (stage_plain)
+    return ctx->cfg.chunk_records ? ctx->cfg.chunk_records : (uint64_t)IBU_BATCH_SIZE;
 }
 
 int process_host_records(ibu_gpu_ctx *ctx, const ibu_record_t *h_records, uint64_t n, uint32_t bc_len,
@@ -640,6 +662,7 @@ int ibu_gpu_ctx_create(int device, const ibu_gpu_config_t *cfg, ibu_gpu_ctx_t **
     DeviceGuard guard(device);
     auto *ctx = new (std::nothrow) ibu_gpu_ctx;
     if (!ctx) return set_error(err, IBU_ERR_NOMEM, 0, 0, 0, "out of memory");
+    g_live_contexts.fetch_add(1, std::memory_order_relaxed);  // (ibu_gpu_ctx_destroy takes it back, also on the error path)
     ctx->device = device;
     ctx->sm_count = prop.multiProcessorCount;
     if (cfg) ctx->cfg = *cfg;
@@ -679,6 +702,7 @@ __attribute__((visibility("hidden"))) void ibu_stream_detach(struct ibu_gpu_stre
 
 void ibu_gpu_ctx_destroy(ibu_gpu_ctx_t *ctx) {
     if (!ctx) return;
+    g_live_contexts.fetch_sub(1, std::memory_order_relaxed);
     DeviceGuard guard(ctx->device);
     {   // a stream that is still open is detached: its later calls fail, its close only frees it
         std::lock_guard<std::mutex> lock(ctx->pipe_mutex);

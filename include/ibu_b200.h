@@ -154,7 +154,7 @@ void ibu_writer_close(ibu_writer_t *w);
 typedef struct ibu_gpu_ctx ibu_gpu_ctx_t;
 
 typedef struct ibu_gpu_config {
-    uint32_t chunk_records; /* records per staged chunk; 0 = 4 * IBU_BATCH_SIZE */
+    uint32_t chunk_records; /* records per staged chunk (and per on_chunk call); 0 = IBU_BATCH_SIZE */
     uint32_t n_slots;       /* chunk slots (streams) in flight; 0 = 3 */
     uint32_t copy_threads;  /* host threads for pageable->pinned staging; 0 = auto: all cores, divided
                              by LOCAL_WORLD_SIZE when a launcher (torchrun) sets it */

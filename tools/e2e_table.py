@@ -42,7 +42,7 @@ def main():
         for s in range(0, n, step):
             w.write_batch(oc.generate_records(s, min(step, n - s), 16, 12, args.gen, args.param, 7))
     reader = ibu.MmapReader(path)
-    ctx = ibu.GpuContext(0, chunk_records=4 << 20, n_slots=3)
+    ctx = ibu.GpuContext(0)  # library defaults: 1 Mi-record chunks, 3 slots
     # link probe: pinned host -> device, what a plain copy of the file's bytes gets
     pin = ibu.PinnedBuffer(1 << 30)
     d = ctx.malloc(1 << 30)
