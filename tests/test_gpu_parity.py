@@ -435,6 +435,41 @@ def test_barcode_table_reference_pattern_closed_form(ctx):
     assert np.all(rows["n_records"] == 10) and np.all(rows["n_distinct_umi"] == 1)
 
 
+@pytest.mark.parametrize("gen,param,shape", [(2, 0, "pattern"), (3, (20 << 32) | 1_000_000, "whitelist")])
+def test_barcode_table_three_partition_levels_closed_form(ctx, gen, param, shape):
+    """1.5 x 10^8 unsorted records: 2^18 buckets, i.e. three levels of the staged partition (two levels
+    cover up to 2^17).  The table of the whole input equals the sum of the tables of its thirds
+    (n_records adds by barcode; both are checked against closed forms where one exists)."""
+    n = 150_000_000
+    d = Dev(ctx, 24 * n)
+    ctx.generate_records_async(d, 0, n, 16, 12, gen, param, 9)
+    ctx.synchronize()
+    rows, info = ctx.barcode_count(d, n, mode=ibu.count_lens(16, 12))
+    assert not info["input_was_sorted"] and int(rows["n_records"].sum()) == n
+    assert np.all(np.diff(rows["barcode"].astype(np.int64)) > 0)
+    if shape == "pattern":  # examples/parallel.rs:65-69: barcode i % 10^6 always meets umi 31 i % 10^6
+        assert len(rows) == 1_000_000 and info["n_distinct_pairs"] == 1_000_000
+        assert np.all(rows["n_records"] == 150) and np.all(rows["n_distinct_umi"] == 1)
+    else:
+        third = n // 3
+        acc = {}
+        for k in range(3):  # each third takes the two-level path
+            part, _ = ctx.barcode_count(d.ptr + 24 * third * k, third, mode=ibu.count_lens(16, 12))
+            assert int(part["n_records"].sum()) == third
+            acc[k] = part
+        cat = np.concatenate(list(acc.values()))
+        order = np.argsort(cat["barcode"], kind="stable")
+        bc, cnt = cat["barcode"][order], cat["n_records"][order]
+        head = np.ones(len(bc), bool)
+        head[1:] = bc[1:] != bc[:-1]
+        assert np.array_equal(bc[head], rows["barcode"])
+        assert np.array_equal(np.add.reduceat(cnt, np.flatnonzero(head)), rows["n_records"])
+        assert np.all(rows["n_distinct_umi"] <= 20) and info["n_distinct_pairs"] == int(rows["n_distinct_umi"].sum())
+        # umi space 20, 150 records per barcode on average: nearly every barcode has seen all 20 umis
+        assert (rows["n_distinct_umi"] == 20).mean() > 0.95
+    d.free()
+
+
 def test_barcode_table_capacity_retry(ctx):
     """More distinct barcodes than the optimistic 8 Mi-row table: the exact-size second pass."""
     n = 9_000_000
