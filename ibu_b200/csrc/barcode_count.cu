@@ -585,6 +585,162 @@ k_radix_scatter(const uint64_t *__restrict__ in, uint64_t *__restrict__ out, uin
     }
 }
 
+// ------------------------------------------------------------------ one-sweep form of a digit pass
+// The three-kernel pass reads every element twice (histogram, scatter) and round-trips a
+// [256][tiles] offset matrix through a scan kernel: 72 B per 24-byte element.  One sweep (Adinets &
+// Merrill): ALL digit histograms of the sort come from one pass over the keys (k_hist_all), and a
+// digit pass is ONE kernel that ranks its tile, publishes the tile's 256 digit counts and obtains
+// its global offsets by decoupled look-back over the tiles before it — 48 B per element.  Tiles take
+// their number from an atomic ticket, so a tile only ever waits on tiles that are already running.
+// The tile is loaded with coalesced 16-byte loads and stays in shared memory; only digits and ranks
+// live in registers (the three-kernel scatter held the elements in registers: 80 of them, 3 CTAs).
+constexpr uint32_t kSweepAgg = 1u << 30, kSweepPrefix = 2u << 30, kSweepMask = (1u << 30) - 1u;
+constexpr int kSweepMaxPasses = 24;
+
+struct HistAllArgs {
+    const uint64_t *in;
+    uint64_t n;
+    uint32_t n_passes;
+    uint32_t word[kSweepMaxPasses], shift[kSweepMaxPasses];
+    uint32_t *hist;  // [n_passes][256], zeroed
+};
+
+template <int STRIDE>
+__global__ void __launch_bounds__(kBlockThreads) k_hist_all(const HistAllArgs a) {
+    extern __shared__ uint32_t h[];  // [n_passes][256]
+    for (uint32_t i = threadIdx.x; i < a.n_passes * 256; i += kBlockThreads) h[i] = 0;
+    __syncthreads();
+    for (uint64_t i = (uint64_t)blockIdx.x * kBlockThreads + threadIdx.x; i < a.n; i += (uint64_t)gridDim.x * kBlockThreads) {
+        uint64_t w[STRIDE];
+#pragma unroll
+        for (int k = 0; k < STRIDE; k++) w[k] = a.in[i * STRIDE + k];
+        for (uint32_t p = 0; p < a.n_passes; p++) {
+            uint64_t key = w[0];
+#pragma unroll
+            for (int k = 1; k < STRIDE; k++)
+                if (a.word[p] == (uint32_t)k) key = w[k];
+            atomicAdd(&h[p * 256 + (uint32_t)((key >> a.shift[p]) & 0xFFu)], 1u);
+        }
+    }
+    __syncthreads();
+    for (uint32_t i = threadIdx.x; i < a.n_passes * 256; i += kBlockThreads)
+        if (h[i]) atomicAdd(a.hist + i, h[i]);
+}
+
+struct SweepArgs {
+    const uint64_t *in;
+    uint64_t *out;
+    uint64_t n;
+    uint32_t word, shift;
+    const uint32_t *digit_total;  // [256] of this pass
+    uint32_t *state;              // [tiles][256], zeroed: 2 flag bits | 30-bit count
+    uint32_t *ticket;             // zeroed
+    uint32_t *fail;               // set when a look-back gives up
+};
+
+template <int STRIDE>
+__global__ void __launch_bounds__(kBlockThreads, 3) k_onesweep(const SweepArgs a) {
+    extern __shared__ __align__(16) uint64_t tile[];  // kSortTile elements as loaded
+    __shared__ uint32_t warp_cnt[kWarpsPerBlock][256];
+    __shared__ uint32_t tile_off[256], base[256], gdst[kSortTile];
+    __shared__ uint16_t srcidx[kSortTile];
+    __shared__ uint64_t scan_tmp[kWarpsPerBlock];
+    __shared__ uint32_t s_tile;
+    const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+    if (tid == 0) s_tile = atomicAdd(a.ticket, 1u);
+    for (int w = 0; w < kWarpsPerBlock; w++) warp_cnt[w][tid] = 0;
+    __syncthreads();
+    const uint64_t tile_id = s_tile;
+    const uint64_t first = tile_id * kSortTile;
+    const uint32_t count = (uint32_t)min((uint64_t)kSortTile, a.n - first);
+    {   // the tile, as it lies in memory (its start is 16-byte aligned: kSortTile * STRIDE * 8 bytes per tile)
+        const uint32_t words = count * STRIDE;
+        const uint4 *src16 = reinterpret_cast<const uint4 *>(a.in + first * STRIDE);
+        uint4 *dst16 = reinterpret_cast<uint4 *>(tile);
+        for (uint32_t x = tid; x < words / 2; x += kBlockThreads) dst16[x] = ldg_stream(src16 + x);
+        if ((words & 1u) && tid == 0) tile[words - 1] = a.in[first * STRIDE + words - 1];
+    }
+    __syncthreads();
+    // warp w ranks elements [w*256, w*256+256); item k of lane l is element w*256 + 32k + l (stable order)
+    uint32_t rank[kSortItems], dig[kSortItems];
+#pragma unroll
+    for (int k = 0; k < kSortItems; k++) {
+        const uint32_t i = warp * (kSortTile / kWarpsPerBlock) + 32 * k + lane;
+        const bool live = i < count;
+        const uint32_t d = live ? (uint32_t)((tile[i * STRIDE + a.word] >> a.shift) & 0xFFu) : 0x100u;
+        dig[k] = d;
+        uint32_t peers = 0xffffffffu;
+#pragma unroll
+        for (int bit = 0; bit < 9; bit++) {
+            const uint32_t m = __ballot_sync(0xffffffffu, (d >> bit) & 1u);
+            peers &= ((d >> bit) & 1u) ? m : ~m;
+        }
+        const uint32_t leader = __ffs(peers) - 1;
+        uint32_t old = 0;
+        if (live && lane == leader) {
+            old = warp_cnt[warp][d];
+            warp_cnt[warp][d] = old + __popc(peers);
+        }
+        old = __shfl_sync(0xffffffffu, old, leader);
+        rank[k] = old + __popc(peers & ((1u << lane) - 1u));
+        __syncwarp();
+    }
+    __syncthreads();
+    // thread = digit: this tile's count, published; offsets of the warps; look-back for the tiles before
+    uint32_t c = 0;
+    for (int w = 0; w < kWarpsPerBlock; w++) {
+        const uint32_t x = warp_cnt[w][tid];
+        warp_cnt[w][tid] = c;
+        c += x;
+    }
+    volatile uint32_t *state = a.state;
+    uint32_t before = 0;  // elements with this digit in earlier tiles
+    if (tile_id == 0) {
+        state[tid] = c | kSweepPrefix;
+    } else {
+        state[tile_id * 256 + tid] = c | kSweepAgg;
+        uint64_t look = tile_id - 1;
+        uint32_t spins = 0;
+        for (;;) {
+            const uint32_t v = state[look * 256 + tid];
+            const uint32_t flag = v & ~kSweepMask;
+            if (flag == 0) {
+                if (++spins > (1u << 26)) {  // watchdog: never hang the GPU (the host then reports an error)
+                    *a.fail = 1;
+                    break;
+                }
+                __nanosleep(32);
+                continue;
+            }
+            before += v & kSweepMask;
+            if (flag == kSweepPrefix) break;
+            look--;  // (tile 0 always publishes a prefix)
+        }
+        state[tile_id * 256 + tid] = (before + c) | kSweepPrefix;
+    }
+    const uint32_t off = (uint32_t)block_excl_scan64(c, scan_tmp);  // first tile-local position of the digit
+    __syncthreads();
+    const uint32_t gexcl = (uint32_t)block_excl_scan64(a.digit_total[tid], scan_tmp);  // digits below, whole input
+    tile_off[tid] = off;
+    base[tid] = gexcl + before - off;  // global position of sorted tile element j with this digit: base + j
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < kSortItems; k++) {
+        if (dig[k] < 0x100u) {
+            const uint32_t i = warp * (kSortTile / kWarpsPerBlock) + 32 * k + lane;
+            const uint32_t pos = tile_off[dig[k]] + warp_cnt[warp][dig[k]] + rank[k];
+            srcidx[pos] = (uint16_t)i;
+            gdst[pos] = base[dig[k]] + pos;
+        }
+    }
+    __syncthreads();
+    // out, word by word in sorted order: neighbouring threads store neighbouring words of a digit run
+    for (uint32_t x = tid; x < STRIDE * count; x += kBlockThreads) {
+        const uint32_t j = x / STRIDE, k = x - STRIDE * j;
+        a.out[(uint64_t)STRIDE * gdst[j] + k] = tile[STRIDE * (uint32_t)srcidx[j] + k];
+    }
+}
+
 // ============================================================ hash aggregation (unsorted inputs)
 // Unsorted records are first folded into distinct (barcode, umi, multiplicity) pairs with an
 // open-addressing table in HBM/L2 (linear probing, 32-byte slots {barcode, umi, count, pad},
@@ -947,6 +1103,53 @@ static int radix_sort(ibu_gpu_ctx *ctx, const uint64_t *in, uint64_t *first_dst,
     if (n >= (1ull << 32))  // per-digit tile offsets are kept in 32 bits
         return set_error(err, IBU_ERR_ARG, 0, n, 0, "device sort supports fewer than 2^32 elements per call");
     const uint64_t n_tiles = (n + kSortTile - 1) / kSortTile;
+    static const bool sweep_off = getenv("IBU_B200_ONESWEEP") && getenv("IBU_B200_ONESWEEP")[0] == '0';  // tuning
+    if (!sweep_off && n < (1ull << 30) && (((uintptr_t)in | (uintptr_t)first_dst | (uintptr_t)other) & 15u) == 0) {
+        // ---- one sweep: all histograms first, then one kernel per digit pass ----
+        HistAllArgs h{};
+        h.in = in;
+        h.n = n;
+        for (int k = 0; k < n_keys; k++)
+            for (uint32_t shift = 0; shift < 64; shift += 8)
+                if ((vary[key_order[k]] >> shift) & 0xFFull) {
+                    h.word[h.n_passes] = (uint32_t)key_order[k];
+                    h.shift[h.n_passes] = shift;
+                    h.n_passes++;
+                }
+        if (h.n_passes == 0) {
+            *result = in;
+            return IBU_OK;
+        }
+        uint32_t *state, *ctl;
+        IBU_CUDA(sc.alloc(&h.hist, (size_t)h.n_passes * 1024));
+        IBU_CUDA(sc.alloc(&state, n_tiles * 1024));
+        IBU_CUDA(sc.alloc(&ctl, 256));  // [0] ticket, [1] fail
+        IBU_CUDA(cudaMemsetAsync(h.hist, 0, (size_t)h.n_passes * 1024, s));
+        IBU_CUDA(cudaMemsetAsync(ctl, 0, 256, s));
+        const uint64_t blocks = (n + kBlockThreads - 1) / kBlockThreads;
+        k_hist_all<STRIDE><<<(int)std::min<uint64_t>(blocks, (uint64_t)ctx->sm_count * 8), kBlockThreads, h.n_passes * 1024, s>>>(h);
+        g_launches.fetch_add(1, std::memory_order_relaxed);
+        if (cudaError_t e__ = cudaGetLastError()) return cuda_fail(err, e__, "k_hist_all");
+        IBU_CUDA(cudaFuncSetAttribute(k_onesweep<STRIDE>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSortTile * STRIDE * 8));
+        const uint64_t *src = in;
+        uint64_t *dst = first_dst, *spare = other;
+        for (uint32_t p = 0; p < h.n_passes; p++) {
+            IBU_CUDA(cudaMemsetAsync(state, 0, n_tiles * 1024, s));
+            IBU_CUDA(cudaMemsetAsync(ctl, 0, 4, s));
+            SweepArgs a{src, dst, n, h.word[p], h.shift[p], h.hist + p * 256, state, ctl, ctl + 1};
+            k_onesweep<STRIDE><<<(int)n_tiles, kBlockThreads, kSortTile * STRIDE * 8, s>>>(a);
+            g_launches.fetch_add(1, std::memory_order_relaxed);
+            if (cudaError_t e__ = cudaGetLastError()) return cuda_fail(err, e__, "k_onesweep");
+            src = dst;
+            std::swap(dst, spare);
+        }
+        uint32_t failed = 0;
+        IBU_CUDA(cudaMemcpyAsync(&failed, ctl + 1, 4, cudaMemcpyDeviceToHost, s));
+        IBU_CUDA(cudaStreamSynchronize(s));
+        if (failed) return set_error(err, IBU_ERR_CUDA, 0, 0, 0, "device sort: look-back watchdog expired");
+        *result = src;
+        return IBU_OK;
+    }
     uint64_t *digit_total;
     uint32_t *hist;
     IBU_CUDA(sc.alloc(&hist, 256 * n_tiles * 4));
@@ -1132,7 +1335,7 @@ static int hash_aggregate(ibu_gpu_ctx *ctx, const uint64_t *recs, uint64_t n, bo
 
 static size_t sort_scratch_bytes(uint64_t n, int elem_bytes) {
     const uint64_t n_tiles = (n + kSortTile - 1) / kSortTile;
-    return n * 2 * elem_bytes + n_tiles * 1024 + 16 * 256;
+    return n * 2 * elem_bytes + n_tiles * 1024 + 16 * 256 + kSweepMaxPasses * 1024 + 1024;
 }
 
 // The pre-partition unsorted path: hash-aggregate into a global table (or, when nearly every pair is

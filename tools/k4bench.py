@@ -92,7 +92,7 @@ def main():
             passes = 4 + 3
             print(json.dumps(dict(case="ibu_gpu_sort_records (random bc16/umi12, index = i)", records=m, ms_best=ts[0],
                                   ms_mean=sum(ts) / len(ts), ms_first_call=first, digit_passes=passes,
-                                  gbs_of_72B_per_pass=72 * m * passes / ts[0] / 1e6,
+                                  gbs_of_48B_per_pass=48 * m * passes / ts[0] / 1e6,
                                   timing="wall clock of the blocking call")), flush=True)
     ctx.close()
 
