@@ -296,7 +296,8 @@ int k4_job_begin(ibu_gpu_ctx *ctx, uint64_t n, const K4Hints &hints, const K4Sam
     job->ub = ub;
     job->r_est = r_est;
     job->weighted = weighted;
-    job->P = std::min<uint64_t>(std::max<uint64_t>(pow2_ceil((n + 1023) / 1024), 2), 1u << 21);
+    static const uint64_t per_bucket = getenv("IBU_B200_K4_BUCKET") ? std::max(64, atoi(getenv("IBU_B200_K4_BUCKET"))) : 1024;  // tuning
+    job->P = std::min<uint64_t>(std::max<uint64_t>(pow2_ceil((n + per_bucket - 1) / per_bucket), 2), 1u << 21);
     job->pb = log2_of(job->P);
     // fan-out per level: at most 2^8 from the records, 2^9 from keys (a 4096-key tile then leaves
     // runs of 16 / 8 keys per bucket); up to 2^9 buckets the records are only turned into keys first

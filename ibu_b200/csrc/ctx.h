@@ -4,6 +4,7 @@
 #include <atomic>
 #include <cuda_runtime.h>
 #include <mutex>
+#include <thread>
 #include <vector>
 
 #include "common.h"
@@ -42,6 +43,7 @@ struct ibu_gpu_ctx {
     std::array<ibu_result_scratch, kResultRing> result_ring;
     std::atomic<uint32_t> result_next{0};
     std::mutex pipe_mutex;  // the chunk slots serve one host-buffer call at a time
+    std::atomic<std::thread::id> pipe_owner{};  // who holds it: a chunk callback that calls back in is refused, not deadlocked
     // the streaming ingest that owns the slots between its open and close (guarded by pipe_mutex, which
     // is NOT held across calls: a stream may be closed from another thread, or after the context)
     struct ibu_gpu_stream *open_stream = nullptr;

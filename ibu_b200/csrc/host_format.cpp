@@ -220,12 +220,17 @@ void ibu_shard_range(uint64_t len, uint32_t rank, uint32_t world, uint64_t *star
 // large files are read here by several threads with pread, each faulting in and filling its own
 // slice of the fresh allocation (2.4 GB: 2.1 s single-threaded, bound by first-touch page
 // faults).  Same result, same error for a file that ends early.
+// (false: errno holds the failing thread's errno, EIO for an unexpected end of file)
 static bool read_all(int fd, void *dst, size_t len) {
-    auto pread_exact = [fd](uint8_t *p, size_t n, off_t off) {
+    std::atomic<int> sys{0};
+    auto pread_exact = [fd, &sys](uint8_t *p, size_t n, off_t off) {
         while (n) {
             ssize_t got = ::pread(fd, p, n, off);
             if (got < 0 && errno == EINTR) continue;
-            if (got <= 0) return false;  // error or unexpected EOF
+            if (got <= 0) {  // error or unexpected EOF (errno is thread-local: carried back explicitly)
+                sys = got < 0 ? errno : EIO;
+                return false;
+            }
             p += got;
             off += got;
             n -= (size_t)got;
@@ -235,7 +240,11 @@ static bool read_all(int fd, void *dst, size_t len) {
     const size_t kPiece = 32u << 20;
     unsigned threads = (unsigned)std::min<size_t>(std::min(16u, std::max(1u, std::thread::hardware_concurrency())),
                                                   len / kPiece);
-    if (threads <= 1) return pread_exact((uint8_t *)dst, len, IBU_HEADER_SIZE);
+    if (threads <= 1) {
+        const bool ok1 = pread_exact((uint8_t *)dst, len, IBU_HEADER_SIZE);
+        if (!ok1) errno = sys.load();
+        return ok1;
+    }
     const size_t per = ((len + threads - 1) / threads + 4095) / 4096 * 4096;
     std::atomic<bool> ok{true};
     std::vector<std::thread> pool;
@@ -248,6 +257,7 @@ static bool read_all(int fd, void *dst, size_t len) {
         });
     }
     for (auto &t : pool) t.join();
+    if (!ok) errno = sys.load();
     return ok;
 }
 

@@ -796,6 +796,23 @@ static unsigned tile_grid(uint64_t n_tiles) { return (unsigned)((n_tiles + 1 + k
 // to the pair: unpack bc16/umi12 on 10^8 records runs in 0.864 ms at the default (6 CTAs, 28 KB
 // L1), 0.766 at 75 % (5 CTAs), 0.763 at 64 % (4 CTAs, 92 KB L1), 0.800 at 50 % (3 CTAs); padding the
 // request to get 4 CTAs WITHOUT enlarging L1 gave 0.876.  profiles/r1_carveout_sweep*.txt.
+// MaxDynamicSharedMemorySize is an attribute of the function (per device), not of a launch: setting
+// it to each launch's own request let two host threads launching one runtime-length instantiation
+// with different lengths interleave set(large), set(small), launch(large) -> invalid value.  It is
+// set once per kernel and device to the most any length can ask for.
+static int set_max_dyn_smem(const void *kern, int device, size_t bytes, ibu_error_t *err) {
+    static std::mutex m;
+    static std::vector<std::pair<const void *, int>> done;
+    std::lock_guard<std::mutex> lock(m);
+    for (const auto &d : done)
+        if (d.first == kern && d.second == device) return IBU_OK;
+    IBU_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    done.emplace_back(kern, device);
+    return IBU_OK;
+}
+constexpr size_t kUnpackMaxSmem = (size_t)(kTileBytes + 2 * kTileRecords * 32) * kWarpsPerBlock;  // any lengths: 90 KB
+constexpr size_t kPackMaxSmem = (size_t)(128 * 24 + 2 * (128 * 32 + 16)) * kWarpsPerBlock;      // Q = 4 rows per lane: 89 KB
+
 static int set_carveout(const void *kern, int carve, ibu_error_t *err) {
     static const int env = getenv("IBU_CARVEOUT") ? atoi(getenv("IBU_CARVEOUT")) : -2;  // tuning hook
     if (env != -2) carve = env;
@@ -852,7 +869,7 @@ static int launch_unpack(ibu_gpu_ctx *ctx, UnpackArgs &a, cudaStream_t s, ibu_er
     // 28 KB L1) costs 13 % and 3 CTAs 5 %.
     const int five_ctas = (int)std::min<size_t>(100, (5 * (smem + 1536) * 100 + 233471) / 233472);
     if (int rc = set_carveout((const void *)kern, kStaged ? five_ctas : -1, err)) return rc;
-    IBU_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (int rc = set_max_dyn_smem((const void *)kern, ctx->device, kUnpackMaxSmem, err)) return rc;
     const unsigned grid = tile_grid(a.n / kTileRecords);
     kern<<<grid, kBlockThreads, smem, s>>>(a);
     g_launches.fetch_add(1, std::memory_order_relaxed);
@@ -876,7 +893,7 @@ static int launch_pack_q(ibu_gpu_ctx *ctx, PackArgs &a, cudaStream_t s, ibu_erro
     const size_t smem = (size_t)off * kWarpsPerBlock;
     auto kern = k_pack<BC, UMI, Q, MINB>;
     if (int rc = set_carveout((const void *)kern, -1, err)) return rc;
-    IBU_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (int rc = set_max_dyn_smem((const void *)kern, ctx->device, kPackMaxSmem, err)) return rc;
     const unsigned grid = tile_grid(a.n / kRows);
     kern<<<grid, kBlockThreads, smem, s>>>(a);
     g_launches.fetch_add(1, std::memory_order_relaxed);
@@ -906,8 +923,7 @@ static int launch_pack_rt(ibu_gpu_ctx *ctx, PackArgs &a, cudaStream_t s, bool *d
     a.warp_smem_bytes = off;
     auto kern = k_pack_rt<Q, 4>;
     if (int rc = set_carveout((const void *)kern, -1, err)) return rc;
-    static std::once_flag once;  // (the attribute is per function: set to the largest request once)
-    std::call_once(once, [&] { cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 56 << 10); });
+    if (int rc = set_max_dyn_smem((const void *)kern, ctx->device, 56u << 10, err)) return rc;
     const uint64_t tiles = a.n / kRows + 1;  // (+1: the warp that owns the ragged tail)
     const uint64_t warps = (tiles + kPackRtTpw - 1) / kPackRtTpw;
     const unsigned grid = (unsigned)std::max<uint64_t>(1, (warps + kWarpsPerBlock - 1) / kWarpsPerBlock);

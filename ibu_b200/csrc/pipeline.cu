@@ -215,8 +215,11 @@ void parallel_memcpy(void *dst, const void *src, size_t bytes, unsigned threads,
 // The same fan-out with pread(2): no page tables are populated for the mapping and an I/O error
 // is a return code, not a SIGBUS.  Each thread reads 64 KB pieces into a cache-resident bounce
 // buffer and streams them on (pread straight into the pinned buffer is the 38 GB/s case above).
+// Returns false on failure with errno set to the failing worker's errno (EIO for an unexpected end of
+// file, which sets none): errno is thread-local, so the worker's value is carried back explicitly.
 bool parallel_pread(void *dst, int fd, uint64_t file_off, size_t bytes, unsigned threads, bool plain = false) {
     std::atomic<bool> ok{true};
+    std::atomic<int> sys{0};
     for_pieces(bytes, threads, bytes >= (32u << 20) ? (1u << 20) : (64u << 10), [&](size_t off, size_t len) {
         constexpr size_t kBounce = 64u << 10;
         alignas(64) uint8_t bounce[kBounce];
@@ -226,6 +229,7 @@ bool parallel_pread(void *dst, int fd, uint64_t file_off, size_t bytes, unsigned
             ssize_t got = ::pread(fd, plain ? p : bounce, std::min(len, plain ? len : kBounce), (off_t)fo);
             if (got < 0 && errno == EINTR) continue;
             if (got <= 0) {
+                sys = got < 0 ? errno : EIO;
                 ok = false;
                 return;
             }
@@ -235,6 +239,7 @@ bool parallel_pread(void *dst, int fd, uint64_t file_off, size_t bytes, unsigned
             len -= (size_t)got;
         }
     });
+    if (!ok) errno = sys.load();
     return ok;
 }
 
@@ -276,6 +281,21 @@ unsigned copy_threads(const ibu_gpu_ctx *ctx) {
     const unsigned hc = std::thread::hardware_concurrency();
     return std::max(2u, std::min(32u, hc / ranks));
 }
+
+// The context's chunk slots serve one host-buffer call at a time.  A chunk callback (on_chunk) runs
+// while the lock is held: calling a host-buffer entry point of the same context from it is refused
+// with IBU_ERR_ARG instead of deadlocking on the non-recursive mutex.
+struct PipeOwner {
+    ibu_gpu_ctx *ctx;
+    explicit PipeOwner(ibu_gpu_ctx *c) : ctx(c) { ctx->pipe_owner.store(std::this_thread::get_id()); }
+    ~PipeOwner() { ctx->pipe_owner.store(std::thread::id()); }
+};
+#define IBU_PIPE_LOCK(ctx)                                                                                        \
+    if ((ctx)->pipe_owner.load() == std::this_thread::get_id())                                                   \
+        return set_error(err, IBU_ERR_ARG, 0, 0, 0, "re-entered from a chunk callback: the context is in use");   \
+    std::lock_guard<std::mutex> lock((ctx)->pipe_mutex);                                                          \
+    PipeOwner pipe_owner_guard(ctx);                                                                              \
+    if ((ctx)->open_stream) return set_error(err, IBU_ERR_ARG, 0, 0, 0, "context busy: a streaming ingest is open on it")
 
 // What one chunk moves: inputs (host -> device) and outputs (device -> host) as byte spans
 // relative to the slot's device buffers.
@@ -395,8 +415,7 @@ int process_host_records(ibu_gpu_ctx *ctx, const ibu_record_t *h_records, uint64
                          ibu_chunk_cb on_chunk, void *user, ibu_error_t *err, int fd = -1,
                          uint64_t file_off = 0) {
     DeviceGuard guard(ctx->device);
-    std::lock_guard<std::mutex> lock(ctx->pipe_mutex);
-    if (ctx->open_stream) return set_error(err, IBU_ERR_ARG, 0, 0, 0, "context busy: a streaming ingest is open on it");
+    IBU_PIPE_LOCK(ctx);
     memset(h_result, 0, sizeof(*h_result));
     if (n == 0) return IBU_OK;  // an empty range never calls on_batch_complete (mmap.rs:502-519)
     const uint64_t chunk = chunk_records(ctx);
@@ -466,8 +485,7 @@ int ibu::process_records_ops(ibu_gpu_ctx *ctx, const ibu_record_t *h_records, ui
     if (!want_table && !keep && !unpack)
         return process_host_records(ctx, h_records, n, bc_len, umi_len, first_record, h_result, on_chunk, user, err, fd, file_off);
     DeviceGuard guard(ctx->device);
-    std::lock_guard<std::mutex> lock(ctx->pipe_mutex);
-    if (ctx->open_stream) return set_error(err, IBU_ERR_ARG, 0, 0, 0, "context busy: a streaming ingest is open on it");
+    IBU_PIPE_LOCK(ctx);
     memset(h_result, 0, sizeof(*h_result));
     if (want_table && req->table) {
         req->table->n_records = n;
@@ -1190,8 +1208,7 @@ int ibu_gpu_load_to_device(ibu_gpu_ctx_t *ctx, const char *path, uint64_t start,
         return rc;
     }
     DeviceGuard guard(ctx->device);
-    std::lock_guard<std::mutex> lock(ctx->pipe_mutex);
-    if (ctx->open_stream) return set_error(err, IBU_ERR_ARG, 0, 0, 0, "context busy: a streaming ingest is open on it");
+    IBU_PIPE_LOCK(ctx);
     const uint64_t count = end - start;
     void *dev = nullptr;
     cudaError_t e = cudaMalloc(&dev, count ? count * IBU_RECORD_SIZE : kAlign);
@@ -1247,8 +1264,7 @@ int ibu_gpu_write_records(ibu_gpu_ctx_t *ctx, ibu_writer_t *writer, const ibu_re
     if (!ctx || !writer || (!d_records && n)) return set_error(err, IBU_ERR_ARG, 0, 0, 0, "null argument");
     if (n == 0) return IBU_OK;
     DeviceGuard guard(ctx->device);
-    std::lock_guard<std::mutex> lock(ctx->pipe_mutex);
-    if (ctx->open_stream) return set_error(err, IBU_ERR_ARG, 0, 0, 0, "context busy: a streaming ingest is open on it");
+    IBU_PIPE_LOCK(ctx);
     const uint64_t chunk = chunk_records(ctx);
     const uint64_t n_chunks = (n + chunk - 1) / chunk;
     const size_t n_slots = ctx->slots.size();
@@ -1289,8 +1305,7 @@ int ibu_gpu_unpack_host(ibu_gpu_ctx_t *ctx, const ibu_record_t *h_records, uint6
     if (h_result) *h_result = total;
     if (n == 0) return IBU_OK;
     DeviceGuard guard(ctx->device);
-    std::lock_guard<std::mutex> lock(ctx->pipe_mutex);
-    if (ctx->open_stream) return set_error(err, IBU_ERR_ARG, 0, 0, 0, "context busy: a streaming ingest is open on it");
+    IBU_PIPE_LOCK(ctx);
     const uint64_t chunk = chunk_records(ctx);
     const uint64_t n_chunks = (n + chunk - 1) / chunk;
     const bool pin_in = is_pinned(h_records), pin_bc = is_pinned(h_bc_ascii), pin_umi = is_pinned(h_umi_ascii),
@@ -1339,8 +1354,7 @@ int ibu_gpu_pack_host(ibu_gpu_ctx_t *ctx, const uint8_t *h_bc_ascii, const uint8
     if (h_result) *h_result = total;
     if (n == 0) return IBU_OK;
     DeviceGuard guard(ctx->device);
-    std::lock_guard<std::mutex> lock(ctx->pipe_mutex);
-    if (ctx->open_stream) return set_error(err, IBU_ERR_ARG, 0, 0, 0, "context busy: a streaming ingest is open on it");
+    IBU_PIPE_LOCK(ctx);
     const uint64_t chunk = chunk_records(ctx);
     const uint64_t n_chunks = (n + chunk - 1) / chunk;
     const bool pin_bc = is_pinned(h_bc_ascii), pin_umi = is_pinned(h_umi_ascii),

@@ -355,7 +355,12 @@ int ibu_gpu_generate_ascii_async(ibu_gpu_ctx_t *ctx, uint8_t *d_ascii, uint64_t 
  * reduced on device.  `on_chunk` (nullable) is the on_batch_complete analogue
  * (parallel.rs:141-151): called on the calling thread after each chunk's result
  * has landed, in chunk order, with that chunk's result; a non-zero return
- * aborts with IBU_ERR_PROCESS. */
+ * aborts with IBU_ERR_PROCESS.  A chunk is IBU_BATCH_SIZE records unless the context
+ * was configured otherwise — the reference's own batch (mmap.rs:284, 322-326).
+ * The callback runs while the context's chunk slots are in use: host-buffer entry
+ * points of the SAME context called from it (process_*, unpack_host, pack_host,
+ * load_to_device, write_records, table_to_host, stream_open) return IBU_ERR_ARG;
+ * device-pointer (_async) calls and other contexts are fine. */
 typedef int (*ibu_chunk_cb)(void *user, uint64_t chunk_start, uint64_t chunk_n,
                             const ibu_reduce_result_t *chunk_result);
 int ibu_gpu_process_mmap(ibu_gpu_ctx_t *ctx, const ibu_mmap_reader_t *reader, uint64_t start,

@@ -102,6 +102,26 @@ def test_process_gpu_callback_error_aborts(ctx, tmp_ibu):  # parallel.rs:338-352
     assert calls == [0, 1 << 18]
 
 
+def test_chunk_callback_cannot_reenter_its_context(ctx, tmp_ibu):
+    """on_chunk runs while the context's chunk slots are in use: a host-buffer call on the same
+    context from inside it is refused (IBU_ERR_ARG), not deadlocked; device-pointer calls are fine."""
+    recs = oc.generate_records(0, 600_000, 16, 12, 0, 0, 2)
+    write(tmp_ibu, recs)
+    seen = []
+
+    def cb(start, cnt, res):
+        try:
+            ctx.process_host(recs[:1000], 16, 12)
+            seen.append("ran")
+        except ibu.ArgError:
+            seen.append("refused")
+        return 0
+
+    red = ibu.MmapReader(tmp_ibu).process_gpu(ctx, on_chunk=cb)
+    assert red == oc.reduce_records(recs, 16, 12) and seen and set(seen) == {"refused"}
+    assert ctx.process_host(recs[:1000], 16, 12)["n_records"] == 1000  # and the context is usable afterwards
+
+
 def test_process_host_pinned_and_pageable(ctx):
     n = 600_001
     recs = oc.generate_records(9, n, 20, 10, 1, 10_000, 8)
