@@ -185,6 +185,16 @@ int k4_sample(ibu_gpu_ctx *ctx, const uint64_t *recs, uint64_t n, cudaStream_t s
     return IBU_OK;
 }
 
+// What the sample says about the whole input: distinct (barcode, umi) pairs and distinct barcodes
+// (Chao1 lower bounds, capped at n).
+void k4_estimates(const K4Sample &smp, uint64_t n, double *d_est, double *r_est) {
+    *d_est = *r_est = 0;
+    if (!smp.valid || n == 0) return;
+    const bool whole = smp.m >= n;
+    *d_est = whole ? smp.pairs : std::min((double)n, chao1(smp.pairs, smp.pair_f1, smp.pair_f2, (double)n));
+    *r_est = whole ? smp.barcodes : std::min((double)n, chao1(smp.barcodes, smp.bc_f1, smp.bc_f2, (double)n));
+}
+
 // One table build of the partition path, in three steps so that an ingest pipeline can feed it chunk by
 // chunk: begin (sizes from the sample, scratch), add (level-1 partition of a chunk's keys, stream
 // ordered, any stream that waited for ready()), finish (further levels, de-duplicate, rows).

@@ -962,7 +962,7 @@ static size_t seg_scratch_bytes(uint64_t n) {
 // counts are sums of the records' index words.  *unsorted is set when the order check failed.
 static int segment_pass(ibu_gpu_ctx *ctx, const uint64_t *src, int stride, uint64_t n, cudaStream_t s,
                         bool pair_mode, bool weighted, uint64_t **rows_out, uint64_t *n_rows, uint64_t *n_pairs,
-                        bool *unsorted, ibu_error_t *err) {
+                        bool *unsorted, ibu_error_t *err, uint64_t rows_hint = 0) {
     Trace tr;
     *rows_out = nullptr;
     *n_rows = *n_pairs = 0;
@@ -988,7 +988,8 @@ static int segment_pass(ibu_gpu_ctx *ctx, const uint64_t *src, int stride, uint6
     const int grid = (int)std::min<uint64_t>((uint64_t)ctx->sm_count * std::max(per_sm, 1),
                                              (n_tiles + tiles_per_cta - 1) / tiles_per_cta);
 
-    uint64_t capacity = seg_capacity(n);  // optimistic: <= 8 Mi rows
+    // optimistic: <= 8 Mi rows, unless the caller knows better (a sample said: about this many rows)
+    uint64_t capacity = std::max(seg_capacity(n), std::min<uint64_t>(n, rows_hint + rows_hint / 4));
     for (int attempt = 0; attempt < 2; attempt++) {
         IBU_CUDA(sc.alloc(&tmp_rows, capacity * 24));
         IBU_CUDA(cudaMemsetAsync(desc, 0, n_tiles * 16, s));
@@ -1178,7 +1179,8 @@ static int radix_sort(ibu_gpu_ctx *ctx, const uint64_t *in, uint64_t *first_dst,
 
 // Table of an unsorted input: sort by (barcode, umi), then the streaming segment pass.
 static int unsorted_table(ibu_gpu_ctx *ctx, const uint64_t *recs, uint64_t n, cudaStream_t s, bool pair_mode,
-                          bool weighted, uint64_t **rows, uint64_t *n_rows, uint64_t *n_pairs, ibu_error_t *err) {
+                          bool weighted, uint64_t **rows, uint64_t *n_rows, uint64_t *n_pairs, ibu_error_t *err,
+                          uint64_t rows_hint = 0) {
     Scratch sc(ctx);
     static const int order[2] = {1, 0};  // umi is the minor key, barcode the major one
     uint64_t vary[3];
@@ -1221,7 +1223,7 @@ static int unsorted_table(ibu_gpu_ctx *ctx, const uint64_t *recs, uint64_t n, cu
     }
     bool still_unsorted = false;
     if (int rc = segment_pass(ctx, sorted, stride, n, s, pair_mode, weighted, rows, n_rows, n_pairs,
-                              &still_unsorted, err))
+                              &still_unsorted, err, rows_hint))
         return rc;
     if (still_unsorted)
         return set_error(err, IBU_ERR_CUDA, 0, 0, 0, "internal error: radix sort left the keys unsorted");
@@ -1341,14 +1343,17 @@ static size_t sort_scratch_bytes(uint64_t n, int elem_bytes) {
 // The pre-partition unsorted path: hash-aggregate into a global table (or, when nearly every pair is
 // distinct, radix sort 16-byte pairs), then the segment pass.  Caller holds ctx->arena_mutex.
 int k4_legacy_unsorted(ibu_gpu_ctx *ctx, const uint64_t *src, uint64_t n, cudaStream_t s, bool pair_mode,
-                       bool weighted, uint64_t **rows, uint64_t *n_rows, uint64_t *n_pairs, ibu_error_t *err) {
+                       bool weighted, uint64_t **rows, uint64_t *n_rows, uint64_t *n_pairs, ibu_error_t *err,
+                       double d_est, double r_est) {
     // duplicate-heavy inputs: fold to distinct pairs first, then sort/count only those
     // room for the first table (256 MiB), the compacted pairs and their sort; a larger
     // full-size table falls back to a one-off allocation inside Scratch
     IBU_CUDA(arena_reset(ctx, (768ull << 20) + seg_scratch_bytes(std::min<uint64_t>(n, 8ull << 20))));
     Trace tr;
     tr.mark("table: arena");
-    bool use_sort = getenv("IBU_B200_NO_HASH") != nullptr;
+    // (a sample that says "nearly every pair is distinct" skips the hash attempt: it would only find that out again)
+    bool use_sort = getenv("IBU_B200_NO_HASH") != nullptr || d_est > 0.4 * (double)n;
+    const uint64_t rows_hint = (uint64_t)(pair_mode ? d_est : r_est);
     if (!use_sort) {
         Scratch sc(ctx);
         uint64_t *pairs = nullptr, k = 0;
@@ -1360,8 +1365,9 @@ int k4_legacy_unsorted(ibu_gpu_ctx *ctx, const uint64_t *src, uint64_t n, cudaSt
             return rc;
         }
     }
-    IBU_CUDA(arena_reset(ctx, sort_scratch_bytes(n, weighted ? 24 : 16) + seg_scratch_bytes(n)));
-    return unsorted_table(ctx, src, n, s, pair_mode, weighted, rows, n_rows, n_pairs, err);
+    IBU_CUDA(arena_reset(ctx, sort_scratch_bytes(n, weighted ? 24 : 16) + seg_scratch_bytes(n) +
+                              std::min<uint64_t>(n, rows_hint + rows_hint / 4) * 24));
+    return unsorted_table(ctx, src, n, s, pair_mode, weighted, rows, n_rows, n_pairs, err, rows_hint);
 }
 
 int k4_sort_rows(ibu_gpu_ctx *ctx, const uint64_t *rows, uint64_t n, const uint64_t vary[3], const int *key_order,
@@ -1422,7 +1428,9 @@ int k4_build_table(ibu_gpu_ctx *ctx, const ibu_record_t *d_records, uint64_t n, 
             tr.mark("table: partition path total");
             if (handled) return IBU_OK;
         }
-        return k4_legacy_unsorted(ctx, src, n, s, pair_mode, weighted, rows, n_rows, n_pairs, err);
+        double d_est = 0, r_est = 0;
+        k4_estimates(smp, n, &d_est, &r_est);
+        return k4_legacy_unsorted(ctx, src, n, s, pair_mode, weighted, rows, n_rows, n_pairs, err, d_est, r_est);
     }
     return IBU_OK;
 }

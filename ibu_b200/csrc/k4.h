@@ -59,8 +59,11 @@ K4Hints k4_hints_of(int mode);  // from the upper bits of `mode` / `flags` (IBU_
 
 // Legacy unsorted path: global hash aggregation or 16-byte pair radix sort, then the segment pass.
 // *rows comes from cudaMallocAsync on `s` (3 u64 per row).
+// d_est / r_est (0 = unknown): the sample's estimates of distinct pairs / barcodes — a near-distinct
+// input skips the hash-aggregation attempt, and the segment pass starts with room for its rows.
 int k4_legacy_unsorted(ibu_gpu_ctx *ctx, const uint64_t *recs, uint64_t n, cudaStream_t s, bool pair_mode,
-                       bool weighted, uint64_t **rows, uint64_t *n_rows, uint64_t *n_pairs, ibu_error_t *err);
+                       bool weighted, uint64_t **rows, uint64_t *n_rows, uint64_t *n_pairs, ibu_error_t *err,
+                       double d_est = 0, double r_est = 0);
 
 // Stable LSD radix sort of n 3-word rows by the key words listed in key_order (least significant
 // first), restricted to the bits set in vary[word]; the sorted rows are written to dst (n * 24 B).
@@ -81,6 +84,7 @@ struct K4Sample {
     uint32_t hist[130] = {};                 // [2][65] bit widths of the barcode / umi words
 };
 int k4_sample(ibu_gpu_ctx *ctx, const uint64_t *recs, uint64_t n, cudaStream_t s, K4Sample *out, ibu_error_t *err);
+void k4_estimates(const K4Sample &smp, uint64_t n, double *d_est, double *r_est);  // Chao1, capped at n
 
 // Partition-then-aggregate table of an unsorted input.  *handled = false (and nothing produced)
 // when the input does not suit this path (keys wider than 64 bits, too few distinct keys, too
