@@ -83,3 +83,35 @@ def test_barcode_table_sort_and_pairs(n, seed, nb, us, presort, weird):
         c.d2h(got, o)
         assert np.array_equal(got, recs[np.lexsort((recs["index"], recs["umi"], recs["barcode"]))])
     c.free(d), c.free(o)
+
+
+@settings(max_examples=60, deadline=None, suppress_health_check=list(HealthCheck))
+@given(n=st.integers(1, 400_000), seed=st.integers(0, 2**32), nb=st.integers(1, 200_000), us=st.integers(1, 1 << 24),
+       gen=st.sampled_from([3, 5, 2, 1]), weird=st.sampled_from([0, 0, 1, 2]), hint=st.booleans(),
+       chunk=st.sampled_from([1 << 12, 1 << 14, 1 << 16]), ranks=st.sampled_from([1, 2, 3]))
+def test_partition_path_everywhere(n, seed, nb, us, gen, weird, hint, chunk, ranks):
+    """The partition path (forced, whatever the sample would choose) over random shapes — whitelist,
+    Zipf, the example pattern, dirty random records; a few records with words wider than the key
+    layout or the all-ones key — through its three routes: a resident array, the chunked ingest
+    pipeline (records arrive piece by piece on several streams) and the multi-rank group (pair mode +
+    weighted owner count).  All three must equal the oracle's table."""
+    param = {3: (us << 32) | nb, 5: (us << 32) | nb, 2: 0, 1: 20_000}[gen]
+    recs = oc.generate_records(seed % 997, n, 16, 12, gen, param, seed)
+    if weird and n:
+        recs["umi"][:: max(1, n // 11)] |= np.uint64(1 << 55)  # wider than umi12: the side list
+        if weird == 2:
+            recs["barcode"][:: max(1, n // 3)] = np.uint64(2**64 - 1)
+    want = on.barcode_table(recs)
+    mode = 2 | ibu.COUNT_PATH_PARTITION | (ibu.count_lens(16, 12) if hint else 0)
+    c = ctx()
+    d = c.malloc(max(24 * n, 32))
+    c.h2d(d, recs)
+    rows, info = c.barcode_count(d, n, mode)
+    c.free(d)
+    assert np.array_equal(rows, want) and info["n_distinct_pairs"] == int(want["n_distinct_umi"].sum())
+    with ibu.GpuContext(0, chunk_records=chunk, n_slots=3) as c2:
+        red, out = c2.process_host_ops(recs, 16, 12, table=True, table_mode=mode)
+        assert red == oc.reduce_records(recs, 16, 12, 1) and np.array_equal(out.rows, want)
+    with ibu.GpuGroup([0] * ranks, chunk_records=chunk) as g:
+        red, out = g.process_host(recs, 16, 12, table=True, table_mode=mode)
+        assert red == oc.reduce_records(recs, 16, 12, 1) and np.array_equal(out.rows, want)
