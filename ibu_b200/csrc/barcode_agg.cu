@@ -216,6 +216,7 @@ struct K4Job {
     uint64_t P = 0, wide_cap = 0;
     double r_est = 0;
     bool exact = false, weighted = false, packed = false;
+    bool ordered = false;  // order-preserving keys and k_bucket_rows instead of the hash table (k4_ordered.cuh)
     std::vector<K4Level> levels;  // levels[0] is filled by add(); the last one feeds the de-duplication
     // chunked mode: add() takes the records in pieces of `chunk` records, partitions a piece into a
     // small level-0 area of its stream (written and read back while still in L2) and straight on
@@ -290,11 +291,15 @@ int k4_job_begin(ibu_gpu_ctx *ctx, uint64_t n, const K4Hints &hints, const K4Sam
         fprintf(stderr, "[ibu trace] sample: m=%llu pairs %.0f (f1 %.0f f2 %.0f coll %.0f) barcodes %.0f (f1 %.0f f2 %.0f) -> D~%.3g R~%.3g bb=%u ub=%u\n",
                 (unsigned long long)smp.m, smp.pairs, smp.pair_f1, smp.pair_f2, smp.pair_coll, smp.barcodes, smp.bc_f1,
                 smp.bc_f2, d_est, r_est, bb, ub);
-    if (!forced) {
-        if (d_est < 65536.0) return IBU_OK;  // a tiny global table is L2 resident: legacy hash path
-        // about as many barcodes as records: the rows would need a full-size sort (and a table far
-        // outside L2); the sort-based path handles that shape
-        if (!pair_mode && r_est > 8.0e6 && r_est > 0.05 * (double)n) return IBU_OK;
+    if (!forced && d_est < 65536.0) return IBU_OK;  // a tiny global table is L2 resident: legacy hash path
+    // about as many barcodes as records: a table far outside L2 and a full-size sort of its rows
+    // afterwards — the buckets are cut by the barcode's own top bits instead and finished in
+    // barcode order (k4_ordered.cuh); IBU_B200_K4_ORDERED=0/1 forces the choice (tests, tuning)
+    bool ordered = !pair_mode && r_est > 8.0e6 && r_est > 0.05 * (double)n;
+    if (const char *e = getenv("IBU_B200_K4_ORDERED")) ordered = !pair_mode && atoi(e) != 0;
+    if (ordered && weighted) {
+        if (!forced) return IBU_OK;  // (the multiplicities would have to travel through the bucket sort: sort fallback)
+        ordered = false;
     }
 
     // ---- sizes ----
@@ -309,6 +314,11 @@ int k4_job_begin(ibu_gpu_ctx *ctx, uint64_t n, const K4Hints &hints, const K4Sam
     static const uint64_t per_bucket = getenv("IBU_B200_K4_BUCKET") ? std::max(64, atoi(getenv("IBU_B200_K4_BUCKET"))) : 1024;  // tuning
     job->P = std::min<uint64_t>(std::max<uint64_t>(pow2_ceil((n + per_bucket - 1) / per_bucket), 2), 1u << 21);
     job->pb = log2_of(job->P);
+    if (ordered && job->pb + 1 > bb) {  // fewer barcode bits than bucket bits: a barcode would span buckets
+        if (!forced) return IBU_OK;
+        ordered = false;
+    }
+    job->ordered = ordered;
     // fan-out per level: at most 2^8 from the records, 2^9 from keys (a 4096-key tile then leaves
     // runs of 16 / 8 keys per bucket); up to 2^9 buckets the records are only turned into keys first
     const uint32_t pb = job->pb;
@@ -326,7 +336,8 @@ int k4_job_begin(ibu_gpu_ctx *ctx, uint64_t n, const K4Hints &hints, const K4Sam
         // uniform layout with mean + 6 sigma room per bucket
         const double buckets = (double)(1ull << used);
         const double mean = (double)n / buckets, sigma = std::sqrt(sum_sq / buckets);
-        lv.cap = ((uint64_t)(mean + 6.0 * sigma) + 64 + 15) & ~15ull;
+        // (ordered keys are only as uniform as the barcodes' top bits: a quarter more room)
+        lv.cap = ((uint64_t)((ordered ? 1.25 : 1.0) * mean + 6.0 * sigma) + 64 + 15) & ~15ull;
         if (l + 1 < bits.size()) {
             // a level whose loads are this uneven (a few keys hold most of the records) is not worth
             // laying out: the global hash of the legacy path keeps such keys in L2
@@ -339,7 +350,7 @@ int k4_job_begin(ibu_gpu_ctx *ctx, uint64_t n, const K4Hints &hints, const K4Sam
     const double mean = (double)n / (double)job->P;
     // when duplicates make the final loads too uneven for the uniform layout (or the first attempt
     // overflows) the final buckets are laid out exactly from a histogram of the level before
-    job->exact = chunking.force_exact || (double)last.cap > 3.0 * mean + 256.0;
+    job->exact = ordered || chunking.force_exact || (double)last.cap > 3.0 * mean + 256.0;
     bytes += job->exact ? n * (weighted ? 16 : 8) : job->P * last.cap * (weighted ? 16 : 8);
     if (bytes > (64ull << 30)) return IBU_OK;
     // shared-memory table: 1.6 slots per key of the fullest bucket the uniform layout admits (all of
@@ -403,7 +414,8 @@ int k4_job_add(K4Job *job, const uint64_t *recs, uint64_t cnt, cudaStream_t s, i
     job->added += cnt;
     const K4Level &l0 = job->levels[0];
     auto part1 = [&](const uint64_t *r, uint64_t c, uint32_t *cursors, uint64_t *keys, uint64_t *wts) -> int {
-        Part1Args a{r, c, job->bb, job->ub, l0.bits, l0.cap, cursors, keys, wts, job->wide, job->wide_cap, job->ctr};
+        Part1Args a{r, c, job->bb, job->ub, l0.bits, l0.cap, cursors, keys, wts, job->wide, job->wide_cap, job->ctr,
+                    job->ordered ? 1u : 0u};
         const uint32_t grid = (uint32_t)((c + kPartTile - 1) / kPartTile);
         if (job->weighted) k_part1<true><<<grid, kBlockThreads, (size_t)kPartTile * 16, s>>>(a);
         else k_part1<false><<<grid, kBlockThreads, (size_t)kPartTile * 8, s>>>(a);
@@ -434,6 +446,113 @@ int k4_job_add(K4Job *job, const uint64_t *recs, uint64_t cnt, cudaStream_t s, i
                     l1.cap, nullptr, l1.cursors, l1.keys, l1.wts, job->ctr, L == 2 ? (uint32_t)kFlagBucket : (uint32_t)kFlagLevel};
         if (int rc = launch_part2<false>(job->ctx, a, 1ull << l1.bits_in, job->weighted, s, err)) return rc;
     }
+    return IBU_OK;
+}
+
+// The ordered form of the last stage: every final bucket sorted in shared memory, its rows written in
+// place (k4_ordered.cuh).  The job's last level is laid out exactly (job->bases) when this runs.
+static int finish_ordered(K4Job *job, uint64_t **rows_out, uint64_t *n_rows, uint64_t *n_pairs, bool *handled,
+                          ibu_error_t *err) {
+    ibu_gpu_ctx *ctx = job->ctx;
+    cudaStream_t s = job->s0;
+    PoolScratch &sc = job->sc;
+    unsigned long long *mail = ctx->h_mail, *ctr = job->ctr;
+    const uint64_t n = job->added, P = job->P;
+    const K4Level &last = job->levels.back();
+    // IBU_B200_K4_ORDERED=2 (tests): an input this path has to hand to the sort fallback is an error
+    auto give_up = [&]() -> int {
+        const char *e = getenv("IBU_B200_K4_ORDERED");
+        if (e && atoi(e) == 2) return set_error(err, IBU_ERR_ARG, 0, mail[kCtrFlags], 0, "ordered table path gave up");
+        return IBU_OK;
+    };
+    // the wide list is complete: its size (and the overflow flags of the levels) before the buckets are read
+    IBU_CUDA(cudaMemcpyAsync(mail, ctr, kCtrWords * 8, cudaMemcpyDeviceToHost, s));
+    IBU_CUDA(cudaStreamSynchronize(s));
+    const uint64_t n_wide = mail[kCtrWide];
+    if (job->trace)
+        fprintf(stderr, "[ibu trace] ordered: %zu levels to P=2^%u, wide %llu flags %llx\n", job->levels.size(), job->pb,
+                (unsigned long long)n_wide, mail[kCtrFlags]);
+    if ((mail[kCtrFlags] & (kFlagLevel | kFlagWide | kFlagBucket)) || mail[kCtrSpecial]) {
+        job->overflowed = false;  // (nothing a second attempt of this path would change)
+        return give_up();
+    }
+    uint64_t *wrows = nullptr, wn = 0, wp = 0;
+    uint32_t *wstart = nullptr;
+    struct FreeRows {  // rows of the wide list: cudaMallocAsync'ed by the legacy path
+        uint64_t *&p;
+        cudaStream_t s;
+        ~FreeRows() {
+            if (p && cudaFreeAsync(p, s) != cudaSuccess) cudaGetLastError();
+        }
+    } free_wrows{wrows, s};
+    if (n_wide) {
+        if (int rc = k4_legacy_unsorted(ctx, job->wide, n_wide, s, false, true, &wrows, &wn, &wp, err)) return rc;
+        if (wn >= (1ull << 32)) return give_up();
+        IBU_CUDA(sc.alloc(&wstart, (P + 1) * 4));
+        k_wide_starts<<<(uint32_t)((P + 1 + kBlockThreads - 1) / kBlockThreads), kBlockThreads, 0, s>>>(
+            wrows, (uint32_t)wn, (uint32_t)P, job->bb - job->pb, wstart);
+        IBU_LAUNCHED("k_wide_starts");
+        job->timer.lap("wide list");
+    }
+    uint32_t *rows_of;
+    uint64_t *row_base;
+    IBU_CUDA(sc.alloc(&rows_of, P * 4));
+    IBU_CUDA(sc.alloc(&row_base, (P + 1) * 8));
+    IBU_CUDA(cudaMemsetAsync(rows_of, 0, P * 4, s));
+    IBU_CUDA(cudaMemsetAsync(ctr + kCtrClaimed, 0, (kCtrWords - kCtrClaimed) * 8, s));
+    // rows: at most one per record; handed to the caller as it is unless far too large
+    uint64_t *out = nullptr;
+    const uint64_t rows_cap = std::max<uint64_t>(n, 1);
+    IBU_CUDA(alloc_result_rows(ctx, &out, rows_cap * 24, s));
+    auto fail = [&](int rc) {
+        if (cudaFreeAsync(out, s) != cudaSuccess) cudaGetLastError();
+        return rc;
+    };
+    // the mean bucket has 512 - 1024 keys; k_bucket_sort holds two key arrays, k_bucket_emit one and the row starts
+    const uint32_t cap = 2048;
+    if (int rc = set_max_smem(k_bucket_sort, ctx->device, 4096 * 16, err)) return fail(rc);
+    if (int rc = set_max_smem(k_bucket_emit, ctx->device, 4096 * 12 + 8, err)) return fail(rc);
+    OrdArgs a{job->bases, last.keys, (uint32_t)P, job->pb, job->bb, cap, wrows, wstart, rows_of, row_base, ctr, out, rows_cap};
+    k_bucket_sort<<<(uint32_t)std::min<uint64_t>(P, (uint64_t)ctx->sm_count * 5), kBlockThreads, (size_t)cap * 16, s>>>(a);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    if (cudaError_t e = cudaGetLastError()) return fail(cuda_fail(err, e, "k_bucket_sort"));
+    job->timer.lap("k_bucket_sort");
+    k_bucket_bases<<<1, 1024, 0, s>>>(rows_of, (uint32_t)P, row_base);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    k_bucket_emit<<<(uint32_t)std::min<uint64_t>(P, (uint64_t)ctx->sm_count * 6), kBlockThreads, (size_t)cap * 12 + 8, s>>>(a);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    if (cudaError_t e = cudaGetLastError()) return fail(cuda_fail(err, e, "k_bucket_emit"));
+    if (wn) {
+        k_wide_tail<<<ctx->sm_count, kBlockThreads, 0, s>>>(wrows, (uint32_t)wn, wstart, (uint32_t)P, row_base, out, rows_cap, ctr);
+        g_launches.fetch_add(1, std::memory_order_relaxed);
+        if (cudaError_t e = cudaGetLastError()) return fail(cuda_fail(err, e, "k_wide_tail"));
+    }
+    job->timer.lap("k_bucket_emit");
+    cudaError_t e = cudaMemcpyAsync(mail, ctr, kCtrWords * 8, cudaMemcpyDeviceToHost, s);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(mail + kCtrWords, row_base + P, 8, cudaMemcpyDeviceToHost, s);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+    if (e != cudaSuccess) return fail(cuda_fail(err, e, "k_bucket_emit"));
+    const uint64_t R = mail[kCtrWords] + mail[kCtrTail];
+    if (job->trace)
+        fprintf(stderr, "[ibu trace] ordered: rows %llu (+%llu beyond the layout) pairs %llu flags %llx\n", mail[kCtrWords],
+                mail[kCtrTail], mail[kCtrPairs] + (unsigned long long)wp, mail[kCtrFlags]);
+    if (mail[kCtrFlags] & (kFlagSmem | kFlagPairsOut)) return fail(give_up());  // a bucket that does not fit: sort fallback
+    if (R * 2 < rows_cap) {  // far fewer barcodes than records after all: a block of the right size
+        uint64_t *fit = nullptr;
+        e = alloc_result_rows(ctx, &fit, R * 24, s);
+        if (e == cudaSuccess && R) e = cudaMemcpyAsync(fit, out, R * 24, cudaMemcpyDeviceToDevice, s);
+        if (e != cudaSuccess) {
+            if (fit && cudaFreeAsync(fit, s) != cudaSuccess) cudaGetLastError();
+            return fail(cuda_fail(err, e, "barcode rows"));
+        }
+        if (cudaFreeAsync(out, s) != cudaSuccess) cudaGetLastError();
+        out = fit;
+        if ((e = cudaStreamSynchronize(s)) != cudaSuccess) return fail(cuda_fail(err, e, "barcode rows"));
+    }
+    *rows_out = out;
+    *n_rows = R;
+    *n_pairs = mail[kCtrPairs] + wp;
+    *handled = true;
     return IBU_OK;
 }
 
@@ -505,6 +624,8 @@ int k4_job_finish(K4Job *job, const uint64_t *all_recs, bool pair_mode, bool pai
         if (rc < 0) return IBU_OK;
         if (rc) return rc;
     }
+
+    if (job->ordered) return finish_ordered(job, rows_out, n_rows, n_pairs, handled, err);
 
     // ---- per-bucket de-duplication into the barcode table (grown if the estimate was short) ----
     // barcode table: generous (skewed barcode frequencies make the estimate a lower bound); only the
@@ -624,7 +745,7 @@ int k4_job_finish(K4Job *job, const uint64_t *all_recs, bool pair_mode, bool pai
         IBU_LAUNCHED("k_table_rows");
         timer.lap("k_table_rows");
     }
-    IBU_CUDA(cudaMallocAsync((void **)&out, (R + ones) ? (R + ones) * 24 : 256, s));
+    IBU_CUDA(alloc_result_rows(ctx, &out, (R + ones) * 24, s));
     int rc = IBU_OK;
     if (R) {
         const uint64_t vary[3] = {n_wide ? ~0ull : (1ull << bb) - 1, 0, 0};

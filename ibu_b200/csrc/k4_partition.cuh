@@ -39,6 +39,7 @@ enum {
     kCtrCursor = 5,    // append cursor (pair output / row output)
     kCtrOnesRec = 6,   // n_records of barcode 0xFFFF'FFFF'FFFF'FFFF (collides with the table's empty marker)
     kCtrOnesDist = 7,  // n_distinct_umi of that barcode
+    kCtrTail = 8,      // ordered path: wide rows appended after the last bucket
     kCtrWords = 16
 };
 enum { kFlagBucket = 1, kFlagWide = 2, kFlagTable = 4, kFlagSmem = 8, kFlagPairsOut = 16, kFlagLevel = 32 };
@@ -251,3 +252,4 @@ __global__ void __launch_bounds__(kBlockThreads) k_extra_pairs(const ExtraArgs a
 }  // namespace ibu
 
 #include "k4_staged.cuh"
+#include "k4_ordered.cuh"

@@ -31,6 +31,7 @@ struct Part1Args {
     uint64_t *wide;        // records that do not fit the key layout
     uint64_t wide_cap;
     unsigned long long *ctr;
+    uint32_t ordered;      // 1: order-preserving keys, (barcode << ub | umi) left-aligned (k4_ordered.cuh), instead of mixed ones
 };
 
 // block-wide exclusive scan of one value per thread (256 threads); `tmp` holds 8 words
@@ -93,7 +94,8 @@ __global__ void __launch_bounds__(kBlockThreads, WEIGHTED ? 2 : K4_PART_MINB) k_
             uint64_t k = kEmpty;  // kEmpty = not staged
             if (first + q < a.n) {
                 if (((bc[q] >> a.bb) | (um[q] >> a.ub)) == 0ull) {
-                    k = mix64((bc[q] << a.ub) | um[q]);
+                    const uint64_t raw = (bc[q] << a.ub) | um[q];
+                    k = a.ordered ? raw << (64u - a.bb - a.ub) : mix64(raw);
                     if (k == kEmpty) atomicAdd(a.ctr + kCtrSpecial, (unsigned long long)(WEIGHTED ? w[q] : 1ull));
                 } else {
                     const uint64_t pos = atomicAdd(a.ctr + kCtrWide, 1ull);

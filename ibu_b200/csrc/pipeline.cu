@@ -753,6 +753,7 @@ void ibu_gpu_ctx_destroy(ibu_gpu_ctx_t *ctx) {
     }
     if (ctx->arena_base) cudaFree(ctx->arena_base);
     if (ctx->h_mail) cudaFreeHost(ctx->h_mail);
+    if (ctx->rows_ev) cudaEventDestroy(ctx->rows_ev);
     delete ctx;
 }
 

@@ -545,6 +545,28 @@ def test_barcode_table_random_rs_full_width_umis(ctx):
         assert np.array_equal(rows, want) and len(rows) == 1000
 
 
+def test_barcode_table_about_as_many_barcodes_as_records(ctx):
+    """3 x 10^7 random records (bc16 / umi12, 1 % with an unmasked word): nearly every record has a barcode
+    of its own — the ordered form of the partition path (k4_ordered.cuh), chosen by the sample.  Whole
+    table against the oracle; the forced sort fallback must give the same rows."""
+    import os
+
+    n = 30_000_000
+    recs = oc.generate_records(0, n, 16, 12, 1, 10_000, 77)
+    recs[n // 2:n // 2 + 1_000_000] = recs[:1_000_000]  # some repeated records ...
+    recs["umi"][n // 2:n // 2 + 500_000] ^= U64(5)      # ... half of them with another UMI
+    want = on.barcode_table(recs)
+    old = os.environ.get("IBU_B200_K4_ORDERED")
+    os.environ["IBU_B200_K4_ORDERED"] = "2"  # strict: falling back to the sort is an error here
+    try:
+        rows, info = gpu_table(ctx, recs, mode=2 | ibu.count_lens(16, 12))
+    finally:
+        os.environ.pop("IBU_B200_K4_ORDERED") if old is None else os.environ.__setitem__("IBU_B200_K4_ORDERED", old)
+    assert np.array_equal(rows, want) and info["n_distinct_pairs"] == int(want["n_distinct_umi"].sum())
+    rows2, info2 = gpu_table(ctx, recs, mode=2 | ibu.COUNT_PATH_SORT)
+    assert np.array_equal(rows2, want) and info2["n_distinct_pairs"] == info["n_distinct_pairs"]
+
+
 def test_barcode_table_sorted_full_size_closed_form(ctx):
     """10^8 sorted records (1000 per barcode, 5 per umi): 10^5 rows x 1000 records x 200 UMIs,
     streamed in one pass (24 B/record)."""

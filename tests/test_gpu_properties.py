@@ -115,3 +115,65 @@ def test_partition_path_everywhere(n, seed, nb, us, gen, weird, hint, chunk, ran
     with ibu.GpuGroup([0] * ranks, chunk_records=chunk) as g:
         red, out = g.process_host(recs, 16, 12, table=True, table_mode=mode)
         assert red == oc.reduce_records(recs, 16, 12, 1) and np.array_equal(out.rows, want)
+
+
+class _Env:
+    """An environment variable for the duration of a block (the library reads these per call)."""
+
+    def __init__(self, key, value):
+        self.key, self.value = key, value
+
+    def __enter__(self):
+        import os
+
+        self.old = os.environ.get(self.key)
+        os.environ[self.key] = self.value
+
+    def __exit__(self, *exc):
+        import os
+
+        if self.old is None:
+            os.environ.pop(self.key, None)
+        else:
+            os.environ[self.key] = self.old
+
+
+@settings(max_examples=60, deadline=None, suppress_health_check=list(HealthCheck))
+@given(n=st.integers(1, 400_000), seed=st.integers(0, 2**32), lens=st.sampled_from([(16, 12), (16, 16), (12, 8), (20, 10), (9, 5)]),
+       dup=st.sampled_from([0, 0, 3, 40]), ppm=st.sampled_from([0, 10_000, 200_000]), weird=st.sampled_from([0, 1, 2]),
+       hint=st.booleans(), chunk=st.sampled_from([1 << 12, 1 << 16]))
+def test_ordered_path_everywhere(n, seed, lens, dup, ppm, weird, hint, chunk):
+    """The ordered form of the partition path (about as many barcodes as records: buckets cut by the
+    barcode's top bits, sorted in shared memory, rows written in barcode order), forced and strict
+    (IBU_B200_K4_ORDERED=2: handing the input to the sort fallback is an error) over random
+    barcodes with repeats of a record, of a barcode with other UMIs, words wider than the layout
+    (merged from the side list, inside a bucket's range and beyond the last bucket) and the all-ones
+    barcode — as a resident array and through the chunked ingest pipeline."""
+    bc, umi = lens
+    recs = oc.generate_records(seed % 997, n, bc, umi, 1 if ppm else 0, ppm, seed)
+    rng = np.random.default_rng(seed)
+    if dup:  # repeats: whole records, and barcodes that come back with another UMI
+        src = rng.integers(0, n, n // 2)
+        recs[n - len(src):] = recs[src]
+        again = rng.integers(0, n, n // dup + 1)
+        recs["umi"][again] = rng.integers(0, 1 << (2 * umi), len(again), dtype=np.uint64)
+    if weird and n:
+        recs["umi"][:: max(1, n // 11)] |= np.uint64(1 << (2 * umi + 1)) if 2 * umi + 1 < 64 else np.uint64(0)
+        if weird == 2:
+            recs["barcode"][:: max(1, n // 3)] = np.uint64(2**64 - 1)
+            recs["barcode"][1:: max(1, n // 5)] |= np.uint64(1 << 63)
+    want = on.barcode_table(recs)
+    mode = 2 | ibu.COUNT_PATH_PARTITION | (ibu.count_lens(bc, umi) if hint else 0)
+    c = ctx()
+    # strict unless a fifth of the records are wider than the layout (the side list takes an eighth), or the
+    # layout has to come from a sample of words like that
+    strict = ppm <= 10_000 and (hint or not (ppm or weird))
+    with _Env("IBU_B200_K4_ORDERED", "2" if strict else "1"):
+        d = c.malloc(max(24 * n, 32))
+        c.h2d(d, recs)
+        rows, info = c.barcode_count(d, n, mode)
+        c.free(d)
+        assert np.array_equal(rows, want) and info["n_distinct_pairs"] == int(want["n_distinct_umi"].sum())
+        with ibu.GpuContext(0, chunk_records=chunk, n_slots=3) as c2:
+            red, out = c2.process_host_ops(recs, bc, umi, table=True, table_mode=mode)
+            assert red == oc.reduce_records(recs, bc, umi, 1) and np.array_equal(out.rows, want)

@@ -46,6 +46,8 @@ def main():
     ap.add_argument("--only", default="")
     ap.add_argument("--lens", type=int, default=1, help="pass the header's lengths as a hint")
     ap.add_argument("--path", default="", help="partition | legacy | sort: force one unsorted path")
+    ap.add_argument("--ctx-stream", type=int, default=0, help="run the table on the context's own stream")
+    ap.add_argument("--verbose", type=int, default=0, help="every call's time on stderr")
     ap.add_argument("--sort", type=int, default=0, help="also time ibu_gpu_sort_records on this many random bc16/umi12 records")
     args = ap.parse_args()
     n, pk = args.records, peak()
@@ -61,12 +63,16 @@ def main():
                 continue
             ctx.generate_records_async(recs, 0, n, 16, 12, gen, param, 3, stream)
             stream.synchronize()
-            ts, info = [], None
+            ts, fs, info = [], [], None
             for _ in range(args.iters + 1):  # the first call sizes the scratch pools
                 t0 = time.perf_counter()
-                table, info = ctx.barcode_count_device(recs, n, mode | extra, stream)
-                ts.append((time.perf_counter() - t0) * 1e3)
+                table, info = ctx.barcode_count_device(recs, n, mode | extra, None if args.ctx_stream else stream)
+                t1 = time.perf_counter()
                 ctx.table_free(table)
+                ts.append((t1 - t0) * 1e3)
+                fs.append((time.perf_counter() - t1) * 1e3)
+            if args.verbose:
+                print("# calls ms:", [round(t, 2) for t in ts], "table_free ms:", [round(t, 2) for t in fs], file=sys.stderr)
             first, ts = ts[0], sorted(ts[1:])
             print(json.dumps(dict(case=name, records=n, ms_best=ts[0], ms_mean=sum(ts) / len(ts), ms_first_call=first,
                                   grec_s=n / ts[0] / 1e6, achieved_gbs=24 * n / ts[0] / 1e6, frac=24 * n / ts[0] / 1e6 / pk,
