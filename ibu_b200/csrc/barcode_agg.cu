@@ -37,6 +37,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdlib>
+#include <functional>
 #include <memory>
 #include <mutex>
 #include <set>
@@ -134,6 +135,7 @@ struct StageTimer {
     }
 };
 
+constexpr uint32_t kOrdCap = 2048;  // keys of one bucket the ordered kernels hold in shared memory
 constexpr size_t kDedupMaxSmem = 8192 * 18;  // 8 Ki slots x (key + 64-bit count + list entry)
 
 template <bool W, bool P>
@@ -350,7 +352,7 @@ int k4_job_begin(ibu_gpu_ctx *ctx, uint64_t n, const K4Hints &hints, const K4Sam
     const double mean = (double)n / (double)job->P;
     // when duplicates make the final loads too uneven for the uniform layout (or the first attempt
     // overflows) the final buckets are laid out exactly from a histogram of the level before
-    job->exact = ordered || chunking.force_exact || (double)last.cap > 3.0 * mean + 256.0;
+    job->exact = chunking.force_exact || (double)last.cap > 3.0 * mean + 256.0 || (ordered && last.cap > kOrdCap);
     bytes += job->exact ? n * (weighted ? 16 : 8) : job->P * last.cap * (weighted ? 16 : 8);
     if (bytes > (64ull << 30)) return IBU_OK;
     // shared-memory table: 1.6 slots per key of the fullest bucket the uniform layout admits (all of
@@ -451,14 +453,14 @@ int k4_job_add(K4Job *job, const uint64_t *recs, uint64_t cnt, cudaStream_t s, i
 
 // The ordered form of the last stage: every final bucket sorted in shared memory, its rows written in
 // place (k4_ordered.cuh).  The job's last level is laid out exactly (job->bases) when this runs.
-static int finish_ordered(K4Job *job, uint64_t **rows_out, uint64_t *n_rows, uint64_t *n_pairs, bool *handled,
-                          ibu_error_t *err) {
+static int finish_ordered(K4Job *job, const std::function<int()> &layout_exact, uint64_t **rows_out, uint64_t *n_rows,
+                          uint64_t *n_pairs, bool *handled, ibu_error_t *err) {
     ibu_gpu_ctx *ctx = job->ctx;
     cudaStream_t s = job->s0;
     PoolScratch &sc = job->sc;
     unsigned long long *mail = ctx->h_mail, *ctr = job->ctr;
     const uint64_t n = job->added, P = job->P;
-    const K4Level &last = job->levels.back();
+    K4Level &last = job->levels.back();
     // IBU_B200_K4_ORDERED=2 (tests): an input this path has to hand to the sort fallback is an error
     auto give_up = [&]() -> int {
         const char *e = getenv("IBU_B200_K4_ORDERED");
@@ -472,6 +474,20 @@ static int finish_ordered(K4Job *job, uint64_t **rows_out, uint64_t *n_rows, uin
     if (job->trace)
         fprintf(stderr, "[ibu trace] ordered: %zu levels to P=2^%u, wide %llu flags %llx\n", job->levels.size(), job->pb,
                 (unsigned long long)n_wide, mail[kCtrFlags]);
+    if ((mail[kCtrFlags] & kFlagBucket) && !job->exact && !(job->chunked && job->levels.size() == 2)) {
+        // the barcodes' top bits are not uniform enough for the uniform layout of the last level: the
+        // level before is intact, lay the buckets out exactly from a histogram and go on
+        const unsigned long long keep[3] = {mail[kCtrWide], mail[kCtrFlags] & ~(unsigned long long)kFlagBucket, mail[kCtrSpecial]};
+        IBU_CUDA(cudaMemcpyAsync(ctr, keep, sizeof(keep), cudaMemcpyHostToDevice, s));
+        sc.free_now(last.keys);
+        last.keys = nullptr;
+        job->exact = true;
+        const int rc = layout_exact();
+        if (rc < 0) return give_up();
+        if (rc) return rc;
+        IBU_CUDA(cudaMemcpyAsync(mail, ctr, kCtrWords * 8, cudaMemcpyDeviceToHost, s));
+        IBU_CUDA(cudaStreamSynchronize(s));
+    }
     if ((mail[kCtrFlags] & (kFlagLevel | kFlagWide | kFlagBucket)) || mail[kCtrSpecial]) {
         job->overflowed = false;  // (nothing a second attempt of this path would change)
         return give_up();
@@ -509,10 +525,11 @@ static int finish_ordered(K4Job *job, uint64_t **rows_out, uint64_t *n_rows, uin
         return rc;
     };
     // the mean bucket has 512 - 1024 keys; k_bucket_sort holds two key arrays, k_bucket_emit one and the row starts
-    const uint32_t cap = 2048;
+    const uint32_t cap = kOrdCap;
     if (int rc = set_max_smem(k_bucket_sort, ctx->device, 4096 * 16, err)) return fail(rc);
     if (int rc = set_max_smem(k_bucket_emit, ctx->device, 4096 * 12 + 8, err)) return fail(rc);
-    OrdArgs a{job->bases, last.keys, (uint32_t)P, job->pb, job->bb, cap, wrows, wstart, rows_of, row_base, ctr, out, rows_cap};
+    OrdArgs a{job->exact ? job->bases : nullptr, last.cursors, last.cap, last.keys, (uint32_t)P, job->pb, job->bb, cap, wrows, wstart,
+              rows_of, row_base, ctr, out, rows_cap};
     k_bucket_sort<<<(uint32_t)std::min<uint64_t>(P, (uint64_t)ctx->sm_count * 5), kBlockThreads, (size_t)cap * 16, s>>>(a);
     g_launches.fetch_add(1, std::memory_order_relaxed);
     if (cudaError_t e = cudaGetLastError()) return fail(cuda_fail(err, e, "k_bucket_sort"));
@@ -625,7 +642,7 @@ int k4_job_finish(K4Job *job, const uint64_t *all_recs, bool pair_mode, bool pai
         if (rc) return rc;
     }
 
-    if (job->ordered) return finish_ordered(job, rows_out, n_rows, n_pairs, handled, err);
+    if (job->ordered) return finish_ordered(job, layout_exact, rows_out, n_rows, n_pairs, handled, err);
 
     // ---- per-bucket de-duplication into the barcode table (grown if the estimate was short) ----
     // barcode table: generous (skewed barcode frequencies make the estimate a lower bound); only the

@@ -35,7 +35,9 @@ constexpr uint32_t kOrdMaxWide = kBlockThreads;  // wide rows one bucket merges
 constexpr uint32_t kOrdMaxBin = 256;             // a bin this full (heavily repeated barcodes) voids the call: O(bin^2)
 
 struct OrdArgs {
-    const uint64_t *bases;  // exact layout: bucket b owns keys[bases[b] .. bases[b + 1])
+    const uint64_t *bases;  // exact layout: bucket b owns keys[bases[b] .. bases[b + 1]); NULL: the uniform layout,
+    const uint32_t *cursors;  //   cursors[b] keys at keys[b * lcap]
+    uint64_t lcap;
     uint64_t *keys;         // ((barcode << ub) | umi) << (64 - bb - ub); sorted in place, bucket by bucket
     uint32_t n_buckets, pb, bb;
     uint32_t cap;           // keys of one bucket that fit the shared-memory arrays (<= 4096)
@@ -89,9 +91,9 @@ __global__ void __launch_bounds__(kBlockThreads, 5) k_bucket_sort(const OrdArgs 
     uint32_t my_pairs = 0, my_flags = 0;  // (a thread sees fewer than 2^32 keys)
 
     for (uint32_t b = blockIdx.x; b < a.n_buckets; b += gridDim.x) {
-        const uint64_t first = a.bases[b];
-        uint32_t cnt = (uint32_t)min(a.bases[b + 1] - first, (uint64_t)0xffffffffu);
-        if (cnt > a.cap) {  // does not fit: the call is void
+        const uint64_t first = a.bases ? a.bases[b] : (uint64_t)b * a.lcap;
+        uint32_t cnt = a.bases ? (uint32_t)min(a.bases[b + 1] - first, (uint64_t)0xffffffffu) : a.cursors[b];
+        if (cnt > a.cap || (!a.bases && cnt > a.lcap)) {  // does not fit: the call is void
             my_flags |= kFlagSmem;
             cnt = 0;
         }
@@ -172,10 +174,10 @@ __global__ void __launch_bounds__(kBlockThreads, 6) k_bucket_emit(const OrdArgs 
     uint32_t my_flags = 0;
 
     for (uint32_t b = blockIdx.x; b < a.n_buckets; b += gridDim.x) {
-        const uint64_t first = a.bases[b], base = a.row_base[b];
+        const uint64_t first = a.bases ? a.bases[b] : (uint64_t)b * a.lcap, base = a.row_base[b];
         const uint32_t n_out = (uint32_t)(a.row_base[b + 1] - base);
-        uint32_t cnt = (uint32_t)min(a.bases[b + 1] - first, (uint64_t)0xffffffffu);
-        if (cnt > a.cap) cnt = 0;  // (k_bucket_sort raised the flag)
+        uint32_t cnt = a.bases ? (uint32_t)min(a.bases[b + 1] - first, (uint64_t)0xffffffffu) : a.cursors[b];
+        if (cnt > a.cap || (!a.bases && cnt > a.lcap)) cnt = 0;  // (k_bucket_sort raised the flag)
         for (uint32_t i = tid; i < cnt; i += kBlockThreads) kA[i] = ldg_stream64(a.keys + first + i);
         __syncthreads();
         // a new barcode starts a row, a new pair adds to its distinct count

@@ -567,6 +567,26 @@ def test_barcode_table_about_as_many_barcodes_as_records(ctx):
     assert np.array_equal(rows2, want) and info2["n_distinct_pairs"] == info["n_distinct_pairs"]
 
 
+def test_barcode_table_ordered_path_exact_layout_after_overflow(ctx):
+    """Barcodes whose 7th bit from the top is 0 for 70 % of the records: the first partition level (top 6
+    bits) is even, the final buckets are not, the uniform layout of the last level overflows and the
+    ordered path lays it out again exactly from a histogram — still without the sort fallback."""
+    import os
+
+    n = 3_000_000
+    recs = oc.generate_records(0, n, 16, 12, 0, 0, 78)
+    rng = np.random.default_rng(79)
+    recs["barcode"][rng.random(n) < 0.7] &= ~U64(1 << 25)
+    want = on.barcode_table(recs)
+    old = os.environ.get("IBU_B200_K4_ORDERED")
+    os.environ["IBU_B200_K4_ORDERED"] = "2"
+    try:
+        rows, info = gpu_table(ctx, recs, mode=2 | ibu.COUNT_PATH_PARTITION | ibu.count_lens(16, 12))
+    finally:
+        os.environ.pop("IBU_B200_K4_ORDERED") if old is None else os.environ.__setitem__("IBU_B200_K4_ORDERED", old)
+    assert np.array_equal(rows, want) and info["n_distinct_pairs"] == int(want["n_distinct_umi"].sum())
+
+
 def test_barcode_table_sorted_full_size_closed_form(ctx):
     """10^8 sorted records (1000 per barcode, 5 per umi): 10^5 rows x 1000 records x 200 UMIs,
     streamed in one pass (24 B/record)."""
