@@ -90,16 +90,40 @@ __global__ void __launch_bounds__(kBlockThreads, 5) k_bucket_sort(const OrdArgs 
     const uint32_t bshift = 64 - a.pb - kOrdBinBits, sh = 64 - a.bb;
     uint32_t my_pairs = 0, my_flags = 0;  // (a thread sees fewer than 2^32 keys)
 
-    for (uint32_t b = blockIdx.x; b < a.n_buckets; b += gridDim.x) {
-        const uint64_t first = a.bases ? a.bases[b] : (uint64_t)b * a.lcap;
-        uint32_t cnt = a.bases ? (uint32_t)min(a.bases[b + 1] - first, (uint64_t)0xffffffffu) : a.cursors[b];
-        if (cnt > a.cap || (!a.bases && cnt > a.lcap)) {  // does not fit: the call is void
-            my_flags |= kFlagSmem;
-            cnt = 0;
+    // the first 1024 keys of the next bucket travel while the current one is finished
+    uint64_t nfirst = 0, nk[4];
+    uint32_t ncnt = 0;
+    auto fetch = [&](uint32_t b) {
+        ncnt = 0;
+        if (b < a.n_buckets) {
+            nfirst = a.bases ? a.bases[b] : (uint64_t)b * a.lcap;
+            ncnt = a.bases ? (uint32_t)min(a.bases[b + 1] - nfirst, (uint64_t)0xffffffffu) : a.cursors[b];
+            if (ncnt > a.cap || (!a.bases && ncnt > a.lcap)) {  // does not fit: the call is void
+                my_flags |= kFlagSmem;
+                ncnt = 0;
+            }
         }
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            const uint32_t i = q * kBlockThreads + tid;
+            nk[q] = i < ncnt ? ldg_stream64(a.keys + nfirst + i) : 0ull;
+        }
+    };
+    fetch(blockIdx.x);
+    for (uint32_t b = blockIdx.x; b < a.n_buckets; b += gridDim.x) {
+        const uint64_t first = nfirst;
+        uint32_t cnt = ncnt;
         reinterpret_cast<uint4 *>(hist)[tid] = make_uint4(0, 0, 0, 0);
         __syncthreads();
-        for (uint32_t i = tid; i < cnt; i += kBlockThreads) {
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            const uint32_t i = q * kBlockThreads + tid;
+            if (i < cnt) {
+                kA[i] = nk[q];
+                atomicAdd(&hist[(uint32_t)(nk[q] >> bshift) & (kOrdBins - 1u)], 1u);
+            }
+        }
+        for (uint32_t i = tid + 4 * kBlockThreads; i < cnt; i += kBlockThreads) {
             const uint64_t k = ldg_stream64(a.keys + first + i);
             kA[i] = k;
             atomicAdd(&hist[(uint32_t)(k >> bshift) & (kOrdBins - 1u)], 1u);
@@ -131,6 +155,7 @@ __global__ void __launch_bounds__(kBlockThreads, 5) k_bucket_sort(const OrdArgs 
             kA[s0 + less] = k;
         }
         __syncthreads();
+        fetch(b + gridDim.x);
         // the sorted keys back in place; rows (distinct barcodes) and distinct pairs counted on the way
         uint32_t rows = 0;
         for (uint32_t i = tid; i < cnt; i += kBlockThreads) {
@@ -173,12 +198,32 @@ __global__ void __launch_bounds__(kBlockThreads, 6) k_bucket_emit(const OrdArgs 
     const uint32_t sh = 64 - a.bb;
     uint32_t my_flags = 0;
 
+    uint64_t nfirst = 0, nk[4];
+    uint32_t ncnt = 0;
+    auto fetch = [&](uint32_t b) {  // the first 1024 keys of the next bucket travel while the current one is written
+        ncnt = 0;
+        if (b < a.n_buckets) {
+            nfirst = a.bases ? a.bases[b] : (uint64_t)b * a.lcap;
+            ncnt = a.bases ? (uint32_t)min(a.bases[b + 1] - nfirst, (uint64_t)0xffffffffu) : a.cursors[b];
+            if (ncnt > a.cap || (!a.bases && ncnt > a.lcap)) ncnt = 0;  // (k_bucket_sort raised the flag)
+        }
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            const uint32_t i = q * kBlockThreads + tid;
+            nk[q] = i < ncnt ? ldg_stream64(a.keys + nfirst + i) : 0ull;
+        }
+    };
+    fetch(blockIdx.x);
     for (uint32_t b = blockIdx.x; b < a.n_buckets; b += gridDim.x) {
-        const uint64_t first = a.bases ? a.bases[b] : (uint64_t)b * a.lcap, base = a.row_base[b];
+        const uint64_t first = nfirst, base = a.row_base[b];
         const uint32_t n_out = (uint32_t)(a.row_base[b + 1] - base);
-        uint32_t cnt = a.bases ? (uint32_t)min(a.bases[b + 1] - first, (uint64_t)0xffffffffu) : a.cursors[b];
-        if (cnt > a.cap || (!a.bases && cnt > a.lcap)) cnt = 0;  // (k_bucket_sort raised the flag)
-        for (uint32_t i = tid; i < cnt; i += kBlockThreads) kA[i] = ldg_stream64(a.keys + first + i);
+        const uint32_t cnt = ncnt;
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            const uint32_t i = q * kBlockThreads + tid;
+            if (i < cnt) kA[i] = nk[q];
+        }
+        for (uint32_t i = tid + 4 * kBlockThreads; i < cnt; i += kBlockThreads) kA[i] = ldg_stream64(a.keys + first + i);
         __syncthreads();
         // a new barcode starts a row, a new pair adds to its distinct count
         const uint32_t per = (cnt + kBlockThreads - 1) / kBlockThreads;
@@ -216,6 +261,7 @@ __global__ void __launch_bounds__(kBlockThreads, 6) k_bucket_emit(const OrdArgs 
             rpairs[nrows] = (uint16_t)npairs;
         }
         __syncthreads();
+        fetch(b + gridDim.x);
         uint32_t w0 = 0, wcnt = 0;
         if (a.wrows) {
             w0 = a.wstart[b];

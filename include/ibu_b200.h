@@ -266,9 +266,12 @@ typedef struct ibu_barcode_table {
  * mode 0 = auto: one streaming pass that also verifies the (barcode, umi) order
  *          (the header's `sorted` flag is advisory: examples/parallel.rs:52-53 sets it on
  *          unsorted data); if the order does not hold, the records are partitioned by a hash of
- *          their (barcode, umi) key and de-duplicated bucket by bucket in shared memory (inputs
- *          that do not suit that — keys wider than 64 bits, a handful of distinct keys, about as
- *          many barcodes as records — are hash-aggregated in a global table or radix sorted);
+ *          their (barcode, umi) key and de-duplicated bucket by bucket in shared memory; with
+ *          about as many barcodes as records they are partitioned by the barcode's own top bits
+ *          instead and every bucket is sorted in shared memory, its rows written in barcode order
+ *          (inputs that suit neither — keys wider than 64 bits, a handful of distinct keys, a
+ *          few barcodes that hold most of many — are hash-aggregated in a global table or radix
+ *          sorted);
  * mode 1 = streaming pass only: unsorted input is not an error, it returns
  *          input_was_sorted = 0 and no rows;
  * mode 2 = skip the streaming attempt.
