@@ -1408,6 +1408,21 @@ int k4_build_table(ibu_gpu_ctx *ctx, const ibu_record_t *d_records, uint64_t n, 
         IBU_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->rows_ev, 0));
         s = ctx->stream;
     }
+    struct PoolTrace {  // IBU_B200_TRACE_ALLOC: what the device's pool holds when a build starts and ends
+        int dev;
+        void say(const char *when) const {
+            cudaMemPool_t pool;
+            unsigned long long reserved = 0, used = 0, thr = 0;
+            if (cudaDeviceGetDefaultMemPool(&pool, dev) != cudaSuccess) return;
+            cudaMemPoolGetAttribute(pool, cudaMemPoolAttrReservedMemCurrent, &reserved);
+            cudaMemPoolGetAttribute(pool, cudaMemPoolAttrUsedMemCurrent, &used);
+            cudaMemPoolGetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+            fprintf(stderr, "[ibu trace] pool %s: reserved %.3f GB used %.3f GB release threshold %llx\n", when, reserved / 1e9, used / 1e9, thr);
+        }
+        explicit PoolTrace(int d) : dev(d) { say("at entry"); }
+        ~PoolTrace() { say("at exit"); }
+    };
+    std::unique_ptr<PoolTrace> pool_trace(getenv("IBU_B200_TRACE_ALLOC") ? new PoolTrace(ctx->device) : nullptr);
     bool unsorted = mode == 2;
     // Below 64 Ki records everything is launch latency and the round-1 flow is as good.  Above, a
     // sample decides first: unsorted input (the common case: the header's flag is advisory) never

@@ -1,5 +1,8 @@
 // ctx.h — the GPU context behind ibu_gpu_ctx_t (internal).
 #pragma once
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
 #include <array>
 #include <atomic>
 #include <cuda_runtime.h>
@@ -91,7 +94,12 @@ struct DeviceGuard {
 // allocation and release share a stream.  Caller holds ctx->arena_mutex (rows_ev).
 inline cudaError_t alloc_result_rows(ibu_gpu_ctx *ctx, uint64_t **out, size_t bytes, cudaStream_t user) {
     *out = nullptr;
+    const auto t0 = std::chrono::steady_clock::now();
     cudaError_t e = cudaMallocAsync((void **)out, bytes ? bytes : 256, ctx->stream);
+    if (getenv("IBU_B200_TRACE_ALLOC")) {
+        const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+        if (ms > 0.2) fprintf(stderr, "[ibu trace] cudaMallocAsync (result rows) of %.3f GB took %.2f ms\n", bytes / 1e9, ms);
+    }
     if (e != cudaSuccess || user == ctx->stream) return e;
     if (!ctx->rows_ev) e = cudaEventCreateWithFlags(&ctx->rows_ev, cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaEventRecord(ctx->rows_ev, ctx->stream);

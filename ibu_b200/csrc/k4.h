@@ -2,6 +2,9 @@
 //   barcode_count.cu  streaming sorted path (k_segments), radix sort, legacy global-hash path, C ABI
 //   barcode_agg.cu    partition-then-aggregate path for unsorted inputs
 #pragma once
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
 #include <vector>
 
 #include "ctx.h"
@@ -24,7 +27,13 @@ struct PoolScratch {
     template <class T>
     cudaError_t alloc(T **out, size_t bytes) {
         void *p = nullptr;
+        static const bool trace = getenv("IBU_B200_TRACE_ALLOC") != nullptr;  // tuning: allocations that took long
+        const auto t0 = std::chrono::steady_clock::now();
         cudaError_t e = cudaMallocAsync(&p, bytes ? bytes : 256, s);
+        if (trace) {
+            const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+            if (ms > 0.2) fprintf(stderr, "[ibu trace] cudaMallocAsync of %.3f GB took %.2f ms\n", bytes / 1e9, ms);
+        }
         if (e == cudaSuccess) ptrs.push_back(p);
         *out = (T *)p;
         return e;
