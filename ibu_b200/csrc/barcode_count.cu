@@ -638,40 +638,35 @@ struct SweepArgs {
     uint32_t *fail;               // set when a look-back gives up
 };
 
-template <int STRIDE>
-__global__ void __launch_bounds__(kBlockThreads, 3) k_onesweep(const SweepArgs a) {
-    extern __shared__ __align__(16) uint64_t tile[];  // kSortTile elements as loaded
-    __shared__ uint32_t warp_cnt[kWarpsPerBlock][256];
-    __shared__ uint32_t tile_off[256], base[256], gdst[kSortTile];
-    __shared__ uint16_t srcidx[kSortTile];
-    __shared__ uint64_t scan_tmp[kWarpsPerBlock];
-    __shared__ uint32_t s_tile;
-    const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
-    if (tid == 0) s_tile = atomicAdd(a.ticket, 1u);
-    for (int w = 0; w < kWarpsPerBlock; w++) warp_cnt[w][tid] = 0;
-    __syncthreads();
-    const uint64_t tile_id = s_tile;
-    const uint64_t first = tile_id * kSortTile;
-    const uint32_t count = (uint32_t)min((uint64_t)kSortTile, a.n - first);
-    {   // the tile, as it lies in memory (its start is 16-byte aligned: kSortTile * STRIDE * 8 bytes per tile)
-        const uint32_t words = count * STRIDE;
-        const uint4 *src16 = reinterpret_cast<const uint4 *>(a.in + first * STRIDE);
-        uint4 *dst16 = reinterpret_cast<uint4 *>(tile);
-        for (uint32_t x = tid; x < words / 2; x += kBlockThreads) dst16[x] = ldg_stream(src16 + x);
-        if ((words & 1u) && tid == 0) tile[words - 1] = a.in[first * STRIDE + words - 1];
-    }
-    __syncthreads();
-    // warp w ranks elements [w*256, w*256+256); item k of lane l is element w*256 + 32k + l (stable order)
-    uint32_t rank[kSortItems], dig[kSortItems];
+// ncu on the first form of this kernel (profiles/r2_sort_onesweep_ncu_summary.json): issue slots 42 % busy,
+// long-scoreboard 6 warps per issue — a CTA's phases run strictly one after the other (ticket, three
+// batches of four tile loads, ranking, a look-back that walked ONE predecessor per L2 round trip, output)
+// with only 3 CTAs per SM to overlap them.  Now the whole tile is requested at once with cp.async (12 x 16
+// bytes per thread in flight, no registers), the digit totals are read before anything waits, full tiles
+// rank with eight ballots instead of nine, and the look-back reads four predecessors per round trip:
+// 1.54 -> 1.42 ms per pass over 10^8 records, 10^9 records 119-121 -> 112-114 ms.
+__device__ __forceinline__ uint32_t ld_relaxed_u32(const uint32_t *p) {
+    uint32_t v;
+    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_relaxed_u32(uint32_t *p, uint32_t v) {
+    asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+template <int STRIDE, bool FULL>
+__device__ __forceinline__ void sweep_rank(const uint64_t *tile, uint32_t count, uint32_t word, uint32_t shift,
+                                           uint32_t (*warp_cnt)[256], uint32_t *rank, uint32_t *dig) {
+    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
 #pragma unroll
     for (int k = 0; k < kSortItems; k++) {
         const uint32_t i = warp * (kSortTile / kWarpsPerBlock) + 32 * k + lane;
-        const bool live = i < count;
-        const uint32_t d = live ? (uint32_t)((tile[i * STRIDE + a.word] >> a.shift) & 0xFFu) : 0x100u;
+        const bool live = FULL || i < count;
+        const uint32_t d = live ? (uint32_t)((tile[i * STRIDE + word] >> shift) & 0xFFu) : 0x100u;
         dig[k] = d;
         uint32_t peers = 0xffffffffu;
 #pragma unroll
-        for (int bit = 0; bit < 9; bit++) {
+        for (int bit = 0; bit < (FULL ? 8 : 9); bit++) {
             const uint32_t m = __ballot_sync(0xffffffffu, (d >> bit) & 1u);
             peers &= ((d >> bit) & 1u) ? m : ~m;
         }
@@ -685,6 +680,39 @@ __global__ void __launch_bounds__(kBlockThreads, 3) k_onesweep(const SweepArgs a
         rank[k] = old + __popc(peers & ((1u << lane) - 1u));
         __syncwarp();
     }
+}
+
+template <int STRIDE>
+__global__ void __launch_bounds__(kBlockThreads, 3) k_onesweep(const SweepArgs a) {
+    extern __shared__ __align__(16) uint64_t tile[];  // kSortTile elements as loaded
+    __shared__ uint32_t warp_cnt[kWarpsPerBlock][256];
+    __shared__ uint32_t tile_off[256], base[256], gdst[kSortTile];
+    __shared__ uint16_t srcidx[kSortTile];
+    __shared__ uint64_t scan_tmp[kWarpsPerBlock];
+    __shared__ uint32_t s_tile;
+    const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+    if (tid == 0) s_tile = atomicAdd(a.ticket, 1u);
+    const uint32_t total = a.digit_total[tid];  // arrives while the ticket and the tile do
+    for (int w = 0; w < kWarpsPerBlock; w++) warp_cnt[w][tid] = 0;
+    __syncthreads();
+    const uint64_t tile_id = s_tile;
+    const uint64_t first = tile_id * kSortTile;
+    const uint32_t count = (uint32_t)min((uint64_t)kSortTile, a.n - first);
+    {   // the tile, as it lies in memory (its start is 16-byte aligned: kSortTile * STRIDE * 8 bytes per tile)
+        const uint32_t words = count * STRIDE;
+        const uint4 *src16 = reinterpret_cast<const uint4 *>(a.in + first * STRIDE);
+        const uint32_t dst = (uint32_t)__cvta_generic_to_shared(tile);
+        for (uint32_t x = tid; x < words / 2; x += kBlockThreads)
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + 16u * x), "l"(src16 + x) : "memory");
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        if ((words & 1u) && tid == 0) tile[words - 1] = a.in[first * STRIDE + words - 1];
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+    }
+    __syncthreads();
+    // warp w ranks elements [w*256, w*256+256); item k of lane l is element w*256 + 32k + l (stable order)
+    uint32_t rank[kSortItems], dig[kSortItems];
+    if (count == kSortTile) sweep_rank<STRIDE, true>(tile, count, a.word, a.shift, warp_cnt, rank, dig);
+    else sweep_rank<STRIDE, false>(tile, count, a.word, a.shift, warp_cnt, rank, dig);
     __syncthreads();
     // thread = digit: this tile's count, published; offsets of the warps; look-back for the tiles before
     uint32_t c = 0;
@@ -693,34 +721,47 @@ __global__ void __launch_bounds__(kBlockThreads, 3) k_onesweep(const SweepArgs a
         warp_cnt[w][tid] = c;
         c += x;
     }
-    volatile uint32_t *state = a.state;
     uint32_t before = 0;  // elements with this digit in earlier tiles
     if (tile_id == 0) {
-        state[tid] = c | kSweepPrefix;
+        st_relaxed_u32(a.state + tid, c | kSweepPrefix);
     } else {
-        state[tile_id * 256 + tid] = c | kSweepAgg;
-        uint64_t look = tile_id - 1;
+        st_relaxed_u32(a.state + tile_id * 256 + tid, c | kSweepAgg);
+        int64_t look = (int64_t)tile_id - 1;
         uint32_t spins = 0;
-        for (;;) {
-            const uint32_t v = state[look * 256 + tid];
-            const uint32_t flag = v & ~kSweepMask;
-            if (flag == 0) {
-                if (++spins > (1u << 26)) {  // watchdog: never hang the GPU (the host then reports an error)
+        bool done = false;
+        while (!done) {
+            uint32_t v[4];
+#pragma unroll
+            for (int i = 0; i < 4; i++) v[i] = look - i >= 0 ? ld_relaxed_u32(a.state + (look - i) * 256 + tid) : 0u;
+            bool stop = false;
+            uint32_t used = 0;
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                const uint32_t flag = v[i] & ~kSweepMask;
+                if (!stop) {
+                    if (flag == 0) {
+                        stop = true;
+                    } else {
+                        before += v[i] & kSweepMask;
+                        used++;
+                        if (flag == kSweepPrefix) done = stop = true;  // (tile 0 always publishes a prefix)
+                    }
+                }
+            }
+            look -= used;
+            if (!done && used == 0) {
+                if (++spins > (1u << 24)) {  // watchdog: never hang the GPU (the host then reports an error)
                     *a.fail = 1;
                     break;
                 }
-                __nanosleep(32);
-                continue;
+                __nanosleep(20);
             }
-            before += v & kSweepMask;
-            if (flag == kSweepPrefix) break;
-            look--;  // (tile 0 always publishes a prefix)
         }
-        state[tile_id * 256 + tid] = (before + c) | kSweepPrefix;
+        st_relaxed_u32(a.state + tile_id * 256 + tid, (before + c) | kSweepPrefix);
     }
     const uint32_t off = (uint32_t)block_excl_scan64(c, scan_tmp);  // first tile-local position of the digit
     __syncthreads();
-    const uint32_t gexcl = (uint32_t)block_excl_scan64(a.digit_total[tid], scan_tmp);  // digits below, whole input
+    const uint32_t gexcl = (uint32_t)block_excl_scan64(total, scan_tmp);  // digits below, whole input
     tile_off[tid] = off;
     base[tid] = gexcl + before - off;  // global position of sorted tile element j with this digit: base + j
     __syncthreads();
@@ -928,6 +969,7 @@ struct Scratch {
         }
         void *p = nullptr;
         cudaError_t e = cudaMalloc(&p, bytes);
+        if (getenv("IBU_B200_TRACE_ALLOC")) fprintf(stderr, "[ibu trace] arena overflow: cudaMalloc of %zu bytes\n", bytes);
         if (e == cudaSuccess) owned.push_back(p);
         *out = (T *)p;
         return e;
@@ -943,6 +985,7 @@ static cudaError_t arena_reset(ibu_gpu_ctx *ctx, size_t bytes) {
     ctx->arena_base = nullptr;
     ctx->arena_cap = 0;
     cudaError_t e = cudaMalloc(&ctx->arena_base, bytes);
+    if (getenv("IBU_B200_TRACE_ALLOC")) fprintf(stderr, "[ibu trace] arena grows to %.3f GB\n", bytes / 1e9);
     if (e == cudaSuccess) ctx->arena_cap = bytes;
     return e;
 }
@@ -1547,7 +1590,7 @@ int ibu_gpu_sort_records(ibu_gpu_ctx_t *ctx, const ibu_record_t *d_records, uint
     DeviceGuard guard(ctx->device);
     cudaStream_t s = pick_stream(ctx, stream);
     std::lock_guard<std::mutex> lock(ctx->arena_mutex);
-    IBU_CUDA(arena_reset(ctx, n * 24 + ((n + kSortTile - 1) / kSortTile) * 1024 + 16 * 256));
+    IBU_CUDA(arena_reset(ctx, sort_scratch_bytes(n, 12)));  // spare + look-back state + histograms: no allocation in steady state
     Scratch sc(ctx);
     uint64_t *spare;
     IBU_CUDA(sc.alloc(&spare, n * 24));
