@@ -603,17 +603,30 @@ struct HistAllArgs {
     uint32_t n_passes;
     uint32_t word[kSweepMaxPasses], shift[kSweepMaxPasses];
     uint32_t *hist;  // [n_passes][256], zeroed
+    unsigned long long *masks;  // MASKS: k_key_masks' seven words (OR / AND per word, descents of the last word)
 };
 
-template <int STRIDE>
+// MASKS: the same pass also produces what k_key_masks produces (which bits vary at all, whether the last
+// word ever descends).  ibu_gpu_sort_records guesses the digits to histogram from a sample, and this
+// kernel's exact masks confirm the guess: one pass over the records instead of two.
+template <int STRIDE, bool MASKS>
 __global__ void __launch_bounds__(kBlockThreads) k_hist_all(const HistAllArgs a) {
     extern __shared__ uint32_t h[];  // [n_passes][256]
     for (uint32_t i = threadIdx.x; i < a.n_passes * 256; i += kBlockThreads) h[i] = 0;
     __syncthreads();
+    uint64_t o[STRIDE], n[STRIDE];
+#pragma unroll
+    for (int k = 0; k < STRIDE; k++) { o[k] = 0; n[k] = ~0ull; }
+    uint32_t descents = 0;
     for (uint64_t i = (uint64_t)blockIdx.x * kBlockThreads + threadIdx.x; i < a.n; i += (uint64_t)gridDim.x * kBlockThreads) {
         uint64_t w[STRIDE];
 #pragma unroll
         for (int k = 0; k < STRIDE; k++) w[k] = a.in[i * STRIDE + k];
+        if (MASKS) {
+#pragma unroll
+            for (int k = 0; k < STRIDE; k++) { o[k] |= w[k]; n[k] &= w[k]; }
+            if (i) descents += w[STRIDE - 1] < a.in[(i - 1) * STRIDE + STRIDE - 1];
+        }
         for (uint32_t p = 0; p < a.n_passes; p++) {
             uint64_t key = w[0];
 #pragma unroll
@@ -622,9 +635,66 @@ __global__ void __launch_bounds__(kBlockThreads) k_hist_all(const HistAllArgs a)
             atomicAdd(&h[p * 256 + (uint32_t)((key >> a.shift[p]) & 0xFFu)], 1u);
         }
     }
+    if (MASKS) {
+        descents = __reduce_add_sync(0xffffffffu, descents);
+        if ((threadIdx.x & 31u) == 0 && descents) atomicAdd(a.masks + 6, (unsigned long long)descents);
+#pragma unroll
+        for (int k = 0; k < STRIDE; k++) {
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) {
+                o[k] |= __shfl_xor_sync(0xffffffffu, o[k], off);
+                n[k] &= __shfl_xor_sync(0xffffffffu, n[k], off);
+            }
+            if ((threadIdx.x & 31u) == 0) {
+                atomicOr(a.masks + 2 * k, o[k]);
+                atomicAnd(a.masks + 2 * k + 1, n[k]);
+            }
+        }
+    }
     __syncthreads();
     for (uint32_t i = threadIdx.x; i < a.n_passes * 256; i += kBlockThreads)
         if (h[i]) atomicAdd(a.hist + i, h[i]);
+}
+
+// OR / AND of every word and descents of the third over m records spread evenly over the input (the
+// guess that k_hist_all<3, true> then confirms)
+__global__ void __launch_bounds__(kBlockThreads)
+k_sample_masks(const uint64_t *__restrict__ recs, uint64_t n, uint64_t m, unsigned long long *__restrict__ masks) {
+    const uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    uint64_t o[3] = {0, 0, 0}, a[3] = {~0ull, ~0ull, ~0ull};
+    uint32_t desc = 0;
+    if (j < m) {
+        const uint64_t i = j * (n / m);
+#pragma unroll
+        for (int k = 0; k < 3; k++) o[k] = a[k] = recs[3 * i + k];
+        if (i + 1 < n) {
+            uint64_t w[3];
+#pragma unroll
+            for (int k = 0; k < 3; k++) {
+                w[k] = recs[3 * i + 3 + k];
+                o[k] |= w[k];
+                a[k] &= w[k];
+            }
+            desc = w[2] < recs[3 * i + 2];
+        }
+    }
+    desc = __reduce_add_sync(0xffffffffu, desc);
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+            o[k] |= __shfl_xor_sync(0xffffffffu, o[k], off);
+            a[k] &= __shfl_xor_sync(0xffffffffu, a[k], off);
+        }
+    }
+    if ((threadIdx.x & 31u) == 0) {
+        if (desc) atomicAdd(masks + 6, (unsigned long long)desc);
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+            atomicOr(masks + 2 * k, o[k]);
+            atomicAnd(masks + 2 * k + 1, a[k]);
+        }
+    }
 }
 
 struct SweepArgs {
@@ -682,7 +752,7 @@ __device__ __forceinline__ void sweep_rank(const uint64_t *tile, uint32_t count,
     }
 }
 
-template <int STRIDE>
+template <int STRIDE, int LOOK>
 __global__ void __launch_bounds__(kBlockThreads, 3) k_onesweep(const SweepArgs a) {
     extern __shared__ __align__(16) uint64_t tile[];  // kSortTile elements as loaded
     __shared__ uint32_t warp_cnt[kWarpsPerBlock][256];
@@ -730,13 +800,16 @@ __global__ void __launch_bounds__(kBlockThreads, 3) k_onesweep(const SweepArgs a
         uint32_t spins = 0;
         bool done = false;
         while (!done) {
-            uint32_t v[4];
+            // kLook predecessors per L2 round trip (measured: 4 beats 1, 8 and 16 — past 4 the loads that find
+            // nothing published yet cost more than the round trips they save)
+            constexpr int kLook = LOOK;
+            uint32_t v[kLook];
 #pragma unroll
-            for (int i = 0; i < 4; i++) v[i] = look - i >= 0 ? ld_relaxed_u32(a.state + (look - i) * 256 + tid) : 0u;
+            for (int i = 0; i < kLook; i++) v[i] = look - i >= 0 ? ld_relaxed_u32(a.state + (look - i) * 256 + tid) : 0u;
             bool stop = false;
             uint32_t used = 0;
 #pragma unroll
-            for (int i = 0; i < 4; i++) {
+            for (int i = 0; i < kLook; i++) {
                 const uint32_t flag = v[i] & ~kSweepMask;
                 if (!stop) {
                     if (flag == 0) {
@@ -1136,6 +1209,11 @@ static int count_passes(const uint64_t vary[3], const int *key_order, int n_keys
     return p;
 }
 
+static bool sweep_eligible(uint64_t n, const void *in, const void *a, const void *b) {
+    static const bool sweep_off = getenv("IBU_B200_ONESWEEP") && getenv("IBU_B200_ONESWEEP")[0] == '0';  // tuning
+    return !sweep_off && n < (1ull << 30) && (((uintptr_t)in | (uintptr_t)a | (uintptr_t)b) & 15u) == 0;
+}
+
 // LSD radix sort of n elements of STRIDE words.  key_order lists the key words from the least
 // to the most significant.  `in` is only read; passes ping-pong between `first_dst` and `other`
 // (the first pass writes first_dst).  *result is where the sorted elements end up (`in` itself
@@ -1143,12 +1221,11 @@ static int count_passes(const uint64_t vary[3], const int *key_order, int n_keys
 template <int STRIDE>
 static int radix_sort(ibu_gpu_ctx *ctx, const uint64_t *in, uint64_t *first_dst, uint64_t *other, uint64_t n,
                       const uint64_t vary[3], const int *key_order, int n_keys, cudaStream_t s, Scratch &sc,
-                      const uint64_t **result, ibu_error_t *err) {
+                      const uint64_t **result, ibu_error_t *err, const HistAllArgs *pre = nullptr) {
     if (n >= (1ull << 32))  // per-digit tile offsets are kept in 32 bits
         return set_error(err, IBU_ERR_ARG, 0, n, 0, "device sort supports fewer than 2^32 elements per call");
     const uint64_t n_tiles = (n + kSortTile - 1) / kSortTile;
-    static const bool sweep_off = getenv("IBU_B200_ONESWEEP") && getenv("IBU_B200_ONESWEEP")[0] == '0';  // tuning
-    if (!sweep_off && n < (1ull << 30) && (((uintptr_t)in | (uintptr_t)first_dst | (uintptr_t)other) & 15u) == 0) {
+    if (sweep_eligible(n, in, first_dst, other)) {
         // ---- one sweep: all histograms first, then one kernel per digit pass ----
         HistAllArgs h{};
         h.in = in;
@@ -1165,23 +1242,38 @@ static int radix_sort(ibu_gpu_ctx *ctx, const uint64_t *in, uint64_t *first_dst,
             return IBU_OK;
         }
         uint32_t *state, *ctl;
-        IBU_CUDA(sc.alloc(&h.hist, (size_t)h.n_passes * 1024));
+        const uint32_t *totals[kSweepMaxPasses];  // the 256 digit totals of each pass
         IBU_CUDA(sc.alloc(&state, n_tiles * 1024));
         IBU_CUDA(sc.alloc(&ctl, 256));  // [0] ticket, [1] fail
-        IBU_CUDA(cudaMemsetAsync(h.hist, 0, (size_t)h.n_passes * 1024, s));
         IBU_CUDA(cudaMemsetAsync(ctl, 0, 256, s));
-        const uint64_t blocks = (n + kBlockThreads - 1) / kBlockThreads;
-        k_hist_all<STRIDE><<<(int)std::min<uint64_t>(blocks, (uint64_t)ctx->sm_count * 8), kBlockThreads, h.n_passes * 1024, s>>>(h);
-        g_launches.fetch_add(1, std::memory_order_relaxed);
-        if (cudaError_t e__ = cudaGetLastError()) return cuda_fail(err, e__, "k_hist_all");
-        IBU_CUDA(cudaFuncSetAttribute(k_onesweep<STRIDE>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSortTile * STRIDE * 8));
+        if (pre) {  // the caller's histograms cover these passes (it checked) and were counted over `in`
+            for (uint32_t p = 0; p < h.n_passes; p++) {
+                totals[p] = nullptr;
+                for (uint32_t q = 0; q < pre->n_passes; q++)
+                    if (pre->word[q] == h.word[p] && pre->shift[q] == h.shift[p]) totals[p] = pre->hist + q * 256;
+                if (!totals[p]) return set_error(err, IBU_ERR_ARG, 0, p, 0, "device sort: a pass without a histogram");
+            }
+        } else {
+            IBU_CUDA(sc.alloc(&h.hist, (size_t)h.n_passes * 1024));
+            IBU_CUDA(cudaMemsetAsync(h.hist, 0, (size_t)h.n_passes * 1024, s));
+            const uint64_t blocks = (n + kBlockThreads - 1) / kBlockThreads;
+            k_hist_all<STRIDE, false><<<(int)std::min<uint64_t>(blocks, (uint64_t)ctx->sm_count * 8), kBlockThreads,
+                                        h.n_passes * 1024, s>>>(h);
+            g_launches.fetch_add(1, std::memory_order_relaxed);
+            if (cudaError_t e__ = cudaGetLastError()) return cuda_fail(err, e__, "k_hist_all");
+            for (uint32_t p = 0; p < h.n_passes; p++) totals[p] = h.hist + p * 256;
+        }
+        // predecessors per look-back round trip: 4 (10^9 records: 108.0 ms; 8: 108.7; 16: 113.9; one at a time, the first form: 119)
+        static const int look = getenv("IBU_B200_LOOK") ? atoi(getenv("IBU_B200_LOOK")) : 4;  // tuning
+        auto sweep = look == 2 ? k_onesweep<STRIDE, 2> : look == 8 ? k_onesweep<STRIDE, 8> : k_onesweep<STRIDE, 4>;
+        IBU_CUDA(cudaFuncSetAttribute(sweep, cudaFuncAttributeMaxDynamicSharedMemorySize, kSortTile * STRIDE * 8));
         const uint64_t *src = in;
         uint64_t *dst = first_dst, *spare = other;
         for (uint32_t p = 0; p < h.n_passes; p++) {
             IBU_CUDA(cudaMemsetAsync(state, 0, n_tiles * 1024, s));
             IBU_CUDA(cudaMemsetAsync(ctl, 0, 4, s));
-            SweepArgs a{src, dst, n, h.word[p], h.shift[p], h.hist + p * 256, state, ctl, ctl + 1};
-            k_onesweep<STRIDE><<<(int)n_tiles, kBlockThreads, kSortTile * STRIDE * 8, s>>>(a);
+            SweepArgs a{src, dst, n, h.word[p], h.shift[p], totals[p], state, ctl, ctl + 1};
+            sweep<<<(int)n_tiles, kBlockThreads, kSortTile * STRIDE * 8, s>>>(a);
             g_launches.fetch_add(1, std::memory_order_relaxed);
             if (cudaError_t e__ = cudaGetLastError()) return cuda_fail(err, e__, "k_onesweep");
             src = dst;
@@ -1598,8 +1690,70 @@ int ibu_gpu_sort_records(ibu_gpu_ctx_t *ctx, const ibu_record_t *d_records, uint
     uint64_t *dst = reinterpret_cast<uint64_t *>(d_sorted);
     uint64_t vary[3];
     uint64_t descents = 0;
-    if (int rc = key_masks<3>(ctx, src, n, nullptr, s, sc, vary, err, &descents)) return rc;
     static const int order[3] = {2, 1, 0};  // Record's Ord: barcode, then umi, then index (record.rs:58)
+    // Which digits vary (and whether the index ever descends) decides the passes, and the passes decide which
+    // histograms to count: two scans of the records.  Instead a sample guesses the digits, ONE scan counts
+    // their histograms together with the exact masks, and the guess stands when it covers what the masks say
+    // (a guessed digit that does not vary after all is just not sorted).  A wrong guess — a bit that is set in
+    // a handful of records the sample missed — costs the second scan the two-step form always paid.
+    HistAllArgs pre{};
+    bool have_pre = false;
+    if (n >= (1ull << 20) && sweep_eligible(n, src, dst, spare)) {
+        unsigned long long *masks;
+        IBU_CUDA(sc.alloc(&masks, 2 * 7 * 8));
+        const unsigned long long init[14] = {0ull, ~0ull, 0ull, ~0ull, 0ull, ~0ull, 0ull, 0ull, ~0ull, 0ull, ~0ull, 0ull, ~0ull, 0ull};
+        IBU_CUDA(cudaMemcpyAsync(masks, init, sizeof(init), cudaMemcpyHostToDevice, s));
+        const uint64_t m = 1ull << 16;
+        k_sample_masks<<<(int)(m / kBlockThreads), kBlockThreads, 0, s>>>(src, n, m, masks);
+        g_launches.fetch_add(1, std::memory_order_relaxed);
+        unsigned long long g[7];
+        IBU_CUDA(cudaMemcpyAsync(g, masks, sizeof(g), cudaMemcpyDeviceToHost, s));
+        IBU_CUDA(cudaStreamSynchronize(s));
+        uint64_t guess[3];
+        for (int k = 0; k < 3; k++) {  // every bit below the highest varying one is taken to vary too
+            uint64_t v = g[2 * k] ^ g[2 * k + 1];
+            for (int sh = 1; sh < 64; sh <<= 1) v |= v >> sh;
+            guess[k] = v;
+        }
+        const bool guess_index = g[6] != 0;
+        pre.in = src;
+        pre.n = n;
+        pre.masks = masks + 7;
+        for (int k = guess_index ? 0 : 1; k < 3; k++)
+            for (uint32_t shift = 0; shift < 64; shift += 8)
+                if (((guess[order[k]] >> shift) & 0xFFull) && pre.n_passes < (uint32_t)kSweepMaxPasses) {
+                    pre.word[pre.n_passes] = (uint32_t)order[k];
+                    pre.shift[pre.n_passes] = shift;
+                    pre.n_passes++;
+                }
+        if (pre.n_passes) {
+            IBU_CUDA(sc.alloc(&pre.hist, (size_t)pre.n_passes * 1024));
+            IBU_CUDA(cudaMemsetAsync(pre.hist, 0, (size_t)pre.n_passes * 1024, s));
+            const uint64_t blocks = (n + kBlockThreads - 1) / kBlockThreads;
+            k_hist_all<3, true><<<(int)std::min<uint64_t>(blocks, (uint64_t)ctx->sm_count * 8), kBlockThreads,
+                                  pre.n_passes * 1024, s>>>(pre);
+            g_launches.fetch_add(1, std::memory_order_relaxed);
+            if (cudaError_t e__ = cudaGetLastError()) return cuda_fail(err, e__, "k_hist_all");
+            unsigned long long x[7];
+            IBU_CUDA(cudaMemcpyAsync(x, pre.masks, sizeof(x), cudaMemcpyDeviceToHost, s));
+            IBU_CUDA(cudaStreamSynchronize(s));
+            for (int k = 0; k < 3; k++) vary[k] = x[2 * k] ^ x[2 * k + 1];
+            descents = x[6];
+            have_pre = true;  // the exact masks, whatever the guess was worth
+            bool covered = !descents || guess_index;
+            for (int k = descents ? 0 : 1; k < 3 && covered; k++)
+                for (uint32_t shift = 0; shift < 64; shift += 8)
+                    if ((vary[order[k]] >> shift) & 0xFFull) {
+                        bool found = false;
+                        for (uint32_t q = 0; q < pre.n_passes; q++)
+                            found |= pre.word[q] == (uint32_t)order[k] && pre.shift[q] == shift;
+                        covered &= found;
+                    }
+            if (!covered) pre.n_passes = 0;  // radix_sort counts its own histograms from the exact masks
+        }
+    }
+    if (!have_pre)
+        if (int rc = key_masks<3>(ctx, src, n, nullptr, s, sc, vary, err, &descents)) return rc;
     // Records that already come in index order (what a writer that numbers reads as it goes produces)
     // need no index passes: the sort is stable, so ties on (barcode, umi) keep their input order.
     const int *keys = descents ? order : order + 1;
@@ -1608,7 +1762,7 @@ int ibu_gpu_sort_records(ibu_gpu_ctx_t *ctx, const ibu_record_t *d_records, uint
     const uint64_t *result = nullptr;
     // an odd number of passes must start into d_sorted to end there
     if (int rc = radix_sort<3>(ctx, src, (passes & 1) ? dst : spare, (passes & 1) ? spare : dst, n, vary, keys, n_keys,
-                               s, sc, &result, err))
+                               s, sc, &result, err, pre.n_passes ? &pre : nullptr))
         return rc;
     if (result != dst) IBU_CUDA(cudaMemcpyAsync(dst, result, n * 24, cudaMemcpyDeviceToDevice, s));
     IBU_CUDA(cudaStreamSynchronize(s));

@@ -632,6 +632,18 @@ def test_sort_records_matches_record_ord(ctx, n, bc, umi, mode, param, index_ord
         assert info["input_was_sorted"] and np.array_equal(rows, on.barcode_table(recs))
 
 
+@pytest.mark.parametrize("word,bit", [("barcode", 60), ("umi", 41), ("index", 35)])
+def test_sort_records_bits_the_sample_misses(ctx, word, bit):
+    """ibu_gpu_sort_records guesses the digits to sort from 2^16 sampled records and confirms the guess
+    with exact masks: ONE record with a bit far above every other's must still end up in its place
+    (the digit passes it needs are not in the guess), and so must an index word that breaks the order."""
+    n = 2_500_003
+    recs = oc.generate_records(0, n, 16, 12, 0, 0, 33)
+    recs[word][n // 2 + 7] |= np.uint64(1) << np.uint64(bit)
+    got = gpu_sort(ctx, recs)
+    assert np.array_equal(got, sort_records(recs))
+
+
 def np_pair_table(recs, weighted=False):
     order = np.lexsort((recs["umi"], recs["barcode"]))
     b, u, w = recs["barcode"][order], recs["umi"][order], recs["index"][order]
