@@ -855,6 +855,11 @@ __global__ void __launch_bounds__(kBlockThreads, 3) k_onesweep(const SweepArgs a
     }
 }
 
+// Measured and dropped: the look-back run UNDER the ranking (the tile's counts taken first from a plain
+// shared-memory histogram and published a ranking phase earlier; one look-back round trip per ranked item):
+// 11.08 against 10.97 ms per 10^8 records, 109.0 against 107.9 ms per 10^9 — ncu's samples sit between the two
+// barriers around the look-back (38 %), but the walk is not what the tile waits for.
+
 // ============================================================ hash aggregation (unsorted inputs)
 // Unsorted records are first folded into distinct (barcode, umi, multiplicity) pairs with an
 // open-addressing table in HBM/L2 (linear probing, 32-byte slots {barcode, umi, count, pad},
@@ -1264,8 +1269,7 @@ static int radix_sort(ibu_gpu_ctx *ctx, const uint64_t *in, uint64_t *first_dst,
             for (uint32_t p = 0; p < h.n_passes; p++) totals[p] = h.hist + p * 256;
         }
         // predecessors per look-back round trip: 4 (10^9 records: 108.0 ms; 8: 108.7; 16: 113.9; one at a time, the first form: 119)
-        static const int look = getenv("IBU_B200_LOOK") ? atoi(getenv("IBU_B200_LOOK")) : 4;  // tuning
-        auto sweep = look == 2 ? k_onesweep<STRIDE, 2> : look == 8 ? k_onesweep<STRIDE, 8> : k_onesweep<STRIDE, 4>;
+        auto sweep = k_onesweep<STRIDE, 4>;
         IBU_CUDA(cudaFuncSetAttribute(sweep, cudaFuncAttributeMaxDynamicSharedMemorySize, kSortTile * STRIDE * 8));
         const uint64_t *src = in;
         uint64_t *dst = first_dst, *spare = other;
