@@ -259,26 +259,39 @@ def kernel_block(ibu, ctx, torch, dev, stream, n, peak):
             add(name, "bc16/umi12, ibu_gpu_barcode_count (blocking call, rows left on the device)", 24,
                 sum(ts) / len(ts), ts[0], rows=info["n_rows"], distinct_pairs=info["n_distinct_pairs"],
                 sorted_input=info["input_was_sorted"], timing="wall clock")
-        # device sort by Record's Ord: general input (11 digit passes: 32 + 24 + 27 bits) and
-        # input that already comes in index order (the index passes are skipped: 7)
+        # device sort by Record's Ord: by partition (two levels on order-preserving keys that
+        # carry the index, buckets sorted in shared memory) whatever the order of the index word, and the LSD
+        # one-sweep radix sort that takes the inputs the partition does not suit (IBU_B200_SORT_MSD=0 forces it)
         back = u8(24 * n)
-        for name, descending in (("ibu_gpu_sort_records, index in input order", False), ("ibu_gpu_sort_records, index descending", True)):
+        for name, descending, lsd in (("ibu_gpu_sort_records, index in input order", False, False),
+                                      ("ibu_gpu_sort_records, index descending", True, False),
+                                      ("ibu_gpu_sort_records, LSD fallback forced, index in input order", False, True)):
             ctx.generate_records_async(recs, 0, n, 16, 12, ibu.GEN_CLEAN, 0, 5, stream)
             if descending:
                 words = recs.view(torch.int64).view(-1, 3)
                 words[:, 2] = (n - 1) - words[:, 2]
             stream.synchronize()
-            ts = []
-            for _ in range(4):
-                t0 = time.perf_counter()
-                ctx.sort_records(recs, n, back, stream)
-                ts.append((time.perf_counter() - t0) * 1e3)
+            old_env = os.environ.get("IBU_B200_SORT_MSD")
+            if lsd:
+                os.environ["IBU_B200_SORT_MSD"] = "0"
+            try:
+                ts = []
+                for _ in range(4):
+                    t0 = time.perf_counter()
+                    ctx.sort_records(recs, n, back, stream)
+                    ts.append((time.perf_counter() - t0) * 1e3)
+            finally:
+                if lsd:
+                    os.environ.pop("IBU_B200_SORT_MSD") if old_env is None else os.environ.__setitem__("IBU_B200_SORT_MSD", old_env)
             ts = sorted(ts[1:])
-            passes = 7 + (4 if descending else 0)
-            add(name, f"bc16/umi12 random, blocking call, {passes} one-sweep 8-bit digit passes of 48 B/record + one 24 B scan "
-                      "(digit histograms and key masks together; the digits are guessed from a 2^16-record sample)",
-                48 * passes + 24, sum(ts) / len(ts), ts[0], timing="wall clock",
-                roofline_note="alg_bytes is what the one-sweep LSD radix moves, not a lower bound of sorting")
+            if lsd:
+                add(name, "bc16/umi12 random, blocking call, 7 one-sweep 8-bit digit passes of 48 B/record + one 24 B scan",
+                    48 * 7 + 24, sum(ts) / len(ts), ts[0], timing="wall clock",
+                    roofline_note="alg_bytes is what the one-sweep LSD radix moves, not a lower bound of sorting")
+            else:
+                add(name, "bc16/umi12 random, blocking call, k_part1 (24 R + 16 W) + k_part2 (16 R + 16 W) + k_bucket_sort_records "
+                          "(16 R + 24 W)", 112, sum(ts) / len(ts), ts[0], timing="wall clock",
+                    roofline_note="alg_bytes is what the partition sort moves, not a lower bound of sorting")
         del recs, back
     return out
 
@@ -588,14 +601,18 @@ def mmap_block(ibu, ctx, torch, dev, np, rank, world, local, host_barrier, dist,
     page-locked shard (ibu_mmap_pin_range); the CPU oracle's process_parallel on the same file."""
     from oracle import oracle_c as oc
 
-    n_file = (N_RECORDS // 2) * world  # 1.2 GB per GPU
     path = f"/dev/shm/ibu_bench_mmap_{os.getpid() if world == 1 else os.environ.get('MASTER_PORT', '0')}.ibu"
     if rank == 0:
+        n_file = N_RECORDS * world  # the headline's 10^8 records (2.4 GB) per GPU
+        st = os.statvfs("/dev/shm")
+        if 24 * n_file + (30 << 30) > st.f_bavail * st.f_frsize:  # (leave the table block's 24 GB file its room)
+            n_file //= 2
         make_file(ibu, ctx, torch, dev, path, n_file, ibu.GEN_DIRTY, DIRTY_PPM, np)
     host_barrier()
     out = None
     try:
         reader = ibu.MmapReader(path)
+        n_file = reader.len()  # (rank 0 chose it)
         s, e = ibu.shard_range(n_file, rank, world)
 
         def timed(fn, reps=3):

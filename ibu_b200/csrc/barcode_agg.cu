@@ -219,6 +219,7 @@ struct K4Job {
     double r_est = 0;
     bool exact = false, weighted = false, packed = false;
     bool ordered = false;  // order-preserving keys and k_bucket_rows instead of the hash table (k4_ordered.cuh)
+    uint64_t *sort_out = nullptr;  // record sort (k4_sort_records_msd): the weights are indices, the result is the sorted records
     std::vector<K4Level> levels;  // levels[0] is filled by add(); the last one feeds the de-duplication
     // chunked mode: add() takes the records in pieces of `chunk` records, partitions a piece into a
     // small level-0 area of its stream (written and read back while still in L2) and straight on
@@ -275,7 +276,11 @@ int k4_job_begin(ibu_gpu_ctx *ctx, uint64_t n, const K4Hints &hints, const K4Sam
     // ---- what the sample says ----
     const double m = (double)smp.m;
     uint32_t bb, ub;
-    if (hints.bc_len && hints.umi_len) {
+    const bool sorting = hints.sort_records;
+    if (sorting) {  // every word the sample saw must fit: a sort has no side list
+        bb = width_of(smp.hist, 0);
+        ub = width_of(smp.hist + 65, 0);
+    } else if (hints.bc_len && hints.umi_len) {
         bb = 2 * hints.bc_len;
         ub = 2 * hints.umi_len;
     } else {  // widths that hold 97 % of the sample; what does not fit goes to the wide list
@@ -293,13 +298,14 @@ int k4_job_begin(ibu_gpu_ctx *ctx, uint64_t n, const K4Hints &hints, const K4Sam
         fprintf(stderr, "[ibu trace] sample: m=%llu pairs %.0f (f1 %.0f f2 %.0f coll %.0f) barcodes %.0f (f1 %.0f f2 %.0f) -> D~%.3g R~%.3g bb=%u ub=%u\n",
                 (unsigned long long)smp.m, smp.pairs, smp.pair_f1, smp.pair_f2, smp.pair_coll, smp.barcodes, smp.bc_f1,
                 smp.bc_f2, d_est, r_est, bb, ub);
-    if (!forced && d_est < 65536.0) return IBU_OK;  // a tiny global table is L2 resident: legacy hash path
+    if (!forced && !sorting && d_est < 65536.0) return IBU_OK;  // a tiny global table is L2 resident: legacy hash path
     // about as many barcodes as records: a table far outside L2 and a full-size sort of its rows
     // afterwards — the buckets are cut by the barcode's own top bits instead and finished in
     // barcode order (k4_ordered.cuh); IBU_B200_K4_ORDERED=0/1 forces the choice (tests, tuning)
     bool ordered = !pair_mode && r_est > 8.0e6 && r_est > 0.05 * (double)n;
     if (const char *e = getenv("IBU_B200_K4_ORDERED")) ordered = !pair_mode && atoi(e) != 0;
-    if (ordered && weighted) {
+    if (sorting) ordered = true;
+    if (ordered && weighted && !sorting) {
         if (!forced) return IBU_OK;  // (the multiplicities would have to travel through the bucket sort: sort fallback)
         ordered = false;
     }
@@ -316,7 +322,8 @@ int k4_job_begin(ibu_gpu_ctx *ctx, uint64_t n, const K4Hints &hints, const K4Sam
     static const uint64_t per_bucket = getenv("IBU_B200_K4_BUCKET") ? std::max(64, atoi(getenv("IBU_B200_K4_BUCKET"))) : 1024;  // tuning
     job->P = std::min<uint64_t>(std::max<uint64_t>(pow2_ceil((n + per_bucket - 1) / per_bucket), 2), 1u << 21);
     job->pb = log2_of(job->P);
-    if (ordered && job->pb + 1 > bb) {  // fewer barcode bits than bucket bits: a barcode would span buckets
+    if (sorting && job->pb > bb + ub) return IBU_OK;  // more buckets than keys
+    if (ordered && !sorting && job->pb + 1 > bb) {  // fewer barcode bits than bucket bits: a barcode would span buckets
         if (!forced) return IBU_OK;
         ordered = false;
     }
@@ -340,6 +347,11 @@ int k4_job_begin(ibu_gpu_ctx *ctx, uint64_t n, const K4Hints &hints, const K4Sam
         const double mean = (double)n / buckets, sigma = std::sqrt(sum_sq / buckets);
         // (ordered keys are only as uniform as the barcodes' top bits: a quarter more room)
         lv.cap = ((uint64_t)((ordered ? 1.25 : 1.0) * mean + 6.0 * sigma) + 64 + 15) & ~15ull;
+        // (a sort has no second chance for a level before the last — the last one can be laid out exactly — so
+        // those get room for key ranges twice as full as the mean where memory allows: the reference's example
+        // pattern puts 3 records on the first 30 % of its barcodes and 2 on the rest)
+        if (sorting && l + 1 < bits.size() && n <= 400000000ull)
+            lv.cap = ((uint64_t)(2.0 * mean + 6.0 * sigma) + 64 + 15) & ~15ull;
         if (l + 1 < bits.size()) {
             // a level whose loads are this uneven (a few keys hold most of the records) is not worth
             // laying out: the global hash of the legacy path keeps such keys in L2
@@ -573,6 +585,61 @@ static int finish_ordered(K4Job *job, const std::function<int()> &layout_exact, 
     return IBU_OK;
 }
 
+// The last stage of a record sort: the final buckets' sizes -> where each bucket's records go, then every
+// bucket sorted by (key, index) in shared memory and written out as records (k_bucket_sort_records).
+static int finish_sort(K4Job *job, const std::function<int()> &layout_exact, bool *handled, ibu_error_t *err) {
+    ibu_gpu_ctx *ctx = job->ctx;
+    cudaStream_t s = job->s0;
+    PoolScratch &sc = job->sc;
+    unsigned long long *mail = ctx->h_mail, *ctr = job->ctr;
+    const uint64_t n = job->added, P = job->P;
+    K4Level &last = job->levels.back();
+    IBU_CUDA(cudaMemcpyAsync(mail, ctr, kCtrWords * 8, cudaMemcpyDeviceToHost, s));
+    IBU_CUDA(cudaStreamSynchronize(s));
+    if (job->trace)
+        fprintf(stderr, "[ibu trace] sort: %zu levels to P=2^%u, bb=%u ub=%u, wide %llu flags %llx\n", job->levels.size(), job->pb,
+                job->bb, job->ub, mail[kCtrWide], mail[kCtrFlags]);
+    if ((mail[kCtrFlags] & kFlagBucket) && !job->exact && !mail[kCtrWide] && !(mail[kCtrFlags] & kFlagLevel)) {
+        // the keys' top bits are not uniform enough for the uniform layout of the last level: the level
+        // before is intact, lay the buckets out exactly from a histogram and go on
+        const unsigned long long keep[3] = {0ull, mail[kCtrFlags] & ~(unsigned long long)kFlagBucket, mail[kCtrSpecial]};
+        IBU_CUDA(cudaMemcpyAsync(ctr, keep, sizeof(keep), cudaMemcpyHostToDevice, s));
+        sc.free_now(last.keys);
+        sc.free_now(last.wts);
+        last.keys = last.wts = nullptr;
+        job->exact = true;
+        const int rc = layout_exact();
+        if (rc < 0) return IBU_OK;
+        if (rc) return rc;
+        IBU_CUDA(cudaMemcpyAsync(mail, ctr, kCtrWords * 8, cudaMemcpyDeviceToHost, s));
+        IBU_CUDA(cudaStreamSynchronize(s));
+    }
+    // a record wider than the sample's words, the one key that doubles as the empty marker, a level that
+    // overflowed: the LSD sort takes the input
+    if ((mail[kCtrFlags] & (kFlagLevel | kFlagWide | kFlagBucket)) || mail[kCtrSpecial] || mail[kCtrWide]) return IBU_OK;
+    uint64_t *out_base;
+    IBU_CUDA(sc.alloc(&out_base, (P + 1) * 8));
+    k_bucket_bases<<<1, 1024, 0, s>>>(last.cursors, (uint32_t)P, out_base);
+    IBU_LAUNCHED("k_bucket_bases");
+    // buckets of the uniform layout are bounded by its slab: 1536 pairs = 30 KB of shared memory leave room for
+    // 5 CTAs per SM instead of 4
+    const uint32_t cap = (!job->exact && last.cap <= 1536) ? 1536u : kOrdCap;
+    const uint32_t per_sm = cap == 1536u ? 5u : 4u;
+    if (int rc = set_max_smem(k_bucket_sort_records, ctx->device, (size_t)kOrdCap * 20, err)) return rc;
+    SortRecArgs a{job->exact ? job->bases : nullptr, last.cursors, last.cap, last.keys, last.wts, (uint32_t)P, job->pb, job->bb,
+                  job->ub, cap, out_base, job->sort_out, ctr};
+    k_bucket_sort_records<<<(uint32_t)std::min<uint64_t>(P, (uint64_t)ctx->sm_count * per_sm), kBlockThreads, (size_t)cap * 20, s>>>(a);
+    IBU_LAUNCHED("k_bucket_sort_records");
+    job->timer.lap("k_bucket_sort_records");
+    IBU_CUDA(cudaMemcpyAsync(mail, ctr, kCtrWords * 8, cudaMemcpyDeviceToHost, s));
+    IBU_CUDA(cudaMemcpyAsync(mail + kCtrWords, out_base + P, 8, cudaMemcpyDeviceToHost, s));
+    IBU_CUDA(cudaStreamSynchronize(s));
+    if (job->trace) fprintf(stderr, "[ibu trace] sort: %llu of %llu records placed, flags %llx\n", mail[kCtrWords], (unsigned long long)n, mail[kCtrFlags]);
+    if ((mail[kCtrFlags] & kFlagSmem) || mail[kCtrWords] != n) return IBU_OK;  // a bucket that does not fit: LSD sort
+    *handled = true;
+    return IBU_OK;
+}
+
 // Everything after the first level, on the job's stream (which must have waited for every stream
 // that added).  *handled = false: nothing produced, take another path.
 int k4_job_finish(K4Job *job, const uint64_t *all_recs, bool pair_mode, bool pairs_sorted, uint64_t **rows_out,
@@ -643,6 +710,7 @@ int k4_job_finish(K4Job *job, const uint64_t *all_recs, bool pair_mode, bool pai
         if (rc) return rc;
     }
 
+    if (job->sort_out) return finish_sort(job, layout_exact, handled, err);
     if (job->ordered) return finish_ordered(job, layout_exact, rows_out, n_rows, n_pairs, handled, err);
 
     // ---- per-bucket de-duplication into the barcode table (grown if the estimate was short) ----
@@ -805,6 +873,28 @@ int k4_partition_table(ibu_gpu_ctx *ctx, const uint64_t *recs, uint64_t n, const
         if (!job) return IBU_OK;
         int rc = k4_job_add(job, recs, n, s, err);
         if (rc == IBU_OK) rc = k4_job_finish(job, recs, pair_mode, pairs_sorted, rows_out, n_rows, n_pairs, handled, err);
+        const bool again = rc == IBU_OK && !*handled && k4_job_overflowed(job) && attempt == 0;
+        k4_job_destroy(job);
+        if (!again) return rc;
+    }
+    return IBU_OK;
+}
+
+int k4_sort_records_msd(ibu_gpu_ctx *ctx, const uint64_t *recs, uint64_t n, const K4Sample &smp, uint64_t *out,
+                        cudaStream_t s, bool *handled, ibu_error_t *err) {
+    *handled = false;
+    K4Hints hints;
+    hints.sort_records = true;
+    for (int attempt = 0; attempt < 2; attempt++) {
+        K4Job *job = nullptr;
+        K4Chunking ch;
+        ch.force_exact = attempt == 1;
+        if (int rc = k4_job_begin(ctx, n, hints, smp, false, true, ch, s, &job, err)) return rc;
+        if (!job) return IBU_OK;
+        job->sort_out = out;
+        uint64_t *rows = nullptr, n_rows = 0, n_pairs = 0;
+        int rc = k4_job_add(job, recs, n, s, err);
+        if (rc == IBU_OK) rc = k4_job_finish(job, recs, false, false, &rows, &n_rows, &n_pairs, handled, err);
         const bool again = rc == IBU_OK && !*handled && k4_job_overflowed(job) && attempt == 0;
         k4_job_destroy(job);
         if (!again) return rc;

@@ -1686,12 +1686,30 @@ int ibu_gpu_sort_records(ibu_gpu_ctx_t *ctx, const ibu_record_t *d_records, uint
     DeviceGuard guard(ctx->device);
     cudaStream_t s = pick_stream(ctx, stream);
     std::lock_guard<std::mutex> lock(ctx->arena_mutex);
+    const uint64_t *src = reinterpret_cast<const uint64_t *>(d_records);
+    uint64_t *dst = reinterpret_cast<uint64_t *>(d_sorted);
+    // From 2^20 records on, by partition first (k4_sort_records_msd: 112 bytes moved per record instead of 24 + 48
+    // per 8-bit digit); the LSD sort below takes what does not suit it.  IBU_B200_SORT_MSD=0 turns the attempt
+    // off, =2 makes an input it gives up on an error (how the tests prove which path ran).
+    const char *msd_env = getenv("IBU_B200_SORT_MSD");
+    if (n >= (1ull << 20) && !(msd_env && msd_env[0] == '0') && (((uintptr_t)src | (uintptr_t)dst) & 31u) == 0) {
+        if (s != ctx->stream) {  // scratch from the stream-ordered pool: always on the context's stream (k4_build_table)
+            if (!ctx->rows_ev) IBU_CUDA(cudaEventCreateWithFlags(&ctx->rows_ev, cudaEventDisableTiming));
+            IBU_CUDA(cudaEventRecord(ctx->rows_ev, s));
+            IBU_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->rows_ev, 0));
+            s = ctx->stream;
+        }
+        K4Sample smp;
+        if (int rc = k4_sample(ctx, src, n, s, &smp, err)) return rc;
+        bool handled = false;
+        if (int rc = k4_sort_records_msd(ctx, src, n, smp, dst, s, &handled, err)) return rc;
+        if (handled) return IBU_OK;  // (synchronised)
+        if (msd_env && msd_env[0] == '2') return set_error(err, IBU_ERR_ARG, 0, n, 0, "sort by partition gave up");
+    }
     IBU_CUDA(arena_reset(ctx, sort_scratch_bytes(n, 12)));  // spare + look-back state + histograms: no allocation in steady state
     Scratch sc(ctx);
     uint64_t *spare;
     IBU_CUDA(sc.alloc(&spare, n * 24));
-    const uint64_t *src = reinterpret_cast<const uint64_t *>(d_records);
-    uint64_t *dst = reinterpret_cast<uint64_t *>(d_sorted);
     uint64_t vary[3];
     uint64_t descents = 0;
     static const int order[3] = {2, 1, 0};  // Record's Ord: barcode, then umi, then index (record.rs:58)

@@ -60,6 +60,7 @@ struct PoolScratch {
 struct K4Hints {
     uint32_t bc_len = 0, umi_len = 0;  // header lengths in bases
     int force_path = 0;                // 0 auto, 1 partition, 2 composite sort, 3 legacy (tests / tuning)
+    bool sort_records = false;         // the job partitions (key, index) pairs for k4_sort_records_msd, not for a table
 };
 enum { kPathAuto = 0, kPathPartition = 1, kPathSort = 2, kPathLegacy = 3 };
 K4Hints k4_hints_of(int mode);  // from the upper bits of `mode` / `flags` (IBU_COUNT_LENS, IBU_COUNT_PATH_*)
@@ -102,6 +103,15 @@ int k4_partition_table(ibu_gpu_ctx *ctx, const uint64_t *recs, uint64_t n, const
                        bool pair_mode, bool pairs_sorted, bool weighted, cudaStream_t s, uint64_t **rows,
                        uint64_t *n_rows, uint64_t *n_pairs, bool *handled, ibu_error_t *err);
 
+
+// ibu_gpu_sort_records by partition (MSD) instead of LSD digit passes: the partition levels above on
+// order-preserving (barcode, umi) keys that carry the record's index, then every final bucket sorted in
+// shared memory and written as records at its final place (k4_ordered.cuh: k_bucket_sort_records).
+// *handled = false (nothing written that matters) when the input does not suit it: words wider than the
+// sample saw, keys beyond 64 bits, key ranges that hold far more records than a bucket (a few barcodes
+// with most of the records) — the LSD sort then takes the input.  `out` must not alias `recs`.
+int k4_sort_records_msd(ibu_gpu_ctx *ctx, const uint64_t *recs, uint64_t n, const K4Sample &smp, uint64_t *out,
+                        cudaStream_t s, bool *handled, ibu_error_t *err);
 
 // The same in three steps, for an ingest pipeline that feeds the table chunk by chunk while the
 // next chunk is still on the link (pipeline.cu).  begin leaves *job NULL when the input does not

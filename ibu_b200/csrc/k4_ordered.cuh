@@ -186,6 +186,121 @@ __global__ void __launch_bounds__(kBlockThreads, 5) k_bucket_sort(const OrdArgs 
     if (lane == 0 && my_pairs) atomicAdd(a.ctr + kCtrPairs, (unsigned long long)my_pairs);
 }
 
+// ---- the same buckets as the last stage of a record SORT (ibu_gpu_sort_records, barcode_agg.cu: k4_sort_records_msd) ----
+// k_part1<true> / k_part2<true> carry a second word per key (the multi-GPU merge's multiplicity); for a sort
+// that word is the record's index, and a final bucket holds the (key, index) pairs of one key range.  A CTA
+// round sorts one bucket by (key, index) — bins by the next 10 key bits, a pair's place = its bin's start + the
+// number of smaller pairs in the bin — and writes the RECORDS {barcode, umi, index} at their final place:
+// out_base[b] is the number of records in the buckets before b.  24 R + 16 W, 16 R + 16 W per level, 16 R +
+// 24 W here: 112 bytes per record against 24 + 48 per 8-bit digit of the LSD sort (360 for bc16/umi12).
+struct SortRecArgs {
+    const uint64_t *bases;    // exact layout (bucket b owns [bases[b], bases[b + 1])) or NULL: cursors[b] pairs at b * lcap
+    const uint32_t *cursors;
+    uint64_t lcap;
+    const uint64_t *keys, *wts;
+    uint32_t n_buckets, pb, bb, ub;
+    uint32_t cap;             // pairs of one bucket that fit the shared-memory arrays
+    const uint64_t *out_base; // [n_buckets + 1]
+    uint64_t *out;            // records
+    unsigned long long *ctr;
+};
+
+__global__ void __launch_bounds__(kBlockThreads, 4) k_bucket_sort_records(const SortRecArgs a) {
+    extern __shared__ __align__(16) unsigned long long smem[];
+    unsigned long long *kA = smem, *wA = smem + a.cap;               // as loaded
+    uint16_t *iB = reinterpret_cast<uint16_t *>(smem + 2 * a.cap);   // slots grouped by bin
+    uint16_t *ord = iB + a.cap;                                      // slot of the j-th smallest pair
+    __shared__ __align__(16) uint32_t hist[kOrdBins], off[kOrdBins];
+    __shared__ uint32_t tmp[8];
+    const uint32_t tid = threadIdx.x;
+    const uint32_t bshift = 64 - a.pb - kOrdBinBits, sh_bc = 64 - a.bb, sh_um = 64 - a.bb - a.ub;
+    const uint64_t umask = (1ull << a.ub) - 1ull;
+    uint32_t my_flags = 0;
+
+    uint64_t nfirst = 0, nk[4], nw[4];
+    uint32_t ncnt = 0;
+    auto fetch = [&](uint32_t b) {
+        ncnt = 0;
+        if (b < a.n_buckets) {
+            nfirst = a.bases ? a.bases[b] : (uint64_t)b * a.lcap;
+            ncnt = a.bases ? (uint32_t)min(a.bases[b + 1] - nfirst, (uint64_t)0xffffffffu) : a.cursors[b];
+            if (ncnt > a.cap || (!a.bases && ncnt > a.lcap)) {  // does not fit: the call is void
+                my_flags |= kFlagSmem;
+                ncnt = 0;
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            const uint32_t i = q * kBlockThreads + tid;
+            nk[q] = i < ncnt ? ldg_stream64(a.keys + nfirst + i) : 0ull;
+            nw[q] = i < ncnt ? ldg_stream64(a.wts + nfirst + i) : 0ull;
+        }
+    };
+    fetch(blockIdx.x);
+    for (uint32_t b = blockIdx.x; b < a.n_buckets; b += gridDim.x) {
+        const uint64_t first = nfirst;
+        uint32_t cnt = ncnt;
+        reinterpret_cast<uint4 *>(hist)[tid] = make_uint4(0, 0, 0, 0);
+        __syncthreads();  // (also: every thread has finished the previous bucket's output)
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            const uint32_t i = q * kBlockThreads + tid;
+            if (i < cnt) {
+                kA[i] = nk[q];
+                wA[i] = nw[q];
+                atomicAdd(&hist[(uint32_t)(nk[q] >> bshift) & (kOrdBins - 1u)], 1u);
+            }
+        }
+        for (uint32_t i = tid + 4 * kBlockThreads; i < cnt; i += kBlockThreads) {
+            const uint64_t k = ldg_stream64(a.keys + first + i);
+            kA[i] = k;
+            wA[i] = ldg_stream64(a.wts + first + i);
+            atomicAdd(&hist[(uint32_t)(k >> bshift) & (kOrdBins - 1u)], 1u);
+        }
+        __syncthreads();
+        const uint4 c = reinterpret_cast<const uint4 *>(hist)[tid];
+        uint32_t total;
+        const uint32_t st = block_excl_scan(c.x + c.y + c.z + c.w, tmp, total);
+        reinterpret_cast<uint4 *>(off)[tid] = make_uint4(st, st + c.x, st + c.x + c.y, st + c.x + c.y + c.z);
+        const bool lumpy = __syncthreads_or(max(max(c.x, c.y), max(c.z, c.w)) > kOrdMaxBin) != 0;
+        if (lumpy) {  // hundreds of records under a few keys: O(bin^2) here, the LSD sort takes the input
+            my_flags |= kFlagSmem;
+            cnt = 0;
+        }
+        for (uint32_t i = tid; i < cnt; i += kBlockThreads)
+            iB[atomicAdd(&off[(uint32_t)(kA[i] >> bshift) & (kOrdBins - 1u)], 1u)] = (uint16_t)i;
+        __syncthreads();  // off[bin] is now the bin's end
+        for (uint32_t p = tid; p < cnt; p += kBlockThreads) {
+            const uint32_t i = iB[p];
+            const uint64_t k = kA[i], w = wA[i];
+            const uint32_t bin = (uint32_t)(k >> bshift) & (kOrdBins - 1u);
+            const uint32_t en = off[bin], s0 = en - hist[bin];
+            uint32_t less = 0;
+            for (uint32_t q = s0; q < en; q++) {
+                const uint32_t iq = iB[q];
+                const uint64_t kq = kA[iq];
+                if (kq < k) {
+                    less++;
+                } else if (kq == k) {
+                    const uint64_t wq = wA[iq];
+                    less += (wq < w) | ((wq == w) & (q < p));
+                }
+            }
+            ord[s0 + less] = (uint16_t)i;
+        }
+        __syncthreads();
+        fetch(b + gridDim.x);
+        // the records, word by word in sorted order: neighbouring threads store neighbouring words
+        uint64_t *dst = a.out + 3 * a.out_base[b];
+        for (uint32_t x = tid; x < 3 * cnt; x += kBlockThreads) {
+            const uint32_t j = x / 3u, f = x - 3u * j, i = ord[j];
+            const uint64_t k = kA[i];
+            dst[x] = f == 0 ? k >> sh_bc : f == 1 ? (k >> sh_um) & umask : wA[i];
+        }
+    }
+    if (my_flags) atomicOr(a.ctr + kCtrFlags, (unsigned long long)my_flags);
+}
+
 __global__ void __launch_bounds__(kBlockThreads, 6) k_bucket_emit(const OrdArgs a) {
     extern __shared__ __align__(16) unsigned long long smem[];
     unsigned long long *kA = smem;

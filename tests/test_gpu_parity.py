@@ -644,6 +644,53 @@ def test_sort_records_bits_the_sample_misses(ctx, word, bit):
     assert np.array_equal(got, sort_records(recs))
 
 
+@pytest.mark.parametrize("shape", ["random", "repeats", "pattern", "uneven top bits", "sorted already", "few umis"])
+@pytest.mark.parametrize("index_order", ["ascending", "descending", "shuffled"])
+def test_sort_records_by_partition(ctx, shape, index_order):
+    """From 2^20 records on ibu_gpu_sort_records partitions (key, index) pairs by the key's top bits and sorts
+    every final bucket in shared memory (k4_sort_records_msd).  IBU_B200_SORT_MSD=2: handing the input to the
+    LSD sort is an error here, so these shapes prove that path; the result is Record's Ord (record.rs:58)."""
+    import os
+
+    n = 2_300_007
+    rng = np.random.default_rng(91)
+    if shape == "pattern":
+        recs = oc.generate_records(0, n, 16, 12, 2, 0, 34)
+    elif shape == "sorted already":
+        recs = oc.generate_records(0, n, 16, 12, 4, (5 << 32) | 1000, 34)
+    else:
+        recs = oc.generate_records(0, n, 16, 12, 0, 0, 34)
+    if shape == "repeats":  # whole records again (equal keys AND equal indices), and keys again with other indices
+        recs[n // 2:n // 2 + 400_000] = recs[:400_000]
+        recs["barcode"][n - 300_000:] = recs["barcode"][:300_000]
+        recs["umi"][n - 300_000:] = recs["umi"][:300_000]
+    if shape == "uneven top bits":  # the uniform layout of the last level overflows: exact layout from a histogram
+        recs["barcode"][rng.random(n) < 0.7] &= ~U64(1 << 25)
+    if shape == "few umis":  # 16 UMIs: long runs of one barcode's records differ only far down the key
+        recs["barcode"] >>= U64(12)
+        recs["umi"] &= U64(15)
+    if index_order == "descending":
+        recs["index"] = recs["index"][::-1].copy()
+    elif index_order == "shuffled":
+        recs["index"] = rng.permutation(n).astype(U64) * U64(1 << 20)  # (wide index words)
+    want = sort_records(recs)
+    old = os.environ.get("IBU_B200_SORT_MSD")
+    # ("sorted already": barcodes 0..2299 fill 56 % of their 12-bit range, the first level's uniform layout
+    # overflows and the LSD sort takes over — allowed, the result must be right either way)
+    os.environ["IBU_B200_SORT_MSD"] = "1" if shape == "sorted already" else "2"
+    try:
+        got = gpu_sort(ctx, recs)
+    finally:
+        os.environ.pop("IBU_B200_SORT_MSD") if old is None else os.environ.__setitem__("IBU_B200_SORT_MSD", old)
+    assert np.array_equal(got, want)
+    os.environ["IBU_B200_SORT_MSD"] = "0"  # and the LSD sort agrees
+    try:
+        got = gpu_sort(ctx, recs)
+    finally:
+        os.environ.pop("IBU_B200_SORT_MSD") if old is None else os.environ.__setitem__("IBU_B200_SORT_MSD", old)
+    assert np.array_equal(got, want)
+
+
 def np_pair_table(recs, weighted=False):
     order = np.lexsort((recs["umi"], recs["barcode"]))
     b, u, w = recs["barcode"][order], recs["umi"][order], recs["index"][order]
