@@ -1702,7 +1702,16 @@ int ibu_gpu_sort_records(ibu_gpu_ctx_t *ctx, const ibu_record_t *d_records, uint
         K4Sample smp;
         if (int rc = k4_sample(ctx, src, n, s, &smp, err)) return rc;
         bool handled = false;
-        if (int rc = k4_sort_records_msd(ctx, src, n, smp, dst, s, &handled, err)) return rc;
+        ibu_error_t attempt{};
+        if (int rc = k4_sort_records_msd(ctx, src, n, smp, dst, s, &handled, &attempt)) {
+            // no room for the partition's scratch (about 40 bytes per record): the LSD sort needs 24
+            if (rc != IBU_ERR_CUDA || attempt.sys != (int)cudaErrorMemoryAllocation) {
+                if (err) *err = attempt;
+                return rc;
+            }
+            cudaGetLastError();
+            handled = false;
+        }
         if (handled) return IBU_OK;  // (synchronised)
         if (msd_env && msd_env[0] == '2') return set_error(err, IBU_ERR_ARG, 0, n, 0, "sort by partition gave up");
     }
