@@ -526,7 +526,10 @@ def run_ours(args):
     # ---- rank 0: the other kernels, the file-based blocks; the other ranks idle on the host ----
     kernels = e2e_mmap = table = None
     if rank == 0 and not args.quick:
-        kernels = kernel_block(ibu, ctx, torch, dev, stream, n, peak)
+        try:
+            kernels = kernel_block(ibu, ctx, torch, dev, stream, n, peak)
+        except Exception as exc:  # the headline stands on its own
+            kernels = [{"name": "kernel block failed", "error": repr(exc)}]
     host_barrier()
     if not args.quick:
         e2e_mmap = mmap_block(ibu, ctx, torch, dev, np, rank, world, local, host_barrier, dist, link)
@@ -605,11 +608,22 @@ def mmap_block(ibu, ctx, torch, dev, np, rank, world, local, host_barrier, dist,
     if rank == 0:
         n_file = N_RECORDS * world  # the headline's 10^8 records (2.4 GB) per GPU
         st = os.statvfs("/dev/shm")
-        if 24 * n_file + (30 << 30) > st.f_bavail * st.f_frsize:  # (leave the table block's 24 GB file its room)
+        free_b = st.f_bavail * st.f_frsize
+        while 24 * n_file + (4 << 30) > free_b and n_file > 1_000_000 * world:  # (a full tmpfs is a SIGBUS, not an exception)
             n_file //= 2
-        make_file(ibu, ctx, torch, dev, path, n_file, ibu.GEN_DIRTY, DIRTY_PPM, np)
+        try:
+            if 24 * n_file + (1 << 30) > free_b:
+                raise OSError("no room in /dev/shm")
+            make_file(ibu, ctx, torch, dev, path, n_file, ibu.GEN_DIRTY, DIRTY_PPM, np)
+        except Exception as exc:  # the other ranks must not wait for a file that will not come
+            sys.stderr.write(f"[bench] e2e_mmap skipped: {exc!r}\n")
+            if os.path.exists(path):
+                os.unlink(path)
     host_barrier()
     out = None
+    if not os.path.exists(path):
+        host_barrier()
+        return {"error": "the test file could not be written"} if rank == 0 else None
     try:
         reader = ibu.MmapReader(path)
         n_file = reader.len()  # (rank 0 chose it)
