@@ -205,7 +205,7 @@ struct SortRecArgs {
     unsigned long long *ctr;
 };
 
-__global__ void __launch_bounds__(kBlockThreads, 4) k_bucket_sort_records(const SortRecArgs a) {
+__global__ void __launch_bounds__(kBlockThreads, 5) k_bucket_sort_records(const SortRecArgs a) {
     extern __shared__ __align__(16) unsigned long long smem[];
     unsigned long long *kA = smem, *wA = smem + a.cap;               // as loaded
     uint16_t *iB = reinterpret_cast<uint16_t *>(smem + 2 * a.cap);   // slots grouped by bin
@@ -217,11 +217,12 @@ __global__ void __launch_bounds__(kBlockThreads, 4) k_bucket_sort_records(const 
     const uint64_t umask = (1ull << a.ub) - 1ull;
     uint32_t my_flags = 0;
 
-    uint64_t nfirst = 0, nk[4], nw[4];
+    uint64_t nfirst = 0, nout = 0, nk[4], nw[4];
     uint32_t ncnt = 0;
     auto fetch = [&](uint32_t b) {
         ncnt = 0;
         if (b < a.n_buckets) {
+            nout = a.out_base[b];  // (needed a bucket later: its latency stays out of the output loop)
             nfirst = a.bases ? a.bases[b] : (uint64_t)b * a.lcap;
             ncnt = a.bases ? (uint32_t)min(a.bases[b + 1] - nfirst, (uint64_t)0xffffffffu) : a.cursors[b];
             if (ncnt > a.cap || (!a.bases && ncnt > a.lcap)) {  // does not fit: the call is void
@@ -239,6 +240,7 @@ __global__ void __launch_bounds__(kBlockThreads, 4) k_bucket_sort_records(const 
     fetch(blockIdx.x);
     for (uint32_t b = blockIdx.x; b < a.n_buckets; b += gridDim.x) {
         const uint64_t first = nfirst;
+        uint64_t *dst = a.out + 3 * nout;
         uint32_t cnt = ncnt;
         reinterpret_cast<uint4 *>(hist)[tid] = make_uint4(0, 0, 0, 0);
         __syncthreads();  // (also: every thread has finished the previous bucket's output)
@@ -291,11 +293,12 @@ __global__ void __launch_bounds__(kBlockThreads, 4) k_bucket_sort_records(const 
         __syncthreads();
         fetch(b + gridDim.x);
         // the records, word by word in sorted order: neighbouring threads store neighbouring words
-        uint64_t *dst = a.out + 3 * a.out_base[b];
+        // (branch-free: both words of the pair are read, shift and mask picked by the field)
         for (uint32_t x = tid; x < 3 * cnt; x += kBlockThreads) {
             const uint32_t j = x / 3u, f = x - 3u * j, i = ord[j];
-            const uint64_t k = kA[i];
-            dst[x] = f == 0 ? k >> sh_bc : f == 1 ? (k >> sh_um) & umask : wA[i];
+            const uint64_t k = kA[i], w = wA[i];
+            const uint64_t v = (k >> (f == 0 ? sh_bc : sh_um)) & (f == 0 ? ~0ull : umask);
+            dst[x] = f == 2 ? w : v;
         }
     }
     if (my_flags) atomicOr(a.ctr + kCtrFlags, (unsigned long long)my_flags);
