@@ -1355,9 +1355,31 @@ static int unsorted_table(ibu_gpu_ctx *ctx, const uint64_t *recs, uint64_t n, cu
     } else {  // the multiplicity (index word) travels with its key: sort whole records
         uint64_t *a, *b;
         IBU_CUDA(sc.alloc(&a, n * 24));
-        IBU_CUDA(sc.alloc(&b, n * 24));
-        if (int rc = key_masks<2>(ctx, recs, n, nullptr, s, sc, vary, err)) return rc;
-        if (int rc = radix_sort<3>(ctx, recs, a, b, n, vary, order, 2, s, sc, &sorted, err)) return rc;
+        // by partition where that suits the keys (ibu_gpu_sort_records' first choice: the multiplicity is sorted
+        // as a third key, which does no harm) — the weighted near-distinct input of a multi-GPU owner count
+        bool by_partition = false;
+        const char *msd_env = getenv("IBU_B200_SORT_MSD");
+        if (n >= (1ull << 20) && !(msd_env && msd_env[0] == '0') && (((uintptr_t)recs | (uintptr_t)a) & 31u) == 0) {
+            K4Sample smp;
+            ibu_error_t attempt{};
+            int rc = k4_sample(ctx, recs, n, s, &smp, &attempt);
+            if (rc == IBU_OK) rc = k4_sort_records_msd(ctx, recs, n, smp, a, s, &by_partition, &attempt);
+            if (rc != IBU_OK) {
+                if (rc != IBU_ERR_CUDA || attempt.sys != (int)cudaErrorMemoryAllocation) {
+                    if (err) *err = attempt;
+                    return rc;
+                }
+                cudaGetLastError();
+                by_partition = false;
+            }
+        }
+        if (by_partition) {
+            sorted = a;
+        } else {
+            IBU_CUDA(sc.alloc(&b, n * 24));
+            if (int rc = key_masks<2>(ctx, recs, n, nullptr, s, sc, vary, err)) return rc;
+            if (int rc = radix_sort<3>(ctx, recs, a, b, n, vary, order, 2, s, sc, &sorted, err)) return rc;
+        }
         stride = 3;
     }
     bool still_unsorted = false;

@@ -754,6 +754,42 @@ def test_weighted_merge_of_shard_pair_tables_is_exact(ctx, world):
     assert np.array_equal(rows, on.barcode_table(recs)) and info["n_records"] == len(merged)
 
 
+def test_weighted_count_of_near_distinct_pairs(ctx):
+    """The owner count of a multi-GPU merge over near-distinct data: (barcode, umi, multiplicity) rows with about
+    as many barcodes as rows.  Neither table form of the partition path takes weighted near-distinct input; the
+    sort behind the segment pass does — by partition (k4_sort_records_msd) and, forced, by LSD digits."""
+    import os
+
+    n = 2_200_003
+    rng = np.random.default_rng(5)
+    recs = oc.generate_records(0, n, 16, 12, 0, 0, 35)
+    recs[n - 200_000:] = recs[:200_000]                       # the same pair from two shards
+    recs["umi"][n - 100_000:] ^= U64(3)                       # ... and the same barcode with another UMI
+    recs["index"] = rng.integers(1, 6, n).astype(U64)         # multiplicities
+    order = np.lexsort((recs["umi"], recs["barcode"]))
+    b, u, w = recs["barcode"][order], recs["umi"][order], recs["index"][order]
+    new_bc = np.ones(n, bool)
+    new_bc[1:] = b[1:] != b[:-1]
+    new_pair = new_bc.copy()
+    new_pair[1:] |= u[1:] != u[:-1]
+    seg = np.cumsum(new_bc) - 1
+    want_bc = b[new_bc]
+    want_rec = np.bincount(seg, weights=w.astype(np.float64)).astype(U64)
+    want_dist = np.bincount(seg, weights=new_pair.astype(np.float64)).astype(U64)
+    d = Dev(ctx, recs.nbytes, recs)
+    old = os.environ.get("IBU_B200_SORT_MSD")
+    try:
+        for env in (None, "0"):
+            if env is not None:
+                os.environ["IBU_B200_SORT_MSD"] = env
+            rows, info = ctx.barcode_count(d, n, ibu.COUNT_WEIGHTED | 2)
+            assert np.array_equal(rows["barcode"], want_bc) and np.array_equal(rows["n_records"], want_rec)
+            assert np.array_equal(rows["n_distinct_umi"], want_dist)
+    finally:
+        os.environ.pop("IBU_B200_SORT_MSD", None) if old is None else os.environ.__setitem__("IBU_B200_SORT_MSD", old)
+        d.free()
+
+
 def test_partition_by_owner_and_emulated_all_to_all(ctx):
     """The exchange of ibu_b200.distributed.exact_barcode_table emulated on one GPU: per-shard pair
     tables -> owner buckets -> every owner counts what it would receive -> concatenated rows."""
