@@ -19,6 +19,10 @@ constexpr int kPartMaxFan = 512;
 #ifndef K4_PART_MINB
 #define K4_PART_MINB 3  // resident CTAs per SM the partition kernels are compiled for (tools/k4lab3.cu sweeps it)
 #endif
+#ifndef K4_PART_MINB_W
+#define K4_PART_MINB_W 2  // the same for the weighted instantiations (keys and a second word: 64 KB of staging per CTA);
+                          // 3 (80 registers, 140 - 280 bytes spilled) measured: k_part1 1.03 -> 1.17 ms, k_part2 0.89 -> 1.09 per 10^8
+#endif
 
 struct Part1Args {
     const uint64_t *recs;
@@ -58,7 +62,7 @@ __device__ __forceinline__ uint32_t block_excl_scan(uint32_t v, uint32_t *tmp, u
 
 // Level 1: records -> keys grouped by the top pb1 bits of the mixed key.
 template <bool WEIGHTED>
-__global__ void __launch_bounds__(kBlockThreads, WEIGHTED ? 2 : K4_PART_MINB) k_part1(const Part1Args a) {
+__global__ void __launch_bounds__(kBlockThreads, WEIGHTED ? K4_PART_MINB_W : K4_PART_MINB) k_part1(const Part1Args a) {
     extern __shared__ __align__(16) unsigned long long stage[];  // [kPartTile] keys (+ [kPartTile] weights)
     __shared__ uint32_t hist[256], start[256], delta[256], tmp[8];
     const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
@@ -173,7 +177,7 @@ struct Part2Args {
 // A further level: the keys of one input bucket -> 2^pb output buckets each.  COUNT_ONLY: the
 // histogram of the exact layout (cursors_out[b] = keys of bucket b; nothing stored).
 template <bool WEIGHTED, bool COUNT_ONLY>
-__global__ void __launch_bounds__(kBlockThreads, WEIGHTED ? 2 : K4_PART_MINB) k_part2(const Part2Args a) {
+__global__ void __launch_bounds__(kBlockThreads, WEIGHTED ? K4_PART_MINB_W : K4_PART_MINB) k_part2(const Part2Args a) {
     extern __shared__ __align__(16) unsigned long long stage[];
     __shared__ uint32_t hist[kPartMaxFan], start[kPartMaxFan], delta[kPartMaxFan], tmp[8];
     const uint32_t b1 = blockIdx.x / a.tiles_per_bucket;
