@@ -183,6 +183,7 @@ int k4_sample(ibu_gpu_ctx *ctx, const uint64_t *recs, uint64_t n, cudaStream_t s
     out->pair_f2 = (double)(long long)mail[kSmpPairF2];
     out->bc_f1 = (double)(long long)mail[kSmpBcF1];
     out->bc_f2 = (double)(long long)mail[kSmpBcF2];
+    out->bc_max = std::max<uint64_t>(1, mail[kSmpBcMax]);
     memcpy(out->hist, mail + kSmpWords, sizeof(out->hist));
     return IBU_OK;
 }
@@ -323,6 +324,25 @@ int k4_job_begin(ibu_gpu_ctx *ctx, uint64_t n, const K4Hints &hints, const K4Sam
     job->P = std::min<uint64_t>(std::max<uint64_t>(pow2_ceil((n + per_bucket - 1) / per_bucket), 2), 1u << 21);
     job->pb = log2_of(job->P);
     if (sorting && job->pb > bb + ub) return IBU_OK;  // more buckets than keys
+    // one barcode's records share a final bucket (the bucket bits lie within the barcode): a barcode the sample
+    // met far more often than one that just fills a bucket would be met (Poisson: its mean + 6 sigma + 6) ends the
+    // attempt before it starts — it would partition everything first and fail in the last kernel.  (Cell
+    // barcodes with 10^4 - 10^5 reads each: the LSD sort's case.)
+    if (sorting && job->pb <= bb && !whole) {
+        const double lam = (double)kOrdCap * m / (double)n;
+        if ((double)smp.bc_max > lam + 6.0 * std::sqrt(lam) + 6.0) return IBU_OK;
+    }
+    // k_bucket_sort_records ranks a pair among the pairs of its bin — the pairs that share the key's top
+    // pb + 10 bits — so its cost grows with the bin: 3.7 ms per 10^8 records at 0.75 pairs per bin, 25 ms at 100
+    // (10^6 barcodes with 100 records each: all of a barcode's records in one bin), against 9 - 11 ms for the
+    // LSD sort.  Distinct prefixes of that length, from the sample's estimates: the barcodes, times what the
+    // prefix sees of the UMI, at most the distinct pairs.
+    if (sorting) {
+        const uint32_t L = job->pb + 10;
+        double prefixes = std::ldexp(1.0, (int)std::min<uint32_t>(L, 62));
+        prefixes = std::min(prefixes, L > bb ? std::min(d_est, r_est * std::ldexp(1.0, (int)std::min<uint32_t>(L - bb, 40))) : r_est);
+        if ((double)n / std::max(prefixes, 1.0) > 24.0) return IBU_OK;
+    }
     if (ordered && !sorting && job->pb + 1 > bb) {  // fewer barcode bits than bucket bits: a barcode would span buckets
         if (!forced) return IBU_OK;
         ordered = false;

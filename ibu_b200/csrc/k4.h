@@ -91,6 +91,7 @@ struct K4Sample {
     uint64_t unordered = 0;                  // sampled records whose successor is smaller: 0 for sorted input
     double pair_coll = 0;                    // sum over pairs of C(occurrences, 2)
     double pair_f1 = 0, pair_f2 = 0, bc_f1 = 0, bc_f2 = 0;  // seen exactly once / twice
+    uint64_t bc_max = 0;                     // most sampled records under one barcode (1 if none repeats)
     uint32_t hist[130] = {};                 // [2][65] bit widths of the barcode / umi words
 };
 int k4_sample(ibu_gpu_ctx *ctx, const uint64_t *recs, uint64_t n, cudaStream_t s, K4Sample *out, ibu_error_t *err);

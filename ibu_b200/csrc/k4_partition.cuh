@@ -56,7 +56,7 @@ struct SampleArgs {
     uint32_t *hist;           // [2][65]: bit width of barcode / umi words
 };
 enum { kSmpPairs = 0, kSmpBarcodes = 1, kSmpUnordered = 2, kSmpPairColl = 3, kSmpPairF1 = 4, kSmpPairF2 = 5,
-       kSmpBcF1 = 6, kSmpBcF2 = 7, kSmpWords = 8 };
+       kSmpBcF1 = 6, kSmpBcF2 = 7, kSmpBcMax = 8 /* most sampled records under one barcode */, kSmpWords = 9 };
 
 // Inserts a fingerprint and returns how often it had been seen before (0 = new).
 __device__ __forceinline__ uint32_t fp_insert(uint64_t *tab, uint32_t *cnt, uint64_t mask, uint64_t fp) {
@@ -80,7 +80,7 @@ __global__ void __launch_bounds__(kBlockThreads) k_sample(const SampleArgs a) {
     __shared__ uint32_t h[2][65];
     for (uint32_t i = threadIdx.x; i < 130; i += blockDim.x) (&h[0][0])[i] = 0;
     __syncthreads();
-    uint32_t np = 0, nb = 0, bad = 0, coll = 0;
+    uint32_t np = 0, nb = 0, bad = 0, coll = 0, bc_max = 0;
     int32_t pf1 = 0, pf2 = 0, bf1 = 0, bf2 = 0;
     for (uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; j < a.m; j += (uint64_t)gridDim.x * blockDim.x) {
         const uint64_t i = a.m >= a.n ? j : mix64(j ^ 0x5bd1e995u) % a.n;  // hashed positions: no aliasing with periodic data
@@ -94,8 +94,12 @@ __global__ void __launch_bounds__(kBlockThreads) k_sample(const SampleArgs a) {
         const uint32_t before = fp_insert(a.ptab, a.pcnt, a.mask, mix64(bc ^ mix64(um + 0x9E3779B97F4A7C15ull)));
         coll += before;
         tally(before, np, pf1, pf2);
-        tally(fp_insert(a.btab, a.bcnt, a.mask, mix64(bc)), nb, bf1, bf2);
+        const uint32_t bc_before = fp_insert(a.btab, a.bcnt, a.mask, mix64(bc));
+        tally(bc_before, nb, bf1, bf2);
+        bc_max = max(bc_max, bc_before + 1u);
     }
+    bc_max = __reduce_max_sync(0xffffffffu, bc_max);
+    if ((threadIdx.x & 31u) == 0 && bc_max > 1u) atomicMax(a.out + kSmpBcMax, (unsigned long long)bc_max);
     const uint32_t vals[8] = {np, nb, bad, coll, (uint32_t)pf1, (uint32_t)pf2, (uint32_t)bf1, (uint32_t)bf2};
 #pragma unroll
     for (int k = 0; k < 8; k++) {  // (f1 / f2 deltas may be negative: two's-complement sums are exact)

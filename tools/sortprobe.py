@@ -21,7 +21,9 @@ def main():
     ap.add_argument("--records", type=int, default=100_000_000)
     ap.add_argument("--iters", type=int, default=4)
     ap.add_argument("--orders", default="asc,desc,random")
-    ap.add_argument("--check", action="store_true", help="verify sortedness with K4's sorted-stream probe")
+    ap.add_argument("--check", action="store_true", help="verify the order and the column sums with torch")
+    ap.add_argument("--gen", default="clean", choices=["clean", "zipf", "whitelist"],
+                    help="random barcodes / Zipf over 10^6 barcodes (hot barcodes: the partition declines) / 10x-like whitelist")
     args = ap.parse_args()
     n = args.records
     dev = torch.device("cuda", 0)
@@ -31,7 +33,9 @@ def main():
         recs = torch.empty(24 * n, dtype=torch.uint8, device=dev)
         back = torch.empty(24 * n, dtype=torch.uint8, device=dev)
         for order in args.orders.split(","):
-            ctx.generate_records_async(recs, 0, n, 16, 12, ibu.GEN_CLEAN, 0, 5, stream)
+            gen, param = {"clean": (ibu.GEN_CLEAN, 0), "zipf": (ibu.GEN_ZIPF, (4096 << 32) | 1_000_000),
+                          "whitelist": (ibu.GEN_WHITELIST, (20 << 32) | 1_000_000)}[args.gen]
+            ctx.generate_records_async(recs, 0, n, 16, 12, gen, param, 5, stream)
             words = recs.view(torch.int64).view(-1, 3)
             if order == "desc":
                 words[:, 2] = (n - 1) - words[:, 2]
@@ -48,7 +52,7 @@ def main():
                 b.record(stream)
                 stream.synchronize()
                 evms.append(a.elapsed_time(b))
-            line = dict(order=order, records=n, sweep=os.environ.get("IBU_B200_SWEEP", "2"),
+            line = dict(order=order, records=n, gen=args.gen, msd=os.environ.get("IBU_B200_SORT_MSD", "1"),
                         wall_ms=[round(x, 3) for x in wall], event_ms=[round(x, 3) for x in evms])
             if args.check:
                 out = back.view(torch.int64).view(-1, 3)
