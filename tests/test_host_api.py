@@ -40,6 +40,29 @@ def test_abi_exports_every_declared_symbol():
     assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
 
 
+def test_product_path_does_not_touch_the_oracle():
+    """oracle/ is test infrastructure: nothing under ibu_b200/ may import, link or execute it, and the
+    library carries device code for sm_100a only (no fallback path to fall back to)."""
+    import glob
+    import shutil
+    import subprocess
+
+    pkg = os.path.join(ROOT, "ibu_b200")
+    for path in glob.glob(os.path.join(pkg, "**", "*"), recursive=True):
+        if not os.path.isfile(path) or not path.endswith((".py", ".cu", ".cuh", ".cpp", ".h", "Makefile")):
+            continue
+        text = open(path, errors="replace").read()
+        code = re.sub(r"#.*|//.*|/\*.*?\*/|\"\"\".*?\"\"\"", "", text, flags=re.S if path.endswith(".py") else 0)
+        assert not re.search(r"^\s*(from|import)\s+oracle\b", code, flags=re.M), path
+        assert "libibu_oracle" not in code and "oracle_c" not in code and "oracle_np" not in code, path
+    ldd = subprocess.run(["ldd", _lib.LIB_PATH], capture_output=True, text=True).stdout
+    assert "oracle" not in ldd, ldd
+    if shutil.which("cuobjdump"):
+        elf = subprocess.run(["cuobjdump", "-lelf", _lib.LIB_PATH], capture_output=True, text=True).stdout
+        archs = set(re.findall(r"sm_\d+a?", elf))
+        assert archs == {"sm_100a"}, archs
+
+
 def test_host_stream_copy_any_alignment_and_size():
     """The non-temporal staging copy (head to 16-byte alignment, 64-byte body, tail) is exact."""
     rng = np.random.default_rng(7)
